@@ -1,0 +1,66 @@
+// common.cuh -- shared helpers for libarpde (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#define ARPDE_OK 0
+#define ARPDE_ERR_ARG 1
+#define ARPDE_ERR_CUDA 2
+#define ARPDE_ERR_UNSUPPORTED 3
+
+// thread-local last-error string (the only mutable global state of the library)
+void arpde_set_error(const char* fmt, ...);
+
+#define ARPDE_CHECK_ARG(cond, ...)                 \
+  do {                                             \
+    if (!(cond)) {                                 \
+      arpde_set_error(__VA_ARGS__);                \
+      return ARPDE_ERR_ARG;                        \
+    }                                              \
+  } while (0)
+
+#define ARPDE_CUDA(call)                                                             \
+  do {                                                                               \
+    cudaError_t e__ = (call);                                                        \
+    if (e__ != cudaSuccess) {                                                        \
+      arpde_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+      return ARPDE_ERR_CUDA;                                                         \
+    }                                                                                \
+  } while (0)
+
+#define ARPDE_LAUNCH_CHECK() ARPDE_CUDA(cudaGetLastError())
+
+int arpde_num_sms();   // cached cudaDevAttrMultiProcessorCount of the current device
+
+static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// block-wide double sum; result valid in thread 0.  blockDim.x multiple of 32, <= 1024.
+__device__ __forceinline__ double block_sum_d(double v) {
+  __shared__ double s_part[32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  v = warp_sum_d(v);
+  __syncthreads();
+  if (lane == 0) s_part[wid] = v;
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  v = (threadIdx.x < nw) ? s_part[threadIdx.x] : 0.0;
+  if (wid == 0) v = warp_sum_d(v);
+  return v;
+}
+
+__device__ __forceinline__ int wrap(int i, int n) {  // i in [-n, 2n)
+  return i < 0 ? i + n : (i >= n ? i - n : i);
+}

@@ -1,0 +1,39 @@
+// conv_common.cuh -- descriptors shared by the convolution kernels and the DenseED program runner.
+#pragma once
+#include "common.cuh"
+
+struct ConvDesc {
+  int N, cin, H, W;        // input dims (H = 1 for 1D), before the optional nearest x2
+  int cout, kh, kw, stride, up;
+  int relu_in;             // ReLU after the per-channel affine of the prologue
+  int act;                 // output activation (ARPDE_ACT_*)
+  int y_ctot, y_coff;      // output buffer channel count / channel offset (concat-free dense block)
+  int n_per_group;         // samples sharing one weight set (SWAG: ICs per weight sample)
+};
+
+struct ConvFwdArgs {
+  const float* x; long long x_bs;
+  int cin, H, W, up, up_h;
+  const float* w; long long w_gs;
+  const float* scale; const float* shift; long long ss_gs;
+  int relu_in;
+  float* y; int y_ctot, y_coff, cout, Ho, Wo, act;
+  double* stats;
+  int n_per_group, N;
+  int tiles_x, tiles_y, co_tiles, TH, TW, pitch, ci_chunk;
+};
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  switch (act) {
+    case 1: return tanhf(v);
+    case 2: return fmaxf(v, 0.f);
+    case 3: return v > 0.f ? v : 0.01f * v;
+    case 4: return 1.f / (1.f + expf(-v));
+    case 5: return 4.f * v > 20.f ? v : 0.25f * log1pf(expf(4.f * v));
+    default: return v;
+  }
+}
+
+int arpde_conv_fwd_launch(const ConvDesc& d, const float* x, long long x_bs, const float* w, long long w_gs,
+                          const float* scale, const float* shift, long long ss_gs, float* y, double* stats,
+                          cudaStream_t stream);

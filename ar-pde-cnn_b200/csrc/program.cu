@@ -1,0 +1,148 @@
+// program.cu -- DenseED "program" runner: executes the whole encoder-decoder as a short list of fused
+// conv ops (host-side C++ loop, no Python between launches) and the auto-regressive rollout on top.
+//
+// Replaces DenseED.forward (2D-Burgers-SWAG/nn/denseEDcirc2d.py:313-314, 1D-*/nn/denseEDcirc.py:306-307
+// resp. :294-295), i.e. nn.Sequential over ~30 modules / ~180 ATen ops, and the Python AR loops of
+// main.py test()/testSample() (2D :112-135,:160-179; 1D :106-121,:148-163).
+#include <vector>
+#include "common.cuh"
+#include "conv_common.cuh"
+#include "bn.cuh"
+#include "../../include/arpde.h"
+
+static int check_program(const arpde_op_t* ops, int n_ops, const arpde_buf_t* bufs, int n_bufs, int n_params) {
+  ARPDE_CHECK_ARG(ops && n_ops > 0 && (bufs || n_bufs == 0), "densed: empty program");
+  for (int i = 0; i < n_ops; ++i) {
+    const arpde_op_t& o = ops[i];
+    ARPDE_CHECK_ARG(o.in_buf >= -1 && o.in_buf < n_bufs, "densed: op %d bad in_buf %d", i, o.in_buf);
+    ARPDE_CHECK_ARG(o.out_buf == -2 || (o.out_buf >= 0 && o.out_buf < n_bufs), "densed: op %d bad out_buf %d", i, o.out_buf);
+    ARPDE_CHECK_ARG(o.w_param >= 0 && o.w_param < n_params, "densed: op %d bad w_param", i);
+    ARPDE_CHECK_ARG(o.bn_param == -1 || (o.bn_param >= 0 && o.bn_param + 4 < n_params), "densed: op %d bad bn_param", i);
+  }
+  return ARPDE_OK;
+}
+
+struct RunCtx {
+  const arpde_op_t* ops; int n_ops;
+  const arpde_buf_t* bufs; int n_bufs;
+  void* const* params; const int64_t* gstride; int n_params;
+  int N, n_per_group, groups, H, W;
+  float* work; float* ss; int bn_total; double* stats; float* saved;
+  float momentum, eps;
+  cudaStream_t stream;
+};
+
+static int fold_eval(const RunCtx& c) {
+  BnTable t; t.n = 0;
+  for (int i = 0; i < c.n_ops; ++i) {
+    const arpde_op_t& o = c.ops[i];
+    if (o.bn_param < 0) continue;
+    BnDesc& d = t.d[t.n++];
+    d.gamma = (const float*)c.params[o.bn_param]; d.beta = (const float*)c.params[o.bn_param + 1];
+    d.rmean = (const float*)c.params[o.bn_param + 2]; d.rvar = (const float*)c.params[o.bn_param + 3];
+    d.g_gs = c.gstride[o.bn_param]; d.b_gs = c.gstride[o.bn_param + 1]; d.C = o.cin; d.off = o.bn_off;
+    if (t.n == BN_TABLE_MAX) {
+      int rc = arpde_bn_fold_eval_launch(t, c.groups, c.ss, c.ss + (long long)c.groups * c.bn_total, c.bn_total, c.eps, c.stream);
+      if (rc) return rc; t.n = 0;
+    }
+  }
+  return arpde_bn_fold_eval_launch(t, c.groups, c.ss, c.ss + (long long)c.groups * c.bn_total, c.bn_total, c.eps, c.stream);
+}
+
+// one pass over the ops.  x: network input (batch stride x_bs), y: output tensor with y_ctot channels, written at y_coff
+static int run_ops(const RunCtx& c, const float* x, long long x_bs, float* y, int y_ctot, int y_coff, int training) {
+  for (int i = 0; i < c.n_ops; ++i) {
+    const arpde_op_t& o = c.ops[i];
+    ConvDesc d;
+    d.N = c.N; d.cin = o.cin; d.cout = o.cout; d.kh = o.kh; d.kw = o.kw; d.stride = o.stride; d.up = o.up;
+    d.relu_in = o.bn_param >= 0; d.act = o.act; d.n_per_group = c.n_per_group;
+    const float* in; long long in_bs;
+    if (o.in_buf < 0) { in = x; in_bs = x_bs; d.H = c.H; d.W = c.W; }
+    else { const arpde_buf_t& b = c.bufs[o.in_buf]; in = c.work + b.offset; in_bs = (long long)b.ctot * b.h * b.w; d.H = b.h; d.W = b.w; }
+    float* out; double* st = nullptr;
+    if (o.out_buf == -2) { out = y; d.y_ctot = y_ctot; d.y_coff = y_coff; }
+    else {
+      const arpde_buf_t& b = c.bufs[o.out_buf]; out = c.work + b.offset; d.y_ctot = b.ctot; d.y_coff = o.out_coff;
+      if (training) st = c.stats + b.stats_off;
+    }
+    const float *scale = nullptr, *shift = nullptr;
+    if (o.bn_param >= 0) {
+      scale = c.ss + o.bn_off; shift = c.ss + (long long)c.groups * c.bn_total + o.bn_off;
+      if (training) {
+        const arpde_buf_t& b = c.bufs[o.in_buf];
+        float* sm = c.saved ? c.saved + o.bn_off : nullptr;
+        int rc = arpde_bn_finalize_train_launch(c.stats + b.stats_off, (double)c.N * b.h * b.w, (const float*)c.params[o.bn_param],
+                                                (const float*)c.params[o.bn_param + 1], (float*)c.params[o.bn_param + 2],
+                                                (float*)c.params[o.bn_param + 3], (long long*)c.params[o.bn_param + 4], c.momentum,
+                                                c.eps, (float*)scale, (float*)shift, sm, sm ? sm + c.bn_total : nullptr, o.cin, c.stream);
+        if (rc) return rc;
+      }
+    }
+    int rc = arpde_conv_fwd_launch(d, in, in_bs, (const float*)c.params[o.w_param], c.gstride[o.w_param], scale, shift,
+                                   c.bn_total, out, st, c.stream);
+    if (rc) return rc;
+  }
+  return ARPDE_OK;
+}
+
+static int make_ctx(RunCtx* c, const arpde_op_t* ops, int n_ops, const arpde_buf_t* bufs, int n_bufs, void* const* params,
+                    const int64_t* gstride, int n_params, int N, int n_per_group, int H, int W, float* work, float* ss,
+                    int bn_total, double* stats, float* saved, double momentum, double eps, cudaStream_t stream) {
+  int rc = check_program(ops, n_ops, bufs, n_bufs, n_params); if (rc) return rc;
+  ARPDE_CHECK_ARG(params && gstride, "densed: null parameter table");
+  ARPDE_CHECK_ARG(N > 0 && H > 0 && W > 0, "densed: bad dims N=%d H=%d W=%d", N, H, W);
+  if (n_per_group <= 0) n_per_group = N;
+  ARPDE_CHECK_ARG(N % n_per_group == 0, "densed: N=%d not a multiple of n_per_group=%d", N, n_per_group);
+  c->ops = ops; c->n_ops = n_ops; c->bufs = bufs; c->n_bufs = n_bufs; c->params = params; c->gstride = gstride; c->n_params = n_params;
+  c->N = N; c->n_per_group = n_per_group; c->groups = N / n_per_group; c->H = H; c->W = W;
+  c->work = work; c->ss = ss; c->bn_total = bn_total; c->stats = stats; c->saved = saved;
+  c->momentum = (float)momentum; c->eps = (float)eps; c->stream = stream;
+  return ARPDE_OK;
+}
+
+extern "C" int arpde_densed_forward(const arpde_op_t* ops, int n_ops, const arpde_buf_t* bufs, int n_bufs, void* const* params_host,
+                                    const int64_t* param_gstride_host, int n_params, const float* x, int64_t x_bstride, int N,
+                                    int n_per_group, int H, int W, float* y, int y_ctot, int y_coff, float* workspace,
+                                    float* scale_shift, int bn_total, double* stats, int64_t stats_len, float* saved_mean_invstd,
+                                    int training, double momentum, double eps, arpde_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  RunCtx c;
+  int rc = make_ctx(&c, ops, n_ops, bufs, n_bufs, params_host, param_gstride_host, n_params, N, n_per_group, H, W, workspace,
+                    scale_shift, bn_total, stats, saved_mean_invstd, momentum, eps, stream);
+  if (rc) return rc;
+  ARPDE_CHECK_ARG(x && y && (workspace || n_bufs == 0), "densed_forward: null pointer");
+  ARPDE_CHECK_ARG(bn_total == 0 || scale_shift, "densed_forward: scale/shift scratch missing");
+  if (training) {
+    ARPDE_CHECK_ARG(c.groups == 1, "densed_forward: training with grouped weights is not defined");
+    ARPDE_CHECK_ARG(stats && stats_len > 0, "densed_forward: training needs the stats scratch");
+    ARPDE_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * stats_len, stream));
+  } else {
+    rc = fold_eval(c); if (rc) return rc;
+  }
+  return run_ops(c, x, x_bstride, y, y_ctot, y_coff, training);
+}
+
+// Auto-regressive rollout, eval mode.  traj: [N, traj_ctot, H, W] with traj_ctot = c_hist + T*c_out; the caller fills the first
+// c_hist channels (the repeated initial condition); step t reads channels [t*c_out, t*c_out + c_in) and writes the prediction
+// to channels [c_hist + t*c_out, +c_out): the sliding history window of the reference loops without any copy or cat.
+extern "C" int arpde_rollout(const arpde_op_t* ops, int n_ops, const arpde_buf_t* bufs, int n_bufs, void* const* params_host,
+                             const int64_t* param_gstride_host, int n_params, float* traj, int traj_ctot, int c_in, int c_hist,
+                             int c_out, int T, int N, int n_per_group, int H, int W, float* workspace, float* scale_shift,
+                             int bn_total, double eps, arpde_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  RunCtx c;
+  int rc = make_ctx(&c, ops, n_ops, bufs, n_bufs, params_host, param_gstride_host, n_params, N, n_per_group, H, W, workspace,
+                    scale_shift, bn_total, nullptr, nullptr, 0.1, eps, stream);
+  if (rc) return rc;
+  ARPDE_CHECK_ARG(traj && T >= 0 && c_in > 0 && c_out > 0 && c_hist >= c_in, "rollout: bad args");
+  ARPDE_CHECK_ARG(traj_ctot >= c_hist + T * c_out, "rollout: trajectory has %d channels, needs %d", traj_ctot, c_hist + T * c_out);
+  ARPDE_CHECK_ARG(ops[0].cin == c_in && ops[n_ops - 1].cout == c_out, "rollout: program does not match c_in/c_out");
+  rc = fold_eval(c); if (rc) return rc;
+  const long long HW = (long long)H * W, bs = (long long)traj_ctot * HW;
+  for (int t = 0; t < T; ++t) {
+    const float* x = traj + (long long)(c_hist - c_in + t * c_out) * HW;
+    rc = run_ops(c, x, bs, traj, traj_ctot, c_hist + t * c_out, 0);
+    if (rc) return rc;
+  }
+  return ARPDE_OK;
+}

@@ -1,0 +1,551 @@
+// stencil.cu -- fused periodic finite-difference time integrators (Crank-Nicolson / backward
+// Euler) for 2D coupled Burgers, 1D Burgers and 1D Kuramoto-Sivashinsky, forward + adjoint,
+// with an optional fused sum-of-squared-errors reduction (the physics-constrained loss).
+//
+// Replaces (reference file:line):
+//   2D-Burgers-SWAG/nn/burger2DFiniteDifference.py:148-211  Burger2DIntegrate.{backwardEuler,crankNicolson}
+//   1D-Burger-SWAG/nn/burgerFiniteDifference.py:264-302     BurgerIntegrate.{backwardEuler,crankNicolson}
+//   1D-KS-SWAG/nn/ksFiniteDifference.py:139-173             KSIntegrate.{backwardEuler,crankNicolson}
+// and the autograd graphs torch builds through them (12 / 4 / 6 pad+conv pairs per call).
+//
+// Layout: fp32, NCHW / NCL.  Inputs may be channel-slice views of a history tensor: each input
+// carries its own batch stride (elements); channel stride is H*W (resp. L).  Outputs are compact.
+#include "common.cuh"
+#include "../../include/arpde.h"
+
+// =====================================================================================
+// 2D coupled Burgers
+//   R_u = -gh(u^2/2) - v gv(u) + nu L(u) ;  R_v = -u gh(v) - gv(v^2/2) + nu L(v)
+//   gh = Sobel/8 along W, gv = Sobel/8 along H, L = [[.5,0,.5],[0,-2,0],[.5,0,.5]]
+//   separable form used here, per column x with rows a=y-1, b=y, c=y+1 of field f:
+//       D_f = c - a,  E_f = a + c,  S_f = a + 2b + c
+//   gh(f) = (S_f[x+1]-S_f[x-1])/(8dx); gv(f) = (D_f[x-1]+2D_f[x]+D_f[x+1])/(8dx)
+//   L(f)  = (E_f[x-1]+E_f[x+1]-4 f)/(2dx^2)
+// =====================================================================================
+struct B2Coef {
+  float k1;    // 1/(8 dx)
+  float k1h;   // 1/(16 dx)     (the 1/2 of u^2/2 folded in)
+  float k2;    // nu/(2 dx^2)
+  float c;     // dt/2 (CN) or dt (BE)
+  int cn;      // 1: Crank-Nicolson (adds R(u0)); 0: backward Euler
+};
+
+struct Col6 { float Du, Eu, Squ, Sv, Ev, Dqv; };
+
+__device__ __forceinline__ Col6 colq(float ua, float ub, float uc, float va, float vb, float vc) {
+  Col6 q;
+  q.Du = uc - ua;
+  q.Eu = ua + uc;
+  q.Squ = fmaf(2.f * ub, ub, fmaf(ua, ua, uc * uc));
+  q.Ev = va + vc;
+  q.Sv = fmaf(2.f, vb, q.Ev);
+  q.Dqv = fmaf(vc, vc, -va * va);
+  return q;
+}
+
+__device__ __forceinline__ void rhs_point(const Col6& l, const Col6& m, const Col6& r, float ub, float vb,
+                                          const B2Coef& k, float& Ru, float& Rv) {
+  const float gh_qu = r.Squ - l.Squ;
+  const float gv_u = fmaf(2.f, m.Du, l.Du + r.Du);
+  const float lap_u = fmaf(-4.f, ub, l.Eu + r.Eu);
+  const float gh_v = r.Sv - l.Sv;
+  const float gv_qv = fmaf(2.f, m.Dqv, l.Dqv + r.Dqv);
+  const float lap_v = fmaf(-4.f, vb, l.Ev + r.Ev);
+  Ru = fmaf(-vb, k.k1 * gv_u, fmaf(-k.k1h, gh_qu, k.k2 * lap_u));
+  Rv = fmaf(-ub, k.k1 * gh_v, fmaf(-k.k1h, gv_qv, k.k2 * lap_v));
+}
+
+// ---- generic path: one thread per grid point, any H, W >= 1 (L1/L2 serve the 3x3 reuse) ----
+__device__ __forceinline__ void rhs_generic(const float* __restrict__ u, const float* __restrict__ v, int H, int W,
+                                            int y, int x, const B2Coef& k, float& Ru, float& Rv, float& uc_, float& vc_) {
+  const int ym = wrap(y - 1, H), yp = wrap(y + 1, H), xm = wrap(x - 1, W), xp = wrap(x + 1, W);
+  const int xs[3] = {xm, x, xp};
+  Col6 q[3];
+  float ub = 0.f, vb = 0.f;
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const float ua = u[ym * W + xs[j]], ubj = u[y * W + xs[j]], uc = u[yp * W + xs[j]];
+    const float va = v[ym * W + xs[j]], vbj = v[y * W + xs[j]], vc = v[yp * W + xs[j]];
+    q[j] = colq(ua, ubj, uc, va, vbj, vc);
+    if (j == 1) { ub = ubj; vb = vbj; }
+  }
+  rhs_point(q[0], q[1], q[2], ub, vb, k, Ru, Rv);
+  uc_ = ub; vc_ = vb;
+}
+
+__global__ void __launch_bounds__(256) burgers2d_fwd_generic(const float* __restrict__ up, int64_t up_bs,
+                                                             const float* __restrict__ u0, int64_t u0_bs,
+                                                             float* __restrict__ ustar, double* __restrict__ sse,
+                                                             int N, int H, int W, B2Coef k) {
+  const int64_t HW = (int64_t)H * W, total = (int64_t)N * HW;
+  float acc = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int n = (int)(i / HW), rem = (int)(i - (int64_t)n * HW), y = rem / W, x = rem - y * W;
+    const float* pu = up + n * up_bs; const float* p0 = u0 + n * u0_bs;
+    float Ru, Rv, uu, vv, R0u = 0.f, R0v = 0.f, u0c, v0c;
+    rhs_generic(pu, pu + HW, H, W, y, x, k, Ru, Rv, uu, vv);
+    if (k.cn) rhs_generic(p0, p0 + HW, H, W, y, x, k, R0u, R0v, u0c, v0c);
+    else { u0c = p0[rem]; v0c = p0[HW + rem]; }
+    const float su = fmaf(k.c, Ru + R0u, u0c), sv = fmaf(k.c, Rv + R0v, v0c);
+    if (ustar) { ustar[(int64_t)n * 2 * HW + rem] = su; ustar[(int64_t)n * 2 * HW + HW + rem] = sv; }
+    const float du = su - uu, dv = sv - vv;
+    acc = fmaf(du, du, fmaf(dv, dv, acc));
+  }
+  if (sse) {
+    const double t = block_sum_d((double)acc);
+    if (threadIdx.x == 0) atomicAdd(sse, t);
+  }
+}
+
+// ---- fast path: each thread owns 4 consecutive x (one float4 per field per row) and rolls down RY
+//      rows keeping rows a,b in registers; halo columns come from the neighbour lanes by shuffle.
+//      LX lanes (power of two <= 32) span one row segment of 4*LX points; if the row is wider than
+//      one warp (EDGE) lanes 0/31 rebuild the halo column from global memory.
+struct Row4 { float u[4], v[4]; };
+
+__device__ __forceinline__ Row4 load_row(const float* __restrict__ pu, const float* __restrict__ pv, int off) {
+  Row4 r;
+  const float4 a = __ldg(reinterpret_cast<const float4*>(pu + off));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(pv + off));
+  r.u[0] = a.x; r.u[1] = a.y; r.u[2] = a.z; r.u[3] = a.w;
+  r.v[0] = b.x; r.v[1] = b.y; r.v[2] = b.z; r.v[3] = b.w;
+  return r;
+}
+
+__device__ __forceinline__ Col6 shfl_col(const Col6& q, int src) {
+  Col6 o;
+  o.Du = __shfl_sync(0xffffffffu, q.Du, src); o.Eu = __shfl_sync(0xffffffffu, q.Eu, src);
+  o.Squ = __shfl_sync(0xffffffffu, q.Squ, src); o.Sv = __shfl_sync(0xffffffffu, q.Sv, src);
+  o.Ev = __shfl_sync(0xffffffffu, q.Ev, src); o.Dqv = __shfl_sync(0xffffffffu, q.Dqv, src);
+  return o;
+}
+
+struct Halo2 { float ua, ub, va, vb; };   // rolling rows a,b of one halo column (EDGE lanes only)
+
+template <bool EDGE>
+__device__ __forceinline__ void rhs_row4(const Row4& a, const Row4& b, const Row4& c, int lsrc, int rsrc,
+                                         bool edgeL, bool edgeR, Halo2& hl, Halo2& hr,
+                                         const float* __restrict__ pu, const float* __restrict__ pv, int rowc_off,
+                                         int xl, int xr, const B2Coef& k, float* Ru, float* Rv) {
+  Col6 q[6];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) q[j + 1] = colq(a.u[j], b.u[j], c.u[j], a.v[j], b.v[j], c.v[j]);
+  q[0] = shfl_col(q[4], lsrc);
+  q[5] = shfl_col(q[1], rsrc);
+  if (EDGE) {
+    if (edgeL) {
+      const float uc = __ldg(pu + rowc_off + xl), vc = __ldg(pv + rowc_off + xl);
+      q[0] = colq(hl.ua, hl.ub, uc, hl.va, hl.vb, vc);
+      hl.ua = hl.ub; hl.ub = uc; hl.va = hl.vb; hl.vb = vc;
+    }
+    if (edgeR) {
+      const float uc = __ldg(pu + rowc_off + xr), vc = __ldg(pv + rowc_off + xr);
+      q[5] = colq(hr.ua, hr.ub, uc, hr.va, hr.vb, vc);
+      hr.ua = hr.ub; hr.ub = uc; hr.va = hr.vb; hr.vb = vc;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) rhs_point(q[j], q[j + 1], q[j + 2], b.u[j], b.v[j], k, Ru[j], Rv[j]);
+}
+
+template <int RY, bool EDGE>
+__global__ void __launch_bounds__(256) burgers2d_fwd_vec4(const float* __restrict__ up, int64_t up_bs,
+                                                          const float* __restrict__ u0, int64_t u0_bs,
+                                                          float* __restrict__ ustar, double* __restrict__ sse,
+                                                          int N, int H, int W, int lx_log2, B2Coef k) {
+  const int LX = 1 << lx_log2;                  // lanes per row segment
+  const int lane = threadIdx.x & 31;
+  const int G = 32 >> lx_log2;                  // strip-groups per warp
+  const int segs = (W >> 2) >> lx_log2;         // row segments (1 unless EDGE)
+  const int nstrips = (H + RY - 1) / RY;
+  const int64_t ngroups = (int64_t)N * nstrips * segs;
+  const int64_t warp_id = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int64_t gid = warp_id * G + (lane >> lx_log2);
+  const bool active = gid < ngroups;
+  if (!active) gid = ngroups - 1;               // keep the lane alive for the shuffles
+  const int seg = (int)(gid % segs);
+  const int strip = (int)((gid / segs) % nstrips);
+  const int n = (int)(gid / ((int64_t)segs * nstrips));
+  const int lxi = lane & (LX - 1);
+  const int x0 = ((seg << lx_log2) + lxi) << 2;
+  const int lbase = lane & ~(LX - 1);
+  const int lsrc = lbase | ((lxi - 1) & (LX - 1)), rsrc = lbase | ((lxi + 1) & (LX - 1));
+  const bool edgeL = EDGE && lxi == 0, edgeR = EDGE && lxi == LX - 1;
+  const int xl = wrap(x0 - 1, W), xr = wrap(x0 + 4, W);
+  const int HW = H * W;
+  const float* pu = up + (int64_t)n * up_bs; const float* pv = pu + HW;
+  const float* p0u = u0 + (int64_t)n * u0_bs; const float* p0v = p0u + HW;
+  const int y0 = strip * RY;
+
+  Row4 a = load_row(pu, pv, wrap(y0 - 1, H) * W + x0), b = load_row(pu, pv, y0 * W + x0);
+  Row4 a0, b0;
+  Halo2 hl = {0, 0, 0, 0}, hr = {0, 0, 0, 0}, hl0 = {0, 0, 0, 0}, hr0 = {0, 0, 0, 0};
+  if (k.cn) { a0 = load_row(p0u, p0v, wrap(y0 - 1, H) * W + x0); b0 = load_row(p0u, p0v, y0 * W + x0); }
+  else { a0 = b0 = a; }
+  if (EDGE) {
+    const int ra = wrap(y0 - 1, H) * W, rb = y0 * W;
+    if (edgeL) { hl = {pu[ra + xl], pu[rb + xl], pv[ra + xl], pv[rb + xl]}; if (k.cn) hl0 = {p0u[ra + xl], p0u[rb + xl], p0v[ra + xl], p0v[rb + xl]}; }
+    if (edgeR) { hr = {pu[ra + xr], pu[rb + xr], pv[ra + xr], pv[rb + xr]}; if (k.cn) hr0 = {p0u[ra + xr], p0u[rb + xr], p0v[ra + xr], p0v[rb + xr]}; }
+  }
+  float acc = 0.f;
+  int yc = wrap(y0 + 1, H);
+  Row4 c = load_row(pu, pv, yc * W + x0), c0;
+  if (k.cn) c0 = load_row(p0u, p0v, yc * W + x0); else c0 = c;
+#pragma unroll
+  for (int r = 0; r < RY; ++r) {
+    const int y = y0 + r;
+    // prefetch row y+2 while row y is being computed
+    const int yn = wrap(yc + 1, H);
+    Row4 nx = load_row(pu, pv, yn * W + x0), nx0;
+    if (k.cn) nx0 = load_row(p0u, p0v, yn * W + x0); else nx0 = nx;
+    float Ru[4], Rv[4], Su[4], Sv[4];
+    rhs_row4<EDGE>(a, b, c, lsrc, rsrc, edgeL, edgeR, hl, hr, pu, pv, yc * W, xl, xr, k, Ru, Rv);
+    if (k.cn) {
+      float R0u[4], R0v[4];
+      rhs_row4<EDGE>(a0, b0, c0, lsrc, rsrc, edgeL, edgeR, hl0, hr0, p0u, p0v, yc * W, xl, xr, k, R0u, R0v);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { Su[j] = fmaf(k.c, Ru[j] + R0u[j], b0.u[j]); Sv[j] = fmaf(k.c, Rv[j] + R0v[j], b0.v[j]); }
+    } else {
+      // backward Euler: the previous state enters only as the additive term
+      const Row4 z = load_row(p0u, p0v, wrap(y, H) * W + x0);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { Su[j] = fmaf(k.c, Ru[j], z.u[j]); Sv[j] = fmaf(k.c, Rv[j], z.v[j]); }
+    }
+    if (active && y < H) {
+      if (ustar) {
+        float* o = ustar + (int64_t)n * 2 * HW + y * W + x0;
+        *reinterpret_cast<float4*>(o) = make_float4(Su[0], Su[1], Su[2], Su[3]);
+        *reinterpret_cast<float4*>(o + HW) = make_float4(Sv[0], Sv[1], Sv[2], Sv[3]);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float du = Su[j] - b.u[j], dv = Sv[j] - b.v[j];
+        acc = fmaf(du, du, fmaf(dv, dv, acc));
+      }
+    }
+    a = b; b = c; c = nx; a0 = b0; b0 = c0; c0 = nx0; yc = yn;
+  }
+  if (sse) {
+    const double t = block_sum_d((double)acc);
+    if (threadIdx.x == 0) atomicAdd(sse, t);
+  }
+}
+
+// ---- adjoint, generic: one thread per point.  With G = dL/dustar (gu,gv):
+//   d/du = c [ u gh(gu) + gv(v gu) + nu L(gu) - gv_ gh(v) ],  d/dv = c [ -gu gv(u) + gh(u gv_) + v gv(gv_) + nu L(gv_) ]
+//   (gh, gv antisymmetric => adjoint = -gh, -gv; L symmetric), plus identity G onto uPred0.
+__device__ __forceinline__ void adj_generic(const float* __restrict__ u, const float* __restrict__ v,
+                                            const float* __restrict__ gu, const float* __restrict__ gv, int H, int W,
+                                            int y, int x, const B2Coef& k, float& du, float& dv) {
+  const int ys[3] = {wrap(y - 1, H), y, wrap(y + 1, H)};
+  const int xs[3] = {wrap(x - 1, W), x, wrap(x + 1, W)};
+  float U[3][3], V[3][3], A[3][3], B[3][3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const int o = ys[i] * W + xs[j];
+      U[i][j] = u[o]; V[i][j] = v[o]; A[i][j] = gu[o]; B[i][j] = gv[o];
+    }
+  auto GH = [](float f[3][3]) { return (f[0][2] - f[0][0]) + 2.f * (f[1][2] - f[1][0]) + (f[2][2] - f[2][0]); };
+  auto GV = [](float f[3][3]) { return (f[2][0] - f[0][0]) + 2.f * (f[2][1] - f[0][1]) + (f[2][2] - f[0][2]); };
+  auto LP = [](float f[3][3]) { return f[0][0] + f[0][2] + f[2][0] + f[2][2] - 4.f * f[1][1]; };
+  float VA[3][3], UB[3][3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { VA[i][j] = V[i][j] * A[i][j]; UB[i][j] = U[i][j] * B[i][j]; }
+  const float uc = U[1][1], vc = V[1][1], ac = A[1][1], bc = B[1][1];
+  du = k.c * (k.k1 * (uc * GH(A) + GV(VA) - bc * GH(V)) + k.k2 * LP(A));
+  dv = k.c * (k.k1 * (-ac * GV(U) + GH(UB) + vc * GV(B)) + k.k2 * LP(B));
+}
+
+__global__ void __launch_bounds__(256) burgers2d_bwd_generic(const float* __restrict__ up, int64_t up_bs,
+                                                             const float* __restrict__ u0, int64_t u0_bs,
+                                                             const float* __restrict__ g, float* __restrict__ gup,
+                                                             float* __restrict__ gu0, int N, int H, int W, B2Coef k) {
+  const int64_t HW = (int64_t)H * W, total = (int64_t)N * HW;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int n = (int)(i / HW), rem = (int)(i - (int64_t)n * HW), y = rem / W, x = rem - y * W;
+    const float* pu = up + n * up_bs; const float* p0 = u0 + n * u0_bs;
+    const float* pg = g + (int64_t)n * 2 * HW;
+    float du, dv;
+    adj_generic(pu, pu + HW, pg, pg + HW, H, W, y, x, k, du, dv);
+    gup[(int64_t)n * 2 * HW + rem] = du; gup[(int64_t)n * 2 * HW + HW + rem] = dv;
+    float d0u = 0.f, d0v = 0.f;
+    if (k.cn) adj_generic(p0, p0 + HW, pg, pg + HW, H, W, y, x, k, d0u, d0v);
+    gu0[(int64_t)n * 2 * HW + rem] = d0u + pg[rem]; gu0[(int64_t)n * 2 * HW + HW + rem] = d0v + pg[HW + rem];
+  }
+}
+
+static int make_b2coef(double dx, double nu, double dt, int mode, B2Coef* k) {
+  ARPDE_CHECK_ARG(dx > 0 && (mode == ARPDE_CN || mode == ARPDE_BE), "burgers2d: bad dx=%g or mode=%d", dx, mode);
+  k->k1 = (float)(0.125 / dx); k->k1h = (float)(0.0625 / dx); k->k2 = (float)(nu * 0.5 / (dx * dx));
+  k->cn = mode == ARPDE_CN; k->c = (float)(k->cn ? 0.5 * dt : dt);
+  return ARPDE_OK;
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+extern "C" int arpde_cn_burgers2d_fwd(const float* uPred, int64_t up_bstride, const float* uPred0, int64_t u0_bstride,
+                                      float* ustar, double* sse_out, int N, int H, int W, double dx, double nu,
+                                      double dt, int mode, arpde_stream_t stream_) {
+  ARPDE_CHECK_ARG(uPred && uPred0 && (ustar || sse_out), "burgers2d_fwd: null pointer");
+  ARPDE_CHECK_ARG(N >= 0 && H >= 1 && W >= 1, "burgers2d_fwd: bad dims N=%d H=%d W=%d", N, H, W);
+  B2Coef k; int rc = make_b2coef(dx, nu, dt, mode, &k); if (rc) return rc;
+  if (sse_out) ARPDE_CUDA(cudaMemsetAsync(sse_out, 0, sizeof(double), (cudaStream_t)stream_));
+  if (N == 0) return ARPDE_OK;
+  const int w4 = W >> 2;
+  const bool pow2 = w4 > 0 && (w4 & (w4 - 1)) == 0;
+  const bool vec_ok = (W % 4 == 0) && H >= 2 && aligned16(uPred) && aligned16(uPred0) && (!ustar || aligned16(ustar)) &&
+                      up_bstride % 4 == 0 && u0_bstride % 4 == 0 && (pow2 || w4 % 32 == 0);
+  if (vec_ok) {
+    constexpr int RY = 8;
+    int lx_log2 = 0; while ((1 << lx_log2) < (w4 < 32 ? w4 : 32)) ++lx_log2;
+    const bool edge = w4 > 32;
+    const int G = 32 >> lx_log2, segs = w4 >> lx_log2, nstrips = (H + RY - 1) / RY;
+    const int64_t ngroups = (int64_t)N * nstrips * segs, nwarps = ceil_div64(ngroups, G);
+    const int64_t blocks = ceil_div64(nwarps, 8);
+    if (edge) burgers2d_fwd_vec4<RY, true><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream_>>>(uPred, up_bstride, uPred0, u0_bstride, ustar, sse_out, N, H, W, lx_log2, k);
+    else burgers2d_fwd_vec4<RY, false><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream_>>>(uPred, up_bstride, uPred0, u0_bstride, ustar, sse_out, N, H, W, lx_log2, k);
+  } else {
+    const int64_t total = (int64_t)N * H * W;
+    int64_t blocks = ceil_div64(total, 256); const int64_t cap = (int64_t)arpde_num_sms() * 32; if (blocks > cap) blocks = cap;
+    burgers2d_fwd_generic<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream_>>>(uPred, up_bstride, uPred0, u0_bstride, ustar, sse_out, N, H, W, k);
+  }
+  ARPDE_LAUNCH_CHECK();
+  return ARPDE_OK;
+}
+
+// test hook: force the generic kernel (parity of the two paths is a test)
+extern "C" int arpde_cn_burgers2d_fwd_generic(const float* uPred, int64_t up_bstride, const float* uPred0, int64_t u0_bstride,
+                                              float* ustar, double* sse_out, int N, int H, int W, double dx, double nu,
+                                              double dt, int mode, arpde_stream_t stream_) {
+  ARPDE_CHECK_ARG(uPred && uPred0 && (ustar || sse_out) && N > 0, "burgers2d_fwd_generic: bad args");
+  B2Coef k; int rc = make_b2coef(dx, nu, dt, mode, &k); if (rc) return rc;
+  if (sse_out) ARPDE_CUDA(cudaMemsetAsync(sse_out, 0, sizeof(double), (cudaStream_t)stream_));
+  const int64_t total = (int64_t)N * H * W;
+  int64_t blocks = ceil_div64(total, 256); const int64_t cap = (int64_t)arpde_num_sms() * 32; if (blocks > cap) blocks = cap;
+  burgers2d_fwd_generic<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream_>>>(uPred, up_bstride, uPred0, u0_bstride, ustar, sse_out, N, H, W, k);
+  ARPDE_LAUNCH_CHECK();
+  return ARPDE_OK;
+}
+
+extern "C" int arpde_cn_burgers2d_bwd(const float* uPred, int64_t up_bstride, const float* uPred0, int64_t u0_bstride,
+                                      const float* grad_ustar, float* grad_uPred, float* grad_uPred0, int N, int H, int W,
+                                      double dx, double nu, double dt, int mode, arpde_stream_t stream_) {
+  ARPDE_CHECK_ARG(uPred && uPred0 && grad_ustar && grad_uPred && grad_uPred0, "burgers2d_bwd: null pointer");
+  ARPDE_CHECK_ARG(N >= 0 && H >= 1 && W >= 1, "burgers2d_bwd: bad dims");
+  B2Coef k; int rc = make_b2coef(dx, nu, dt, mode, &k); if (rc) return rc;
+  if (N == 0) return ARPDE_OK;
+  const int64_t total = (int64_t)N * H * W;
+  int64_t blocks = ceil_div64(total, 256); const int64_t cap = (int64_t)arpde_num_sms() * 32; if (blocks > cap) blocks = cap;
+  burgers2d_bwd_generic<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream_>>>(uPred, up_bstride, uPred0, u0_bstride, grad_ustar, grad_uPred, grad_uPred0, N, H, W, k);
+  ARPDE_LAUNCH_CHECK();
+  return ARPDE_OK;
+}
+
+// =====================================================================================
+// 1D systems (periodic, one channel): tap tables up to radius 3.
+//   Burgers: ustar = u0 - c[(u g(u) + u0 g(u0)) - nu (L(u)+L(u0))]           (CN)
+//            ustar = u0 + dt(-0.25 g(u^2) + nu L(u))                          (BE, literal)
+//   KS:      ustar = u0 - c[(g(u^2)/2 + L(u) + nu D4(u)) + (same at u0)]      (CN; BE drops u0 rhs, c=dt)
+// =====================================================================================
+struct Taps1D {
+  float g[7], l[7], d[7];   // centred tap tables (index 3 = centre), pre-divided, times 1/dx^n
+  int r;                    // max radius used
+  float nu, c;
+  int cn, system;
+};
+
+__device__ __forceinline__ void load7(const float* __restrict__ p, int i, int L, int r, float* w) {
+#pragma unroll
+  for (int t = -3; t <= 3; ++t) w[t + 3] = (t >= -r && t <= r) ? p[wrap(i + t, L)] : 0.f;
+}
+
+__device__ __forceinline__ float rhs1d(const float* w, const Taps1D& k) {
+  float g = 0.f, l = 0.f, d = 0.f;
+  if (k.system == ARPDE_SYS_BURGERS1D && k.cn) {
+#pragma unroll
+    for (int t = 0; t < 7; ++t) { g = fmaf(k.g[t], w[t], g); l = fmaf(k.l[t], w[t], l); }
+    return fmaf(w[3], g, -k.nu * l);                       // u g(u) - nu L(u)
+  }
+#pragma unroll
+  for (int t = 0; t < 7; ++t) { g = fmaf(k.g[t], w[t] * w[t], g); l = fmaf(k.l[t], w[t], l); d = fmaf(k.d[t], w[t], d); }
+  if (k.system == ARPDE_SYS_BURGERS1D) return fmaf(0.25f, g, -k.nu * l);   // BE: 0.5*0.5 g(u^2) - nu L(u)
+  return fmaf(0.5f, g, fmaf(k.nu, d, l));                                  // KS
+}
+
+__global__ void __launch_bounds__(256) stencil1d_fwd(const float* __restrict__ up, int64_t up_bs, const float* __restrict__ u0,
+                                                     int64_t u0_bs, float* __restrict__ ustar, double* __restrict__ sse,
+                                                     int N, int L, Taps1D k) {
+  const int64_t total = (int64_t)N * L;
+  float acc = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int n = (int)(i / L), x = (int)(i - (int64_t)n * L);
+    float w[7];
+    load7(up + n * up_bs, x, L, k.r, w);
+    const float uc = w[3];
+    float R = rhs1d(w, k), u0c;
+    if (k.cn) { load7(u0 + n * u0_bs, x, L, k.r, w); R += rhs1d(w, k); u0c = w[3]; }
+    else u0c = u0[n * u0_bs + x];
+    const float s = fmaf(-k.c, R, u0c);
+    if (ustar) ustar[i] = s;
+    const float d = s - uc;
+    acc = fmaf(d, d, acc);
+  }
+  if (sse) {
+    const double t = block_sum_d((double)acc);
+    if (threadIdx.x == 0) atomicAdd(sse, t);
+  }
+}
+
+// adjoint of -c*rhs: g taps antisymmetric (g^T = -g), l and d symmetric.
+//   Burgers CN : d/du = -c[ G g(u) - g(u G) - nu L(G) ]
+//   Burgers BE : d/du = -c[ -0.5 u g(G) - nu L(G) ]
+//   KS         : d/du = -c[ -u g(G) + L(G) + nu D4(G) ]
+__device__ __forceinline__ float adj1d(const float* wu, const float* wg, const Taps1D& k) {
+  float gG = 0.f, lG = 0.f, dG = 0.f, guG = 0.f, gu = 0.f;
+#pragma unroll
+  for (int t = 0; t < 7; ++t) {
+    gG = fmaf(k.g[t], wg[t], gG); lG = fmaf(k.l[t], wg[t], lG); dG = fmaf(k.d[t], wg[t], dG);
+    guG = fmaf(k.g[t], wu[t] * wg[t], guG); gu = fmaf(k.g[t], wu[t], gu);
+  }
+  if (k.system == ARPDE_SYS_BURGERS1D && k.cn) return -k.c * (wg[3] * gu - guG - k.nu * lG);
+  if (k.system == ARPDE_SYS_BURGERS1D) return -k.c * (-0.5f * wu[3] * gG - k.nu * lG);
+  return -k.c * (-wu[3] * gG + lG + k.nu * dG);
+}
+
+__global__ void __launch_bounds__(256) stencil1d_bwd(const float* __restrict__ up, int64_t up_bs, const float* __restrict__ u0,
+                                                     int64_t u0_bs, const float* __restrict__ g, float* __restrict__ gup,
+                                                     float* __restrict__ gu0, int N, int L, Taps1D k) {
+  const int64_t total = (int64_t)N * L;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int n = (int)(i / L), x = (int)(i - (int64_t)n * L);
+    float wu[7], wg[7];
+    load7(g + (int64_t)n * L, x, L, k.r, wg);
+    load7(up + n * up_bs, x, L, k.r, wu);
+    gup[i] = adj1d(wu, wg, k);
+    float d0 = wg[3];
+    if (k.cn) { load7(u0 + n * u0_bs, x, L, k.r, wu); d0 += adj1d(wu, wg, k); }
+    gu0[i] = d0;
+  }
+}
+
+static void put_taps(float* dst, const double* taps, int n, double den, double scale) {
+  for (int i = 0; i < 7; ++i) dst[i] = 0.f;
+  const int r = (n - 1) / 2;
+  for (int i = 0; i < n; ++i) {
+    const float w = (float)taps[i] / (float)den;            // fp32 division as the reference builds its weights
+    dst[3 - r + i] = (float)((double)w / scale);
+  }
+}
+
+static int make_taps(int system, int k1, int k2, int k4, double dx, double nu, double dt, int mode, Taps1D* t) {
+  static const double G3[] = {-1, 0, 1}, G5[] = {1, -8, 0, 8, -1}, G7[] = {-1, 9, -45, 0, 45, -9, 1};
+  static const double L3[] = {1, -2, 1}, L5[] = {-1, 16, -30, 16, -1};
+  static const double D5[] = {1, -4, 6, -4, 1}, D7[] = {-1, 12, -39, 56, -39, 12, -1};
+  ARPDE_CHECK_ARG(system == ARPDE_SYS_BURGERS1D || system == ARPDE_SYS_KS1D, "stencil1d: bad system %d", system);
+  ARPDE_CHECK_ARG(mode == ARPDE_CN || mode == ARPDE_BE, "stencil1d: bad mode %d", mode);
+  ARPDE_CHECK_ARG(dx > 0, "stencil1d: dx must be > 0");
+  memset(t, 0, sizeof(*t));
+  if (k1 == 3) put_taps(t->g, G3, 3, 2, dx); else if (k1 == 5) put_taps(t->g, G5, 5, 12, dx);
+  else if (k1 == 7 && system == ARPDE_SYS_BURGERS1D) put_taps(t->g, G7, 7, 60, dx);
+  else { arpde_set_error("stencil1d: unsupported gradient kernel size %d", k1); return ARPDE_ERR_UNSUPPORTED; }
+  if (k2 == 3) put_taps(t->l, L3, 3, 1, dx * dx); else if (k2 == 5) put_taps(t->l, L5, 5, 12, dx * dx);
+  else { arpde_set_error("stencil1d: unsupported laplacian kernel size %d", k2); return ARPDE_ERR_UNSUPPORTED; }
+  int r = ((k1 > k2 ? k1 : k2) - 1) / 2;
+  if (system == ARPDE_SYS_KS1D) {
+    if (k4 == 5) put_taps(t->d, D5, 5, 1, dx * dx * dx * dx); else if (k4 == 7) put_taps(t->d, D7, 7, 6, dx * dx * dx * dx);
+    else { arpde_set_error("stencil1d: unsupported 4th-derivative kernel size %d", k4); return ARPDE_ERR_UNSUPPORTED; }
+    if ((k4 - 1) / 2 > r) r = (k4 - 1) / 2;
+  }
+  t->r = r; t->nu = (float)nu; t->cn = mode == ARPDE_CN; t->c = (float)(t->cn ? 0.5 * dt : dt); t->system = system;
+  return ARPDE_OK;
+}
+
+extern "C" int arpde_cn_1d_fwd(int system, const float* uPred, int64_t up_bstride, const float* uPred0, int64_t u0_bstride,
+                               float* ustar, double* sse_out, int N, int L, double dx, double nu, double dt, int k1, int k2,
+                               int k4, int mode, arpde_stream_t stream_) {
+  ARPDE_CHECK_ARG(uPred && uPred0 && (ustar || sse_out), "cn_1d_fwd: null pointer");
+  ARPDE_CHECK_ARG(N >= 0 && L >= 1, "cn_1d_fwd: bad dims N=%d L=%d", N, L);
+  Taps1D t; int rc = make_taps(system, k1, k2, k4, dx, nu, dt, mode, &t); if (rc) return rc;
+  ARPDE_CHECK_ARG(L > t.r, "cn_1d_fwd: L=%d must exceed the stencil radius %d", L, t.r);
+  if (sse_out) ARPDE_CUDA(cudaMemsetAsync(sse_out, 0, sizeof(double), (cudaStream_t)stream_));
+  if (N == 0) return ARPDE_OK;
+  int64_t blocks = ceil_div64((int64_t)N * L, 256); const int64_t cap = (int64_t)arpde_num_sms() * 32; if (blocks > cap) blocks = cap;
+  stencil1d_fwd<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream_>>>(uPred, up_bstride, uPred0, u0_bstride, ustar, sse_out, N, L, t);
+  ARPDE_LAUNCH_CHECK();
+  return ARPDE_OK;
+}
+
+extern "C" int arpde_cn_1d_bwd(int system, const float* uPred, int64_t up_bstride, const float* uPred0, int64_t u0_bstride,
+                               const float* grad_ustar, float* grad_uPred, float* grad_uPred0, int N, int L, double dx,
+                               double nu, double dt, int k1, int k2, int k4, int mode, arpde_stream_t stream_) {
+  ARPDE_CHECK_ARG(uPred && uPred0 && grad_ustar && grad_uPred && grad_uPred0, "cn_1d_bwd: null pointer");
+  ARPDE_CHECK_ARG(N >= 0 && L >= 1, "cn_1d_bwd: bad dims");
+  Taps1D t; int rc = make_taps(system, k1, k2, k4, dx, nu, dt, mode, &t); if (rc) return rc;
+  ARPDE_CHECK_ARG(L > t.r, "cn_1d_bwd: L=%d must exceed the stencil radius %d", L, t.r);
+  if (N == 0) return ARPDE_OK;
+  int64_t blocks = ceil_div64((int64_t)N * L, 256); const int64_t cap = (int64_t)arpde_num_sms() * 32; if (blocks > cap) blocks = cap;
+  stencil1d_bwd<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream_>>>(uPred, up_bstride, uPred0, u0_bstride, grad_ustar, grad_uPred, grad_uPred0, N, L, t);
+  ARPDE_LAUNCH_CHECK();
+  return ARPDE_OK;
+}
+
+// =====================================================================================
+// stand-alone periodic filters (the callable filter objects .grad1/.grad2/.grad4 of the
+// reference integrators: GradFilter1D, LaplaceFilter1D, FourthOrderFilter1D, SobelFilter2d.grad_h/
+// grad_v, LapLaceFilter2d).  Every channel is filtered independently.
+// =====================================================================================
+struct W7 { float w[7]; };
+struct W9 { float w[9]; };
+
+__global__ void __launch_bounds__(256) filter1d_kernel(const float* __restrict__ x, float* __restrict__ y, long long rows, int L, W7 k) {
+  const long long total = rows * L;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / L; const int c = (int)(i - r * L);
+    const float* p = x + r * L;
+    float acc = 0.f;
+#pragma unroll
+    for (int t = -3; t <= 3; ++t)
+      if (k.w[t + 3] != 0.f) { int j = (c + t) % L; if (j < 0) j += L; acc = fmaf(k.w[t + 3], p[j], acc); }
+    y[i] = acc;
+  }
+}
+
+__global__ void __launch_bounds__(256) filter2d_kernel(const float* __restrict__ x, float* __restrict__ y, long long imgs, int H, int W, W9 k) {
+  const long long HW = (long long)H * W, total = imgs * HW;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long n = i / HW; const int rem = (int)(i - n * HW), yy = rem / W, xx = rem - yy * W;
+    const float* p = x + n * HW;
+    float acc = 0.f;
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int b = 0; b < 3; ++b) {
+        int r = (yy + a - 1) % H; if (r < 0) r += H;
+        int c = (xx + b - 1) % W; if (c < 0) c += W;
+        acc = fmaf(k.w[a * 3 + b], p[r * W + c], acc);
+      }
+    y[i] = acc;
+  }
+}
+
+extern "C" int arpde_filter1d(const float* x, float* y, int64_t rows, int L, const float* taps7_host, arpde_stream_t stream_) {
+  ARPDE_CHECK_ARG(x && y && taps7_host && rows > 0 && L > 0, "filter1d: bad args");
+  W7 k; for (int i = 0; i < 7; ++i) k.w[i] = taps7_host[i];
+  int64_t blocks = ceil_div64(rows * L, 256); const int64_t cap = (int64_t)arpde_num_sms() * 32; if (blocks > cap) blocks = cap;
+  filter1d_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream_>>>(x, y, rows, L, k);
+  ARPDE_LAUNCH_CHECK();
+  return ARPDE_OK;
+}
+
+extern "C" int arpde_filter2d(const float* x, float* y, int64_t imgs, int H, int W, const float* w9_host, arpde_stream_t stream_) {
+  ARPDE_CHECK_ARG(x && y && w9_host && imgs > 0 && H > 0 && W > 0, "filter2d: bad args");
+  W9 k; for (int i = 0; i < 9; ++i) k.w[i] = w9_host[i];
+  int64_t blocks = ceil_div64(imgs * H * W, 256); const int64_t cap = (int64_t)arpde_num_sms() * 32; if (blocks > cap) blocks = cap;
+  filter2d_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream_>>>(x, y, imgs, H, W, k);
+  ARPDE_LAUNCH_CHECK();
+  return ARPDE_OK;
+}

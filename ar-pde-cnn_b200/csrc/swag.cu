@@ -1,0 +1,98 @@
+// swag.cu -- batched SWAG posterior sampling and predictive moments.
+//
+// Replaces SwagNN.sample (reference */nn/swag.py:80-150; ~766 ATen ops per call, one Python loop
+// iteration per parameter tensor) by one launch over the flat parameter vector x S samples, and the
+// numpy post-processing of post/plotBARContour.py:85-104 (2D) / 1D :123,136-139 by one reduction.
+//
+// Per tensor t and element i (flat index p), sample s:
+//   var = max(sq_mean - mean^2, eps)
+//   diag: w = mean + scale*sqrt(var)*z1[s,p]
+//   full: D[k] = (C[k,i]==0 ? 0 : C[k,i]-mean)      (zero rows = empty slots, left uncentred: swag.py:137)
+//         w = mean + sqrt(1/2) * ( scale*sqrt(var)*z1[s,p] + scale/sqrt(K-1) * sum_k D[k]*z2[s,t,k] )
+// z2 is drawn once per parameter TENSOR (swag.py:139), K = max_models (constructor value, not n_models).
+#include "common.cuh"
+#include "../../include/arpde.h"
+
+#define SWAG_SEG_MAX 80
+struct SwagTable {
+  const float* mean[SWAG_SEG_MAX];
+  const float* sq[SWAG_SEG_MAX];
+  const float* cov[SWAG_SEG_MAX];
+  long long off[SWAG_SEG_MAX + 1];
+  int n;
+};
+
+__global__ void __launch_bounds__(256) swag_sample_kernel(SwagTable t, const float* __restrict__ z1, const float* __restrict__ z2,
+                                                          float* __restrict__ out, int K, float scale, float cov_scale,
+                                                          float eps, int diag) {
+  const long long P = t.off[t.n];
+  const int s = blockIdx.y;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (long long)gridDim.x * blockDim.x) {
+    int lo = 0, hi = t.n - 1;
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (t.off[mid] <= p) lo = mid; else hi = mid - 1; }
+    const long long i = p - t.off[lo], numel = t.off[lo + 1] - t.off[lo];
+    const float m = t.mean[lo][i];
+    const float var = fmaxf(t.sq[lo][i] - m * m, eps);
+    const float sds = scale * sqrtf(var) * z1[(long long)s * P + p];
+    float w;
+    if (diag) {
+      w = m + sds;
+    } else {
+      const float* c = t.cov[lo] + i;
+      const float* z = z2 + ((long long)s * t.n + lo) * K;
+      float acc = 0.f;
+      for (int k = 0; k < K; ++k) {
+        const float ck = c[(long long)k * numel];
+        acc = fmaf(ck == 0.f ? 0.f : ck - m, z[k], acc);
+      }
+      w = m + 0.70710678118654752440f * (sds + cov_scale * acc);
+    }
+    out[(long long)s * P + p] = w;
+  }
+}
+
+extern "C" int arpde_swag_sample(const float* const* mean_host, const float* const* sq_mean_host, const float* const* cov_host,
+                                 const int64_t* numels_host, int n_tensors, const float* z1, const float* z2, float* out, int S,
+                                 int K, int max_models, double scale, double eps, int diag, arpde_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  ARPDE_CHECK_ARG(mean_host && sq_mean_host && numels_host && z1 && out, "swag_sample: null pointer");
+  ARPDE_CHECK_ARG(diag || (cov_host && z2 && K > 0 && max_models > 1), "swag_sample: full covariance needs cov, z2, K>0, max_models>1");
+  ARPDE_CHECK_ARG(n_tensors > 0 && n_tensors <= SWAG_SEG_MAX, "swag_sample: %d parameter tensors (max %d)", n_tensors, SWAG_SEG_MAX);
+  ARPDE_CHECK_ARG(S > 0, "swag_sample: S must be > 0");
+  SwagTable t; t.n = n_tensors; t.off[0] = 0;
+  for (int i = 0; i < n_tensors; ++i) {
+    t.mean[i] = mean_host[i]; t.sq[i] = sq_mean_host[i]; t.cov[i] = diag ? nullptr : cov_host[i];
+    ARPDE_CHECK_ARG(t.mean[i] && t.sq[i] && (diag || t.cov[i]) && numels_host[i] > 0, "swag_sample: bad tensor %d", i);
+    t.off[i + 1] = t.off[i] + numels_host[i];
+  }
+  const long long P = t.off[n_tensors];
+  int64_t bx = ceil_div64(P, 256); if (bx > 4096) bx = 4096;
+  const float cov_scale = diag ? 0.f : (float)(scale / sqrt((double)max_models - 1.0));
+  swag_sample_kernel<<<dim3((unsigned)bx, S), 256, 0, stream>>>(t, z1, z2, out, K, (float)scale, cov_scale, (float)eps, diag);
+  ARPDE_LAUNCH_CHECK();
+  return ARPDE_OK;
+}
+
+// predictive moments over S weight samples: traj [S*n_ic, inner] sample-major, rows bstride apart; mean/var [n_ic, inner]
+//   var = noise + E_s[y^2] - (E_s[y])^2, noise = 1/mean(beta) (2D scripts) or mean(1/beta) (1D scripts)
+__global__ void __launch_bounds__(256) moments_kernel(const float* __restrict__ traj, long long bstride, long long inner, int n_ic,
+                                                      int S, float noise, float* __restrict__ mean, float* __restrict__ var) {
+  const long long total = (long long)n_ic * inner;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long n = i / inner, j = i - n * inner;
+    float s1 = 0.f, s2 = 0.f;
+    for (int s = 0; s < S; ++s) { const float v = traj[((long long)s * n_ic + n) * bstride + j]; s1 += v; s2 = fmaf(v, v, s2); }
+    const float m = s1 / (float)S;
+    mean[i] = m;
+    if (var) var[i] = noise + s2 / (float)S - m * m;
+  }
+}
+
+extern "C" int arpde_predictive_moments(const float* traj, int64_t bstride, int64_t inner, int n_ic, int S, double noise, float* mean,
+                                        float* var, arpde_stream_t stream_) {
+  ARPDE_CHECK_ARG(traj && mean && inner > 0 && bstride >= inner && n_ic > 0 && S > 0, "predictive_moments: bad args");
+  int64_t blocks = ceil_div64((int64_t)n_ic * inner, 256); const int64_t cap = (int64_t)arpde_num_sms() * 16; if (blocks > cap) blocks = cap;
+  moments_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream_>>>(traj, bstride, inner, n_ic, S, (float)noise, mean, var);
+  ARPDE_LAUNCH_CHECK();
+  return ARPDE_OK;
+}

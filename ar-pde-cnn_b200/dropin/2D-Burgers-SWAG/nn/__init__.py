@@ -1,0 +1,1 @@
+"""drop-in nn package (see ../../README.md)"""

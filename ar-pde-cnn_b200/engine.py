@@ -1,0 +1,143 @@
+"""Auto-regressive rollout engine: S weight samples x N initial conditions x T steps in one C call.
+
+Replaces the Python loops of the reference drivers and post scripts
+(2D-Burgers-SWAG/main.py:112-135 test(), :160-179 testSample(); post/plotBARContour.py:31-73;
+1D main.py :106-121, :148-163): `model(input[:, -c_in:])`, `cat([input[:, c_out:], uPred])` and the
+per-step device->host copy become one trajectory tensor written in place by the last convolution.
+"""
+import torch
+
+from . import _lib as L
+from . import program as P
+
+
+def _features_of(model):
+    """DenseED.features of a DenseED / BayesNN / SwagNN."""
+    m = model
+    if hasattr(m, 'base'):
+        m = m.base                      # SwagNN -> BayesNN
+    if not hasattr(m, 'features') and hasattr(m, 'model'):
+        m = m.model                     # BayesNN -> DenseED
+    if not hasattr(m, 'features'):
+        raise TypeError('cannot find DenseED.features in %s' % type(model).__name__)
+    return m.features
+
+
+def _param_table(plan, named_params, flat):
+    """(ptr array, gstride array, keepalive) -- sampled tensors point into `flat` [S,P], the rest at the module."""
+    tensors = P.param_tensors(plan)
+    offs, off = {}, 0
+    if flat is not None:
+        for _, p in named_params:
+            offs[id(p)] = off
+            off += p.numel()
+        if off != flat.shape[1]:
+            raise ValueError('flat weight table has %d columns, model has %d parameters' % (flat.shape[1], off))
+    ptrs, gs = [], []
+    for t in tensors:
+        if flat is not None and id(t) in offs:
+            ptrs.append(flat.data_ptr() + 4 * offs[id(t)])
+            gs.append(flat.shape[1])
+        else:
+            ptrs.append(t.data_ptr())
+            gs.append(0)
+    return L.ptr_array(ptrs), L.i64_array(gs), tensors
+
+
+@torch.no_grad()
+def rollout(model, ic, tsteps, flat_weights=None, named_params=None, out=None):
+    """Eval-mode AR rollout.
+
+    model: DenseED / BayesNN / SwagNN (running BN statistics and, without flat_weights, the weights come from it)
+    ic: [N, c_out, H, W] or [N, c_out, L] initial states (the history is the IC repeated, as the loaders do)
+    flat_weights: optional [S, P] table from SwagNN.sample_flat (P = named_params order) -> S*N rollouts,
+                  sample-major: row s*N + n uses weight sample s on initial condition n
+    returns traj [S*N, T+1, c_out, (H,) W] (index 0 = initial state)
+    """
+    feats = _features_of(model)
+    plan = P.compile_module(feats)
+    if plan.out_is_buf or plan.input_to_buf:
+        raise NotImplementedError('rollout needs a full DenseED')
+    L.require_cuda(ic)
+    one_d = ic.dim() == 3
+    ic4 = (ic.unsqueeze(2) if one_d else ic).contiguous().float()
+    N, c_out, H, W = ic4.shape
+    if c_out != plan.c_out or plan.c_in % c_out:
+        raise ValueError('initial condition has %d channels; model maps %d -> %d' % (c_out, plan.c_in, plan.c_out))
+    if P._spatial(plan, H, W, plan.out_scale) != (H, W):
+        raise ValueError('rollout needs a model whose output grid equals its input grid')
+    S = 1 if flat_weights is None else flat_weights.shape[0]
+    if flat_weights is not None:
+        L.require_cuda(flat_weights)
+        flat_weights = flat_weights.contiguous()
+        if named_params is None:
+            raise ValueError('named_params (the module order flat_weights was built in) is required')
+    NT = S * N
+    c_hist = plan.c_in
+    ctot = c_hist + tsteps * c_out
+    dev = ic.device
+    if out is None:
+        out = torch.empty((NT, ctot, H, W), device=dev, dtype=torch.float32)
+    elif out.shape != (NT, ctot, H, W) or not out.is_contiguous():
+        raise ValueError('out must be a contiguous [%d,%d,%d,%d] tensor' % (NT, ctot, H, W))
+    out.view(S, N, ctot, H, W)[:, :, :c_hist] = ic4.repeat(1, c_hist // c_out, 1, 1).unsqueeze(0)
+    bufs, work_len, _ = P.layout(plan, NT, H, W)
+    ops_c, bufs_c = P.c_tables(plan, bufs)
+    work = torch.empty((max(work_len, 1),), device=dev, dtype=torch.float32)
+    ss = torch.empty((max(2 * S * plan.bn_total, 1),), device=dev, dtype=torch.float32)
+    eps, _ = P.bn_hyper(plan)
+    pp, gs, keep = _param_table(plan, named_params, flat_weights)
+    with torch.cuda.device(dev):
+        L.call('arpde_rollout', ops_c, len(plan.ops), bufs_c, len(bufs), pp, gs, len(keep), L.ptr(out), ctot, plan.c_in, c_hist,
+               c_out, int(tsteps), NT, N, H, W, L.ptr(work), L.ptr(ss), plan.bn_total, float(eps), L.stream())
+    traj = out[:, c_hist - c_out:].view(NT, tsteps + 1, c_out, H, W)
+    return traj.squeeze(3) if one_d else traj
+
+
+@torch.no_grad()
+def predictive_moments(traj, n_samples, betas=None, formula='2d'):
+    """Sample mean and predictive variance over the S weight samples of a sample-major trajectory.
+
+    formula '2d': var = 1/mean(beta) + E[y^2] - E[y]^2      (2D-Burgers-SWAG/post/plotBARContour.py:85-104)
+    formula '1d': var = mean_s(1/beta_s + y_s^2) - mean^2   (1D-Burger-SWAG/post/plotBARContour.py:123,136-139)
+    betas None -> pure sample variance (noise term 0).
+    """
+    L.require_cuda(traj)
+    t = traj
+    inner = t[0].numel()
+    # rows may be a channel-slice view of the rollout buffer (batch stride > row length): no copy
+    row_compact = t[0].is_contiguous()
+    if not row_compact or (t.shape[0] > 1 and t.stride(0) < inner):
+        t = t.contiguous()
+    bstride = t.stride(0) if t.shape[0] > 1 else inner
+    NT = t.shape[0]
+    if NT % n_samples:
+        raise ValueError('%d rollouts is not a multiple of %d samples' % (NT, n_samples))
+    n_ic = NT // n_samples
+    if betas is None:
+        noise = 0.0
+    elif formula == '2d':
+        noise = float(1.0 / betas.double().mean())
+    else:
+        noise = float((1.0 / betas.double()).mean())
+    mean = torch.empty((n_ic,) + tuple(t.shape[1:]), device=t.device, dtype=torch.float32)
+    var = torch.empty_like(mean)
+    with torch.cuda.device(t.device):
+        L.call('arpde_predictive_moments', L.ptr(t), bstride, inner, n_ic, n_samples, noise, L.ptr(mean), L.ptr(var), L.stream())
+    return mean, var
+
+
+@torch.no_grad()
+def swag_rollout(swag_nn, ic, tsteps, n_samples, diagCov=False, scale=1.0, generator=None, noise=None, formula='2d'):
+    """testSample() of the reference in one go: draw S posterior weight samples, roll every (sample, IC)
+    pair out for tsteps, return (traj [S*N, T+1, ...], mean, var, betas)."""
+    flat, names, numels = swag_nn.sample_flat(n_samples, scale=scale, diagCov=diagCov, generator=generator, noise=noise)
+    named = list(swag_nn.base.named_parameters())
+    traj = rollout(swag_nn, ic, tsteps, flat_weights=flat, named_params=named)
+    lb_col = [i for i, (n, _) in enumerate(named) if n.endswith('log_beta')]
+    betas = None
+    if lb_col:
+        off = sum(numels[:lb_col[0]])
+        betas = flat[:, off].exp()
+    mean, var = predictive_moments(traj, n_samples, betas, formula)
+    return traj, mean, var, betas

@@ -1,0 +1,203 @@
+/*
+ * arpde.h -- C ABI of libarpde.so: the B200 (sm_100a) implementation of ar-pde-cnn's hot path.
+ *
+ * The reference (cics-nd/ar-pde-cnn) has no native layer: its hot path is PyTorch calls made from
+ * nn/*.py.  Each entry point below names the reference Python interface it replaces (paths are
+ * relative to the reference root).  The Python host side (ar-pde-cnn_b200/nn/...) binds these
+ * with ctypes; INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; fp32 data, NCHW / NCL;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), allocates nothing
+ *     and keeps no state; scratch memory is passed in by the caller;
+ *   - return value: 0 = ok, otherwise an ARPDE_ERR_* code; arpde_last_error() gives the message of
+ *     the calling thread's last failure.  Nothing throws or aborts.
+ *   - "bstride" = distance in elements between consecutive batch items (inputs may be channel-slice
+ *     views such as input[:, -6:] of a longer history tensor); channel stride is always H*W (or L).
+ */
+#ifndef ARPDE_H
+#define ARPDE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ARPDE_VERSION 100          /* major*100 + minor */
+
+/* error codes */
+#define ARPDE_OK 0
+#define ARPDE_ERR_ARG 1
+#define ARPDE_ERR_CUDA 2
+#define ARPDE_ERR_UNSUPPORTED 3
+
+/* time integrators */
+#define ARPDE_CN 0                 /* crankNicolson */
+#define ARPDE_BE 1                 /* backwardEuler */
+
+/* 1D systems */
+#define ARPDE_SYS_BURGERS1D 1
+#define ARPDE_SYS_KS1D 2
+
+typedef void* arpde_stream_t;      /* cudaStream_t */
+
+int arpde_version(void);
+const char* arpde_last_error(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Physics integrators (the loss target), forward.
+ *   2D: replaces Burger2DIntegrate.crankNicolson / .backwardEuler
+ *       (2D-Burgers-SWAG/nn/burger2DFiniteDifference.py:175-211 / :148-173), grad_kernels=[3,3].
+ *   1D: replaces BurgerIntegrate.crankNicolson/.backwardEuler
+ *       (1D-Burger-SWAG/nn/burgerFiniteDifference.py:284-302 / :264-282) for system=BURGERS1D and
+ *       KSIntegrate.crankNicolson/.backwardEuler (1D-KS-SWAG/nn/ksFiniteDifference.py:155-173 /
+ *       :139-153) for system=KS1D; k1,k2,k4 = grad_kernels (k4 ignored for Burgers).
+ * uPred, uPred0: [N,2,H,W] (2D) / [N,1,L] (1D) with their own batch strides.
+ * ustar (nullable): compact output.  sse_out (nullable): device double, receives
+ *   sum((ustar - uPred)^2), the data term of BayesNN.calc_neg_log_joint (nn/bayesNN.py:113-115),
+ *   without materialising ustar when ustar == NULL.  At least one of the two must be given.
+ * ------------------------------------------------------------------------------------------- */
+int arpde_cn_burgers2d_fwd(const float* uPred, int64_t up_bstride, const float* uPred0, int64_t u0_bstride,
+                           float* ustar, double* sse_out, int N, int H, int W, double dx, double nu, double dt,
+                           int mode, arpde_stream_t stream);
+/* same arithmetic through the one-thread-per-point kernel (any H, W); parity test hook */
+int arpde_cn_burgers2d_fwd_generic(const float* uPred, int64_t up_bstride, const float* uPred0, int64_t u0_bstride,
+                                   float* ustar, double* sse_out, int N, int H, int W, double dx, double nu,
+                                   double dt, int mode, arpde_stream_t stream);
+int arpde_cn_1d_fwd(int system, const float* uPred, int64_t up_bstride, const float* uPred0, int64_t u0_bstride,
+                    float* ustar, double* sse_out, int N, int L, double dx, double nu, double dt, int k1, int k2,
+                    int k4, int mode, arpde_stream_t stream);
+
+/* Adjoint of the above (what torch autograd builds through the reference integrators; the loss
+ * target is NOT detached, 2D-Burgers-SWAG/main.py:71-73): given grad_ustar (compact, same shape
+ * as ustar) writes compact grad_uPred and grad_uPred0. */
+int arpde_cn_burgers2d_bwd(const float* uPred, int64_t up_bstride, const float* uPred0, int64_t u0_bstride,
+                           const float* grad_ustar, float* grad_uPred, float* grad_uPred0, int N, int H, int W,
+                           double dx, double nu, double dt, int mode, arpde_stream_t stream);
+int arpde_cn_1d_bwd(int system, const float* uPred, int64_t up_bstride, const float* uPred0, int64_t u0_bstride,
+                    const float* grad_ustar, float* grad_uPred, float* grad_uPred0, int N, int L, double dx,
+                    double nu, double dt, int k1, int k2, int k4, int mode, arpde_stream_t stream);
+
+/* Stand-alone periodic filters (forward only): the callable .grad1/.grad2/.grad4 objects of the reference
+ * integrators (GradFilter1D / LaplaceFilter1D / FourthOrderFilter1D, ksFiniteDifference.py:6-119;
+ * SobelFilter2d.grad_h/.grad_v and LapLaceFilter2d, burger2DFiniteDifference.py:6-129).  taps7_host: centred
+ * 7-tap table, w9_host: row-major 3x3 weights, both HOST float arrays already scaled by 1/dx^n. */
+int arpde_filter1d(const float* x, float* y, int64_t rows, int L, const float* taps7_host, arpde_stream_t stream);
+int arpde_filter2d(const float* x, float* y, int64_t imgs, int H, int W, const float* w9_host, arpde_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Loss.  Replaces BayesNN.calc_neg_log_joint (nn/bayesNN.py:98-129; constants :29-38).
+ *   params_host / numels_host: HOST arrays of device pointers / element counts of every tensor of
+ *   model.features.parameters().  scratch: 2 device doubles (SSE, prior sum) kept for backward.
+ *   output == target == NULL: scratch[0] already holds the SSE (written by arpde_cn_*_fwd).
+ *   loss_out: device float[1] (the reference returns a shape-(1,) tensor).
+ * bwd: grad_loss device float[1]; any of the grad outputs may be NULL; grad_params_flat is the
+ *   concatenation of the per-tensor gradients in params_host order.
+ * ------------------------------------------------------------------------------------------- */
+int arpde_neg_log_joint_fwd(const float* output, const float* target, int64_t numel, int B, const float* log_beta,
+                            const float* const* params_host, const int64_t* numels_host, int nparams, double ntrain,
+                            double w_shape, double w_rate, double beta_shape, double beta_rate, float* loss_out,
+                            double* scratch, arpde_stream_t stream);
+int arpde_neg_log_joint_bwd(const float* output, const float* target, int64_t numel, int B, const float* log_beta,
+                            const float* const* params_host, const int64_t* numels_host, int nparams, double ntrain,
+                            double w_shape, double w_rate, double beta_shape, double beta_rate, const float* grad_loss,
+                            const double* scratch, float* grad_output, float* grad_target, float* grad_log_beta,
+                            float* grad_params_flat, arpde_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Circular convolution family.  One call replaces F.pad(circular)+conv of an
+ * nn.Conv{1,2}d(padding_mode='circular') of nn/denseEDcirc2d.py / nn/denseEDcirc.py together with
+ * the BatchNorm+ReLU in front of it (scale/shift prologue), the nearest x2 upsample (up=1), the
+ * torch.cat of _DenseLayer.forward (:66-68; output written at channel y_coff of a y_ctot-channel
+ * tensor) and the out_activation.  1D signals use H = 1, kh = 1.
+ *   w: [groups][cout][cin][kh][kw]; sample n uses weight set n / n_per_group (w_gstride elements apart;
+ *      SWAG: one weight sample for n_per_group initial conditions); scale/shift likewise (ss_gstride).
+ *   stats (nullable): device double [y_ctot][2], receives per-channel (sum, sum of squares) of the
+ *      written channels (train-mode BatchNorm of the consumer); must be zeroed by the caller.
+ *   Effective wrap padding: (k-1)/2, and 1 for k=4 (torch<=1.2 semantics, reference README.md:40).
+ * ------------------------------------------------------------------------------------------- */
+#define ARPDE_ACT_NONE 0
+#define ARPDE_ACT_TANH 1
+#define ARPDE_ACT_RELU 2
+#define ARPDE_ACT_LRELU 3
+#define ARPDE_ACT_SIGMOID 4
+#define ARPDE_ACT_SOFTPLUS4 5
+int arpde_conv_fwd(const float* x, int64_t x_bstride, const float* w, int64_t w_gstride, const float* scale,
+                   const float* shift, int64_t ss_gstride, float* y, double* stats, int N, int cin, int H, int W, int cout,
+                   int kh, int kw, int stride, int up, int relu_in, int act, int y_ctot, int y_coff, int n_per_group,
+                   arpde_stream_t stream);
+
+/* BatchNorm bookkeeping (nn.BatchNorm{1,2}d, eps 1e-5, momentum 0.1): per-channel sums of x[N,C(+),HW],
+ * train-mode finalize (scale/shift, saved mean/invstd, running-stat update, num_batches_tracked += 1),
+ * eval-mode fold of the running statistics. */
+int arpde_bn_stats(const float* x, int64_t x_bstride, int N, int C, int64_t HW, double* stats, arpde_stream_t stream);
+int arpde_bn_finalize_train(const double* stats, double count, const float* gamma, const float* beta, float* running_mean,
+                            float* running_var, int64_t* num_batches_tracked, double momentum, double eps, float* scale,
+                            float* shift, float* save_mean, float* save_invstd, int C, arpde_stream_t stream);
+int arpde_bn_fold_eval(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
+                       double eps, float* scale, float* shift, int C, arpde_stream_t stream);
+/* y = act(scale[c]*x + shift[c]) (scale/shift nullable), nearest x2 along H / W when up_h / up_w = 1: the unfused forward of a lone
+ * BatchNorm / ReLU / UpsamplingNearest{1,2}d module (DenseED.forward_test, denseEDcirc2d.py:316-323). */
+int arpde_affine_act(const float* x, int64_t x_bstride, const float* scale, const float* shift, float* y, int N, int C, int H,
+                     int W, int up_h, int up_w, int act, arpde_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Whole-network program.  Replaces DenseED.forward (denseEDcirc2d.py:313-314; 1D :306-307 / :294-295).
+ * The host side flattens model.features into conv ops (every BN+ReLU[+upsample] is the prologue of
+ * the conv that follows it) over a few activation buffers carved out of one workspace.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct arpde_op {
+  int32_t in_buf;      /* activation buffer read (channels [0,cin)); -1 = network input */
+  int32_t out_buf;     /* buffer written; -2 = network output */
+  int32_t cin, cout, kh, kw, stride, up;
+  int32_t out_coff;    /* channel offset inside out_buf (dense-block concat) */
+  int32_t act;         /* ARPDE_ACT_* applied to the output */
+  int32_t w_param;     /* index of the conv weight in the parameter table */
+  int32_t bn_param;    /* index of BN gamma; beta, running_mean, running_var, num_batches_tracked follow; -1 = none */
+  int32_t bn_off;      /* offset of this BN's channels inside the scale/shift scratch */
+} arpde_op_t;
+
+typedef struct arpde_buf {
+  int64_t offset;      /* floats from the workspace base */
+  int64_t stats_off;   /* doubles from the stats base ([ctot][2]) */
+  int32_t ctot, h, w;
+  int32_t pad_;
+} arpde_buf_t;
+
+/* params_host: HOST array of device pointers (n_params entries); param_gstride_host: per-entry distance in
+ * elements between weight sets (0 = shared).  scale_shift: 2*groups*bn_total floats.  Training (groups == 1):
+ * stats = stats_len doubles (zeroed here), saved_mean_invstd (nullable) = 2*bn_total floats for backward;
+ * BatchNorm running statistics in the parameter table are updated in place. */
+int arpde_densed_forward(const arpde_op_t* ops, int n_ops, const arpde_buf_t* bufs, int n_bufs, void* const* params_host,
+                         const int64_t* param_gstride_host, int n_params, const float* x, int64_t x_bstride, int N,
+                         int n_per_group, int H, int W, float* y, int y_ctot, int y_coff, float* workspace,
+                         float* scale_shift, int bn_total, double* stats, int64_t stats_len, float* saved_mean_invstd,
+                         int training, double momentum, double eps, arpde_stream_t stream);
+
+/* Auto-regressive rollout in eval mode: the AR loops of main.py test()/testSample()
+ * (2D-Burgers-SWAG/main.py:112-135,:160-179; 1D main.py :106-121,:148-163) without Python in the loop.
+ * traj [N, traj_ctot, H, W], traj_ctot >= c_hist + T*c_out; channels [0,c_hist) hold the repeated initial
+ * condition; step t reads channels [c_hist-c_in+t*c_out, +c_in) and writes [c_hist+t*c_out, +c_out). */
+int arpde_rollout(const arpde_op_t* ops, int n_ops, const arpde_buf_t* bufs, int n_bufs, void* const* params_host,
+                  const int64_t* param_gstride_host, int n_params, float* traj, int traj_ctot, int c_in, int c_hist, int c_out,
+                  int T, int N, int n_per_group, int H, int W, float* workspace, float* scale_shift, int bn_total, double eps,
+                  arpde_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * SWAG.  arpde_swag_sample replaces SwagNN.sample (nn/swag.py:80-150) for S samples at once:
+ *   mean/sq_mean/cov_host: HOST arrays of per-tensor device pointers in named_parameters() order
+ *   (cov: [K, numel] rows), z1 [S,P] and z2 [S,n_tensors,K] standard-normal noise (the caller draws
+ *   it, so results can be reproduced against the reference's RNG stream), out [S,P] flat weights.
+ * arpde_predictive_moments replaces the sample mean/variance of post/plotBARContour.py:85-104: traj holds
+ *   S*n_ic rows of `inner` floats, sample-major, `bstride` floats apart; var = noise + E[y^2] - E[y]^2. */
+int arpde_swag_sample(const float* const* mean_host, const float* const* sq_mean_host, const float* const* cov_host,
+                      const int64_t* numels_host, int n_tensors, const float* z1, const float* z2, float* out, int S, int K,
+                      int max_models, double scale, double eps, int diag, arpde_stream_t stream);
+int arpde_predictive_moments(const float* traj, int64_t bstride, int64_t inner, int n_ic, int S, double noise, float* mean,
+                             float* var, arpde_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ARPDE_H */

@@ -1,0 +1,129 @@
+"""CPU: host logic, ABI surface, drop-in structure.  No compute calls (there is no GPU here)."""
+import copy
+import os
+import re
+import sys
+
+import pytest
+import torch
+
+from _util import ROOT, SYSTEMS, golden, sub
+import _models as M
+
+import arpde_b200
+from arpde_b200 import _lib as L
+from arpde_b200 import program as P
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, 'include', 'arpde.h')).read()
+    declared = set(re.findall(r'^(?:int|const char\*)\s+(arpde_\w+)\s*\(', hdr, flags=re.M))
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(L.lib, name), name
+    assert declared == set(L.EXPORTS), declared ^ set(L.EXPORTS)
+    assert L.lib.arpde_version() == 100
+
+
+@pytest.mark.parametrize('system', SYSTEMS)
+def test_state_dict_keys_and_strict_load(system):
+    g, cfg, args, model, bayes, swag = M.build(system)
+    ref_keys = set(k[len('sd/'):] for k in g if k.startswith('sd/'))
+    assert set(bayes.state_dict().keys()) == ref_keys
+    M.load_golden_weights(bayes, g)
+    ref_swag = set(k[len('swag/sd/'):] for k in g if k.startswith('swag/sd/'))
+    assert set(swag.state_dict().keys()) == ref_swag
+    swag.load_state_dict(sub(g, 'swag/sd/'), strict=True)
+    # parameter order drives SWAG sampling and the optimizer groups
+    names = [n for n, _ in bayes.named_parameters()]
+    gold_names = [k[len('train/g/'):] for k in g if k.startswith('train/g/')]
+    assert names == gold_names and names[0] == 'model.log_beta'
+
+
+@pytest.mark.parametrize('system', ['burgers1d', 'ks1d'])
+def test_shipped_checkpoint_keys_load_strict(system):
+    gk = golden(system + '_ckpt200')
+    K = int(gk['max_models'])
+    g, cfg, args, model, bayes, swag = M.build(system, max_models=K)
+    sd = sub(gk, 'sd/')
+    if system == 'burgers1d':     # fixture omits the 1.6 MB low-rank rows
+        for k, v in swag.state_dict().items():
+            if k.endswith('_cov_mat_sqrt'):
+                sd[k] = v
+    swag.load_state_dict(sd, strict=True)
+    assert int(swag.n_models) in (90, 100)
+
+
+def test_default_init_matches_reference_rng_stream():
+    """same torch seed -> same default (Kaiming-uniform) weights as the reference constructor order"""
+    g = golden('burgers2d')
+    torch.manual_seed(12345)
+    m = M.CLS['burgers2d'](6, 2, [4], growth_rate=4, init_features=96)
+    w = m.features.In_conv1.weight
+    assert torch.allclose(w, torch.from_numpy(g['sd/model.features.In_conv1.weight']))
+    assert torch.allclose(m.features.LastTransUp.conv3.weight, torch.from_numpy(g['sd/model.features.LastTransUp.conv3.weight']))
+
+
+def test_program_of_default_2d_net():
+    g, cfg, args, model, bayes, swag = M.build('burgers2d')
+    plan = P.compile_module(model.features)
+    assert [(o['cin'], o['cout'], o['kw'], o['stride'], o['up']) for o in plan.ops] == [
+        (6, 96, 5, 1, 0), (96, 48, 3, 2, 0), (48, 4, 3, 1, 0), (52, 4, 3, 1, 0), (56, 4, 3, 1, 0), (60, 4, 3, 1, 0),
+        (64, 32, 1, 1, 0), (32, 16, 3, 1, 1), (16, 2, 5, 1, 0)]
+    assert [b['ctot'] for b in plan.bufs] == [96, 64, 32, 16]
+    assert [o['out_coff'] for o in plan.ops[2:6]] == [48, 52, 56, 60]
+    assert plan.ops[-1]['out_buf'] == -2 and plan.bn_total == 96 + 48 + 52 + 56 + 60 + 64 + 32 + 16
+    bufs, work, stats = P.layout(plan, 2, 64, 64)
+    assert bufs[1][2:] == (64, 32, 32) and work == 2 * (96 * 4096 + 64 * 1024 + 32 * 1024 + 16 * 4096)
+    # plan survives deepcopy and points at the copied modules (SwagNN.sample deep-copies the model)
+    m2 = copy.deepcopy(model)
+    p2 = P.compile_module(m2.features)
+    assert p2.param_slots[0][0] is m2.features.In_conv1
+
+
+def test_program_generic_topology():
+    m = M.CLS['burgers2d'](1, 1, (2, 3, 2), growth_rate=16, init_features=48, out_activation='Tanh')
+    plan = P.compile_module(m.features)
+    ks = [(o['kw'], o['stride'], o['up']) for o in plan.ops]
+    assert (4, 2, 0) in ks and (3, 1, 1) in ks and plan.ops[-1]['act'] == 1
+    assert plan.out_scale == 0 and plan.c_in == 1 and plan.c_out == 1
+    with pytest.raises(ValueError):
+        M.CLS['burgers2d'](1, 1, (2, 2), growth_rate=16, init_features=48)
+
+
+def test_no_cpu_fallback():
+    g, cfg, args, model, bayes, swag = M.build('ks1d')
+    x = torch.zeros(2, 2, 96)
+    with pytest.raises(RuntimeError, match='CUDA'):
+        model(x)
+    integ = M.integrator('ks1d', g, 'cpu')
+    with pytest.raises(RuntimeError, match='CUDA'):
+        integ.crankNicolson(torch.zeros(2, 1, 96), torch.zeros(2, 1, 96), 0.1)
+    with pytest.raises(RuntimeError, match='CUDA'):
+        bayes.calc_neg_log_joint(torch.zeros(2, 1, 96), torch.zeros(2, 1, 96), 3)
+
+
+def test_product_never_imports_oracle():
+    pkg = arpde_b200.PACKAGE_DIR
+    n = 0
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh', '.h', '.sh')):
+                n += 1
+                for line in open(os.path.join(root, f)):
+                    assert not ('oracle' in line and ('import' in line or 'include' in line)), (f, line)
+    assert n > 10
+
+
+def test_dropin_module_names():
+    import importlib
+    import subprocess
+    code = ("import sys; sys.path.insert(0, %r); "
+            "from nn.denseEDcirc2d import DenseED; from nn.bayesNN import BayesNN; from nn.swag import SwagNN; "
+            "from nn.burger2DFiniteDifference import Burger2DIntegrate; print(DenseED.__name__)")
+    out = subprocess.check_output([sys.executable, '-c', code % os.path.join(arpde_b200.PACKAGE_DIR, 'dropin', '2D-Burgers-SWAG')])
+    assert b'DenseED2d' in out
+    for proj, mods in (('1D-Burger-SWAG', 'from nn.denseEDcirc import DenseED; from nn.burgerFiniteDifference import BurgerIntegrate'),
+                       ('1D-KS-SWAG', 'from nn.denseEDcirc import DenseED; from nn.ksFiniteDifference import KSIntegrate')):
+        code = "import sys; sys.path.insert(0, %r); %s; from nn.swag import SwagNN; from nn.bayesNN import BayesNN"
+        subprocess.check_call([sys.executable, '-c', code % (os.path.join(arpde_b200.PACKAGE_DIR, 'dropin', proj), mods)])

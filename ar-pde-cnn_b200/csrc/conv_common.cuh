@@ -5,6 +5,8 @@
 struct ConvDesc {
   int N, cin, H, W;        // input dims (H = 1 for 1D), before the optional nearest x2
   int cout, kh, kw, stride, up;
+  int dilate = 0;          // input is zero-inserted x2 before the conv (transposed conv of a stride-2 layer)
+  int pad_override = -1;   // wrap padding per side; -1 = reference default ((k-1)/2, k=4 -> 1)
   int relu_in;             // ReLU after the per-channel affine of the prologue
   int act;                 // output activation (ARPDE_ACT_*)
   int y_ctot, y_coff;      // output buffer channel count / channel offset (concat-free dense block)
@@ -13,7 +15,7 @@ struct ConvDesc {
 
 struct ConvFwdArgs {
   const float* x; long long x_bs;
-  int cin, H, W, up, up_h;
+  int cin, H, W, up, up_h, dilate, pad_y, pad_x;
   const float* w; long long w_gs;
   const float* scale; const float* shift; long long ss_gs;
   int relu_in;

@@ -40,17 +40,16 @@ __global__ void __launch_bounds__(256) conv_fwd_kernel(ConvFwdArgs a) {
   const int g = n / a.n_per_group;
   const int oy0 = ty_tile * a.TH, ox0 = tx_tile * a.TW, co0 = co_tile * TCO;
   const int Hc = a.H << a.up_h, Wc = a.W << a.up;
-  const int pad = (KH == 4 || KW == 4) ? 1 : 0;            // k=4 -> 1, else (k-1)/2 per dim
-  const int pad_y = KH == 4 ? pad : (KH - 1) / 2, pad_x = KW == 4 ? pad : (KW - 1) / 2;
+  const int pad_y = a.pad_y, pad_x = a.pad_x;
 
   const int tid = threadIdx.y * blockDim.x + threadIdx.x, nthreads = blockDim.x * blockDim.y;
   for (int i = tid; i < PH; i += nthreads) {
     int iy = (oy0 * S - pad_y + i) % Hc; if (iy < 0) iy += Hc;
-    rowmap[i] = iy >> a.up_h;
+    rowmap[i] = (a.dilate && a.up_h && (iy & 1)) ? -1 : (iy >> a.up_h);     // zero-inserted rows read as 0
   }
   for (int i = tid; i < PW; i += nthreads) {
     int ix = (ox0 * S - pad_x + i) % Wc; if (ix < 0) ix += Wc;
-    colmap[i] = ix >> a.up;
+    colmap[i] = (a.dilate && (ix & 1)) ? -1 : (ix >> a.up);
   }
 
   const int nxt = a.TW / PXT;                              // px-threads per tile row
@@ -77,15 +76,19 @@ __global__ void __launch_bounds__(256) conv_fwd_kernel(ConvFwdArgs a) {
     // ---- stage the input patch: one warp per (ci,row); BN scale/shift + ReLU applied here
     for (int r = warp; r < cic * PH; r += nwarps) {
       const int ci = r / PH, py = r - ci * PH;
-      const float* src = xn + (ci0 + ci) * HW + (long long)rowmap[py] * a.W;
+      const int rm = rowmap[py];
+      const float* src = xn + (ci0 + ci) * HW + (long long)(rm < 0 ? 0 : rm) * a.W;
       float sc = 1.f, sh = 0.f;
       if (scale) { sc = scale[ci0 + ci]; sh = shift[ci0 + ci]; }
       float* dst = patch + r * PITCH;
       for (int px = lane; px < PITCH; px += 32) {
         float v = 0.f;
         if (px < PW) {
-          v = fmaf(__ldg(src + colmap[px]), sc, sh);
-          if (a.relu_in) v = fmaxf(v, 0.f);
+          const int cm = colmap[px];
+          if (rm >= 0 && cm >= 0) {
+            v = fmaf(__ldg(src + cm), sc, sh);
+            if (a.relu_in) v = fmaxf(v, 0.f);
+          }
         }
         dst[px] = v;
       }
@@ -201,8 +204,10 @@ int arpde_conv_fwd_launch(const ConvDesc& d, const float* x, long long x_bs, con
   ARPDE_CHECK_ARG(d.stride == 1 || d.stride == 2, "conv_fwd: stride %d unsupported", d.stride);
   ARPDE_CHECK_ARG(d.n_per_group > 0, "conv_fwd: n_per_group must be > 0");
   if (d.N == 0) return ARPDE_OK;
-  const int up_h = (d.H == 1 && d.kh == 1) ? 0 : d.up;      // 1D signals: H stays 1
-  const int Hc = d.H << up_h, Wc = d.W << d.up;
+  ARPDE_CHECK_ARG(!(d.dilate && d.up), "conv_fwd: dilate and up are exclusive");
+  const int up_w = (d.up || d.dilate) ? 1 : 0;
+  const int up_h = (d.H == 1 && d.kh == 1) ? 0 : up_w;      // 1D signals: H stays 1
+  const int Hc = d.H << up_h, Wc = d.W << up_w;
   const int sh = (d.H == 1 && d.kh == 1) ? 1 : d.stride;
   ARPDE_CHECK_ARG(Hc % sh == 0 && Wc % d.stride == 0, "conv_fwd: spatial size %dx%d not divisible by stride %d", Hc, Wc, d.stride);
   const int Ho = Hc / sh, Wo = Wc / d.stride;
@@ -213,7 +218,9 @@ int arpde_conv_fwd_launch(const ConvDesc& d, const float* x, long long x_bs, con
 
   ConvFwdArgs a;
   memset(&a, 0, sizeof(a));
-  a.x = x; a.x_bs = x_bs; a.cin = d.cin; a.H = d.H; a.W = d.W; a.up = d.up; a.up_h = up_h;
+  a.x = x; a.x_bs = x_bs; a.cin = d.cin; a.H = d.H; a.W = d.W; a.up = up_w; a.up_h = up_h; a.dilate = d.dilate;
+  a.pad_y = d.pad_override >= 0 ? (d.kh == 1 ? 0 : d.pad_override) : (d.kh == 4 ? 1 : (d.kh - 1) / 2);
+  a.pad_x = d.pad_override >= 0 ? d.pad_override : (d.kw == 4 ? 1 : (d.kw - 1) / 2);
   a.w = w; a.w_gs = w_gs; a.scale = scale; a.shift = shift; a.ss_gs = ss_gs; a.relu_in = d.relu_in;
   a.y = y; a.y_ctot = d.y_ctot; a.y_coff = d.y_coff; a.cout = d.cout; a.Ho = Ho; a.Wo = Wo; a.act = d.act;
   a.stats = stats; a.n_per_group = d.n_per_group; a.N = d.N;
@@ -260,6 +267,7 @@ extern "C" int arpde_conv_fwd(const float* x, int64_t x_bstride, const float* w,
                               int cout, int kh, int kw, int stride, int up, int relu_in, int act, int y_ctot, int y_coff,
                               int n_per_group, arpde_stream_t stream) {
   ConvDesc d;
+  d.dilate = 0; d.pad_override = -1;
   d.N = N; d.cin = cin; d.H = H; d.W = W; d.cout = cout; d.kh = kh; d.kw = kw; d.stride = stride; d.up = up;
   d.relu_in = relu_in; d.act = act; d.y_ctot = y_ctot; d.y_coff = y_coff; d.n_per_group = n_per_group > 0 ? n_per_group : (N > 0 ? N : 1);
   ARPDE_CHECK_ARG((scale == nullptr) == (shift == nullptr), "conv_fwd: scale/shift must both be given or both be null");

@@ -54,6 +54,7 @@ static int run_ops(const RunCtx& c, const float* x, long long x_bs, float* y, in
   for (int i = 0; i < c.n_ops; ++i) {
     const arpde_op_t& o = c.ops[i];
     ConvDesc d;
+    d.dilate = 0; d.pad_override = -1;
     d.N = c.N; d.cin = o.cin; d.cout = o.cout; d.kh = o.kh; d.kw = o.kw; d.stride = o.stride; d.up = o.up;
     d.relu_in = o.bn_param >= 0; d.act = o.act; d.n_per_group = c.n_per_group;
     const float* in; long long in_bs;

@@ -290,11 +290,11 @@ static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 extern "C" int arpde_cn_burgers2d_fwd(const float* uPred, int64_t up_bstride, const float* uPred0, int64_t u0_bstride,
                                       float* ustar, double* sse_out, int N, int H, int W, double dx, double nu,
                                       double dt, int mode, arpde_stream_t stream_) {
-  ARPDE_CHECK_ARG(uPred && uPred0 && (ustar || sse_out), "burgers2d_fwd: null pointer");
   ARPDE_CHECK_ARG(N >= 0 && H >= 1 && W >= 1, "burgers2d_fwd: bad dims N=%d H=%d W=%d", N, H, W);
   B2Coef k; int rc = make_b2coef(dx, nu, dt, mode, &k); if (rc) return rc;
   if (sse_out) ARPDE_CUDA(cudaMemsetAsync(sse_out, 0, sizeof(double), (cudaStream_t)stream_));
-  if (N == 0) return ARPDE_OK;
+  if (N == 0) return ARPDE_OK;                       // empty batch: nothing to do (pointers may be null)
+  ARPDE_CHECK_ARG(uPred && uPred0 && (ustar || sse_out), "burgers2d_fwd: null pointer");
   const int w4 = W >> 2;
   const bool pow2 = w4 > 0 && (w4 & (w4 - 1)) == 0;
   const bool vec_ok = (W % 4 == 0) && H >= 2 && aligned16(uPred) && aligned16(uPred0) && (!ustar || aligned16(ustar)) &&
@@ -334,10 +334,10 @@ extern "C" int arpde_cn_burgers2d_fwd_generic(const float* uPred, int64_t up_bst
 extern "C" int arpde_cn_burgers2d_bwd(const float* uPred, int64_t up_bstride, const float* uPred0, int64_t u0_bstride,
                                       const float* grad_ustar, float* grad_uPred, float* grad_uPred0, int N, int H, int W,
                                       double dx, double nu, double dt, int mode, arpde_stream_t stream_) {
-  ARPDE_CHECK_ARG(uPred && uPred0 && grad_ustar && grad_uPred && grad_uPred0, "burgers2d_bwd: null pointer");
   ARPDE_CHECK_ARG(N >= 0 && H >= 1 && W >= 1, "burgers2d_bwd: bad dims");
   B2Coef k; int rc = make_b2coef(dx, nu, dt, mode, &k); if (rc) return rc;
   if (N == 0) return ARPDE_OK;
+  ARPDE_CHECK_ARG(uPred && uPred0 && grad_ustar && grad_uPred && grad_uPred0, "burgers2d_bwd: null pointer");
   const int64_t total = (int64_t)N * H * W;
   int64_t blocks = ceil_div64(total, 256); const int64_t cap = (int64_t)arpde_num_sms() * 32; if (blocks > cap) blocks = cap;
   burgers2d_bwd_generic<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream_>>>(uPred, up_bstride, uPred0, u0_bstride, grad_ustar, grad_uPred, grad_uPred0, N, H, W, k);
@@ -467,8 +467,8 @@ static int make_taps(int system, int k1, int k2, int k4, double dx, double nu, d
 extern "C" int arpde_cn_1d_fwd(int system, const float* uPred, int64_t up_bstride, const float* uPred0, int64_t u0_bstride,
                                float* ustar, double* sse_out, int N, int L, double dx, double nu, double dt, int k1, int k2,
                                int k4, int mode, arpde_stream_t stream_) {
-  ARPDE_CHECK_ARG(uPred && uPred0 && (ustar || sse_out), "cn_1d_fwd: null pointer");
   ARPDE_CHECK_ARG(N >= 0 && L >= 1, "cn_1d_fwd: bad dims N=%d L=%d", N, L);
+  ARPDE_CHECK_ARG(N == 0 || (uPred && uPred0 && (ustar || sse_out)), "cn_1d_fwd: null pointer");
   Taps1D t; int rc = make_taps(system, k1, k2, k4, dx, nu, dt, mode, &t); if (rc) return rc;
   ARPDE_CHECK_ARG(L > t.r, "cn_1d_fwd: L=%d must exceed the stencil radius %d", L, t.r);
   if (sse_out) ARPDE_CUDA(cudaMemsetAsync(sse_out, 0, sizeof(double), (cudaStream_t)stream_));
@@ -482,8 +482,8 @@ extern "C" int arpde_cn_1d_fwd(int system, const float* uPred, int64_t up_bstrid
 extern "C" int arpde_cn_1d_bwd(int system, const float* uPred, int64_t up_bstride, const float* uPred0, int64_t u0_bstride,
                                const float* grad_ustar, float* grad_uPred, float* grad_uPred0, int N, int L, double dx,
                                double nu, double dt, int k1, int k2, int k4, int mode, arpde_stream_t stream_) {
-  ARPDE_CHECK_ARG(uPred && uPred0 && grad_ustar && grad_uPred && grad_uPred0, "cn_1d_bwd: null pointer");
   ARPDE_CHECK_ARG(N >= 0 && L >= 1, "cn_1d_bwd: bad dims");
+  ARPDE_CHECK_ARG(N == 0 || (uPred && uPred0 && grad_ustar && grad_uPred && grad_uPred0), "cn_1d_bwd: null pointer");
   Taps1D t; int rc = make_taps(system, k1, k2, k4, dx, nu, dt, mode, &t); if (rc) return rc;
   ARPDE_CHECK_ARG(L > t.r, "cn_1d_bwd: L=%d must exceed the stencil radius %d", L, t.r);
   if (N == 0) return ARPDE_OK;

@@ -32,7 +32,8 @@ __global__ void __launch_bounds__(256) swag_sample_kernel(SwagTable t, const flo
     while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (t.off[mid] <= p) lo = mid; else hi = mid - 1; }
     const long long i = p - t.off[lo], numel = t.off[lo + 1] - t.off[lo];
     const float m = t.mean[lo][i];
-    const float var = fmaxf(t.sq[lo][i] - m * m, eps);
+    // two roundings, like torch's `sq_mean - mean ** 2` (an FMA here changes the result: the difference cancels)
+    const float var = fmaxf(__fsub_rn(t.sq[lo][i], __fmul_rn(m, m)), eps);
     const float sds = scale * sqrtf(var) * z1[(long long)s * P + p];
     float w;
     if (diag) {
@@ -80,11 +81,15 @@ __global__ void __launch_bounds__(256) moments_kernel(const float* __restrict__ 
   const long long total = (long long)n_ic * inner;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long n = i / inner, j = i - n * inner;
-    float s1 = 0.f, s2 = 0.f;
-    for (int s = 0; s < S; ++s) { const float v = traj[((long long)s * n_ic + n) * bstride + j]; s1 += v; s2 = fmaf(v, v, s2); }
-    const float m = s1 / (float)S;
+    float m = 0.f, m2 = 0.f;                 // Welford: E[y^2]-E[y]^2 without the cancellation
+    for (int s = 0; s < S; ++s) {
+      const float v = traj[((long long)s * n_ic + n) * bstride + j];
+      const float d = v - m;
+      m += d / (float)(s + 1);
+      m2 = fmaf(d, v - m, m2);
+    }
     mean[i] = m;
-    if (var) var[i] = noise + s2 / (float)S - m * m;
+    if (var) var[i] = noise + m2 / (float)S;
   }
 }
 

@@ -280,7 +280,7 @@ class _Forward(torch.autograd.Function):
         if plan.out_is_buf:
             off, _, ctot, h, w = bufs[plan.ops[-1]['out_buf']]
             y = work[off:off + N * ctot * h * w].view(N, ctot, h, w)
-            if ctx.needs_input_grad[2] or any(ctx.needs_input_grad[3:]):
+            if torch.is_grad_enabled() and (ctx.needs_input_grad[2] or any(ctx.needs_input_grad[3:])):
                 raise NotImplementedError('stand-alone dense layers/blocks are inference-only')
         ctx.plan, ctx.training, ctx.geom = plan, training, (N, H, W, x_bs, bufs, work_len, stats_len, eps)
         ctx.save_for_backward(x4, work, ss, saved if saved is not None else ss, *[t for t in tensors])

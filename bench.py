@@ -192,6 +192,7 @@ def workload_config(n_gpus):
 
 
 def main():
+    global T_STEPS
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=3)
@@ -207,7 +208,6 @@ def main():
     import torch.distributed as dist
     import arpde_b200
     from arpde_b200 import engine, functional as F_
-    global T_STEPS
     T_STEPS = args.tsteps
 
     rank, world = int(os.environ.get('RANK', '0')), int(os.environ.get('WORLD_SIZE', '1'))

@@ -374,7 +374,7 @@ def mse(a, b):
 
 def rel_err(a, b):
     """max|a-b| / max|b| -- the relative error every parity test in tests/ uses."""
-    a = torch.as_tensor(a, dtype=torch.float64)
-    b = torch.as_tensor(b, dtype=torch.float64)
+    a = torch.as_tensor(a, dtype=torch.float64).detach()
+    b = torch.as_tensor(b, dtype=torch.float64).detach()
     den = float(b.abs().max())
     return float((a - b).abs().max()) / (den if den > 0 else 1.0)

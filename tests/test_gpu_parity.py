@@ -110,7 +110,7 @@ def test_filters_standalone():
 
 def test_integrator_errors():
     with pytest.raises(RuntimeError):
-        L.call('arpde_cn_1d_fwd', 1, 0, 0, 0, 0, 0, 0, 1, 8, 0.1, 0.1, 0.1, 3, 3, 5, 0, L.stream())
+        L.call('arpde_cn_1d_fwd', 1, 0, 8, 0, 8, 0, 0, 1, 8, 0.1, 0.1, 0.1, 3, 3, 5, 0, L.stream())
     with pytest.raises(NotImplementedError):
         I.KSIntegrate(0.1, grad_kernels=[9, 3, 5], device=DEV)
     x = torch.zeros(2, 1, 8, device=DEV)

@@ -1,0 +1,319 @@
+// conv_bwd.cu -- backward of the fused circular-conv op (what torch autograd derives through
+// F.pad(circular)+conv, BatchNorm(train or eval)+ReLU and nearest upsampling in the reference,
+// triggered by loss.backward() at 2D-Burgers-SWAG/main.py:81 and the 1D twins).
+//
+//   forward op:  a = up2?( relu( scale*x + shift ) ),  O = conv_circ(a, w, stride)
+//   given dO:    dW   = sum_{n,pix} dO (x) a                         (wgrad_kernel, split over samples/tiles,
+//                                                                      fp32 per-CTA partials -> fp64 atomics)
+//                da   = conv_circ( zero_insert?(dO), flip(w)^T )     (conv_fwd_kernel, stride-1, pad k-1-p)
+//                dz   = pool2x2?(da) * [z > 0]                       (bn_relu_bwd_reduce: also S1=sum dz, S2=sum dz*xhat)
+//                dx  += scale * (dz - S1/M - xhat*S2/M)   (train)    (bn_bwd_apply; eval: scale*dz)
+//                dgamma = S2, dbeta = S1
+#include "common.cuh"
+#include "conv_common.cuh"
+#include "../../include/arpde.h"
+
+// ------------------------------------------------------------------ weight flip + transpose
+__global__ void weight_flip_transpose_kernel(const float* __restrict__ w, float* __restrict__ wt, int cout, int cin, int kh, int kw) {
+  const int KK = kh * kw, total = cout * cin * KK;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int kk = i % KK, ci = (i / KK) % cin, co = i / (KK * cin);
+    const int ky = kk / kw, kx = kk - ky * kw;
+    wt[((long long)ci * cout + co) * KK + (kh - 1 - ky) * kw + (kw - 1 - kx)] = w[i];
+  }
+}
+
+int arpde_weight_flip_transpose_launch(const float* w, float* wt, int cout, int cin, int kh, int kw, cudaStream_t stream) {
+  const int total = cout * cin * kh * kw;
+  weight_flip_transpose_kernel<<<(total + 255) / 256, 256, 0, stream>>>(w, wt, cout, cin, kh, kw);
+  ARPDE_LAUNCH_CHECK();
+  return ARPDE_OK;
+}
+
+// ------------------------------------------------------------------ BN + ReLU (+ nearest x2) backward, pass 1
+// da: [N, C, H<<up_h, W<<up_w] compact; x: forward input (pre-BN) with batch stride; dz out: [N, C, H, W] compact.
+// has_bn = 0: dz = pooled da (no mask), sums untouched.
+__global__ void __launch_bounds__(256) bn_relu_bwd_reduce_kernel(const float* __restrict__ da, const float* __restrict__ x, long long x_bs,
+                                                                 const float* __restrict__ scale, const float* __restrict__ shift,
+                                                                 const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                                 float* __restrict__ dz, double* __restrict__ sums, int N, int C, int H,
+                                                                 int W, int up_h, int up_w, int chunks) {
+  const int c = blockIdx.x / chunks, ch = blockIdx.x - c * chunks;
+  const long long HW = (long long)H * W, total = (long long)N * HW, per = (total + chunks - 1) / chunks;
+  const long long lo = ch * per, hi = lo + per < total ? lo + per : total;
+  const int Hc = H << up_h, Wc = W << up_w;
+  const float sc = scale ? scale[c] : 1.f, sh = scale ? shift[c] : 0.f;
+  const float mu = mean ? mean[c] : 0.f, is = invstd ? invstd[c] : 1.f;
+  float s1 = 0.f, s2 = 0.f;
+  for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+    const long long n = i / HW; const int r = (int)(i - n * HW), y = r / W, xx = r - y * W;
+    const float* p = da + ((n * C + c) * Hc + ((long long)y << up_h)) * Wc + (xx << up_w);
+    float g = p[0];
+    if (up_w) g += p[1];
+    if (up_h) { g += p[Wc]; if (up_w) g += p[Wc + 1]; }
+    if (scale) {
+      const float xv = x[n * x_bs + (long long)c * HW + r];
+      if (fmaf(xv, sc, sh) <= 0.f) g = 0.f;
+      s1 += g; s2 = fmaf(g, (xv - mu) * is, s2);
+    }
+    dz[(n * C + c) * HW + r] = g;
+  }
+  if (scale) {
+    const double d1 = block_sum_d((double)s1);
+    const double d2 = block_sum_d((double)s2);
+    if (threadIdx.x == 0) { atomicAdd(sums + 2 * c, d1); atomicAdd(sums + 2 * c + 1, d2); }
+  }
+}
+
+// pass 2: gx[n, c] (+)= scale*(dz - S1/M - xhat*S2/M) (train) | scale*dz (eval) ; dgamma = S2, dbeta = S1
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restrict__ dz, const float* __restrict__ x, long long x_bs,
+                                                           const float* __restrict__ scale, const float* __restrict__ mean,
+                                                           const float* __restrict__ invstd, const double* __restrict__ sums,
+                                                           float* __restrict__ gx, long long gx_bs, float* __restrict__ dgamma,
+                                                           float* __restrict__ dbeta, int N, int C, long long HW, int training,
+                                                           int accumulate) {
+  const long long total = (long long)N * C * HW;
+  const double invM = 1.0 / ((double)N * (double)HW);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i % HW; const int c = (int)((i / HW) % C); const long long n = i / (HW * C);
+    float g = dz[i];
+    float v;
+    if (scale) {
+      if (training) {
+        const float xh = (x[n * x_bs + c * HW + r] - mean[c]) * invstd[c];
+        g = g - (float)(sums[2 * c] * invM) - xh * (float)(sums[2 * c + 1] * invM);
+      }
+      v = scale[c] * g;
+    } else {
+      v = g;
+    }
+    float* o = gx + n * gx_bs + c * HW + r;
+    *o = accumulate ? *o + v : v;
+  }
+  if (scale && dgamma && blockIdx.x == 0)
+    for (int c = threadIdx.x; c < C; c += blockDim.x) { dgamma[c] = (float)sums[2 * c + 1]; dbeta[c] = (float)sums[2 * c]; }
+}
+
+int arpde_bn_relu_bwd_launch(const float* da, const float* x, long long x_bs, const float* scale, const float* shift, const float* mean,
+                             const float* invstd, float* dz, double* sums, float* gx, long long gx_bs, float* dgamma, float* dbeta, int N,
+                             int C, int H, int W, int up_h, int up_w, int training, int accumulate, cudaStream_t stream) {
+  const long long HW = (long long)H * W, total = (long long)N * HW;
+  if (scale) ARPDE_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, stream));
+  int chunks = (int)ceil_div64(total, 256 * 32); if (chunks < 1) chunks = 1; if (chunks > 128) chunks = 128;
+  bn_relu_bwd_reduce_kernel<<<C * chunks, 256, 0, stream>>>(da, x, x_bs, scale, shift, mean, invstd, dz, sums, N, C, H, W, up_h, up_w, chunks);
+  ARPDE_LAUNCH_CHECK();
+  int64_t blocks = ceil_div64(total * C, 256 * 4); const int64_t cap = (int64_t)arpde_num_sms() * 16; if (blocks > cap) blocks = cap; if (blocks < 1) blocks = 1;
+  bn_bwd_apply_kernel<<<(unsigned)blocks, 256, 0, stream>>>(dz, x, x_bs, scale, mean, invstd, sums, gx, gx_bs, dgamma, dbeta, N, C, HW, training, accumulate);
+  ARPDE_LAUNCH_CHECK();
+  return ARPDE_OK;
+}
+
+// ------------------------------------------------------------------ output-activation backward (rare: out_activation != None)
+__global__ void act_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ y, float* __restrict__ out, long long n, int act) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = y[i];
+    float d = 1.f;
+    switch (act) {
+      case 1: d = 1.f - v * v; break;
+      case 2: d = v > 0.f ? 1.f : 0.f; break;
+      case 3: d = v > 0.f ? 1.f : 0.01f; break;
+      case 4: d = v * (1.f - v); break;
+      case 5: d = 1.f - expf(-4.f * v); break;      // y = log1p(exp(4x))/4  =>  dy/dx = sigmoid(4x) = 1 - exp(-4y)
+      default: break;
+    }
+    out[i] = gy[i] * d;
+  }
+}
+
+int arpde_act_bwd_launch(const float* gy, const float* y, float* out, long long n, int act, cudaStream_t stream) {
+  int64_t blocks = ceil_div64(n, 256); if (blocks > 4096) blocks = 4096;
+  act_bwd_kernel<<<(unsigned)blocks, 256, 0, stream>>>(gy, y, out, n, act);
+  ARPDE_LAUNCH_CHECK();
+  return ARPDE_OK;
+}
+
+// ------------------------------------------------------------------ weight gradient
+struct WgradArgs {
+  const float* x; long long x_bs; int cin, H, W, up, up_h, pad_y, pad_x;
+  const float* scale; const float* shift; int relu_in;
+  const float* dO; long long dO_bs; int cout, Ho, Wo;
+  double* dW;
+  int N, tiles_x, tiles_y, co_tiles, ci_chunks, TH, TW, pitch, plane, cic, ncg, dpitch;
+};
+
+template <int KH, int KW, int S, int COT>
+__global__ void __launch_bounds__(256) wgrad_kernel(WgradArgs a) {
+  constexpr int KK = KH * KW, PXT = 4;
+  constexpr int SEG = ((PXT - 1) * S + KW + 3) & ~3;
+  extern __shared__ __align__(16) float smem[];
+  const int PH = (a.TH - 1) * S + KH, PW = (a.TW - 1) * S + KW;
+  const int TCO = a.ncg * COT;
+  int* rowmap = reinterpret_cast<int*>(smem);
+  int* colmap = rowmap + PH;
+  float* patch = smem + ((PH + PW + 3) & ~3);
+  float* dsm = patch + a.cic * a.plane;                  // [TCO][TH][dpitch]
+  const int tid = threadIdx.x, nthreads = blockDim.x;
+  const int ci_l = tid % a.cic, tc = tid / a.cic;        // ci lane, co group
+  const bool active = tc < a.ncg;
+  const int bt = blockIdx.x;
+  const int co_tile = bt % a.co_tiles, ci_chunk = bt / a.co_tiles;
+  const int co0 = co_tile * TCO, ci0 = ci_chunk * a.cic;
+  const int cic = min(a.cic, a.cin - ci0);
+  const int Hc = a.H << a.up_h, Wc = a.W << a.up;
+  const long long HW = (long long)a.H * a.W, HoWo = (long long)a.Ho * a.Wo;
+  const int warp = tid >> 5, lane = tid & 31, nwarps = nthreads >> 5;
+  const int tiles = a.tiles_x * a.tiles_y;
+
+  float acc[COT][KK];
+#pragma unroll
+  for (int c = 0; c < COT; ++c)
+#pragma unroll
+    for (int k = 0; k < KK; ++k) acc[c][k] = 0.f;
+
+  for (long long item = blockIdx.y; item < (long long)a.N * tiles; item += gridDim.y) {
+    const int n = (int)(item / tiles), tl = (int)(item - (long long)n * tiles);
+    const int ty_tile = tl / a.tiles_x, tx_tile = tl - ty_tile * a.tiles_x;
+    const int oy0 = ty_tile * a.TH, ox0 = tx_tile * a.TW;
+    __syncthreads();
+    for (int i = tid; i < PH; i += nthreads) { int iy = (oy0 * S - a.pad_y + i) % Hc; if (iy < 0) iy += Hc; rowmap[i] = iy >> a.up_h; }
+    for (int i = tid; i < PW; i += nthreads) { int ix = (ox0 * S - a.pad_x + i) % Wc; if (ix < 0) ix += Wc; colmap[i] = ix >> a.up; }
+    __syncthreads();
+    const float* xn = a.x + (long long)n * a.x_bs;
+    for (int r = warp; r < cic * PH; r += nwarps) {
+      const int ci = r / PH, py = r - ci * PH;
+      const float* src = xn + (ci0 + ci) * HW + (long long)rowmap[py] * a.W;
+      float sc = 1.f, sh = 0.f;
+      if (a.scale) { sc = a.scale[ci0 + ci]; sh = a.shift[ci0 + ci]; }
+      float* dst = patch + ci * a.plane + py * a.pitch;
+      for (int px = lane; px < a.pitch; px += 32) {
+        float v = 0.f;
+        if (px < PW) { v = fmaf(__ldg(src + colmap[px]), sc, sh); if (a.relu_in) v = fmaxf(v, 0.f); }
+        dst[px] = v;
+      }
+    }
+    const float* dn = a.dO + (long long)n * a.dO_bs;
+    for (int r = warp; r < TCO * a.TH; r += nwarps) {
+      const int co = r / a.TH, py = r - co * a.TH;
+      const bool ok = (co0 + co < a.cout) && (oy0 + py < a.Ho);
+      const float* src = dn + (long long)(co0 + co) * HoWo + (long long)(oy0 + py) * a.Wo + ox0;
+      float* dst = dsm + r * a.dpitch;
+      for (int px = lane; px < a.dpitch; px += 32) dst[px] = (ok && px < a.TW && ox0 + px < a.Wo) ? __ldg(src + px) : 0.f;
+    }
+    __syncthreads();
+    if (active && ci_l < cic) {
+      const float* pbase = patch + ci_l * a.plane;
+      for (int py = 0; py < a.TH; ++py) {
+        for (int xg = 0; xg < a.TW; xg += PXT) {
+          float d[COT][PXT];
+#pragma unroll
+          for (int c = 0; c < COT; ++c) {
+            const float4 v = *reinterpret_cast<const float4*>(dsm + ((tc * COT + c) * a.TH + py) * a.dpitch + xg);
+            d[c][0] = v.x; d[c][1] = v.y; d[c][2] = v.z; d[c][3] = v.w;
+          }
+#pragma unroll
+          for (int ky = 0; ky < KH; ++ky) {
+            const float* rowp = pbase + (py * S + ky) * a.pitch + xg * S;
+            float in[SEG];
+#pragma unroll
+            for (int q = 0; q < SEG / 4; ++q) {
+              const float4 v = *reinterpret_cast<const float4*>(rowp + 4 * q);
+              in[4 * q] = v.x; in[4 * q + 1] = v.y; in[4 * q + 2] = v.z; in[4 * q + 3] = v.w;
+            }
+#pragma unroll
+            for (int kx = 0; kx < KW; ++kx)
+#pragma unroll
+              for (int c = 0; c < COT; ++c)
+#pragma unroll
+                for (int p = 0; p < PXT; ++p) acc[c][ky * KW + kx] = fmaf(d[c][p], in[p * S + kx], acc[c][ky * KW + kx]);
+          }
+        }
+      }
+    }
+  }
+  if (active && ci_l < cic) {
+#pragma unroll
+    for (int c = 0; c < COT; ++c) {
+      const int co = co0 + tc * COT + c;
+      if (co < a.cout) {
+        double* o = a.dW + ((long long)co * a.cin + ci0 + ci_l) * KK;
+#pragma unroll
+        for (int k = 0; k < KK; ++k) atomicAdd(o + k, (double)acc[c][k]);
+      }
+    }
+  }
+}
+
+__global__ void d2f_kernel(const double* __restrict__ src, float* __restrict__ dst, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) dst[i] = (float)src[i];
+}
+
+typedef void (*wgrad_fn)(WgradArgs);
+template <int KH, int KW, int S>
+static wgrad_fn pick_w(int* cot) {
+  constexpr int KK = KH * KW;
+  constexpr int C = KK <= 9 ? 8 : (KK <= 25 ? 4 : 2);
+  *cot = C;
+  return wgrad_kernel<KH, KW, S, C>;
+}
+static wgrad_fn pick_wgrad(int kh, int kw, int s, int* cot) {
+#define PK(KH_, KW_, S_) if (kh == KH_ && kw == KW_ && s == S_) return pick_w<KH_, KW_, S_>(cot)
+  PK(1, 1, 1); PK(3, 3, 1); PK(3, 3, 2); PK(5, 5, 1); PK(4, 4, 2); PK(7, 7, 2);
+  PK(1, 3, 1); PK(1, 3, 2); PK(1, 5, 1); PK(1, 4, 2); PK(1, 7, 2);
+#undef PK
+  return nullptr;
+}
+
+// dW (float, [cout][cin][kh][kw]) = sum over batch; dW64 scratch: cout*cin*kh*kw doubles
+int arpde_conv_wgrad_launch(const ConvDesc& d, const float* x, long long x_bs, const float* scale, const float* shift, const float* dO,
+                            long long dO_bs, double* dW64, float* dW, cudaStream_t stream) {
+  ARPDE_CHECK_ARG(x && dO && dW64 && dW, "conv_wgrad: null pointer");
+  int cot = 8;
+  wgrad_fn fn = pick_wgrad(d.kh, d.kw, d.stride, &cot);
+  if (!fn) { arpde_set_error("conv_wgrad: kernel %dx%d stride %d not instantiated", d.kh, d.kw, d.stride); return ARPDE_ERR_UNSUPPORTED; }
+  const int KK = d.kh * d.kw;
+  const long long wn = (long long)d.cout * d.cin * KK;
+  ARPDE_CUDA(cudaMemsetAsync(dW64, 0, sizeof(double) * wn, stream));
+  const int one_d = (d.H == 1 && d.kh == 1);
+  const int up_h = one_d ? 0 : d.up;
+  const int Hc = d.H << up_h, Wc = d.W << d.up;
+  const int sh = one_d ? 1 : d.stride;
+  const int Ho = Hc / sh, Wo = Wc / d.stride;
+  WgradArgs a; memset(&a, 0, sizeof(a));
+  a.x = x; a.x_bs = x_bs; a.cin = d.cin; a.H = d.H; a.W = d.W; a.up = d.up; a.up_h = up_h;
+  a.pad_y = d.kh == 4 ? 1 : (d.kh - 1) / 2; a.pad_x = d.kw == 4 ? 1 : (d.kw - 1) / 2;
+  a.scale = scale; a.shift = shift; a.relu_in = d.relu_in;
+  a.dO = dO; a.dO_bs = dO_bs; a.cout = d.cout; a.Ho = Ho; a.Wo = Wo; a.dW = dW64; a.N = d.N;
+  int ncg = (d.cout + cot - 1) / cot; if (ncg > 24) ncg = 24;
+  int cic = 256 / ncg; if (cic > d.cin) cic = d.cin; if (cic < 1) cic = 1;
+  a.ncg = ncg; a.cic = cic;
+  const int TCO = ncg * cot;
+  a.co_tiles = (d.cout + TCO - 1) / TCO; a.ci_chunks = (d.cin + cic - 1) / cic;
+  int TW = ((Wo + 3) / 4) * 4; if (TW > 64) TW = 64;
+  a.TW = TW; a.tiles_x = (Wo + TW - 1) / TW;
+  const int seg = (((4 - 1) * d.stride + d.kw) + 3) & ~3;
+  const int PW = (TW - 1) * d.stride + d.kw;
+  int pitch = (TW - 4) * d.stride + seg; if (pitch < PW) pitch = PW; pitch = (pitch + 3) & ~3;
+  a.pitch = pitch; a.dpitch = TW;
+  // rows per tile: keep shared memory under ~96 KB
+  int TH = Ho < 8 ? Ho : 8;
+  size_t smem = 0;
+  for (;; --TH) {
+    const int PH = (TH - 1) * sh + d.kh;
+    int plane = PH * pitch; if (((plane >> 2) & 1) == 0) plane += 4;      // odd multiple of 4 floats: conflict-free float4 reads across ci
+    a.plane = plane;
+    smem = ((size_t)((PH + PW + 3) & ~3) + (size_t)cic * plane + (size_t)TCO * TH * TW) * 4;
+    if (smem <= 96 * 1024 || TH == 1) break;
+  }
+  ARPDE_CHECK_ARG(smem <= 200 * 1024, "conv_wgrad: tile needs %zu bytes of shared memory", smem);
+  a.TH = TH; a.tiles_y = (Ho + TH - 1) / TH;
+  if (smem > 48 * 1024) ARPDE_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const long long items = (long long)d.N * a.tiles_x * a.tiles_y;
+  const int gx = a.co_tiles * a.ci_chunks;
+  long long split = (4ll * arpde_num_sms() + gx - 1) / gx; if (split > items) split = items; if (split < 1) split = 1; if (split > 65535) split = 65535;
+  int threads = ((ncg * cic + 31) / 32) * 32;
+  fn<<<dim3(gx, (unsigned)split), threads, smem, stream>>>(a);
+  ARPDE_LAUNCH_CHECK();
+  d2f_kernel<<<(unsigned)ceil_div64(wn, 256), 256, 0, stream>>>(dW64, dW, wn);
+  ARPDE_LAUNCH_CHECK();
+  return ARPDE_OK;
+}

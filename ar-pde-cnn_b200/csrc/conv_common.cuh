@@ -39,3 +39,11 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 int arpde_conv_fwd_launch(const ConvDesc& d, const float* x, long long x_bs, const float* w, long long w_gs,
                           const float* scale, const float* shift, long long ss_gs, float* y, double* stats,
                           cudaStream_t stream);
+
+int arpde_weight_flip_transpose_launch(const float* w, float* wt, int cout, int cin, int kh, int kw, cudaStream_t stream);
+int arpde_bn_relu_bwd_launch(const float* da, const float* x, long long x_bs, const float* scale, const float* shift, const float* mean,
+                             const float* invstd, float* dz, double* sums, float* gx, long long gx_bs, float* dgamma, float* dbeta, int N,
+                             int C, int H, int W, int up_h, int up_w, int training, int accumulate, cudaStream_t stream);
+int arpde_act_bwd_launch(const float* gy, const float* y, float* out, long long n, int act, cudaStream_t stream);
+int arpde_conv_wgrad_launch(const ConvDesc& d, const float* x, long long x_bs, const float* scale, const float* shift, const float* dO,
+                            long long dO_bs, double* dW64, float* dW, cudaStream_t stream);

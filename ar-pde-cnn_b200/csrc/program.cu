@@ -147,3 +147,76 @@ extern "C" int arpde_rollout(const arpde_op_t* ops, int n_ops, const arpde_buf_t
   }
   return ARPDE_OK;
 }
+
+// Backward of arpde_densed_forward (train or eval mode): what loss.backward() does through DenseED in the reference
+// (main.py:81).  Ops are visited in reverse; gradients of the activation buffers live in gwork (same layout as the
+// workspace; the last consumer of a buffer overwrites, earlier consumers accumulate, so no memset is needed).
+extern "C" int arpde_densed_backward(const arpde_op_t* ops, int n_ops, const arpde_buf_t* bufs, int n_bufs, void* const* params_host,
+                                     int n_params, const float* x, int64_t x_bstride, int N, int H, int W, const float* gy,
+                                     const float* y, const float* workspace, const float* scale_shift, int bn_total,
+                                     const float* saved_mean_invstd, float* gwork, float* gx, void* const* grads_host, float* T1,
+                                     float* T2, float* wT, double* d64, int training, arpde_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  int rc = check_program(ops, n_ops, bufs, n_bufs, n_params); if (rc) return rc;
+  ARPDE_CHECK_ARG(params_host && grads_host && x && gy && T1 && T2 && wT && d64, "densed_backward: null pointer");
+  ARPDE_CHECK_ARG((workspace && gwork) || n_bufs == 0, "densed_backward: workspace missing");
+  ARPDE_CHECK_ARG(bn_total == 0 || (scale_shift && saved_mean_invstd), "densed_backward: BN scratch missing");
+  std::vector<char> written(n_bufs > 0 ? n_bufs : 1, 0);
+  for (int i = n_ops - 1; i >= 0; --i) {
+    const arpde_op_t& o = ops[i];
+    const float* in; long long in_bs; int Hin, Win;
+    if (o.in_buf < 0) { in = x; in_bs = x_bstride; Hin = H; Win = W; }
+    else { const arpde_buf_t& b = bufs[o.in_buf]; in = workspace + b.offset; in_bs = (long long)b.ctot * b.h * b.w; Hin = b.h; Win = b.w; }
+    const int one_d = (Hin == 1 && o.kh == 1);
+    const int up_w = o.up, up_h = one_d ? 0 : o.up;
+    const int Hc = Hin << up_h, Wc = Win << up_w;
+    const int Ho = one_d ? 1 : Hc / o.stride, Wo = Wc / o.stride;
+    const float* dO; long long dO_bs;
+    if (o.out_buf == -2) {
+      dO = gy; dO_bs = (long long)o.cout * Ho * Wo;
+      if (o.act != 0) {
+        ARPDE_CHECK_ARG(y != nullptr, "densed_backward: output activation needs the forward output");
+        rc = arpde_act_bwd_launch(gy, y, T2, (long long)N * o.cout * Ho * Wo, o.act, stream); if (rc) return rc;
+        dO = T2;
+      }
+    } else {
+      const arpde_buf_t& b = bufs[o.out_buf];
+      dO = gwork + b.offset + (long long)o.out_coff * b.h * b.w; dO_bs = (long long)b.ctot * b.h * b.w;
+    }
+    const float *scale = nullptr, *shift = nullptr, *mean = nullptr, *invstd = nullptr;
+    if (o.bn_param >= 0) {
+      scale = scale_shift + o.bn_off; shift = scale_shift + bn_total + o.bn_off;
+      mean = saved_mean_invstd + o.bn_off; invstd = saved_mean_invstd + bn_total + o.bn_off;
+    }
+    ConvDesc d;
+    d.N = N; d.cin = o.cin; d.H = Hin; d.W = Win; d.cout = o.cout; d.kh = o.kh; d.kw = o.kw; d.stride = o.stride; d.up = o.up;
+    d.relu_in = o.bn_param >= 0; d.act = 0; d.y_ctot = o.cout; d.y_coff = 0; d.n_per_group = N;
+    float* gw = (float*)grads_host[o.w_param];
+    if (gw) { rc = arpde_conv_wgrad_launch(d, in, in_bs, scale, shift, dO, dO_bs, d64, gw, stream); if (rc) return rc; }
+    const bool need_dx = o.in_buf >= 0 || gx != nullptr;
+    if (!need_dx) continue;
+    rc = arpde_weight_flip_transpose_launch((const float*)params_host[o.w_param], wT, o.cout, o.cin, o.kh, o.kw, stream); if (rc) return rc;
+    ConvDesc g;
+    g.N = N; g.cin = o.cout; g.H = Ho; g.W = Wo; g.cout = o.cin; g.kh = o.kh; g.kw = o.kw; g.stride = 1; g.up = 0;
+    g.dilate = o.stride == 2; g.relu_in = 0; g.act = 0; g.n_per_group = N;
+    const int p = o.kw == 4 ? 1 : (o.kw - 1) / 2;
+    g.pad_override = o.kw - 1 - p;
+    float* dest; long long dest_bs; bool acc = false;
+    if (o.in_buf < 0) { dest = gx; dest_bs = (long long)o.cin * Hin * Win; }
+    else { const arpde_buf_t& b = bufs[o.in_buf]; dest = gwork + b.offset; dest_bs = (long long)b.ctot * b.h * b.w; acc = written[o.in_buf]; }
+    if (o.bn_param < 0 && !o.up && !acc) {
+      g.y_ctot = (int)(dest_bs / ((long long)Hin * Win)); g.y_coff = 0;
+      rc = arpde_conv_fwd_launch(g, dO, dO_bs, wT, 0, nullptr, nullptr, 0, dest, nullptr, stream); if (rc) return rc;
+    } else {
+      g.y_ctot = o.cin; g.y_coff = 0;
+      rc = arpde_conv_fwd_launch(g, dO, dO_bs, wT, 0, nullptr, nullptr, 0, T1, nullptr, stream); if (rc) return rc;
+      float* dgamma = o.bn_param >= 0 ? (float*)grads_host[o.bn_param] : nullptr;
+      float* dbeta = o.bn_param >= 0 ? (float*)grads_host[o.bn_param + 1] : nullptr;
+      rc = arpde_bn_relu_bwd_launch(T1, in, in_bs, scale, shift, mean, invstd, T2, d64, dest, dest_bs, dgamma, dbeta, N, o.cin, Hin, Win,
+                                    up_h, up_w, training, acc ? 1 : 0, stream);
+      if (rc) return rc;
+    }
+    if (o.in_buf >= 0) written[o.in_buf] = 1;
+  }
+  return ARPDE_OK;
+}

@@ -245,7 +245,7 @@ class _Forward(torch.autograd.Function):
     """(x, *float parameters) -> y through arpde_densed_forward; backward through arpde_densed_backward."""
 
     @staticmethod
-    def forward(ctx, plan, training, x, *params):
+    def forward(ctx, plan, training, grad_mode, x, *params):
         L.require_cuda(x, *params)
         tensors = param_tensors(plan)
         x4, x_bs = _in_view(x.detach())
@@ -259,7 +259,6 @@ class _Forward(torch.autograd.Function):
         work = torch.empty((max(work_len, 1),), device=dev, dtype=torch.float32)
         ss = torch.empty((max(2 * plan.bn_total, 1),), device=dev, dtype=torch.float32)
         eps, mom = bn_hyper(plan)
-        need_grad = training and torch.is_grad_enabled()
         stats = torch.empty((max(stats_len, 1),), device=dev, dtype=torch.float64) if training else None
         saved = torch.empty((max(2 * plan.bn_total, 1),), device=dev, dtype=torch.float32) if training else None
         pp = L.ptr_array([t.data_ptr() for t in tensors])
@@ -280,10 +279,11 @@ class _Forward(torch.autograd.Function):
         if plan.out_is_buf:
             off, _, ctot, h, w = bufs[plan.ops[-1]['out_buf']]
             y = work[off:off + N * ctot * h * w].view(N, ctot, h, w)
-            if torch.is_grad_enabled() and (ctx.needs_input_grad[2] or any(ctx.needs_input_grad[3:])):
+            if grad_mode and (ctx.needs_input_grad[3] or any(ctx.needs_input_grad[4:])):
                 raise NotImplementedError('stand-alone dense layers/blocks are inference-only')
         ctx.plan, ctx.training, ctx.geom = plan, training, (N, H, W, x_bs, bufs, work_len, stats_len, eps)
-        ctx.save_for_backward(x4, work, ss, saved if saved is not None else ss, *[t for t in tensors])
+        has_act = any(o['act'] for o in plan.ops)
+        ctx.save_for_backward(x4, work, ss, saved if saved is not None else ss, y if has_act else ss, *[t for t in tensors])
         ctx.x_shape = x.shape
         if x.dim() == 3:
             y = y.squeeze(2)
@@ -300,4 +300,4 @@ def run_module(module, x, training):
     plan = compile_module(module)
     tensors = param_tensors(plan)
     diff = [t for t in tensors if t.dtype.is_floating_point and isinstance(t, nn.Parameter)]
-    return _Forward.apply(plan, bool(training), x, *diff)
+    return _Forward.apply(plan, bool(training), torch.is_grad_enabled(), x, *diff)

@@ -175,6 +175,20 @@ int arpde_densed_forward(const arpde_op_t* ops, int n_ops, const arpde_buf_t* bu
                          float* scale_shift, int bn_total, double* stats, int64_t stats_len, float* saved_mean_invstd,
                          int training, double momentum, double eps, arpde_stream_t stream);
 
+/* Backward of arpde_densed_forward: the autograd pass loss.backward() runs through DenseED in the reference
+ * (2D-Burgers-SWAG/main.py:81).  gy: compact gradient of the output; y: forward output (only read when the last op
+ * has an activation); workspace / scale_shift / saved_mean_invstd: as left by the forward call (eval mode: the caller
+ * fills saved_mean_invstd with running_mean and 1/sqrt(running_var+eps)); gwork: gradient workspace, same size as
+ * workspace; gx (nullable): gradient of the input [N,cin,H,W] compact; grads_host: HOST array (n_params entries) of
+ * device float* receiving each parameter's gradient (NULL = not needed; running-stat slots are ignored).
+ * Scratch: T1 >= max N*cin*Hc*Wc floats over ops (conv-input resolution), T2 >= max(N*cin*H*W, N*cout_last*Ho*Wo) floats,
+ * wT >= max weight numel floats, d64 >= max(weight numel, 2*max cin) doubles. */
+int arpde_densed_backward(const arpde_op_t* ops, int n_ops, const arpde_buf_t* bufs, int n_bufs, void* const* params_host,
+                          int n_params, const float* x, int64_t x_bstride, int N, int H, int W, const float* gy, const float* y,
+                          const float* workspace, const float* scale_shift, int bn_total, const float* saved_mean_invstd,
+                          float* gwork, float* gx, void* const* grads_host, float* T1, float* T2, float* wT, double* d64,
+                          int training, arpde_stream_t stream);
+
 /* Auto-regressive rollout in eval mode: the AR loops of main.py test()/testSample()
  * (2D-Burgers-SWAG/main.py:112-135,:160-179; 1D main.py :106-121,:148-163) without Python in the loop.
  * traj [N, traj_ctot, H, W], traj_ctot >= c_hist + T*c_out; channels [0,c_hist) hold the repeated initial

@@ -53,11 +53,13 @@ _PROTOS = {
     'arpde_bn_fold_eval': [f32p, f32p, f32p, f32p, f64, f32p, f32p, i32, vp],
     'arpde_affine_act': [f32p, i64, f32p, f32p, f32p, i32, i32, i32, i32, i32, i32, i32, vp],
     'arpde_densed_forward': [vp, i32, vp, i32, vp, vp, i32, f32p, i64, i32, i32, i32, i32, f32p, i32, i32, f32p, f32p,
-                             i32, f64p, i64, f32p, i32, f64, f64, vp],
+                             i32, f64p, i64, f32p, i32, f64, f64, f32p, i64, vp],
+    'arpde_conv_fwd_tc': [f32p, i64, f32p, i64, f32p, f32p, i64, f32p, f64p] + [i32] * 14 + [f32p, i64, vp],
     'arpde_densed_backward': [vp, i32, vp, i32, vp, i32, f32p, i64, i32, i32, i32, f32p, f32p, f32p, f32p, i32, f32p,
                               f32p, f32p, vp, f32p, f32p, f32p, f64p, i32, vp],
+    'arpde_conv_tc_plan': [i32] * 8 + [vp],
     'arpde_rollout': [vp, i32, vp, i32, vp, vp, i32, f32p, i32, i32, i32, i32, i32, i32, i32, i32, i32, f32p, f32p,
-                      i32, f64, vp],
+                      i32, f64, f32p, i64, vp],
     'arpde_swag_sample': [vp, vp, vp, vp, i32, f32p, f32p, f32p, i32, i32, i32, f64, f64, i32, vp],
     'arpde_predictive_moments': [f32p, i64, i64, i32, i32, f64, f32p, f32p, vp],
 }
@@ -67,8 +69,13 @@ for _name, _args in _PROTOS.items():
     _fn.restype = C.c_int
 lib.arpde_last_error.restype = C.c_char_p
 lib.arpde_last_error.argtypes = []
+# size queries return a count, not a status
+lib.arpde_densed_tc_scratch_floats.argtypes = [vp, i32, i32]
+lib.arpde_densed_tc_scratch_floats.restype = C.c_int64
+lib.arpde_conv_fwd_tc_scratch_floats.argtypes = [i32, i32, i32, i32, i32]
+lib.arpde_conv_fwd_tc_scratch_floats.restype = C.c_int64
 
-EXPORTS = sorted(list(_PROTOS) + ['arpde_last_error'])
+EXPORTS = sorted(list(_PROTOS) + ['arpde_last_error', 'arpde_densed_tc_scratch_floats', 'arpde_conv_fwd_tc_scratch_floats'])
 
 
 def check(rc, what=''):

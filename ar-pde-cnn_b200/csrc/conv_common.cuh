@@ -47,3 +47,12 @@ int arpde_bn_relu_bwd_launch(const float* da, const float* x, long long x_bs, co
 int arpde_act_bwd_launch(const float* gy, const float* y, float* out, long long n, int act, cudaStream_t stream);
 int arpde_conv_wgrad_launch(const ConvDesc& d, const float* x, long long x_bs, const float* scale, const float* shift, const float* dO,
                             long long dO_bs, double* dW64, float* dW, cudaStream_t stream);
+
+// tensor-core (tcgen05) implicit-GEMM path, conv_tc.cu
+int arpde_tc_enabled();                                          // ARPDE_TC=0 in the environment disables it
+bool arpde_conv_tc_wanted(const ConvDesc& d);                    // layer heuristics + plannability
+long long arpde_conv_tc_wprep_floats(int cin, int cout, int kh, int kw);   // prepared-weight floats per weight group
+int arpde_conv_tc_prep_launch(const ConvDesc& d, const float* w, long long w_gs, int groups, float* wprep, long long wprep_gs,
+                              cudaStream_t stream);
+int arpde_conv_tc_launch(const ConvDesc& d, const float* x, long long x_bs, const float* wprep, long long wprep_gs, const float* scale,
+                         const float* shift, long long ss_gs, float* y, double* stats, cudaStream_t stream);

@@ -30,7 +30,40 @@ struct RunCtx {
   float* work; float* ss; int bn_total; double* stats; float* saved;
   float momentum, eps;
   cudaStream_t stream;
+  float* tc_scratch = nullptr; long long tc_scratch_floats = 0;
+  std::vector<const float*> wprep;          // per op: prepared tensor-core weights (nullptr = fp32 FFMA kernel)
+  std::vector<long long> wprep_gs;
 };
+
+static void op_desc(const RunCtx& c, const arpde_op_t& o, ConvDesc* d) {
+  d->dilate = 0; d->pad_override = -1;
+  d->N = c.N; d->cin = o.cin; d->cout = o.cout; d->kh = o.kh; d->kw = o.kw; d->stride = o.stride; d->up = o.up;
+  d->relu_in = o.bn_param >= 0; d->act = o.act; d->n_per_group = c.n_per_group;
+  if (o.in_buf < 0) { d->H = c.H; d->W = c.W; }
+  else { d->H = c.bufs[o.in_buf].h; d->W = c.bufs[o.in_buf].w; }
+  d->y_ctot = o.cout; d->y_coff = 0;
+}
+
+// Split/arrange the weights of every layer that runs on the tensor cores (once per forward / per rollout).
+static int prep_tc(RunCtx& c) {
+  c.wprep.assign(c.n_ops, nullptr); c.wprep_gs.assign(c.n_ops, 0);
+  if (!c.tc_scratch || !arpde_tc_enabled()) return ARPDE_OK;
+  long long used = 0;
+  for (int i = 0; i < c.n_ops; ++i) {
+    const arpde_op_t& o = c.ops[i];
+    ConvDesc d; op_desc(c, o, &d);
+    if (!arpde_conv_tc_wanted(d)) continue;
+    const long long per_group = arpde_conv_tc_wprep_floats(o.cin, o.cout, o.kh, o.kw);
+    const int wgroups = c.gstride[o.w_param] ? c.groups : 1;
+    if (used + per_group * wgroups > c.tc_scratch_floats) continue;      // scratch too small: stay on the FFMA kernel
+    float* dst = c.tc_scratch + used;
+    int rc = arpde_conv_tc_prep_launch(d, (const float*)c.params[o.w_param], c.gstride[o.w_param], wgroups, dst, per_group, c.stream);
+    if (rc) return rc;
+    c.wprep[i] = dst; c.wprep_gs[i] = wgroups > 1 ? per_group : 0;
+    used += per_group * wgroups;
+  }
+  return ARPDE_OK;
+}
 
 static int fold_eval(const RunCtx& c) {
   BnTable t; t.n = 0;
@@ -79,8 +112,12 @@ static int run_ops(const RunCtx& c, const float* x, long long x_bs, float* y, in
         if (rc) return rc;
       }
     }
-    int rc = arpde_conv_fwd_launch(d, in, in_bs, (const float*)c.params[o.w_param], c.gstride[o.w_param], scale, shift,
-                                   c.bn_total, out, st, c.stream);
+    int rc;
+    if (!c.wprep.empty() && c.wprep[i])
+      rc = arpde_conv_tc_launch(d, in, in_bs, c.wprep[i], c.wprep_gs[i], scale, shift, c.bn_total, out, st, c.stream);
+    else
+      rc = arpde_conv_fwd_launch(d, in, in_bs, (const float*)c.params[o.w_param], c.gstride[o.w_param], scale, shift,
+                                 c.bn_total, out, st, c.stream);
     if (rc) return rc;
   }
   return ARPDE_OK;
@@ -101,16 +138,27 @@ static int make_ctx(RunCtx* c, const arpde_op_t* ops, int n_ops, const arpde_buf
   return ARPDE_OK;
 }
 
+// floats of tensor-core weight scratch arpde_densed_forward / arpde_rollout can use for this program (upper bound)
+extern "C" int64_t arpde_densed_tc_scratch_floats(const arpde_op_t* ops, int n_ops, int groups) {
+  if (!ops || n_ops <= 0) return 0;
+  long long tot = 0;
+  for (int i = 0; i < n_ops; ++i) tot += arpde_conv_tc_wprep_floats(ops[i].cin, ops[i].cout, ops[i].kh, ops[i].kw) * (groups > 0 ? groups : 1);
+  return tot;
+}
+
 extern "C" int arpde_densed_forward(const arpde_op_t* ops, int n_ops, const arpde_buf_t* bufs, int n_bufs, void* const* params_host,
                                     const int64_t* param_gstride_host, int n_params, const float* x, int64_t x_bstride, int N,
                                     int n_per_group, int H, int W, float* y, int y_ctot, int y_coff, float* workspace,
                                     float* scale_shift, int bn_total, double* stats, int64_t stats_len, float* saved_mean_invstd,
-                                    int training, double momentum, double eps, arpde_stream_t stream_) {
+                                    int training, double momentum, double eps, float* tc_scratch, int64_t tc_scratch_floats,
+                                    arpde_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   RunCtx c;
   int rc = make_ctx(&c, ops, n_ops, bufs, n_bufs, params_host, param_gstride_host, n_params, N, n_per_group, H, W, workspace,
                     scale_shift, bn_total, stats, saved_mean_invstd, momentum, eps, stream);
   if (rc) return rc;
+  c.tc_scratch = tc_scratch; c.tc_scratch_floats = tc_scratch_floats;
+  rc = prep_tc(c); if (rc) return rc;
   ARPDE_CHECK_ARG(x && y && (workspace || n_bufs == 0), "densed_forward: null pointer");
   ARPDE_CHECK_ARG(bn_total == 0 || scale_shift, "densed_forward: scale/shift scratch missing");
   if (training) {
@@ -129,12 +177,14 @@ extern "C" int arpde_densed_forward(const arpde_op_t* ops, int n_ops, const arpd
 extern "C" int arpde_rollout(const arpde_op_t* ops, int n_ops, const arpde_buf_t* bufs, int n_bufs, void* const* params_host,
                              const int64_t* param_gstride_host, int n_params, float* traj, int traj_ctot, int c_in, int c_hist,
                              int c_out, int T, int N, int n_per_group, int H, int W, float* workspace, float* scale_shift,
-                             int bn_total, double eps, arpde_stream_t stream_) {
+                             int bn_total, double eps, float* tc_scratch, int64_t tc_scratch_floats, arpde_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   RunCtx c;
   int rc = make_ctx(&c, ops, n_ops, bufs, n_bufs, params_host, param_gstride_host, n_params, N, n_per_group, H, W, workspace,
                     scale_shift, bn_total, nullptr, nullptr, 0.1, eps, stream);
   if (rc) return rc;
+  c.tc_scratch = tc_scratch; c.tc_scratch_floats = tc_scratch_floats;
+  rc = prep_tc(c); if (rc) return rc;
   ARPDE_CHECK_ARG(traj && T >= 0 && c_in > 0 && c_out > 0 && c_hist >= c_in, "rollout: bad args");
   ARPDE_CHECK_ARG(traj_ctot >= c_hist + T * c_out, "rollout: trajectory has %d channels, needs %d", traj_ctot, c_hist + T * c_out);
   ARPDE_CHECK_ARG(ops[0].cin == c_in && ops[n_ops - 1].cout == c_out, "rollout: program does not match c_in/c_out");

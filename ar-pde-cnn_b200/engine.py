@@ -87,9 +87,11 @@ def rollout(model, ic, tsteps, flat_weights=None, named_params=None, out=None):
     ss = torch.empty((max(2 * S * plan.bn_total, 1),), device=dev, dtype=torch.float32)
     eps, _ = P.bn_hyper(plan)
     pp, gs, keep = _param_table(plan, named_params, flat_weights)
+    tc_len = int(L.lib.arpde_densed_tc_scratch_floats(ops_c, len(plan.ops), S))
+    tc = torch.empty((max(tc_len, 1),), device=dev, dtype=torch.float32)
     with torch.cuda.device(dev):
         L.call('arpde_rollout', ops_c, len(plan.ops), bufs_c, len(bufs), pp, gs, len(keep), L.ptr(out), ctot, plan.c_in, c_hist,
-               c_out, int(tsteps), NT, N, H, W, L.ptr(work), L.ptr(ss), plan.bn_total, float(eps), L.stream())
+               c_out, int(tsteps), NT, N, H, W, L.ptr(work), L.ptr(ss), plan.bn_total, float(eps), L.ptr(tc), tc_len, L.stream())
     traj = out[:, c_hist - c_out:].view(NT, tsteps + 1, c_out, H, W)
     return traj.squeeze(3) if one_d else traj
 

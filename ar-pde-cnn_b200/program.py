@@ -272,10 +272,12 @@ class _Forward(torch.autograd.Function):
         if plan.input_to_buf:
             off, _, ctot, h, w = bufs[0]
             work[off:off + N * ctot * h * w].view(N, ctot, h, w)[:, :Cin].copy_(x4)
+        tc_len = int(L.lib.arpde_densed_tc_scratch_floats(ops_c, len(plan.ops), 1))
+        tc = torch.empty((max(tc_len, 1),), device=dev, dtype=torch.float32)
         with torch.cuda.device(dev):
             L.call('arpde_densed_forward', ops_c, len(plan.ops), bufs_c, len(bufs), pp, gs, len(tensors), L.ptr(x4), x_bs, N, N,
                    H, W, y_ptr, y_ctot, 0, L.ptr(work), L.ptr(ss), plan.bn_total, L.ptr(stats), stats_len if training else 0,
-                   L.ptr(saved), 1 if training else 0, float(mom), float(eps), L.stream())
+                   L.ptr(saved), 1 if training else 0, float(mom), float(eps), L.ptr(tc), tc_len, L.stream())
         if plan.out_is_buf:
             off, _, ctot, h, w = bufs[plan.ops[-1]['out_buf']]
             y = work[off:off + N * ctot * h * w].view(N, ctot, h, w)

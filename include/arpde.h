@@ -128,6 +128,19 @@ int arpde_conv_fwd(const float* x, int64_t x_bstride, const float* w, int64_t w_
                    int kh, int kw, int stride, int up, int relu_in, int act, int y_ctot, int y_coff, int n_per_group,
                    arpde_stream_t stream);
 
+/* The same convolution on the 5th-generation tensor cores (tcgen05, accumulators in TMEM) with an error-compensated
+ * 3xTF32 split, i.e. fp32-grade results (conv_tc.cu).  scratch: arpde_conv_fwd_tc_scratch_floats(...) device floats for the
+ * split weights.  Returns ARPDE_ERR_UNSUPPORTED for shapes the kernel does not cover (cout > 128, > 49 taps). */
+int64_t arpde_conv_fwd_tc_scratch_floats(int cin, int cout, int kh, int kw, int groups);
+int arpde_conv_fwd_tc(const float* x, int64_t x_bstride, const float* w, int64_t w_gstride, const float* scale,
+                      const float* shift, int64_t ss_gstride, float* y, double* stats, int N, int cin, int H, int W, int cout,
+                      int kh, int kw, int stride, int up, int relu_in, int act, int y_ctot, int y_coff, int n_per_group,
+                      float* scratch, int64_t scratch_floats, arpde_stream_t stream);
+
+/* Diagnostic, host only: the tiling the tensor-core kernel uses for a layer (see conv_tc.cu for the field list; out holds
+ * at least 130 int32).  Used by the CPU tests to check the shifted-window index arithmetic without a GPU. */
+int arpde_conv_tc_plan(int cin, int H, int W, int cout, int kh, int kw, int stride, int up, int32_t* out);
+
 /* BatchNorm bookkeeping (nn.BatchNorm{1,2}d, eps 1e-5, momentum 0.1): per-channel sums of x[N,C(+),HW],
  * train-mode finalize (scale/shift, saved mean/invstd, running-stat update, num_batches_tracked += 1),
  * eval-mode fold of the running statistics. */
@@ -173,7 +186,11 @@ int arpde_densed_forward(const arpde_op_t* ops, int n_ops, const arpde_buf_t* bu
                          const int64_t* param_gstride_host, int n_params, const float* x, int64_t x_bstride, int N,
                          int n_per_group, int H, int W, float* y, int y_ctot, int y_coff, float* workspace,
                          float* scale_shift, int bn_total, double* stats, int64_t stats_len, float* saved_mean_invstd,
-                         int training, double momentum, double eps, arpde_stream_t stream);
+                         int training, double momentum, double eps, float* tc_scratch, int64_t tc_scratch_floats,
+                         arpde_stream_t stream);
+/* tc_scratch (nullable): arpde_densed_tc_scratch_floats(ops, n_ops, groups) floats of device memory in which the weights of
+ * the layers that run on the tensor cores are split into TF32 hi/lo parts; NULL keeps every layer on the fp32 FFMA kernel. */
+int64_t arpde_densed_tc_scratch_floats(const arpde_op_t* ops, int n_ops, int groups);
 
 /* Backward of arpde_densed_forward: the autograd pass loss.backward() runs through DenseED in the reference
  * (2D-Burgers-SWAG/main.py:81).  gy: compact gradient of the output; y: forward output (only read when the last op
@@ -196,7 +213,7 @@ int arpde_densed_backward(const arpde_op_t* ops, int n_ops, const arpde_buf_t* b
 int arpde_rollout(const arpde_op_t* ops, int n_ops, const arpde_buf_t* bufs, int n_bufs, void* const* params_host,
                   const int64_t* param_gstride_host, int n_params, float* traj, int traj_ctot, int c_in, int c_hist, int c_out,
                   int T, int N, int n_per_group, int H, int W, float* workspace, float* scale_shift, int bn_total, double eps,
-                  arpde_stream_t stream);
+                  float* tc_scratch, int64_t tc_scratch_floats, arpde_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * SWAG.  arpde_swag_sample replaces SwagNN.sample (nn/swag.py:80-150) for S samples at once:

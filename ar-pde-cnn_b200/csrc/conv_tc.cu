@@ -19,10 +19,15 @@
 //     the accumulators of up to `ntile` M tiles live in TMEM for the whole K loop;
 //   * 3xTF32: x = x_hi + x_lo, w = w_hi + w_lo (both parts rounded to TF32 with cvt.rna); per K step
 //         D[:, 0:2N] += A_hi * [W_hi ; W_lo]^T   (one MMA with N' = 2N: columns [0,N) hi*hi, [N,2N) hi*lo)
-//         D[:, 0:N]  += A_lo * W_hi^T
-//     and the epilogue adds the two column halves (lo*lo ~ 2^-22 relative is dropped);
-//   * warp roles: 8 staging/epilogue warps + 1 MMA-issuing warp, mbarrier rings (2 patch slots, 2 weight
-//     slots) between them; weights arrive pre-split and pre-arranged by conv_tc_wprep_kernel.
+//         D[:, N:2N] += A_lo * W_hi^T
+//     where the hi*lo and lo*hi corrections accumulate in the SECOND column half, so that the main hi*hi chain is not
+//     perturbed by them; the epilogue adds the two halves in fp32 (lo*lo ~ 2^-22 relative is dropped);
+//   * persistent CTAs (one or two per SM) walk a contiguous range of work items (sample, group of `ntile` M tiles);
+//     warp roles: 8 staging warps, 4 epilogue warps, 1 MMA-issuing warp, 1 weight-copy warp, connected by mbarrier
+//     rings: 2 patch slots, 2 accumulator slots in TMEM (the epilogue of item i overlaps the MMAs of item i+1) and
+//     either a 2-slot weight ring fed by cp.async.bulk (large layers) or the whole split weight image resident in
+//     shared memory, reloaded only when the weight group (SWAG sample) changes;
+//   * weights arrive pre-split (hi/lo) and pre-arranged in the UMMA layout by conv_tc_wprep_kernel.
 // M tiles that straddle image rows waste only the (pitch - Wo)/pitch halo positions.
 #include "common.cuh"
 #include "conv_common.cuh"
@@ -32,7 +37,12 @@
 #define TC_MAX_TAPS 49
 #define TC_STAGER_WARPS 8
 #define TC_STAGERS (32 * TC_STAGER_WARPS)
-#define TC_THREADS (TC_STAGERS + 32)
+#define TC_EPI_WARPS 4
+#define TC_WARP_EPI0 TC_STAGER_WARPS
+#define TC_WARP_ISSUER (TC_STAGER_WARPS + TC_EPI_WARPS)
+#define TC_WARP_WPROD (TC_WARP_ISSUER + 1)
+#define TC_THREADS (32 * (TC_WARP_WPROD + 1))
+#define TC_KP_MAX 8                    // a staging thread owns at most 8 patch positions (PHP <= 2048)
 
 struct ConvTcArgs {
   const float* x; long long x_bs;
@@ -42,12 +52,16 @@ struct ConvTcArgs {
   int cin, H, W, up_h, up_w, Hc, Wc, sy, sx;
   int relu_in, act;
   int y_ctot, y_coff, cout, Ho, Wo;
-  int n_per_group;
+  int n_per_group, N;
   int pitch, min_ry, min_rx, ntile, ctas_per_sample, PP, PHP, nplanes;
-  int cchunk, ncc, tchunk, ntc, ntaps, coutP, tmem_cols;
-  int srcoff_bytes, patch_slot_floats, w_slot_floats, nslot_p;
+  int cchunk, nc4_shift, ncc, tchunk, ntc, ntaps, coutP, tmem_cols;
+  int patch_slot_floats, w_slot_floats, nslot_p;
+  int resident;              // 1: the whole split weight image of a group stays in shared memory
+  int nacc, acc_cols;        // accumulator ring in TMEM: nacc slots of acc_cols = ntile * 2 * coutP columns
+  int kp;                    // patch positions per staging thread = ceil(PHP / 256)
   int tap_plane[TC_MAX_TAPS];
   int tap_off[TC_MAX_TAPS];
+  int tap_aoff[TC_MAX_TAPS];  // (tap_plane * cchunk/4 * PP + tap_off): A-operand offset of the tap in 16-byte units
 };
 
 // ------------------------------------------------------------------------------------------ PTX helpers
@@ -59,6 +73,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   uint32_t done = 0;
@@ -66,6 +83,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
                  : "=r"(done) : "r"(addr), "r"(parity) : "memory");
   }
+}
+// 1D bulk copy global -> shared through the async proxy (TMA engine), completion counted in bytes on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -98,6 +121,13 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
   for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]);
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void bar_sync_named(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile("{\n\t.reg .pred px;\n\telect.sync _|px, 0xffffffff;\n\t@px mov.s32 %0, 1;\n\t}\n" : "+r"(pred));
+  return pred != 0;
+}
 
 __device__ __forceinline__ float tf32_rna(float v) {
   uint32_t r;
@@ -130,46 +160,96 @@ __global__ void __launch_bounds__(256) conv_tc_wprep_kernel(const float* __restr
   }
 }
 
+// ------------------------------------------------------------------------------------------ patch staging
+// One channel chunk of the input patch -> shared memory (hi and lo planes).  Thread `stid` owns the patch positions
+// stid + 256*k (k < KP) for every (plane, 4-channel group); PCU such groups are loaded together so that about 32 global
+// loads are in flight per thread before the first one is consumed (the loads come from L2; ncu showed the first version
+// of this loop stalled on long_scoreboard for ~60% of its samples).
+template <int KP, int PCU>
+__device__ __forceinline__ void stage_chunk(const ConvTcArgs& a, const float* __restrict__ xn, const float* __restrict__ scale,
+                                            const float* __restrict__ shift, float4* __restrict__ ph, float4* __restrict__ pl,
+                                            int cc, const int (&off0)[TC_KP_MAX], int stid, long long HW) {
+  const int nc4 = a.cchunk >> 2, npc = a.nplanes * nc4;
+  for (int pc0 = 0; pc0 < npc; pc0 += PCU) {
+    float v[PCU][KP][4];
+    float sc[PCU][4], sh[PCU][4];
+#pragma unroll
+    for (int u = 0; u < PCU; ++u) {
+      const int pc = pc0 + u;
+      const int plane = pc >> a.nc4_shift, c4 = pc & (nc4 - 1);
+      const int c0 = cc * a.cchunk + c4 * 4;
+      const int poff = (plane >> 1) * a.W + (plane & 1);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int c = c0 + e;
+        const bool cok = pc < npc && c < a.cin;
+        const float* src = xn + (long long)(cok ? c : 0) * HW + poff;
+        sc[u][e] = (cok && scale) ? __ldg(scale + c) : (cok ? 1.f : 0.f);
+        sh[u][e] = (cok && scale) ? __ldg(shift + c) : 0.f;
+#pragma unroll
+        for (int k = 0; k < KP; ++k) v[u][k][e] = (cok && stid + k * TC_STAGERS < a.PHP) ? __ldg(src + off0[k]) : 0.f;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < PCU; ++u) {
+      const int pc = pc0 + u;
+      if (pc < npc) {
+        float4* dh = ph + (size_t)pc * a.PP;
+        float4* dl = pl + (size_t)pc * a.PP;
+#pragma unroll
+        for (int k = 0; k < KP; ++k) {
+          const int pos = stid + k * TC_STAGERS;
+          if (pos < a.PHP) {
+            float hi[4], lo[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float t = fmaf(v[u][k][e], sc[u][e], sh[u][e]);
+              if (a.relu_in) t = fmaxf(t, 0.f);
+              hi[e] = tf32_rna(t);
+              lo[e] = tf32_rna(t - hi[e]);
+            }
+            dh[pos] = make_float4(hi[0], hi[1], hi[2], hi[3]);
+            dl[pos] = make_float4(lo[0], lo[1], lo[2], lo[3]);
+          }
+        }
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------ main kernel
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ ConvTcArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  uint64_t* full_p = reinterpret_cast<uint64_t*>(smem_raw);        // [2]
-  uint64_t* empty_p = full_p + 2;                                    // [2]
-  uint64_t* full_w = full_p + 4;                                     // [2]
-  uint64_t* empty_w = full_p + 6;                                    // [2]
-  uint64_t* acc_bar = full_p + 8;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + 96);
-  int* srcoff = reinterpret_cast<int*>(smem_raw + 128);
-  float* patch = reinterpret_cast<float*>(smem_raw + 128 + a.srcoff_bytes);
+  uint64_t* full_p = reinterpret_cast<uint64_t*>(smem_raw);        // [2] patch slot filled (256 stager arrivals)
+  uint64_t* empty_p = full_p + 2;                                    // [2] patch slot consumed (tcgen05.commit)
+  uint64_t* full_w = full_p + 4;                                     // [2] weight slot filled (bulk-copy tx bytes)
+  uint64_t* empty_w = full_p + 6;                                    // [2] weight slot consumed (tcgen05.commit)
+  uint64_t* tmem_full = full_p + 8;                                  // [2] accumulators of an item complete (tcgen05.commit)
+  uint64_t* tmem_empty = full_p + 10;                                // [2] accumulators drained (128 epilogue arrivals)
+  uint64_t* wres_full = full_p + 12;                                 // resident weight image (re)loaded
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + 112);
+  float* patch = reinterpret_cast<float*>(smem_raw + 128);
   float* wbuf = patch + (size_t)a.nslot_p * a.patch_slot_floats;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int n = blockIdx.x / a.ctas_per_sample, b = blockIdx.x - n * a.ctas_per_sample;
-  const int g = n / a.n_per_group;
-  const int q0 = b * a.ntile * 128;
-  const int r0 = q0 / a.pitch, qlocal0 = q0 - r0 * a.pitch;
+  const int items_total = a.N * a.ctas_per_sample;
+  const int per_cta = (items_total + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int it_begin = (int)blockIdx.x * per_cta;
+  const int it_end = min(items_total, it_begin + per_cta);
   const int nc4 = a.cchunk >> 2, nc8 = a.cchunk >> 3, N2 = 2 * a.coutP;
+  const int nchunks = a.ncc * a.ntc;
 
   if (tid == 0) {
-    for (int s = 0; s < 2; ++s) { mbar_init(full_p + s, TC_STAGERS); mbar_init(empty_p + s, 1); mbar_init(full_w + s, TC_STAGERS); mbar_init(empty_w + s, 1); }
-    mbar_init(acc_bar, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(full_p + s, TC_STAGERS); mbar_init(empty_p + s, 1); mbar_init(full_w + s, 1); mbar_init(empty_w + s, 1);
+      mbar_init(tmem_full + s, 1); mbar_init(tmem_empty + s, 32 * TC_EPI_WARPS);
+    }
+    mbar_init(wres_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == TC_STAGER_WARPS) {
+  if (warp == TC_WARP_ISSUER) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(a.tmem_cols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-  }
-  // source offsets of every patch position (shared by all channels): wrap + nearest-upsample folded in
-  {
-    const int sxs = a.sx, PHP = a.PHP;
-    for (int e = tid; e < a.nplanes * PHP; e += TC_THREADS) {
-      const int pl = e / PHP, pos = e - pl * PHP;
-      const int i = pos / a.pitch, j = pos - i * a.pitch;
-      const int py = pl / sxs, px = pl - py * sxs;
-      int cy = ((r0 + a.min_ry + i) * a.sy + py) % a.Hc; if (cy < 0) cy += a.Hc;
-      int cx = ((a.min_rx + j) * a.sx + px) % a.Wc; if (cx < 0) cx += a.Wc;
-      srcoff[e] = (cy >> a.up_h) * a.W + (cx >> a.up_w);
-    }
   }
   tc_fence_before();
   __syncthreads();
@@ -178,137 +258,185 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 
   if (warp < TC_STAGER_WARPS) {
     // =============================== staging warps ===============================
-    const float* xn = a.x + (long long)n * a.x_bs;
-    const float* scale = a.scale ? a.scale + (long long)g * a.ss_gs : nullptr;
-    const float* shift = a.scale ? a.shift + (long long)g * a.ss_gs : nullptr;
-    const float4* wsrc = reinterpret_cast<const float4*>(a.wprep + (long long)g * a.wprep_gs);
     const long long HW = (long long)a.H * a.W;
-    const int w_slot_f4 = a.w_slot_floats >> 2;
-    int chunk = 0;
-    for (int cc = 0; cc < a.ncc; ++cc) {
-      const int ps = cc % a.nslot_p, pk = cc / a.nslot_p;
-      if (pk > 0) mbar_wait(empty_p + ps, (pk - 1) & 1);
-      float4* ph = reinterpret_cast<float4*>(patch + (size_t)ps * a.patch_slot_floats);
-      float4* pl = ph + (a.patch_slot_floats >> 3);
-      for (int pc = 0; pc < a.nplanes * nc4; ++pc) {
-        const int plane = pc / nc4, c4 = pc - plane * nc4;
-        const int c0 = cc * a.cchunk + c4 * 4;
-        float sc[4], sh[4];
-        const float* src[4];
+    for (int it = it_begin; it < it_end; ++it) {
+      const int lit = it - it_begin;
+      const int n = it / a.ctas_per_sample, b = it - n * a.ctas_per_sample;
+      const int g = n / a.n_per_group;
+      const int r0 = (b * a.ntile * 128) / a.pitch;
+      const float* xn = a.x + (long long)n * a.x_bs;
+      const float* scale = a.scale ? a.scale + (long long)g * a.ss_gs : nullptr;
+      const float* shift = a.scale ? a.shift + (long long)g * a.ss_gs : nullptr;
+      // source offset of each owned patch position in plane (0,0): wrap + nearest-upsample folded in
+      int off0[TC_KP_MAX];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int c = c0 + e;
-          const bool ok = c < a.cin;
-          src[e] = ok ? xn + c * HW : nullptr;
-          sc[e] = (ok && scale) ? __ldg(scale + c) : 1.f;
-          sh[e] = (ok && shift) ? __ldg(shift + c) : 0.f;
-        }
-        const int* so = srcoff + plane * a.PHP;
-        float4* dh = ph + (size_t)pc * a.PP;
-        float4* dl = pl + (size_t)pc * a.PP;
-        for (int pos = tid; pos < a.PHP; pos += TC_STAGERS) {
-          const int off = so[pos];
-          float v[4], hi[4], lo[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            v[e] = src[e] ? fmaf(__ldg(src[e] + off), sc[e], sh[e]) : 0.f;
-            if (a.relu_in) v[e] = fmaxf(v[e], 0.f);
-            hi[e] = tf32_rna(v[e]);
-            lo[e] = tf32_rna(v[e] - hi[e]);
-          }
-          dh[pos] = make_float4(hi[0], hi[1], hi[2], hi[3]);
-          dl[pos] = make_float4(lo[0], lo[1], lo[2], lo[3]);
+      for (int k = 0; k < TC_KP_MAX; ++k) {
+        off0[k] = 0;
+        const int pos = tid + k * TC_STAGERS;
+        if (k < a.kp && pos < a.PHP) {
+          const int i = pos / a.pitch, j = pos - i * a.pitch;
+          int R = (r0 + a.min_ry + i) % a.Ho; if (R < 0) R += a.Ho;
+          int C = (a.min_rx + j) % a.Wo; if (C < 0) C += a.Wo;
+          off0[k] = ((R * a.sy) >> a.up_h) * a.W + ((C * a.sx) >> a.up_w);
         }
       }
-      fence_async_smem();
-      mbar_arrive(full_p + ps);
-      for (int tc = 0; tc < a.ntc; ++tc, ++chunk) {
-        const int ws = chunk & 1, wk = chunk >> 1;
-        if (wk > 0) mbar_wait(empty_w + ws, (wk - 1) & 1);
-        float4* dst = reinterpret_cast<float4*>(wbuf + (size_t)ws * a.w_slot_floats);
-        const float4* s4 = wsrc + (size_t)chunk * w_slot_f4;
-        for (int i = tid; i < w_slot_f4; i += TC_STAGERS) dst[i] = __ldg(s4 + i);
-        fence_async_smem();
-        mbar_arrive(full_w + ws);
-      }
-    }
-    // =============================== epilogue ===============================
-    mbar_wait(acc_bar, 0);
-    tc_fence_after();
-    const int lanebase = (warp & 3) * 32, half = warp >> 2, cols_half = a.coutP >> 1;
-    const long long HoWo = (long long)a.Ho * a.Wo;
-    for (int t = 0; t < a.ntile; ++t) {
-      const int q = q0 + t * 128 + lanebase + lane;
-      const int oy = q / a.pitch, ox = q - oy * a.pitch;
-      const bool valid = oy < a.Ho && ox < a.Wo;
-      float* yp = a.y + ((long long)n * a.y_ctot + a.y_coff) * HoWo + (long long)oy * a.Wo + ox;
-      const uint32_t trow = tmem + ((uint32_t)lanebase << 16) + (uint32_t)(t * N2);
-      for (int c0 = half * cols_half; c0 < (half + 1) * cols_half && c0 < a.cout; c0 += 8) {
-        float v1[8], v2[8];
-        tmem_ld8(trow + c0, v1);
-        tmem_ld8(trow + a.coutP + c0, v2);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int co = c0 + j;
-          float val = apply_act(v1[j] + v2[j], a.act);
-          const bool st = valid && co < a.cout;
-          if (st) yp[co * HoWo] = val;
-          if (a.stats) {
-            if (!st) val = 0.f;
-            const float s1 = warp_sum(val), s2 = warp_sum(val * val);
-            if (lane == 0 && co < a.cout) {
-              double* sp = a.stats + 2 * (a.y_coff + co);
-              atomicAdd(sp, (double)s1); atomicAdd(sp + 1, (double)s2);
-            }
-          }
-        }
-      }
-    }
-  } else {
-    // =============================== MMA issuing warp ===============================
-    if (lane == 0) {
-      const uint32_t idesc1 = umma_idesc_tf32(128, N2), idesc2 = umma_idesc_tf32(128, a.coutP);
-      const uint32_t lbo_a = (uint32_t)a.PP * 16u, lbo_b = (uint32_t)N2 * 16u;
-      const uint32_t patch_base = smem_u32(patch), w_base = smem_u32(wbuf);
-      const uint32_t slot_bytes = (uint32_t)a.patch_slot_floats * 4u;
-      int chunk = 0;
       for (int cc = 0; cc < a.ncc; ++cc) {
-        const int ps = cc % a.nslot_p, pk = cc / a.nslot_p;
-        mbar_wait(full_p + ps, pk & 1);
-        const uint32_t pa_hi = patch_base + (uint32_t)ps * slot_bytes, pa_lo = pa_hi + (slot_bytes >> 1);
-        for (int tc = 0; tc < a.ntc; ++tc, ++chunk) {
-          const int ws = chunk & 1, wk = chunk >> 1;
-          mbar_wait(full_w + ws, wk & 1);
-          tc_fence_after();
-          const uint32_t wb = w_base + (uint32_t)ws * (uint32_t)a.w_slot_floats * 4u;
-          for (int t = 0; t < a.ntile; ++t) {
-            const uint32_t d_tmem = tmem + (uint32_t)(t * N2);
-            for (int tl = 0; tl < a.tchunk; ++tl) {
-              const int tap = tc * a.tchunk + tl;
-              const uint32_t pos0 = (uint32_t)(qlocal0 + t * 128 + a.tap_off[tap]);
-              const uint32_t plane = (uint32_t)a.tap_plane[tap];
-              for (int c8 = 0; c8 < nc8; ++c8) {
-                const uint32_t a_off = ((plane * nc4 + 2 * c8) * (uint32_t)a.PP + pos0) * 16u;
-                const uint32_t b_off = (uint32_t)((tl * nc4 + 2 * c8) * N2) * 16u;
-                const uint64_t db = umma_desc(wb + b_off, lbo_b, 128);
-                const uint32_t first = (chunk == 0 && tl == 0 && c8 == 0) ? 0u : 1u;
-                umma_tf32(d_tmem, umma_desc(pa_hi + a_off, lbo_a, 128), db, idesc1, first);
-                umma_tf32(d_tmem, umma_desc(pa_lo + a_off, lbo_a, 128), db, idesc2, 1u);
+        const int pseq = lit * a.ncc + cc;
+        const int ps = pseq % a.nslot_p, pk = pseq / a.nslot_p;
+        if (pk > 0) mbar_wait(empty_p + ps, (pk - 1) & 1);
+        float4* ph = reinterpret_cast<float4*>(patch + (size_t)ps * a.patch_slot_floats);
+        float4* pl = ph + (a.patch_slot_floats >> 3);
+        if (a.kp <= 2) stage_chunk<2, 4>(a, xn, scale, shift, ph, pl, cc, off0, tid, HW);
+        else if (a.kp <= 4) stage_chunk<4, 2>(a, xn, scale, shift, ph, pl, cc, off0, tid, HW);
+        else stage_chunk<8, 1>(a, xn, scale, shift, ph, pl, cc, off0, tid, HW);
+        fence_async_smem();
+        mbar_arrive(full_p + ps);
+      }
+    }
+  } else if (warp < TC_WARP_ISSUER) {
+    // =============================== epilogue warps ===============================
+    const int lanebase = (warp - TC_WARP_EPI0) * 32;           // == (warp % 4) * 32: the TMEM lane quarter this warp may read
+    const long long HoWo = (long long)a.Ho * a.Wo;
+    for (int it = it_begin; it < it_end; ++it) {
+      const int lit = it - it_begin;
+      const int n = it / a.ctas_per_sample, b = it - n * a.ctas_per_sample;
+      const int q0 = b * a.ntile * 128;
+      const int as = lit % a.nacc, ak = lit / a.nacc;
+      mbar_wait(tmem_full + as, ak & 1);
+      tc_fence_after();
+      for (int t = 0; t < a.ntile; ++t) {
+        const int q = q0 + t * 128 + lanebase + lane;
+        const int oy = q / a.pitch, ox = q - oy * a.pitch;
+        const bool valid = oy < a.Ho && ox < a.Wo;
+        float* yp = a.y + ((long long)n * a.y_ctot + a.y_coff) * HoWo + (long long)oy * a.Wo + ox;
+        const uint32_t trow = tmem + ((uint32_t)lanebase << 16) + (uint32_t)(as * a.acc_cols + t * N2);
+        for (int c0 = 0; c0 < a.cout; c0 += 8) {
+          float v1[8], v2[8];
+          tmem_ld8(trow + c0, v1);
+          tmem_ld8(trow + a.coutP + c0, v2);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int co = c0 + j;
+            float val = apply_act(v1[j] + v2[j], a.act);
+            const bool st = valid && co < a.cout;
+            if (st) yp[co * HoWo] = val;
+            if (a.stats) {
+              if (!st) val = 0.f;
+              const float s1 = warp_sum(val), s2 = warp_sum(val * val);
+              if (lane == 0 && co < a.cout) {
+                double* sp = a.stats + 2 * (a.y_coff + co);
+                atomicAdd(sp, (double)s1); atomicAdd(sp + 1, (double)s2);
               }
             }
           }
-          umma_commit(empty_w + ws);
         }
-        umma_commit(empty_p + ps);
       }
-      umma_commit(acc_bar);
+      tc_fence_before();
+      mbar_arrive(tmem_empty + as);
+    }
+  } else if (warp == TC_WARP_ISSUER) {
+    // =============================== MMA issuing warp ===============================
+    // All 32 lanes run the (warp-uniform) loops so that the address arithmetic stays on the uniform datapath; one elected
+    // lane issues the tcgen05 instructions.  (First version: a single lane computed every descriptor in vector registers
+    // and needed ~400 cycles per MMA pair -- the tensor pipe was idle 80-95% of the time.)
+    const bool leader = elect_one();
+    const uint32_t idesc1 = umma_idesc_tf32(128, N2), idesc2 = umma_idesc_tf32(128, a.coutP);
+    const uint32_t PP = (uint32_t)a.PP;
+    // descriptor words: hi = SBO (128 B) | version 1; lo = start address >> 4 | LBO << 16.  Offsets (in 16-byte units) are added
+    // to the low word: every operand lies below 256 KB, so the 14-bit address field cannot carry into the LBO field.
+    const uint32_t desc_hi = (128u >> 4) | (1u << 14);
+    const uint32_t a_lo_base = (smem_u32(patch) >> 4) | (PP << 16);
+    const uint32_t b_lo_base = (smem_u32(wbuf) >> 4) | ((uint32_t)N2 << 16);
+    const uint32_t slot16 = (uint32_t)a.patch_slot_floats >> 2, w_slot16 = (uint32_t)a.w_slot_floats >> 2;
+    int g_loaded = -1, wgen = 0;
+    for (int it = it_begin; it < it_end; ++it) {
+      const int lit = it - it_begin;
+      const int n = it / a.ctas_per_sample, b = it - n * a.ctas_per_sample;
+      const int g = n / a.n_per_group;
+      const int q0 = b * a.ntile * 128;
+      const uint32_t qlocal0 = (uint32_t)(q0 - (q0 / a.pitch) * a.pitch);
+      const int as = lit % a.nacc, ak = lit / a.nacc;
+      if (ak > 0) mbar_wait(tmem_empty + as, (ak - 1) & 1);
+      if (a.resident && g != g_loaded) { mbar_wait(wres_full, wgen & 1); ++wgen; g_loaded = g; }
+      tc_fence_after();
+      const uint32_t acc_base = tmem + (uint32_t)(as * a.acc_cols);
+      for (int cc = 0; cc < a.ncc; ++cc) {
+        const int pseq = lit * a.ncc + cc;
+        const int ps = pseq % a.nslot_p, pk = pseq / a.nslot_p;
+        mbar_wait(full_p + ps, pk & 1);
+        const uint32_t pa_hi = a_lo_base + (uint32_t)ps * slot16 + qlocal0, pa_lo = pa_hi + (slot16 >> 1);
+        for (int tc = 0; tc < a.ntc; ++tc) {
+          const int chunk = cc * a.ntc + tc;
+          uint32_t wb;
+          int ws = 0;
+          if (a.resident) {
+            wb = b_lo_base + (uint32_t)chunk * w_slot16;
+          } else {
+            const int wseq = lit * nchunks + chunk;
+            ws = wseq & 1;
+            mbar_wait(full_w + ws, (wseq >> 1) & 1);
+            wb = b_lo_base + (uint32_t)ws * w_slot16;
+          }
+          tc_fence_after();
+          for (int t = 0; t < a.ntile; ++t) {
+            const uint32_t d_tmem = acc_base + (uint32_t)(t * N2);
+            uint32_t bl = wb;
+            for (int tl = 0; tl < a.tchunk; ++tl) {
+              uint32_t al = (uint32_t)a.tap_aoff[tc * a.tchunk + tl] + (uint32_t)(t * 128);
+              for (int c8 = 0; c8 < nc8; ++c8) {
+                if (leader) {
+                  const uint64_t db = ((uint64_t)desc_hi << 32) | bl;
+                  const uint32_t first = (chunk | tl | c8) ? 1u : 0u;
+                  umma_tf32(d_tmem, ((uint64_t)desc_hi << 32) | (pa_hi + al), db, idesc1, first);                   // hi * [hi;lo]
+                  umma_tf32(d_tmem + (uint32_t)a.coutP, ((uint64_t)desc_hi << 32) | (pa_lo + al), db, idesc2, 1u);   // lo * hi -> correction half
+                }
+                al += 2 * PP;
+                bl += 2 * (uint32_t)N2;
+              }
+            }
+          }
+          if (!a.resident && leader) umma_commit(empty_w + ws);
+        }
+        if (leader) umma_commit(empty_p + ps);
+      }
+      if (leader) umma_commit(tmem_full + as);
+    }
+    __syncwarp();
+  } else {
+    // =============================== weight copy warp ===============================
+    if (lane == 0) {
+      const uint32_t w_slot_bytes = (uint32_t)a.w_slot_floats * 4u;
+      int g_loaded = -1;
+      for (int it = it_begin; it < it_end; ++it) {
+        const int lit = it - it_begin;
+        const int n = it / a.ctas_per_sample;
+        const int g = n / a.n_per_group;
+        const float* wsrc = a.wprep + (long long)g * a.wprep_gs;
+        if (a.resident) {
+          if (g != g_loaded) {
+            if (lit > 0) { const int pl_ = lit - 1; mbar_wait(tmem_full + (pl_ % a.nacc), (pl_ / a.nacc) & 1); }   // MMAs of the old group done
+            mbar_arrive_expect_tx(wres_full, (uint32_t)nchunks * w_slot_bytes);
+            for (int c = 0; c < nchunks; ++c)
+              bulk_g2s(wbuf + (size_t)c * a.w_slot_floats, wsrc + (size_t)c * a.w_slot_floats, w_slot_bytes, wres_full);
+            g_loaded = g;
+          }
+        } else {
+          for (int c = 0; c < nchunks; ++c) {
+            const int wseq = lit * nchunks + c;
+            const int ws = wseq & 1, wk = wseq >> 1;
+            if (wk > 0) mbar_wait(empty_w + ws, (wk - 1) & 1);
+            mbar_arrive_expect_tx(full_w + ws, w_slot_bytes);
+            bulk_g2s(wbuf + (size_t)ws * a.w_slot_floats, wsrc + (size_t)c * a.w_slot_floats, w_slot_bytes, full_w + ws);
+          }
+        }
+      }
     }
     __syncwarp();
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == TC_STAGER_WARPS) {
+  if (warp == TC_WARP_ISSUER) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(a.tmem_cols));
   }
 }
@@ -327,6 +455,7 @@ int arpde_tc_enabled() {
 static bool tc_plan(const ConvDesc& d, ConvTcArgs& a, size_t* smem_out) {
   if (d.dilate || d.pad_override >= 0) return false;
   if (d.stride != 1 && d.stride != 2) return false;
+  if (d.up && d.stride != 1) return false;
   const int one_d = (d.H == 1 && d.kh == 1);
   memset(&a, 0, sizeof(a));
   a.cin = d.cin; a.H = d.H; a.W = d.W; a.up_w = d.up ? 1 : 0; a.up_h = one_d ? 0 : a.up_w;
@@ -336,7 +465,7 @@ static bool tc_plan(const ConvDesc& d, ConvTcArgs& a, size_t* smem_out) {
   a.cout = d.cout; a.coutP = round_up(d.cout, 16);
   if (a.coutP > 128) return false;
   a.ntaps = d.kh * d.kw;
-  if (a.ntaps > TC_MAX_TAPS) return false;
+  if (a.ntaps > TC_MAX_TAPS || d.kh > 7 || d.kw > 7) return false;
   const int pad_y = d.kh == 1 ? 0 : (d.kh == 4 ? 1 : (d.kh - 1) / 2), pad_x = d.kw == 1 ? 0 : (d.kw == 4 ? 1 : (d.kw - 1) / 2);
   int min_ry = 1 << 30, max_ry = -(1 << 30), min_rx = 1 << 30, max_rx = -(1 << 30);
   int ry[8], py[8], rx[8], px[8];
@@ -355,41 +484,44 @@ static bool tc_plan(const ConvDesc& d, ConvTcArgs& a, size_t* smem_out) {
   const int Q = a.Ho * a.pitch, total_tiles = (Q + 127) / 128;
   const int cin8 = round_up(d.cin, 8);
   const int N2 = 2 * a.coutP;
-  int ntile_max = 256 / N2; if (ntile_max < 1) ntile_max = 1; if (ntile_max > 4) ntile_max = 4;
+  int ntile_max = 512 / N2; if (ntile_max > 4) ntile_max = 4;
   if (ntile_max > total_tiles) ntile_max = total_tiles;
-  // search: prefer two resident CTAs per SM (<= 112 KB each), then the largest tile count / channel chunk
-  const size_t budgets[2] = {112 * 1024, 220 * 1024};
-  for (int bi = 0; bi < 2; ++bi) {
-    for (int ntile = ntile_max; ntile >= 1; --ntile) {
-      const int cands[4] = {cin8 <= 32 ? cin8 : 32, 16, 8, 0};
-      for (int ci = 0; cands[ci]; ++ci) {
-        const int cchunk = cands[ci];
-        if (cchunk > cin8 || (ci > 0 && cchunk >= cands[0])) continue;
+  const size_t budget = 225 * 1024;
+  // preference order: weights resident in shared memory (no re-streaming per item), then many M tiles per item (less halo,
+  // fewer weight passes), then wide channel chunks (fewer pipeline hand-offs), then wide tap chunks
+  for (int resident = 1; resident >= 0; --resident)
+    for (int ntile = ntile_max; ntile >= 1; --ntile)
+      for (int cchunk = 32; cchunk >= 8; cchunk >>= 1) {
+        if (cchunk > 8 && cchunk > cin8) continue;
         const int ncc = (d.cin + cchunk - 1) / cchunk;
         const int rows = (a.pitch - 1 + ntile * 128 - 1) / a.pitch + 1 + span_y;
         const int PHP = rows * a.pitch;
+        if (PHP > TC_STAGERS * TC_KP_MAX) continue;
         int PP = a.pitch + ntile * 128 + max_off; if (PP < PHP) PP = PHP; PP = round_up(PP, 8);
         if (PP > 16383) continue;
-        int tchunk = 1;
-        for (int tcand = a.ntaps; tcand >= 1; --tcand)
-          if (a.ntaps % tcand == 0 && (size_t)tcand * (cchunk / 4) * N2 * 16 <= 32 * 1024) { tchunk = tcand; break; }
-        const size_t w_slot = (size_t)tchunk * (cchunk / 4) * N2 * 16;
         const size_t p_slot = (size_t)2 * a.nplanes * (cchunk / 4) * PP * 16;
-        const int nslot_p = ncc > 1 ? 2 : 1;
-        const size_t srcoff_bytes = (size_t)round_up(a.nplanes * PHP * 4, 128);
-        const size_t smem = 128 + srcoff_bytes + nslot_p * p_slot + 2 * w_slot;
-        if (smem > budgets[bi]) continue;
-        a.ntile = ntile; a.cchunk = cchunk; a.ncc = ncc; a.tchunk = tchunk; a.ntc = a.ntaps / tchunk;
-        a.PP = PP; a.PHP = PHP; a.nslot_p = nslot_p; a.srcoff_bytes = (int)srcoff_bytes;
-        a.patch_slot_floats = (int)(p_slot / 4); a.w_slot_floats = (int)(w_slot / 4);
-        a.ctas_per_sample = (total_tiles + ntile - 1) / ntile;
-        int cols = ntile * N2, p2 = 32; while (p2 < cols) p2 <<= 1;
-        a.tmem_cols = p2;
-        *smem_out = smem;
-        return true;
+        for (int tchunk = a.ntaps; tchunk >= 1; --tchunk) {
+          if (a.ntaps % tchunk) continue;
+          const size_t w_slot = (size_t)tchunk * (cchunk / 4) * N2 * 16;
+          if (w_slot > 48 * 1024) continue;
+          const int ntc = a.ntaps / tchunk;
+          const size_t w_bytes = resident ? w_slot * ncc * ntc : 2 * w_slot;
+          const size_t smem = 128 + 2 * p_slot + w_bytes;
+          if (smem > budget) continue;
+          a.resident = resident; a.ntile = ntile; a.cchunk = cchunk; a.nc4_shift = cchunk == 32 ? 3 : (cchunk == 16 ? 2 : 1);
+          a.ncc = ncc; a.tchunk = tchunk; a.ntc = ntc; a.PP = PP; a.PHP = PHP; a.nslot_p = 2;
+          a.kp = (PHP + TC_STAGERS - 1) / TC_STAGERS;
+          a.patch_slot_floats = (int)(p_slot / 4); a.w_slot_floats = (int)(w_slot / 4);
+          a.ctas_per_sample = (total_tiles + ntile - 1) / ntile;
+          for (int t = 0; t < a.ntaps; ++t) a.tap_aoff[t] = a.tap_plane[t] * (cchunk / 4) * PP + a.tap_off[t];
+          a.acc_cols = ntile * N2;
+          a.nacc = 2 * a.acc_cols <= 512 ? 2 : 1;
+          int p2 = 32; while (p2 < a.nacc * a.acc_cols) p2 <<= 1;
+          a.tmem_cols = p2;
+          *smem_out = smem;
+          return true;
+        }
       }
-    }
-  }
   return false;
 }
 
@@ -435,8 +567,13 @@ int arpde_conv_tc_launch(const ConvDesc& d, const float* x, long long x_bs, cons
     ARPDE_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     smem_set = smem;
   }
-  const long long blocks = (long long)d.N * a.ctas_per_sample;
-  ARPDE_CHECK_ARG(blocks < (1ll << 31), "conv_tc: grid too large");
+  a.N = d.N;
+  const long long items = (long long)d.N * a.ctas_per_sample;
+  ARPDE_CHECK_ARG(items < (1ll << 31), "conv_tc: too many work items");
+  // persistent CTAs: two per SM when shared memory and TMEM allow it (more loads in flight while staging)
+  const int per_sm = (smem <= 112 * 1024 && a.tmem_cols <= 256) ? 2 : 1;
+  long long blocks = (long long)arpde_num_sms() * per_sm;
+  if (blocks > items) blocks = items;
   conv_tc_kernel<<<(unsigned)blocks, TC_THREADS, smem, stream>>>(a);
   ARPDE_LAUNCH_CHECK();
   return ARPDE_OK;
@@ -471,9 +608,9 @@ extern "C" int arpde_conv_fwd_tc(const float* x, int64_t x_bstride, const float*
   return arpde_conv_tc_launch(d, x, x_bstride, scratch, per_group, scale, shift, ss_gstride, y, stats, stream);
 }
 
-// Diagnostic (host only, no GPU needed): the tiling conv_tc_kernel would use for a layer.  out[0..23] = pitch, min_ry, min_rx, ntile,
+// Diagnostic (host only, no GPU needed): the tiling conv_tc_kernel would use for a layer.  out[0..26] = pitch, min_ry, min_rx, ntile,
 // ctas_per_sample, PP, PHP, nplanes, cchunk, ncc, tchunk, ntc, ntaps, coutP, tmem_cols, nslot_p, smem bytes, Ho, Wo, Hc, Wc, sy, sx,
-// wanted-by-heuristic; out[32+t] = tap plane, out[32+49+t] = tap offset.  Returns ARPDE_ERR_UNSUPPORTED if not plannable.
+// wanted-by-heuristic, resident, nacc, kp; out[32+t] = tap plane, out[32+49+t] = tap offset.  Returns ARPDE_ERR_UNSUPPORTED if not plannable.
 extern "C" int arpde_conv_tc_plan(int cin, int H, int W, int cout, int kh, int kw, int stride, int up, int32_t* out) {
   ARPDE_CHECK_ARG(out, "conv_tc_plan: null output");
   ConvDesc d;
@@ -481,9 +618,10 @@ extern "C" int arpde_conv_tc_plan(int cin, int H, int W, int cout, int kh, int k
   d.up = up; d.relu_in = 0; d.act = 0; d.y_ctot = cout; d.y_coff = 0; d.n_per_group = 1;
   ConvTcArgs a; size_t smem = 0;
   if (!tc_plan(d, a, &smem)) { arpde_set_error("conv_tc_plan: layer not supported"); return ARPDE_ERR_UNSUPPORTED; }
-  const int v[24] = {a.pitch, a.min_ry, a.min_rx, a.ntile, a.ctas_per_sample, a.PP, a.PHP, a.nplanes, a.cchunk, a.ncc, a.tchunk, a.ntc,
-                     a.ntaps, a.coutP, a.tmem_cols, a.nslot_p, (int)smem, a.Ho, a.Wo, a.Hc, a.Wc, a.sy, a.sx, arpde_conv_tc_wanted(d) ? 1 : 0};
-  for (int i = 0; i < 24; ++i) out[i] = v[i];
+  const int v[27] = {a.pitch, a.min_ry, a.min_rx, a.ntile, a.ctas_per_sample, a.PP, a.PHP, a.nplanes, a.cchunk, a.ncc, a.tchunk, a.ntc,
+                     a.ntaps, a.coutP, a.tmem_cols, a.nslot_p, (int)smem, a.Ho, a.Wo, a.Hc, a.Wc, a.sy, a.sx, arpde_conv_tc_wanted(d) ? 1 : 0,
+                     a.resident, a.nacc, a.kp};
+  for (int i = 0; i < 27; ++i) out[i] = v[i];
   for (int t = 0; t < TC_MAX_TAPS; ++t) { out[32 + t] = t < a.ntaps ? a.tap_plane[t] : 0; out[32 + TC_MAX_TAPS + t] = t < a.ntaps ? a.tap_off[t] : 0; }
   return ARPDE_OK;
 }

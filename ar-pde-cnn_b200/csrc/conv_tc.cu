@@ -53,7 +53,7 @@ struct ConvTcArgs {
   int relu_in, act;
   int y_ctot, y_coff, cout, Ho, Wo;
   int n_per_group, N;
-  int pitch, min_ry, min_rx, ntile, ctas_per_sample, PP, PHP, nplanes;
+  int pitch, min_ry, min_rx, ntile, total_tiles, ctas_per_sample, PP, PHP, nplanes;
   int cchunk, nc4_shift, ncc, tchunk, ntc, ntaps, coutP, tmem_cols;
   int patch_slot_floats, w_slot_floats, nslot_p;
   int resident;              // 1: the whole split weight image of a group stays in shared memory
@@ -120,6 +120,14 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
 #pragma unroll
   for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]);
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                 "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]) : "r"(taddr));
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void bar_sync_named(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
@@ -165,10 +173,10 @@ __global__ void __launch_bounds__(256) conv_tc_wprep_kernel(const float* __restr
 // stid + 256*k (k < KP) for every (plane, 4-channel group); PCU such groups are loaded together so that about 32 global
 // loads are in flight per thread before the first one is consumed (the loads come from L2; ncu showed the first version
 // of this loop stalled on long_scoreboard for ~60% of its samples).
-template <int KP, int PCU>
+template <int KP, int PCU, bool RELU>
 __device__ __forceinline__ void stage_chunk(const ConvTcArgs& a, const float* __restrict__ xn, const float* __restrict__ scale,
                                             const float* __restrict__ shift, float4* __restrict__ ph, float4* __restrict__ pl,
-                                            int cc, const int (&off0)[TC_KP_MAX], int stid, long long HW) {
+                                            int cc, const int (&off0)[TC_KP_MAX], uint32_t kmask, int stid, long long HW) {
   const int nc4 = a.cchunk >> 2, npc = a.nplanes * nc4;
   for (int pc0 = 0; pc0 < npc; pc0 += PCU) {
     float v[PCU][KP][4];
@@ -187,29 +195,30 @@ __device__ __forceinline__ void stage_chunk(const ConvTcArgs& a, const float* __
         sc[u][e] = (cok && scale) ? __ldg(scale + c) : (cok ? 1.f : 0.f);
         sh[u][e] = (cok && scale) ? __ldg(shift + c) : 0.f;
 #pragma unroll
-        for (int k = 0; k < KP; ++k) v[u][k][e] = (cok && stid + k * TC_STAGERS < a.PHP) ? __ldg(src + off0[k]) : 0.f;
+        for (int k = 0; k < KP; ++k) v[u][k][e] = (cok && ((kmask >> k) & 1u)) ? __ldg(src + off0[k]) : 0.f;
       }
     }
 #pragma unroll
     for (int u = 0; u < PCU; ++u) {
       const int pc = pc0 + u;
       if (pc < npc) {
-        float4* dh = ph + (size_t)pc * a.PP;
-        float4* dl = pl + (size_t)pc * a.PP;
+        float4* dh = ph + (size_t)pc * a.PP + stid;
+        float4* dl = pl + (size_t)pc * a.PP + stid;
 #pragma unroll
         for (int k = 0; k < KP; ++k) {
-          const int pos = stid + k * TC_STAGERS;
-          if (pos < a.PHP) {
+          if ((kmask >> k) & 1u) {
             float hi[4], lo[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               float t = fmaf(v[u][k][e], sc[u][e], sh[u][e]);
-              if (a.relu_in) t = fmaxf(t, 0.f);
-              hi[e] = tf32_rna(t);
-              lo[e] = tf32_rna(t - hi[e]);
+              if (RELU) t = fmaxf(t, 0.f);
+              // tf32 round-to-nearest (ties away, == cvt.rna for finite values) in two integer ops; the residual t - hi is exact
+              // in fp32 and is left unrounded: the tensor core drops its low 13 bits (< 2^-22 relative to t)
+              hi[e] = __uint_as_float((__float_as_uint(t) + 0x1000u) & 0xffffe000u);
+              lo[e] = t - hi[e];
             }
-            dh[pos] = make_float4(hi[0], hi[1], hi[2], hi[3]);
-            dl[pos] = make_float4(lo[0], lo[1], lo[2], lo[3]);
+            dh[k * TC_STAGERS] = make_float4(hi[0], hi[1], hi[2], hi[3]);
+            dl[k * TC_STAGERS] = make_float4(lo[0], lo[1], lo[2], lo[3]);
           }
         }
       }
@@ -269,11 +278,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       const float* shift = a.scale ? a.shift + (long long)g * a.ss_gs : nullptr;
       // source offset of each owned patch position in plane (0,0): wrap + nearest-upsample folded in
       int off0[TC_KP_MAX];
+      uint32_t kmask = 0;
 #pragma unroll
       for (int k = 0; k < TC_KP_MAX; ++k) {
         off0[k] = 0;
         const int pos = tid + k * TC_STAGERS;
         if (k < a.kp && pos < a.PHP) {
+          kmask |= 1u << k;
           const int i = pos / a.pitch, j = pos - i * a.pitch;
           int R = (r0 + a.min_ry + i) % a.Ho; if (R < 0) R += a.Ho;
           int C = (a.min_rx + j) % a.Wo; if (C < 0) C += a.Wo;
@@ -286,9 +297,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         if (pk > 0) mbar_wait(empty_p + ps, (pk - 1) & 1);
         float4* ph = reinterpret_cast<float4*>(patch + (size_t)ps * a.patch_slot_floats);
         float4* pl = ph + (a.patch_slot_floats >> 3);
-        if (a.kp <= 2) stage_chunk<2, 4>(a, xn, scale, shift, ph, pl, cc, off0, tid, HW);
-        else if (a.kp <= 4) stage_chunk<4, 2>(a, xn, scale, shift, ph, pl, cc, off0, tid, HW);
-        else stage_chunk<8, 1>(a, xn, scale, shift, ph, pl, cc, off0, tid, HW);
+        if (a.relu_in) {
+          if (a.kp <= 2) stage_chunk<2, 4, true>(a, xn, scale, shift, ph, pl, cc, off0, kmask, tid, HW);
+          else if (a.kp <= 4) stage_chunk<4, 2, true>(a, xn, scale, shift, ph, pl, cc, off0, kmask, tid, HW);
+          else stage_chunk<8, 1, true>(a, xn, scale, shift, ph, pl, cc, off0, kmask, tid, HW);
+        } else {
+          if (a.kp <= 2) stage_chunk<2, 4, false>(a, xn, scale, shift, ph, pl, cc, off0, kmask, tid, HW);
+          else if (a.kp <= 4) stage_chunk<4, 2, false>(a, xn, scale, shift, ph, pl, cc, off0, kmask, tid, HW);
+          else stage_chunk<8, 1, false>(a, xn, scale, shift, ph, pl, cc, off0, kmask, tid, HW);
+        }
         fence_async_smem();
         mbar_arrive(full_p + ps);
       }
@@ -297,6 +314,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     // =============================== epilogue warps ===============================
     const int lanebase = (warp - TC_WARP_EPI0) * 32;           // == (warp % 4) * 32: the TMEM lane quarter this warp may read
     const long long HoWo = (long long)a.Ho * a.Wo;
+    const bool plain = a.act == 0 && a.stats == nullptr;
     for (int it = it_begin; it < it_end; ++it) {
       const int lit = it - it_begin;
       const int n = it / a.ctas_per_sample, b = it - n * a.ctas_per_sample;
@@ -304,29 +322,47 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       const int as = lit % a.nacc, ak = lit / a.nacc;
       mbar_wait(tmem_full + as, ak & 1);
       tc_fence_after();
-      for (int t = 0; t < a.ntile; ++t) {
+      const int nt_item = min(a.ntile, a.total_tiles - b * a.ntile);        // the last item of a sample may hold fewer M tiles
+      for (int t = 0; t < nt_item; ++t) {
         const int q = q0 + t * 128 + lanebase + lane;
         const int oy = q / a.pitch, ox = q - oy * a.pitch;
         const bool valid = oy < a.Ho && ox < a.Wo;
         float* yp = a.y + ((long long)n * a.y_ctot + a.y_coff) * HoWo + (long long)oy * a.Wo + ox;
         const uint32_t trow = tmem + ((uint32_t)lanebase << 16) + (uint32_t)(as * a.acc_cols + t * N2);
-        for (int c0 = 0; c0 < a.cout; c0 += 8) {
-          float v1[8], v2[8];
-          tmem_ld8(trow + c0, v1);
-          tmem_ld8(trow + a.coutP + c0, v2);
-          tmem_ld_wait();
+        if (plain) {
+          // common case (no output activation, no batch statistics): 16 columns per TMEM round trip, straight stores.
+          // (ncu on the first version: the per-element activation switch + statistics branches made the 4 epilogue warps
+          //  the critical path -- ~95% busy, half of their stalls branch_resolving / instruction-cache misses.)
+          for (int c0 = 0; c0 < a.cout; c0 += 16) {
+            float v1[16], v2[16];
+            tmem_ld16(trow + c0, v1);
+            tmem_ld16(trow + a.coutP + c0, v2);
+            tmem_ld_wait();
+            float* pc = yp + c0 * HoWo;
+            if (valid) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int co = c0 + j;
-            float val = apply_act(v1[j] + v2[j], a.act);
-            const bool st = valid && co < a.cout;
-            if (st) yp[co * HoWo] = val;
-            if (a.stats) {
-              if (!st) val = 0.f;
-              const float s1 = warp_sum(val), s2 = warp_sum(val * val);
-              if (lane == 0 && co < a.cout) {
-                double* sp = a.stats + 2 * (a.y_coff + co);
-                atomicAdd(sp, (double)s1); atomicAdd(sp + 1, (double)s2);
+              for (int j = 0; j < 16; ++j)
+                if (c0 + j < a.cout) pc[j * HoWo] = v1[j] + v2[j];
+            }
+          }
+        } else {
+          for (int c0 = 0; c0 < a.cout; c0 += 8) {
+            float v1[8], v2[8];
+            tmem_ld8(trow + c0, v1);
+            tmem_ld8(trow + a.coutP + c0, v2);
+            tmem_ld_wait();
+            for (int j = 0; j < 8; ++j) {
+              const int co = c0 + j;
+              float val = apply_act(v1[j] + v2[j], a.act);
+              const bool st = valid && co < a.cout;
+              if (st) yp[co * HoWo] = val;
+              if (a.stats) {
+                if (!st) val = 0.f;
+                const float s1 = warp_sum(val), s2 = warp_sum(val * val);
+                if (lane == 0 && co < a.cout) {
+                  double* sp = a.stats + 2 * (a.y_coff + co);
+                  atomicAdd(sp, (double)s1); atomicAdd(sp + 1, (double)s2);
+                }
               }
             }
           }
@@ -356,6 +392,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       const int g = n / a.n_per_group;
       const int q0 = b * a.ntile * 128;
       const uint32_t qlocal0 = (uint32_t)(q0 - (q0 / a.pitch) * a.pitch);
+      const int nt_item = min(a.ntile, a.total_tiles - b * a.ntile);
       const int as = lit % a.nacc, ak = lit / a.nacc;
       if (ak > 0) mbar_wait(tmem_empty + as, (ak - 1) & 1);
       if (a.resident && g != g_loaded) { mbar_wait(wres_full, wgen & 1); ++wgen; g_loaded = g; }
@@ -379,7 +416,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             wb = b_lo_base + (uint32_t)ws * w_slot16;
           }
           tc_fence_after();
-          for (int t = 0; t < a.ntile; ++t) {
+          for (int t = 0; t < nt_item; ++t) {
             const uint32_t d_tmem = acc_base + (uint32_t)(t * N2);
             uint32_t bl = wb;
             for (int tl = 0; tl < a.tchunk; ++tl) {
@@ -512,7 +549,7 @@ static bool tc_plan(const ConvDesc& d, ConvTcArgs& a, size_t* smem_out) {
           a.ncc = ncc; a.tchunk = tchunk; a.ntc = ntc; a.PP = PP; a.PHP = PHP; a.nslot_p = 2;
           a.kp = (PHP + TC_STAGERS - 1) / TC_STAGERS;
           a.patch_slot_floats = (int)(p_slot / 4); a.w_slot_floats = (int)(w_slot / 4);
-          a.ctas_per_sample = (total_tiles + ntile - 1) / ntile;
+          a.ctas_per_sample = (total_tiles + ntile - 1) / ntile; a.total_tiles = total_tiles;
           for (int t = 0; t < a.ntaps; ++t) a.tap_aoff[t] = a.tap_plane[t] * (cchunk / 4) * PP + a.tap_off[t];
           a.acc_cols = ntile * N2;
           a.nacc = 2 * a.acc_cols <= 512 ? 2 : 1;

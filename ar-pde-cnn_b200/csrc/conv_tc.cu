@@ -451,8 +451,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         const int g = n / a.n_per_group;
         const float* wsrc = a.wprep + (long long)g * a.wprep_gs;
         if (a.resident) {
+          // follow every accumulator hand-off in order (an mbarrier parity wait is only meaningful one phase behind), so that at a
+          // group change all MMAs that read the old weight image are known to be complete
+          if (lit > 0) { const int pl_ = lit - 1; mbar_wait(tmem_full + (pl_ % a.nacc), (pl_ / a.nacc) & 1); }
           if (g != g_loaded) {
-            if (lit > 0) { const int pl_ = lit - 1; mbar_wait(tmem_full + (pl_ % a.nacc), (pl_ / a.nacc) & 1); }   // MMAs of the old group done
             mbar_arrive_expect_tx(wres_full, (uint32_t)nchunks * w_slot_bytes);
             for (int c = 0; c < nchunks; ++c)
               bulk_g2s(wbuf + (size_t)c * a.w_slot_floats, wsrc + (size_t)c * a.w_slot_floats, w_slot_bytes, wres_full);

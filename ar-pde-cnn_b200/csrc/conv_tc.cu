@@ -40,7 +40,8 @@
 #define TC_EPI_WARPS 4
 #define TC_WARP_EPI0 TC_STAGER_WARPS
 #define TC_WARP_ISSUER (TC_STAGER_WARPS + TC_EPI_WARPS)
-#define TC_WARP_WPROD (TC_WARP_ISSUER + 1)
+#define TC_ISSUERS 2                   // MMA-issuing warps: issuer i owns the M tiles t = i (mod TC_ISSUERS) of every item
+#define TC_WARP_WPROD (TC_WARP_ISSUER + TC_ISSUERS)
 #define TC_THREADS (32 * (TC_WARP_WPROD + 1))
 #define TC_KP_MAX 8                    // a staging thread owns at most 8 patch positions (PHP <= 2048)
 
@@ -59,6 +60,8 @@ struct ConvTcArgs {
   int resident;              // 1: the whole split weight image of a group stays in shared memory
   int nacc, acc_cols;        // accumulator ring in TMEM: nacc slots of acc_cols = ntile * 2 * coutP columns
   int kp;                    // patch positions per staging thread = ceil(PHP / 256)
+  long long* dbg;            // optional cycle counters of CTA 0 (arpde_conv_tc_set_debug), else nullptr
+  int dbg_flags;             // experiments: 1 = skip patch staging work, 2 = skip epilogue loads/stores, 4 = skip MMAs
   int tap_plane[TC_MAX_TAPS];
   int tap_off[TC_MAX_TAPS];
   int tap_aoff[TC_MAX_TAPS];  // (tap_plane * cchunk/4 * PP + tap_off): A-operand offset of the tap in 16-byte units
@@ -142,6 +145,14 @@ __device__ __forceinline__ float tf32_rna(float v) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
   return __uint_as_float(r);
 }
+
+// debug cycle accounting (CTA 0 only, one lane per role): DBG_T(slot, statement) adds the cycles `statement` took to dbg[slot]
+#define DBG_T(slot, stmt)                                                         \
+  do {                                                                            \
+    const long long t__ = (a.dbg != nullptr) ? clock64() : 0;                     \
+    stmt; /* always executed in warp-uniform control flow (tcgen05.ld is .sync.aligned) */ \
+    if (dbg_on) dbg_acc[slot] += clock64() - t__;                                 \
+  } while (0)
 
 // ------------------------------------------------------------------------------------------ weight preparation
 // w [groups][cout][cin][ntaps]  ->  out [groups][ncc][ntc][tchunk][cchunk/4][2*coutP][4]: the exact shared-memory image
@@ -229,12 +240,12 @@ __device__ __forceinline__ void stage_chunk(const ConvTcArgs& a, const float* __
 // ------------------------------------------------------------------------------------------ main kernel
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ ConvTcArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  uint64_t* full_p = reinterpret_cast<uint64_t*>(smem_raw);        // [2] patch slot filled (256 stager arrivals)
+  uint64_t* full_p = reinterpret_cast<uint64_t*>(smem_raw);        // [2] patch slot filled (one arrival per staging warp)
   uint64_t* empty_p = full_p + 2;                                    // [2] patch slot consumed (tcgen05.commit)
   uint64_t* full_w = full_p + 4;                                     // [2] weight slot filled (bulk-copy tx bytes)
   uint64_t* empty_w = full_p + 6;                                    // [2] weight slot consumed (tcgen05.commit)
   uint64_t* tmem_full = full_p + 8;                                  // [2] accumulators of an item complete (tcgen05.commit)
-  uint64_t* tmem_empty = full_p + 10;                                // [2] accumulators drained (128 epilogue arrivals)
+  uint64_t* tmem_empty = full_p + 10;                                // [2] accumulators drained (one arrival per epilogue warp)
   uint64_t* wres_full = full_p + 12;                                 // resident weight image (re)loaded
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + 112);
   float* patch = reinterpret_cast<float*>(smem_raw + 128);
@@ -250,8 +261,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 
   if (tid == 0) {
     for (int s = 0; s < 2; ++s) {
-      mbar_init(full_p + s, TC_STAGERS); mbar_init(empty_p + s, 1); mbar_init(full_w + s, 1); mbar_init(empty_w + s, 1);
-      mbar_init(tmem_full + s, 1); mbar_init(tmem_empty + s, 32 * TC_EPI_WARPS);
+      mbar_init(full_p + s, TC_STAGER_WARPS); mbar_init(empty_p + s, TC_ISSUERS); mbar_init(full_w + s, 1); mbar_init(empty_w + s, TC_ISSUERS);
+      mbar_init(tmem_full + s, TC_ISSUERS); mbar_init(tmem_empty + s, TC_EPI_WARPS);
     }
     mbar_init(wres_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -268,6 +279,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   if (warp < TC_STAGER_WARPS) {
     // =============================== staging warps ===============================
     const long long HW = (long long)a.H * a.W;
+    const bool dbg_on = a.dbg != nullptr && blockIdx.x == 0 && tid == 0;
+    long long dbg_acc[4] = {0, 0, 0, 0};
+    const long long dbg_t0 = dbg_on ? clock64() : 0;
     for (int it = it_begin; it < it_end; ++it) {
       const int lit = it - it_begin;
       const int n = it / a.ctas_per_sample, b = it - n * a.ctas_per_sample;
@@ -294,10 +308,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       for (int cc = 0; cc < a.ncc; ++cc) {
         const int pseq = lit * a.ncc + cc;
         const int ps = pseq % a.nslot_p, pk = pseq / a.nslot_p;
-        if (pk > 0) mbar_wait(empty_p + ps, (pk - 1) & 1);
+        if (pk > 0) DBG_T(0, mbar_wait(empty_p + ps, (pk - 1) & 1));
+        const long long dbg_t1 = dbg_on ? clock64() : 0;
         float4* ph = reinterpret_cast<float4*>(patch + (size_t)ps * a.patch_slot_floats);
         float4* pl = ph + (a.patch_slot_floats >> 3);
-        if (a.relu_in) {
+        if (a.dbg_flags & 1) {
+        } else if (a.relu_in) {
           if (a.kp <= 2) stage_chunk<2, 4, true>(a, xn, scale, shift, ph, pl, cc, off0, kmask, tid, HW);
           else if (a.kp <= 4) stage_chunk<4, 2, true>(a, xn, scale, shift, ph, pl, cc, off0, kmask, tid, HW);
           else stage_chunk<8, 1, true>(a, xn, scale, shift, ph, pl, cc, off0, kmask, tid, HW);
@@ -306,24 +322,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           else if (a.kp <= 4) stage_chunk<4, 2, false>(a, xn, scale, shift, ph, pl, cc, off0, kmask, tid, HW);
           else stage_chunk<8, 1, false>(a, xn, scale, shift, ph, pl, cc, off0, kmask, tid, HW);
         }
-        fence_async_smem();
-        mbar_arrive(full_p + ps);
+        if (dbg_on) dbg_acc[1] += clock64() - dbg_t1;
+        DBG_T(2, fence_async_smem(); __syncwarp(); if (lane == 0) mbar_arrive(full_p + ps));   // one arrival per warp
       }
     }
+    if (dbg_on) { a.dbg[0] = clock64() - dbg_t0; a.dbg[1] = dbg_acc[0]; a.dbg[2] = dbg_acc[1]; a.dbg[3] = dbg_acc[2]; }
   } else if (warp < TC_WARP_ISSUER) {
     // =============================== epilogue warps ===============================
     const int lanebase = (warp - TC_WARP_EPI0) * 32;           // == (warp % 4) * 32: the TMEM lane quarter this warp may read
     const long long HoWo = (long long)a.Ho * a.Wo;
     const bool plain = a.act == 0 && a.stats == nullptr;
+    const bool dbg_on = a.dbg != nullptr && blockIdx.x == 0 && tid == 32 * TC_WARP_EPI0;
+    long long dbg_acc[4] = {0, 0, 0, 0};
+    const long long dbg_t0 = dbg_on ? clock64() : 0;
     for (int it = it_begin; it < it_end; ++it) {
       const int lit = it - it_begin;
       const int n = it / a.ctas_per_sample, b = it - n * a.ctas_per_sample;
       const int q0 = b * a.ntile * 128;
       const int as = lit % a.nacc, ak = lit / a.nacc;
-      mbar_wait(tmem_full + as, ak & 1);
+      DBG_T(0, mbar_wait(tmem_full + as, ak & 1));
       tc_fence_after();
       const int nt_item = min(a.ntile, a.total_tiles - b * a.ntile);        // the last item of a sample may hold fewer M tiles
-      for (int t = 0; t < nt_item; ++t) {
+      for (int t = 0; t < ((a.dbg_flags & 2) ? 0 : nt_item); ++t) {
         const int q = q0 + t * 128 + lanebase + lane;
         const int oy = q / a.pitch, ox = q - oy * a.pitch;
         const bool valid = oy < a.Ho && ox < a.Wo;
@@ -335,14 +355,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           //  the critical path -- ~95% busy, half of their stalls branch_resolving / instruction-cache misses.)
           for (int c0 = 0; c0 < a.cout; c0 += 16) {
             float v1[16], v2[16];
-            tmem_ld16(trow + c0, v1);
-            tmem_ld16(trow + a.coutP + c0, v2);
-            tmem_ld_wait();
+            DBG_T(1, tmem_ld16(trow + c0, v1); tmem_ld16(trow + a.coutP + c0, v2); tmem_ld_wait());
             float* pc = yp + c0 * HoWo;
             if (valid) {
+              if (c0 + 16 <= a.cout) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j)
-                if (c0 + j < a.cout) pc[j * HoWo] = v1[j] + v2[j];
+                for (int j = 0; j < 16; ++j) { *pc = v1[j] + v2[j]; pc += HoWo; }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  if (c0 + j < a.cout) *pc = v1[j] + v2[j];
+                  pc += HoWo;
+                }
+              }
             }
           }
         } else {
@@ -369,14 +394,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         }
       }
       tc_fence_before();
-      mbar_arrive(tmem_empty + as);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty + as);
     }
-  } else if (warp == TC_WARP_ISSUER) {
+    if (dbg_on) { a.dbg[4] = clock64() - dbg_t0; a.dbg[5] = dbg_acc[0]; a.dbg[6] = dbg_acc[1]; }
+  } else if (warp < TC_WARP_WPROD) {
     // =============================== MMA issuing warp ===============================
     // All 32 lanes run the (warp-uniform) loops so that the address arithmetic stays on the uniform datapath; one elected
     // lane issues the tcgen05 instructions.  (First version: a single lane computed every descriptor in vector registers
     // and needed ~400 cycles per MMA pair -- the tensor pipe was idle 80-95% of the time.)
     const bool leader = elect_one();
+    const int issuer = warp - TC_WARP_ISSUER;          // this warp issues the MMAs of tiles issuer, issuer + TC_ISSUERS, ...
     const uint32_t idesc1 = umma_idesc_tf32(128, N2), idesc2 = umma_idesc_tf32(128, a.coutP);
     const uint32_t PP = (uint32_t)a.PP;
     // descriptor words: hi = SBO (128 B) | version 1; lo = start address >> 4 | LBO << 16.  Offsets (in 16-byte units) are added
@@ -386,6 +414,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     const uint32_t b_lo_base = (smem_u32(wbuf) >> 4) | ((uint32_t)N2 << 16);
     const uint32_t slot16 = (uint32_t)a.patch_slot_floats >> 2, w_slot16 = (uint32_t)a.w_slot_floats >> 2;
     int g_loaded = -1, wgen = 0;
+    const bool dbg_on = a.dbg != nullptr && blockIdx.x == 0 && leader && issuer == 0;
+    long long dbg_acc[4] = {0, 0, 0, 0};
+    const long long dbg_t0 = dbg_on ? clock64() : 0;
     for (int it = it_begin; it < it_end; ++it) {
       const int lit = it - it_begin;
       const int n = it / a.ctas_per_sample, b = it - n * a.ctas_per_sample;
@@ -394,14 +425,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       const uint32_t qlocal0 = (uint32_t)(q0 - (q0 / a.pitch) * a.pitch);
       const int nt_item = min(a.ntile, a.total_tiles - b * a.ntile);
       const int as = lit % a.nacc, ak = lit / a.nacc;
-      if (ak > 0) mbar_wait(tmem_empty + as, (ak - 1) & 1);
-      if (a.resident && g != g_loaded) { mbar_wait(wres_full, wgen & 1); ++wgen; g_loaded = g; }
+      if (ak > 0) DBG_T(0, mbar_wait(tmem_empty + as, (ak - 1) & 1));
+      if (a.resident && g != g_loaded) { DBG_T(2, mbar_wait(wres_full, wgen & 1)); ++wgen; g_loaded = g; }
       tc_fence_after();
       const uint32_t acc_base = tmem + (uint32_t)(as * a.acc_cols);
       for (int cc = 0; cc < a.ncc; ++cc) {
         const int pseq = lit * a.ncc + cc;
         const int ps = pseq % a.nslot_p, pk = pseq / a.nslot_p;
-        mbar_wait(full_p + ps, pk & 1);
+        DBG_T(1, mbar_wait(full_p + ps, pk & 1));
         const uint32_t pa_hi = a_lo_base + (uint32_t)ps * slot16 + qlocal0, pa_lo = pa_hi + (slot16 >> 1);
         for (int tc = 0; tc < a.ntc; ++tc) {
           const int chunk = cc * a.ntc + tc;
@@ -412,24 +443,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           } else {
             const int wseq = lit * nchunks + chunk;
             ws = wseq & 1;
-            mbar_wait(full_w + ws, (wseq >> 1) & 1);
+            DBG_T(2, mbar_wait(full_w + ws, (wseq >> 1) & 1));
             wb = b_lo_base + (uint32_t)ws * w_slot16;
           }
           tc_fence_after();
-          for (int t = 0; t < nt_item; ++t) {
-            const uint32_t d_tmem = acc_base + (uint32_t)(t * N2);
-            uint32_t bl = wb;
-            for (int tl = 0; tl < a.tchunk; ++tl) {
-              uint32_t al = (uint32_t)a.tap_aoff[tc * a.tchunk + tl] + (uint32_t)(t * 128);
-              for (int c8 = 0; c8 < nc8; ++c8) {
-                if (leader) {
-                  const uint64_t db = ((uint64_t)desc_hi << 32) | bl;
-                  const uint32_t first = (chunk | tl | c8) ? 1u : 0u;
-                  umma_tf32(d_tmem, ((uint64_t)desc_hi << 32) | (pa_hi + al), db, idesc1, first);                   // hi * [hi;lo]
-                  umma_tf32(d_tmem + (uint32_t)a.coutP, ((uint64_t)desc_hi << 32) | (pa_lo + al), db, idesc2, 1u);   // lo * hi -> correction half
+          if (leader && !(a.dbg_flags & 4)) {
+            // one elected lane walks (tile, tap, 8-channel group); 64-bit descriptors are advanced in place (low word only carries
+            // the 14-bit address field, which never overflows), so each MMA pair costs three 64-bit adds on top of the two UTCHMMA
+            const uint64_t hi64 = (uint64_t)desc_hi << 32;
+            const uint32_t first_chunk = chunk == 0 ? 0u : 1u;
+            for (int t = issuer; t < nt_item; t += TC_ISSUERS) {
+              const uint32_t d_tmem = acc_base + (uint32_t)(t * N2);
+              uint64_t db = hi64 | wb;
+              for (int tl = 0; tl < a.tchunk; ++tl) {
+                const uint32_t al = (uint32_t)a.tap_aoff[tc * a.tchunk + tl] + (uint32_t)(t * 128);
+                uint64_t da_h = hi64 | (pa_hi + al), da_l = hi64 | (pa_lo + al);
+                uint32_t acc = (tl == 0) ? first_chunk : 1u;
+#pragma unroll 2
+                for (int c8 = 0; c8 < nc8; ++c8) {
+                  umma_tf32(d_tmem, da_h, db, idesc1, acc);                            // hi * [hi;lo]
+                  umma_tf32(d_tmem + (uint32_t)a.coutP, da_l, db, idesc2, 1u);         // lo * hi -> correction half
+                  acc = 1u;
+                  da_h += 2 * PP; da_l += 2 * PP; db += 2 * (uint32_t)N2;
                 }
-                al += 2 * PP;
-                bl += 2 * (uint32_t)N2;
               }
             }
           }
@@ -439,6 +475,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       }
       if (leader) umma_commit(tmem_full + as);
     }
+    if (dbg_on) { a.dbg[8] = clock64() - dbg_t0; a.dbg[9] = dbg_acc[0]; a.dbg[10] = dbg_acc[1]; a.dbg[11] = dbg_acc[2]; a.dbg[12] = it_end - it_begin; }
     __syncwarp();
   } else {
     // =============================== weight copy warp ===============================
@@ -592,6 +629,14 @@ int arpde_conv_tc_prep_launch(const ConvDesc& d, const float* w, long long w_gs,
   return ARPDE_OK;
 }
 
+static long long* g_tc_dbg = nullptr;
+static int g_tc_dbg_flags = 0;
+extern "C" int arpde_conv_tc_set_debug_flags(int flags) { g_tc_dbg_flags = flags; return ARPDE_OK; }
+// debug hook: cycle counters of CTA 0 of the following conv_tc launches are written to dev_buf (16 int64):
+// [0..3] stager: total, wait empty_p, staging, fence+arrive; [4,5] epilogue: total, wait tmem_full;
+// [8..12] issuer: total, wait tmem_empty, wait full_p, wait weights, items
+extern "C" int arpde_conv_tc_set_debug(long long* dev_buf) { g_tc_dbg = dev_buf; return ARPDE_OK; }
+
 int arpde_conv_tc_launch(const ConvDesc& d, const float* x, long long x_bs, const float* wprep, long long wprep_gs, const float* scale,
                          const float* shift, long long ss_gs, float* y, double* stats, cudaStream_t stream) {
   ARPDE_CHECK_ARG(x && wprep && y, "conv_tc: null pointer");
@@ -600,7 +645,7 @@ int arpde_conv_tc_launch(const ConvDesc& d, const float* x, long long x_bs, cons
   if (!tc_plan(d, a, &smem)) { arpde_set_error("conv_tc: layer not supported by the tensor-core kernel"); return ARPDE_ERR_UNSUPPORTED; }
   a.x = x; a.x_bs = x_bs; a.scale = scale; a.shift = shift; a.ss_gs = ss_gs; a.wprep = wprep; a.wprep_gs = wprep_gs;
   a.y = y; a.stats = stats; a.relu_in = d.relu_in; a.act = d.act; a.y_ctot = d.y_ctot; a.y_coff = d.y_coff;
-  a.n_per_group = d.n_per_group;
+  a.n_per_group = d.n_per_group; a.dbg = g_tc_dbg; a.dbg_flags = g_tc_dbg_flags;
   static thread_local size_t smem_set = 0;
   if (smem > smem_set) {
     ARPDE_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

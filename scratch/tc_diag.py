@@ -7,6 +7,8 @@ from oracle import arpde_oracle as O
 from arpde_b200 import _lib as L
 DEV = 'cuda:0'
 NB = int(sys.argv[1]) if len(sys.argv) > 1 else 1920
+FLAGS = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+L.lib.arpde_conv_tc_set_debug_flags(FLAGS)
 LAYERS = [('In_conv1', 6, 96, 5, 1, 0, 64, 0), ('In_conv3', 96, 48, 3, 2, 0, 64, 0), ('dense1', 48, 4, 3, 1, 0, 32, 1), ('dense4', 60, 4, 3, 1, 0, 32, 1),
           ('conv1x1', 64, 32, 1, 1, 0, 32, 1), ('conv2up', 32, 16, 3, 1, 1, 32, 1), ('conv3', 16, 2, 5, 1, 0, 64, 1)]
 
@@ -47,6 +49,15 @@ for name, cin, cout, k, s, up, H, relu in LAYERS:
         e1.record(); torch.cuda.synchronize()
         ms[fn] = e0.elapsed_time(e1) / 5
     fl = 2.0 * NB * Ho * Ho * cout * cin * k * k
+    import ctypes
+    dbg = torch.zeros(16, dtype=torch.int64, device=DEV)
+    L.lib.arpde_conv_tc_set_debug.argtypes = [ctypes.c_void_p]
+    L.lib.arpde_conv_tc_set_debug(dbg.data_ptr())
+    run('arpde_conv_fwd_tc', x, w, sc, sh, y, NB, cin, H, cout, k, s, up, relu, scratch); torch.cuda.synchronize()
+    L.lib.arpde_conv_tc_set_debug(0)
+    d = dbg.cpu().tolist(); it = max(d[12], 1)
+    print('   per item (clk): stager total %d wait_empty %d staging %d fence %d | epi total %d wait_full %d tmem_ld %d | issuer total %d wait_tmem_empty %d wait_full_p %d wait_w %d  (items %d)' % (
+        d[0] // it, d[1] // it, d[2] // it, d[3] // it, d[4] // it, d[5] // it, d[6] // it, d[8] // it, d[9] // it, d[10] // it, d[11] // it, d[12]))
     print('%-9s N=%d  ffma %.3f ms (%.1f TF/s) err %.2e | tc %.3f ms (%.1f TF/s) err %.2e' % (
         name, NB, ms['arpde_conv_fwd'], fl / ms['arpde_conv_fwd'] / 1e9, errs['arpde_conv_fwd'],
         ms['arpde_conv_fwd_tc'], fl / ms['arpde_conv_fwd_tc'] / 1e9, errs['arpde_conv_fwd_tc']), flush=True)

@@ -44,6 +44,8 @@
 #define TC_WARP_WPROD (TC_WARP_ISSUER + TC_ISSUERS)
 #define TC_THREADS (32 * (TC_WARP_WPROD + 1))
 #define TC_KP_MAX 8                    // a staging thread owns at most 8 patch positions (PHP <= 2048)
+#define TC_MAX_CIN 256                 // input channels (padded to the channel chunk) the BatchNorm scale/shift table holds
+#define TC_SMEM_HEADER (128 + 4 * TC_MAX_CIN * 4)   // barriers + tmem slot, then the two scale/shift tables
 
 struct ConvTcArgs {
   const float* x; long long x_bs;
@@ -60,6 +62,7 @@ struct ConvTcArgs {
   int resident;              // 1: the whole split weight image of a group stays in shared memory
   int nacc, acc_cols;        // accumulator ring in TMEM: nacc slots of acc_cols = ntile * 2 * coutP columns
   int kp;                    // patch positions per staging thread = ceil(PHP / 256)
+  int pair;                  // stride-2 layer staged with float2 loads (both x parities at once)
   long long* dbg;            // optional cycle counters of CTA 0 (arpde_conv_tc_set_debug), else nullptr
   int dbg_flags;             // experiments: 1 = skip patch staging work, 2 = skip epilogue loads/stores, 4 = skip MMAs
   int tap_plane[TC_MAX_TAPS];
@@ -180,61 +183,191 @@ __global__ void __launch_bounds__(256) conv_tc_wprep_kernel(const float* __restr
 }
 
 // ------------------------------------------------------------------------------------------ patch staging
-// One channel chunk of the input patch -> shared memory (hi and lo planes).  Thread `stid` owns the patch positions
-// stid + 256*k (k < KP) for every (plane, 4-channel group); PCU such groups are loaded together so that about 32 global
-// loads are in flight per thread before the first one is consumed (the loads come from L2; ncu showed the first version
-// of this loop stalled on long_scoreboard for ~60% of its samples).
-template <int KP, int PCU, bool RELU>
-__device__ __forceinline__ void stage_chunk(const ConvTcArgs& a, const float* __restrict__ xn, const float* __restrict__ scale,
-                                            const float* __restrict__ shift, float4* __restrict__ ph, float4* __restrict__ pl,
-                                            int cc, const int (&off0)[TC_KP_MAX], uint32_t kmask, int stid, long long HW) {
-  const int nc4 = a.cchunk >> 2, npc = a.nplanes * nc4;
-  for (int pc0 = 0; pc0 < npc; pc0 += PCU) {
-    float v[PCU][KP][4];
-    float sc[PCU][4], sh[PCU][4];
+// Input patch -> shared memory (hi and lo planes), one channel chunk at a time.  Staging thread `stid` owns the patch
+// positions stid + 256*k (k < KP) of every "unit" = (plane, 4-channel group) -- or, for stride-2 layers (PAIR), of every
+// (pair of x-parity planes, 4-channel group), loaded as one float2 per channel so that every fetched sector is used.
+// The work is a flat sequence of batches of NB units over (item, channel chunk); the loads of batch i+1 are issued
+// before batch i is converted and stored (two register buffers), and they do not wait for the patch slot to be free,
+// so global-load latency overlaps the split arithmetic, the shared-memory stores and the barrier hand-off.
+// (History: v1 consumed each load right away -> 60% long_scoreboard stalls; v2 batched ~32 loads per thread but ran
+//  load -> wait -> convert -> store -> fence strictly in sequence: 2.9k cycles per batch, every layer staging-bound.)
+struct StageCursor { int it, cc, ub; };
+
+template <int KP, int NB, bool PAIR>
+__device__ __forceinline__ void sb_load(const ConvTcArgs& a, const float* __restrict__ xn, long long HW, int cc, int ub,
+                                        const int (&off0)[KP], uint32_t kmask, float (&v)[NB][KP][PAIR ? 8 : 4]) {
+  const int nc4 = a.cchunk >> 2;
+  const int nunits = (PAIR ? (a.nplanes >> 1) : a.nplanes) * nc4;
 #pragma unroll
-    for (int u = 0; u < PCU; ++u) {
-      const int pc = pc0 + u;
-      const int plane = pc >> a.nc4_shift, c4 = pc & (nc4 - 1);
-      const int c0 = cc * a.cchunk + c4 * 4;
-      const int poff = (plane >> 1) * a.W + (plane & 1);
+  for (int i = 0; i < NB; ++i) {
+    const int u = ub * NB + i;
+    const int pl = u >> a.nc4_shift, c4 = u & (nc4 - 1);
+    const int c0 = cc * a.cchunk + c4 * 4;
+    const int poff = PAIR ? pl * a.W : (pl >> 1) * a.W + (pl & 1);
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int c = c0 + e;
-        const bool cok = pc < npc && c < a.cin;
-        const float* src = xn + (long long)(cok ? c : 0) * HW + poff;
-        sc[u][e] = (cok && scale) ? __ldg(scale + c) : (cok ? 1.f : 0.f);
-        sh[u][e] = (cok && scale) ? __ldg(shift + c) : 0.f;
+    for (int e = 0; e < 4; ++e) {
+      const int c = c0 + e;
+      const bool cok = u < nunits && c < a.cin;
+      const float* src = xn + (long long)(cok ? c : 0) * HW + poff;
 #pragma unroll
-        for (int k = 0; k < KP; ++k) v[u][k][e] = (cok && ((kmask >> k) & 1u)) ? __ldg(src + off0[k]) : 0.f;
+      for (int k = 0; k < KP; ++k) {
+        const bool ok = cok && ((kmask >> k) & 1u);
+        if (PAIR) {
+          float2 t = make_float2(0.f, 0.f);
+          if (ok) t = __ldg(reinterpret_cast<const float2*>(src + off0[k]));
+          v[i][k][e] = t.x; v[i][k][4 + e] = t.y;
+        } else {
+          v[i][k][e] = ok ? __ldg(src + off0[k]) : 0.f;
+        }
       }
     }
+  }
+}
+
+template <bool RELU>
+__device__ __forceinline__ void split_store(const float (&x)[4], const float4 sc, const float4 sh, float4* dh, float4* dl) {
+  const float s[4] = {sc.x, sc.y, sc.z, sc.w}, b[4] = {sh.x, sh.y, sh.z, sh.w};
+  float hi[4], lo[4];
 #pragma unroll
-    for (int u = 0; u < PCU; ++u) {
-      const int pc = pc0 + u;
-      if (pc < npc) {
-        float4* dh = ph + (size_t)pc * a.PP + stid;
-        float4* dl = pl + (size_t)pc * a.PP + stid;
+  for (int e = 0; e < 4; ++e) {
+    float t = fmaf(x[e], s[e], b[e]);
+    if (RELU) t = fmaxf(t, 0.f);
+    // tf32 round-to-nearest (ties away, == cvt.rna for finite values) in two integer ops; the residual t - hi is exact in
+    // fp32 and is left unrounded: the tensor core drops its low 13 bits (< 2^-22 relative to t)
+    hi[e] = __uint_as_float((__float_as_uint(t) + 0x1000u) & 0xffffe000u);
+    lo[e] = t - hi[e];
+  }
+  *dh = make_float4(hi[0], hi[1], hi[2], hi[3]);
+  *dl = make_float4(lo[0], lo[1], lo[2], lo[3]);
+}
+
+template <int KP, int NB, bool RELU, bool PAIR>
+__device__ __forceinline__ void sb_store(const ConvTcArgs& a, float4* __restrict__ ph, float4* __restrict__ pl, const float* ss_tab,
+                                         int cc, int ub, uint32_t kmask, int stid, const float (&v)[NB][KP][PAIR ? 8 : 4]) {
+  const int nc4 = a.cchunk >> 2;
+  const int nunits = (PAIR ? (a.nplanes >> 1) : a.nplanes) * nc4;
 #pragma unroll
-        for (int k = 0; k < KP; ++k) {
-          if ((kmask >> k) & 1u) {
-            float hi[4], lo[4];
+  for (int i = 0; i < NB; ++i) {
+    const int u = ub * NB + i;
+    if (u < nunits) {
+      const int plx = u >> a.nc4_shift, c4 = u & (nc4 - 1);
+      const int c0 = cc * a.cchunk + c4 * 4;
+      const float4 sc = *reinterpret_cast<const float4*>(ss_tab + c0);
+      const float4 sh = *reinterpret_cast<const float4*>(ss_tab + TC_MAX_CIN + c0);
+      const int pc = (PAIR ? 2 * plx : plx) * nc4 + c4;              // (plane, c4) index of the first plane written
+      float4* dh = ph + (size_t)pc * a.PP + stid;
+      float4* dl = pl + (size_t)pc * a.PP + stid;
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              float t = fmaf(v[u][k][e], sc[u][e], sh[u][e]);
-              if (RELU) t = fmaxf(t, 0.f);
-              // tf32 round-to-nearest (ties away, == cvt.rna for finite values) in two integer ops; the residual t - hi is exact
-              // in fp32 and is left unrounded: the tensor core drops its low 13 bits (< 2^-22 relative to t)
-              hi[e] = __uint_as_float((__float_as_uint(t) + 0x1000u) & 0xffffe000u);
-              lo[e] = t - hi[e];
-            }
-            dh[k * TC_STAGERS] = make_float4(hi[0], hi[1], hi[2], hi[3]);
-            dl[k * TC_STAGERS] = make_float4(lo[0], lo[1], lo[2], lo[3]);
+      for (int k = 0; k < KP; ++k) {
+        if ((kmask >> k) & 1u) {
+          const float x0[4] = {v[i][k][0], v[i][k][1], v[i][k][2], v[i][k][3]};
+          split_store<RELU>(x0, sc, sh, dh + k * TC_STAGERS, dl + k * TC_STAGERS);
+          if (PAIR) {
+            const float x1[4] = {v[i][k][4], v[i][k][5], v[i][k][6], v[i][k][7]};
+            split_store<RELU>(x1, sc, sh, dh + (size_t)nc4 * a.PP + k * TC_STAGERS, dl + (size_t)nc4 * a.PP + k * TC_STAGERS);
           }
         }
       }
     }
   }
+}
+
+template <int KP, int NB, bool RELU, bool PAIR>
+__device__ __noinline__ void stager_loop(const ConvTcArgs& a, float* patch, float* ss_tab, uint64_t* full_p, uint64_t* empty_p,
+                                         int it_begin, int it_end, int tid, int lane) {
+  constexpr int NV = PAIR ? 8 : 4;
+  const long long HW = (long long)a.H * a.W;
+  const int nc4 = a.cchunk >> 2;
+  const int nunits = (PAIR ? (a.nplanes >> 1) : a.nplanes) * nc4;
+  const int nbat = (nunits + NB - 1) / NB;
+  const bool dbg_on = a.dbg != nullptr && blockIdx.x == 0 && tid == 0;
+  long long dbg_acc[4] = {0, 0, 0, 0}, dbg_ld = 0;
+  const long long dbg_t0 = dbg_on ? clock64() : 0;
+  uint32_t kmask = 0;
+#pragma unroll
+  for (int k = 0; k < KP; ++k)
+    if (tid + k * TC_STAGERS < a.PHP) kmask |= 1u << k;
+
+  // ---- load-side context (item of the load cursor)
+  const float* xn = nullptr;
+  int off0[KP];
+  int g_tab = -1;
+  auto enter_item = [&](int it) {
+    const int n = it / a.ctas_per_sample, b = it - n * a.ctas_per_sample;
+    const int g = n / a.n_per_group;
+    const int r0 = (b * a.ntile * 128) / a.pitch;
+    xn = a.x + (long long)n * a.x_bs;
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+      off0[k] = 0;
+      const int pos = tid + k * TC_STAGERS;
+      if (pos < a.PHP) {
+        const int i = pos / a.pitch, j = pos - i * a.pitch;
+        int R = (r0 + a.min_ry + i) % a.Ho; if (R < 0) R += a.Ho;
+        int C = (a.min_rx + j) % a.Wo; if (C < 0) C += a.Wo;
+        off0[k] = ((R * a.sy) >> a.up_h) * a.W + ((C * a.sx) >> a.up_w);
+      }
+    }
+    if (g != g_tab) {
+      // BatchNorm scale/shift of this weight group -> shared table (two tables, alternating with the group, because the
+      // store side may still be one batch behind in the previous group)
+      float* tab = ss_tab + (g & 1) * 2 * TC_MAX_CIN;
+      const int cpad = a.ncc * a.cchunk;
+      for (int c = tid; c < cpad; c += TC_STAGERS) {
+        const bool ok = c < a.cin;
+        tab[c] = ok ? (a.scale ? __ldg(a.scale + (long long)g * a.ss_gs + c) : 1.f) : 0.f;
+        tab[TC_MAX_CIN + c] = (ok && a.scale) ? __ldg(a.shift + (long long)g * a.ss_gs + c) : 0.f;
+      }
+      bar_sync_named(1, TC_STAGERS);
+      g_tab = g;
+    }
+  };
+  auto advance = [&](StageCursor c) {
+    if (++c.ub == nbat) { c.ub = 0; if (++c.cc == a.ncc) { c.cc = 0; ++c.it; } }
+    return c;
+  };
+  // ---- store side of one batch (+ the barrier hand-off at chunk boundaries)
+  auto finish = [&](const StageCursor& c, const float (&v)[NB][KP][NV]) {
+    const int pseq = (c.it - it_begin) * a.ncc + c.cc;
+    const int ps = pseq % a.nslot_p, pk = pseq / a.nslot_p;
+    if (c.ub == 0 && pk > 0) DBG_T(0, mbar_wait(empty_p + ps, (pk - 1) & 1));
+    const long long t1 = dbg_on ? clock64() : 0;
+    float4* ph = reinterpret_cast<float4*>(patch + (size_t)ps * a.patch_slot_floats);
+    float4* pl = ph + (a.patch_slot_floats >> 3);
+    const int n = c.it / a.ctas_per_sample;
+    const float* tab = ss_tab + ((n / a.n_per_group) & 1) * 2 * TC_MAX_CIN;
+    if (!(a.dbg_flags & 1)) sb_store<KP, NB, RELU, PAIR>(a, ph, pl, tab, c.cc, c.ub, kmask, tid, v);
+    if (dbg_on) dbg_acc[1] += clock64() - t1;
+    if (c.ub == nbat - 1) DBG_T(2, fence_async_smem(); __syncwarp(); if (lane == 0) mbar_arrive(full_p + ps));
+  };
+
+  float va[NB][KP][NV], vb[NB][KP][NV];
+  StageCursor cur = {it_begin, 0, 0};
+  if (cur.it < it_end) {
+    enter_item(cur.it);
+    sb_load<KP, NB, PAIR>(a, xn, HW, cur.cc, cur.ub, off0, kmask, va);
+    while (true) {
+      StageCursor nxt = advance(cur);
+      bool more = nxt.it < it_end;
+      if (more) {
+        if (nxt.it != cur.it) DBG_T(3, enter_item(nxt.it));
+        { const long long tl__ = dbg_on ? clock64() : 0; sb_load<KP, NB, PAIR>(a, xn, HW, nxt.cc, nxt.ub, off0, kmask, vb); if (dbg_on) dbg_ld += clock64() - tl__; }
+      }
+      finish(cur, va);
+      if (!more) break;
+      cur = nxt;
+      nxt = advance(cur);
+      more = nxt.it < it_end;
+      if (more) {
+        if (nxt.it != cur.it) DBG_T(3, enter_item(nxt.it));
+        { const long long tl__ = dbg_on ? clock64() : 0; sb_load<KP, NB, PAIR>(a, xn, HW, nxt.cc, nxt.ub, off0, kmask, va); if (dbg_on) dbg_ld += clock64() - tl__; }
+      }
+      finish(cur, vb);
+      if (!more) break;
+      cur = nxt;
+    }
+  }
+  if (dbg_on) { a.dbg[0] = clock64() - dbg_t0; a.dbg[1] = dbg_acc[0]; a.dbg[2] = dbg_acc[1]; a.dbg[3] = dbg_acc[2]; a.dbg[13] = dbg_ld; a.dbg[14] = dbg_acc[3]; }
 }
 
 // ------------------------------------------------------------------------------------------ main kernel
@@ -248,7 +381,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   uint64_t* tmem_empty = full_p + 10;                                // [2] accumulators drained (one arrival per epilogue warp)
   uint64_t* wres_full = full_p + 12;                                 // resident weight image (re)loaded
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + 112);
-  float* patch = reinterpret_cast<float*>(smem_raw + 128);
+  float* ss_tab = reinterpret_cast<float*>(smem_raw + 128);          // [2 groups][scale | shift][TC_MAX_CIN]
+  float* patch = reinterpret_cast<float*>(smem_raw + TC_SMEM_HEADER);
   float* wbuf = patch + (size_t)a.nslot_p * a.patch_slot_floats;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -278,55 +412,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 
   if (warp < TC_STAGER_WARPS) {
     // =============================== staging warps ===============================
-    const long long HW = (long long)a.H * a.W;
-    const bool dbg_on = a.dbg != nullptr && blockIdx.x == 0 && tid == 0;
-    long long dbg_acc[4] = {0, 0, 0, 0};
-    const long long dbg_t0 = dbg_on ? clock64() : 0;
-    for (int it = it_begin; it < it_end; ++it) {
-      const int lit = it - it_begin;
-      const int n = it / a.ctas_per_sample, b = it - n * a.ctas_per_sample;
-      const int g = n / a.n_per_group;
-      const int r0 = (b * a.ntile * 128) / a.pitch;
-      const float* xn = a.x + (long long)n * a.x_bs;
-      const float* scale = a.scale ? a.scale + (long long)g * a.ss_gs : nullptr;
-      const float* shift = a.scale ? a.shift + (long long)g * a.ss_gs : nullptr;
-      // source offset of each owned patch position in plane (0,0): wrap + nearest-upsample folded in
-      int off0[TC_KP_MAX];
-      uint32_t kmask = 0;
-#pragma unroll
-      for (int k = 0; k < TC_KP_MAX; ++k) {
-        off0[k] = 0;
-        const int pos = tid + k * TC_STAGERS;
-        if (k < a.kp && pos < a.PHP) {
-          kmask |= 1u << k;
-          const int i = pos / a.pitch, j = pos - i * a.pitch;
-          int R = (r0 + a.min_ry + i) % a.Ho; if (R < 0) R += a.Ho;
-          int C = (a.min_rx + j) % a.Wo; if (C < 0) C += a.Wo;
-          off0[k] = ((R * a.sy) >> a.up_h) * a.W + ((C * a.sx) >> a.up_w);
-        }
-      }
-      for (int cc = 0; cc < a.ncc; ++cc) {
-        const int pseq = lit * a.ncc + cc;
-        const int ps = pseq % a.nslot_p, pk = pseq / a.nslot_p;
-        if (pk > 0) DBG_T(0, mbar_wait(empty_p + ps, (pk - 1) & 1));
-        const long long dbg_t1 = dbg_on ? clock64() : 0;
-        float4* ph = reinterpret_cast<float4*>(patch + (size_t)ps * a.patch_slot_floats);
-        float4* pl = ph + (a.patch_slot_floats >> 3);
-        if (a.dbg_flags & 1) {
-        } else if (a.relu_in) {
-          if (a.kp <= 2) stage_chunk<2, 4, true>(a, xn, scale, shift, ph, pl, cc, off0, kmask, tid, HW);
-          else if (a.kp <= 4) stage_chunk<4, 2, true>(a, xn, scale, shift, ph, pl, cc, off0, kmask, tid, HW);
-          else stage_chunk<8, 1, true>(a, xn, scale, shift, ph, pl, cc, off0, kmask, tid, HW);
-        } else {
-          if (a.kp <= 2) stage_chunk<2, 4, false>(a, xn, scale, shift, ph, pl, cc, off0, kmask, tid, HW);
-          else if (a.kp <= 4) stage_chunk<4, 2, false>(a, xn, scale, shift, ph, pl, cc, off0, kmask, tid, HW);
-          else stage_chunk<8, 1, false>(a, xn, scale, shift, ph, pl, cc, off0, kmask, tid, HW);
-        }
-        if (dbg_on) dbg_acc[1] += clock64() - dbg_t1;
-        DBG_T(2, fence_async_smem(); __syncwarp(); if (lane == 0) mbar_arrive(full_p + ps));   // one arrival per warp
-      }
+#define TC_STAGE(KP_, NB_, PAIR_)                                                                                        \
+  do {                                                                                                                   \
+    if (a.relu_in) stager_loop<KP_, NB_, true, PAIR_>(a, patch, ss_tab, full_p, empty_p, it_begin, it_end, tid, lane);   \
+    else stager_loop<KP_, NB_, false, PAIR_>(a, patch, ss_tab, full_p, empty_p, it_begin, it_end, tid, lane);            \
+  } while (0)
+    if (a.pair) {
+      if (a.kp <= 2) TC_STAGE(2, 2, true);
+      else TC_STAGE(4, 1, true);
+    } else {
+      if (a.kp <= 2) TC_STAGE(2, 4, false);
+      else if (a.kp <= 4) TC_STAGE(4, 2, false);
+      else TC_STAGE(8, 1, false);
     }
-    if (dbg_on) { a.dbg[0] = clock64() - dbg_t0; a.dbg[1] = dbg_acc[0]; a.dbg[2] = dbg_acc[1]; a.dbg[3] = dbg_acc[2]; }
+#undef TC_STAGE
   } else if (warp < TC_WARP_ISSUER) {
     // =============================== epilogue warps ===============================
     const int lanebase = (warp - TC_WARP_EPI0) * 32;           // == (warp % 4) * 32: the TMEM lane quarter this warp may read
@@ -539,7 +638,7 @@ static bool tc_plan(const ConvDesc& d, ConvTcArgs& a, size_t* smem_out) {
   if (a.Hc % a.sy || a.Wc % a.sx) return false;
   a.Ho = a.Hc / a.sy; a.Wo = a.Wc / a.sx;
   a.cout = d.cout; a.coutP = round_up(d.cout, 16);
-  if (a.coutP > 128) return false;
+  if (a.coutP > 128 || round_up(d.cin, 32) > TC_MAX_CIN) return false;
   a.ntaps = d.kh * d.kw;
   if (a.ntaps > TC_MAX_TAPS || d.kh > 7 || d.kw > 7) return false;
   const int pad_y = d.kh == 1 ? 0 : (d.kh == 4 ? 1 : (d.kh - 1) / 2), pad_x = d.kw == 1 ? 0 : (d.kw == 4 ? 1 : (d.kw - 1) / 2);
@@ -582,7 +681,7 @@ static bool tc_plan(const ConvDesc& d, ConvTcArgs& a, size_t* smem_out) {
           if (w_slot > 48 * 1024) continue;
           const int ntc = a.ntaps / tchunk;
           const size_t w_bytes = resident ? w_slot * ncc * ntc : 2 * w_slot;
-          const size_t smem = 128 + 2 * p_slot + w_bytes;
+          const size_t smem = TC_SMEM_HEADER + 2 * p_slot + w_bytes;
           if (smem > budget) continue;
           a.resident = resident; a.ntile = ntile; a.cchunk = cchunk; a.nc4_shift = cchunk == 32 ? 3 : (cchunk == 16 ? 2 : 1);
           a.ncc = ncc; a.tchunk = tchunk; a.ntc = ntc; a.PP = PP; a.PHP = PHP; a.nslot_p = 2;
@@ -646,6 +745,8 @@ int arpde_conv_tc_launch(const ConvDesc& d, const float* x, long long x_bs, cons
   a.x = x; a.x_bs = x_bs; a.scale = scale; a.shift = shift; a.ss_gs = ss_gs; a.wprep = wprep; a.wprep_gs = wprep_gs;
   a.y = y; a.stats = stats; a.relu_in = d.relu_in; a.act = d.act; a.y_ctot = d.y_ctot; a.y_coff = d.y_coff;
   a.n_per_group = d.n_per_group; a.dbg = g_tc_dbg; a.dbg_flags = g_tc_dbg_flags;
+  a.pair = (a.sx == 2 && !a.up_w && a.kp <= 4 && (a.W & 1) == 0 && (x_bs & 1) == 0 && (((uintptr_t)x) & 7) == 0 &&
+            (((long long)a.H * a.W) & 1) == 0) ? 1 : 0;
   static thread_local size_t smem_set = 0;
   if (smem > smem_set) {
     ARPDE_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

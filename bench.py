@@ -286,7 +286,7 @@ def main():
     e2e_value = units / (ms_e2e * 1e-3)
 
     # ---- per-kernel rooflines, measured live with CUDA events on the launching stream ------------------
-    # (1) dominant kernel of the job: the fused circular conv (conv_fwd_kernel) -- time one full AR step (9 launches)
+    # (1) one full AR step (9 fused convs: 8 on the tensor-core kernel, the 16->2 output conv on the FFMA kernel)
     flat, _, _ = swag.sample_flat(S_SAMPLES, generator=gen)
     reps = 5
     engine.rollout(swag, ic_dev, 1, flat_weights=flat, named_params=named)
@@ -297,12 +297,34 @@ def main():
     e1.record(); torch.cuda.synchronize()
     step_ms = e0.elapsed_time(e1) / reps
     conv_tflops = NT * MODEL_MFLOP * 1e6 / (step_ms * 1e-3) / 1e12
+    # (1b) the dominant launch of the step, timed alone through the C ABI on the rollout batch:
+    #      conv_tc_kernel on In_conv3 (96 -> 48, 3x3 stride 2, 64x64 -> 32x32), 1920 samples, 30 weight groups
+    import arpde_b200._lib as L
+    xin = torch.randn((NT, 96, NEL, NEL), device=dev)
+    w3 = torch.randn((S_SAMPLES, 48, 96, 3, 3), device=dev) / (96 * 9) ** 0.5
+    y3 = torch.empty((NT, 48, NEL // 2, NEL // 2), device=dev)
+    n_scr = int(L.lib.arpde_conv_fwd_tc_scratch_floats(96, 48, 3, 3, S_SAMPLES))
+    scr = torch.empty((n_scr,), device=dev)
+    def k1():
+        L.call('arpde_conv_fwd_tc', L.ptr(xin), 96 * NEL * NEL, L.ptr(w3), 48 * 96 * 9, 0, 0, 0, L.ptr(y3), 0, NT, 96, NEL, NEL, 48, 3, 3, 2, 0, 0, 0,
+               48, 0, N_IC, L.ptr(scr), n_scr, L.stream())
+    for _ in range(3):
+        k1()
+    torch.cuda.synchronize()
+    nrep = 10
+    e0.record()
+    for _ in range(nrep):
+        k1()
+    e1.record(); torch.cuda.synchronize()
+    k1_ms = e0.elapsed_time(e1) / nrep
+    k1_flops = 2.0 * NT * (NEL // 2) ** 2 * 48 * 96 * 9
+    k1_tflops = k1_flops / (k1_ms * 1e-3) / 1e12
+    del xin, y3
     # (2) the stencil-loss kernel (K2) on the rollout batch: 1920 states x 64x64 x 24 B = 189 MB > L2
     up = traj_buf[:, 6:8]
     u0 = traj_buf[:, 4:6]
     ustar = torch.empty((NT, 2, NEL, NEL), device=dev)
     bs = traj_buf.stride(0)
-    import arpde_b200._lib as L
     def k2():
         L.call('arpde_cn_burgers2d_fwd', L.ptr(up), bs, L.ptr(u0), bs, L.ptr(ustar), 0, NT, NEL, NEL, 1.0 / NEL, 0.005, 0.005, 0, L.stream())
     for _ in range(3):
@@ -323,18 +345,22 @@ def main():
         return
 
     n_ops = 9
-    launches = args.steps * (T_STEPS * n_ops + 1 + 1 + 1)            # convs + bn fold + swag sample + moments
+    launches = args.steps * (T_STEPS * n_ops + 8 + 1 + 1 + 1)        # convs + 8 weight-split launches + bn fold + swag sample + moments
     line = {
         'metric': 'ar_steps_x_samples_per_s', 'value': value, 'unit': 'sample-steps/s', 'n_gpus': world, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(world), 'clocks': clocks, 'gpu_launches': launches,
         'e2e': {'value': e2e_value, 'unit': 'sample-steps/s', 'ms_per_step': ms_e2e / args.steps,
                 'h2d_bytes_per_step': ic_host.numel() * 4, 'd2h_bytes_per_step': 2 * mean_host.numel() * 4},
-        'roofline': {'kernel': 'conv_fwd_kernel (all 9 fused circular convs of one AR step)', 'bound': 'tensor',
-                     'achieved': conv_tflops, 'peak': peaks['bf16_tflops'], 'unit': 'TFLOP/s', 'frac': conv_tflops / peaks['bf16_tflops'],
-                     'traffic': None, 'peak_source': peaks['source'] + ' bf16 dense',
-                     'note': 'fp32 FFMA direct conv (1e-5 parity); nominal fp32 FMA-pipe peak 74.5 TFLOP/s -> frac_fp32 %.3f' % (conv_tflops / 74.5),
-                     'flops_per_launch_set': NT * MODEL_MFLOP * 1e6, 'ms': step_ms},
+        'roofline': {'kernel': 'conv_tc_kernel on In_conv3 (96->48, 3x3/s2, 1920 samples): tcgen05 implicit GEMM, 3xTF32 split (+ its weight-split launch)',
+                     'bound': 'tensor', 'achieved': k1_tflops, 'peak': peaks['bf16_tflops'], 'unit': 'TFLOP/s', 'frac': k1_tflops / peaks['bf16_tflops'],
+                     'traffic': None, 'peak_source': peaks['source'] + ' bf16 dense (burst)',
+                     'note': 'achieved = algorithmic fp32 FLOPs (2*N*Ho*Wo*cout*cin*k^2) / CUDA-event time; the 1e-5 parity contract needs the 3-term '
+                             'TF32 split (3 tensor MACs per algorithmic MAC) and TF32 runs at half the bf16 rate, so the attainable ceiling is '
+                             'peak/6 = %.0f TFLOP/s -> frac_of_3xtf32_ceiling %.3f' % (peaks['bf16_tflops'] / 6, k1_tflops / (peaks['bf16_tflops'] / 6)),
+                     'flops_per_launch': k1_flops, 'ms': k1_ms,
+                     'ar_step': {'ms': step_ms, 'tflops': conv_tflops, 'flops': NT * MODEL_MFLOP * 1e6,
+                                 'what': 'all 9 convs of one AR step (8 on conv_tc_kernel, the 16->2 output conv on the fp32 FFMA kernel)'}},
         'roofline_stencil': {'kernel': 'burgers2d_fwd_vec4 (fused periodic stencil + Crank-Nicolson, API form)', 'bound': 'hbm',
                              'achieved': k2_gbs, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': k2_gbs / peaks['hbm_gbs'],
                              'traffic': None, 'bytes_per_launch': k2_bytes, 'ms': k2_ms, 'peak_source': peaks['source']},

@@ -141,6 +141,12 @@ int arpde_conv_fwd_tc(const float* x, int64_t x_bstride, const float* w, int64_t
  * at least 130 int32).  Used by the CPU tests to check the shifted-window index arithmetic without a GPU. */
 int arpde_conv_tc_plan(int cin, int H, int W, int cout, int kh, int kw, int stride, int up, int32_t* out);
 
+/* Profiling hooks of the tensor-core kernel (development only; both default to off).  set_debug: per-role cycle counters of
+ * CTA 0 of every following arpde_conv_fwd_tc / program launch are written to dev_buf (16 device int64; NULL = off).
+ * set_debug_flags: ablation switches (1 = skip patch staging, 2 = skip the epilogue, 4 = skip the MMAs; results are garbage). */
+int arpde_conv_tc_set_debug(long long* dev_buf);
+int arpde_conv_tc_set_debug_flags(int flags);
+
 /* BatchNorm bookkeeping (nn.BatchNorm{1,2}d, eps 1e-5, momentum 0.1): per-channel sums of x[N,C(+),HW],
  * train-mode finalize (scale/shift, saved mean/invstd, running-stat update, num_batches_tracked += 1),
  * eval-mode fold of the running statistics. */

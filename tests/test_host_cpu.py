@@ -17,7 +17,7 @@ from arpde_b200 import program as P
 
 def test_library_exports_every_declared_symbol():
     hdr = open(os.path.join(ROOT, 'include', 'arpde.h')).read()
-    declared = set(re.findall(r'^(?:int|const char\*)\s+(arpde_\w+)\s*\(', hdr, flags=re.M))
+    declared = set(re.findall(r'^(?:int|int64_t|const char\*)\s+(arpde_\w+)\s*\(', hdr, flags=re.M))
     assert len(declared) >= 20
     for name in declared:
         assert hasattr(L.lib, name), name

@@ -33,6 +33,7 @@
 #include "conv_common.cuh"
 #include "../../include/arpde.h"
 #include <stdlib.h>
+#include <cuda.h>          // CUtensorMap + enums only; cuTensorMapEncodeTiled is resolved through cudaGetDriverEntryPoint
 
 #define TC_MAX_TAPS 49
 #define TC_STAGER_WARPS 8
@@ -41,11 +42,12 @@
 #define TC_WARP_EPI0 TC_STAGER_WARPS
 #define TC_WARP_ISSUER (TC_STAGER_WARPS + TC_EPI_WARPS)
 #define TC_ISSUERS 2                   // MMA-issuing warps: issuer i owns the M tiles t = i (mod TC_ISSUERS) of every item
-#define TC_WARP_WPROD (TC_WARP_ISSUER + TC_ISSUERS)
-#define TC_THREADS (32 * (TC_WARP_WPROD + 1))
+#define TC_WARP_WPROD (TC_WARP_ISSUER + TC_ISSUERS)     // weight copy warp
+#define TC_WARP_IPROD (TC_WARP_WPROD + 1)              // input copy warp (TMA rows of the input tensor)
+#define TC_THREADS (32 * (TC_WARP_IPROD + 1))
 #define TC_KP_MAX 8                    // a staging thread owns at most 8 patch positions (PHP <= 2048)
 #define TC_MAX_CIN 256                 // input channels (padded to the channel chunk) the BatchNorm scale/shift table holds
-#define TC_SMEM_HEADER (128 + 4 * TC_MAX_CIN * 4)   // barriers + tmem slot, then the two scale/shift tables
+#define TC_SMEM_HEADER (256 + 4 * TC_MAX_CIN * 4)   // barriers + tmem slot, then the two scale/shift tables
 
 struct ConvTcArgs {
   const float* x; long long x_bs;
@@ -63,6 +65,9 @@ struct ConvTcArgs {
   int nacc, acc_cols;        // accumulator ring in TMEM: nacc slots of acc_cols = ntile * 2 * coutP columns
   int kp;                    // patch positions per staging thread = ceil(PHP / 256)
   int pair;                  // stride-2 layer staged with float2 loads (both x parities at once)
+  int tma;                   // 1: input rows arrive by TMA into the raw ring and the staging warps convert smem -> smem
+  int row_mode;              // 0: stride 1, 1: nearest x2 upsampled input, 2: stride 2 (parity planes)
+  int RS, raw_slot_floats;   // source rows per (item, channel chunk) and floats per raw ring slot [RS][cchunk][W]
   long long* dbg;            // optional cycle counters of CTA 0 (arpde_conv_tc_set_debug), else nullptr
   int dbg_flags;             // experiments: 1 = skip patch staging work, 2 = skip epilogue loads/stores, 4 = skip MMAs
   int tap_plane[TC_MAX_TAPS];
@@ -94,6 +99,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
                "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// 4D tiled TMA load (coordinates innermost first: x, y, channel, sample), completion counted in bytes on an mbarrier
+__device__ __forceinline__ void tma_load_4d(void* dst_smem, const CUtensorMap* tmap, int c0, int c1, int c2, int c3, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                : "memory");
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -370,8 +382,115 @@ __device__ __noinline__ void stager_loop(const ConvTcArgs& a, float* patch, floa
   if (dbg_on) { a.dbg[0] = clock64() - dbg_t0; a.dbg[1] = dbg_acc[0]; a.dbg[2] = dbg_acc[1]; a.dbg[3] = dbg_acc[2]; a.dbg[13] = dbg_ld; a.dbg[14] = dbg_acc[3]; }
 }
 
+// ------------------------------------------------------------------------------------------ patch staging, TMA path
+// The input copy warp brings the source rows of an (item, channel chunk) into a raw ring slot [RS rows][cchunk][W] by
+// TMA (one box per row, vertical wrap = row index mod H, channels beyond cin zero-filled by the TMA unit); the staging
+// warps only convert shared -> shared: thread `stid` owns patch positions stid + 256*k and, per 4-channel group, reads
+// 4 floats (conflict-free: consecutive lanes = consecutive columns), applies BN/ReLU, splits and writes hi/lo float4.
+// Horizontal wrap, nearest-upsampling and the stride-2 parity split are constant per-thread index arithmetic.
+template <int KP, bool RELU, bool PAIR>
+__device__ __noinline__ void converter_loop(const ConvTcArgs& a, const float* raw, float* patch, float* ss_tab, uint64_t* full_p,
+                                            uint64_t* empty_p, uint64_t* raw_full, uint64_t* raw_empty, int it_begin, int it_end, int tid,
+                                            int lane) {
+  const int nc4 = a.cchunk >> 2;
+  const int nunits = (PAIR ? (a.nplanes >> 1) : a.nplanes) * nc4;
+  const int rowf = a.cchunk * a.W;                     // floats per raw row
+  const bool dbg_on = a.dbg != nullptr && blockIdx.x == 0 && tid == 0;
+  long long dbg_acc[4] = {0, 0, 0, 0};
+  const long long dbg_t0 = dbg_on ? clock64() : 0;
+  // constant part of the raw offset of every owned position (plane (0,0), channel 0)
+  int irow[KP], coff[KP];
+  uint32_t kmask = 0;
+#pragma unroll
+  for (int k = 0; k < KP; ++k) {
+    irow[k] = 0; coff[k] = 0;
+    const int pos = tid + k * TC_STAGERS;
+    if (pos < a.PHP) {
+      kmask |= 1u << k;
+      const int i = pos / a.pitch, j = pos - i * a.pitch;
+      int C = (a.min_rx + j) % a.Wo; if (C < 0) C += a.Wo;
+      irow[k] = i;
+      coff[k] = (C * a.sx) >> a.up_w;
+    }
+  }
+  int g_tab = -1;
+  for (int it = it_begin; it < it_end; ++it) {
+    const int lit = it - it_begin;
+    const int n = it / a.ctas_per_sample, b = it - n * a.ctas_per_sample;
+    const int g = n / a.n_per_group;
+    const int rbase = (b * a.ntile * 128) / a.pitch + a.min_ry;
+    if (g != g_tab) {        // BatchNorm scale/shift of this weight group -> shared table (padded channels: 0, 0)
+      bar_sync_named(1, TC_STAGERS);                    // every staging thread is done with the previous group's table
+      const int cpad = a.ncc * a.cchunk;
+      for (int c = tid; c < cpad; c += TC_STAGERS) {
+        const bool ok = c < a.cin;
+        ss_tab[c] = ok ? (a.scale ? __ldg(a.scale + (long long)g * a.ss_gs + c) : 1.f) : 0.f;
+        ss_tab[TC_MAX_CIN + c] = (ok && a.scale) ? __ldg(a.shift + (long long)g * a.ss_gs + c) : 0.f;
+      }
+      bar_sync_named(1, TC_STAGERS);
+      g_tab = g;
+    }
+    int roff[KP];
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+      const int rl = a.row_mode == 1 ? ((irow[k] + (rbase & 1)) >> 1) : (a.row_mode == 2 ? 2 * irow[k] : irow[k]);
+      roff[k] = rl * rowf + coff[k];
+    }
+    for (int cc = 0; cc < a.ncc; ++cc) {
+      const int pseq = lit * a.ncc + cc;
+      const int ps = pseq % a.nslot_p, pk = pseq / a.nslot_p;
+      const int rs = pseq & 1, rk = pseq >> 1;
+      DBG_T(3, mbar_wait(raw_full + rs, rk & 1));
+      if (pk > 0) DBG_T(0, mbar_wait(empty_p + ps, (pk - 1) & 1));
+      const long long t1 = dbg_on ? clock64() : 0;
+      const float* rw = raw + (size_t)rs * a.raw_slot_floats;
+      float4* ph = reinterpret_cast<float4*>(patch + (size_t)ps * a.patch_slot_floats) + tid;
+      float4* pl = ph + (a.patch_slot_floats >> 3);
+      if (!(a.dbg_flags & 1)) {
+        for (int u = 0; u < nunits; ++u) {
+          const int plx = u >> a.nc4_shift, c4 = u & (nc4 - 1);
+          const float4 sc = *reinterpret_cast<const float4*>(ss_tab + cc * a.cchunk + c4 * 4);
+          const float4 sh = *reinterpret_cast<const float4*>(ss_tab + TC_MAX_CIN + cc * a.cchunk + c4 * 4);
+          // raw offset of (unit, channel 0): 4-channel group, and for stride 2 the parity plane (py -> next source row, px -> next column)
+          const int uoff = c4 * 4 * a.W + (PAIR ? plx * rowf : (plx >> 1) * rowf + (plx & 1));
+          const int pc = (PAIR ? 2 * plx : plx) * nc4 + c4;
+          float v[KP][PAIR ? 8 : 4];
+#pragma unroll
+          for (int k = 0; k < KP; ++k) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              if (PAIR) {
+                const float2 t2 = ((kmask >> k) & 1u) ? *reinterpret_cast<const float2*>(rw + roff[k] + uoff + e * a.W) : make_float2(0.f, 0.f);
+                v[k][e] = t2.x; v[k][4 + e] = t2.y;
+              } else {
+                v[k][e] = ((kmask >> k) & 1u) ? rw[roff[k] + uoff + e * a.W] : 0.f;
+              }
+            }
+          }
+          float4* dh = ph + (size_t)pc * a.PP;
+          float4* dl = pl + (size_t)pc * a.PP;
+#pragma unroll
+          for (int k = 0; k < KP; ++k) {
+            if ((kmask >> k) & 1u) {
+              const float x0[4] = {v[k][0], v[k][1], v[k][2], v[k][3]};
+              split_store<RELU>(x0, sc, sh, dh + k * TC_STAGERS, dl + k * TC_STAGERS);
+              if (PAIR) {
+                const float x1[4] = {v[k][4], v[k][5], v[k][6], v[k][7]};
+                split_store<RELU>(x1, sc, sh, dh + (size_t)nc4 * a.PP + k * TC_STAGERS, dl + (size_t)nc4 * a.PP + k * TC_STAGERS);
+              }
+            }
+          }
+        }
+      }
+      if (dbg_on) dbg_acc[1] += clock64() - t1;
+      DBG_T(2, fence_async_smem(); __syncwarp(); if (lane == 0) { mbar_arrive(full_p + ps); mbar_arrive(raw_empty + rs); });
+    }
+  }
+  if (dbg_on) { a.dbg[0] = clock64() - dbg_t0; a.dbg[1] = dbg_acc[0]; a.dbg[2] = dbg_acc[1]; a.dbg[3] = dbg_acc[2]; a.dbg[13] = 0; a.dbg[14] = dbg_acc[3]; }
+}
+
 // ------------------------------------------------------------------------------------------ main kernel
-__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ ConvTcArgs a) {
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ ConvTcArgs a, const __grid_constant__ CUtensorMap tmap) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* full_p = reinterpret_cast<uint64_t*>(smem_raw);        // [2] patch slot filled (one arrival per staging warp)
   uint64_t* empty_p = full_p + 2;                                    // [2] patch slot consumed (tcgen05.commit)
@@ -380,9 +499,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   uint64_t* tmem_full = full_p + 8;                                  // [2] accumulators of an item complete (tcgen05.commit)
   uint64_t* tmem_empty = full_p + 10;                                // [2] accumulators drained (one arrival per epilogue warp)
   uint64_t* wres_full = full_p + 12;                                 // resident weight image (re)loaded
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + 112);
-  float* ss_tab = reinterpret_cast<float*>(smem_raw + 128);          // [2 groups][scale | shift][TC_MAX_CIN]
-  float* patch = reinterpret_cast<float*>(smem_raw + TC_SMEM_HEADER);
+  uint64_t* raw_full = full_p + 14;                                  // [2] raw input rows landed (TMA tx bytes)
+  uint64_t* raw_empty = full_p + 16;                                 // [2] raw slot converted (one arrival per staging warp)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + 192);
+  float* ss_tab = reinterpret_cast<float*>(smem_raw + 256);          // [2 groups][scale | shift][TC_MAX_CIN]
+  float* raw = reinterpret_cast<float*>(smem_raw + TC_SMEM_HEADER);  // [2 slots][RS][cchunk][W] (TMA path only)
+  float* patch = raw + (a.tma ? 2 * (size_t)a.raw_slot_floats : 0);
   float* wbuf = patch + (size_t)a.nslot_p * a.patch_slot_floats;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -399,6 +521,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       mbar_init(tmem_full + s, TC_ISSUERS); mbar_init(tmem_empty + s, TC_EPI_WARPS);
     }
     mbar_init(wres_full, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(raw_full + s, 1); mbar_init(raw_empty + s, TC_STAGER_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == TC_WARP_ISSUER) {
@@ -417,7 +540,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     if (a.relu_in) stager_loop<KP_, NB_, true, PAIR_>(a, patch, ss_tab, full_p, empty_p, it_begin, it_end, tid, lane);   \
     else stager_loop<KP_, NB_, false, PAIR_>(a, patch, ss_tab, full_p, empty_p, it_begin, it_end, tid, lane);            \
   } while (0)
-    if (a.pair) {
+#define TC_CONVERT(KP_, PAIR_)                                                                                                     \
+  do {                                                                                                                             \
+    if (a.relu_in) converter_loop<KP_, true, PAIR_>(a, raw, patch, ss_tab, full_p, empty_p, raw_full, raw_empty, it_begin, it_end, tid, lane);  \
+    else converter_loop<KP_, false, PAIR_>(a, raw, patch, ss_tab, full_p, empty_p, raw_full, raw_empty, it_begin, it_end, tid, lane);           \
+  } while (0)
+    if (a.tma) {
+      if (a.row_mode == 2 && a.kp <= 4) { if (a.kp <= 2) TC_CONVERT(2, true); else TC_CONVERT(4, true); }
+      else if (a.kp <= 2) TC_CONVERT(2, false);
+      else if (a.kp <= 4) TC_CONVERT(4, false);
+      else TC_CONVERT(8, false);
+    } else if (a.pair) {
       if (a.kp <= 2) TC_STAGE(2, 2, true);
       else TC_STAGE(4, 1, true);
     } else {
@@ -426,6 +559,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       else TC_STAGE(8, 1, false);
     }
 #undef TC_STAGE
+#undef TC_CONVERT
   } else if (warp < TC_WARP_ISSUER) {
     // =============================== epilogue warps ===============================
     const int lanebase = (warp - TC_WARP_EPI0) * 32;           // == (warp % 4) * 32: the TMEM lane quarter this warp may read
@@ -576,7 +710,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     }
     if (dbg_on) { a.dbg[8] = clock64() - dbg_t0; a.dbg[9] = dbg_acc[0]; a.dbg[10] = dbg_acc[1]; a.dbg[11] = dbg_acc[2]; a.dbg[12] = it_end - it_begin; }
     __syncwarp();
-  } else {
+  } else if (warp == TC_WARP_WPROD) {
     // =============================== weight copy warp ===============================
     if (lane == 0) {
       const uint32_t w_slot_bytes = (uint32_t)a.w_slot_floats * 4u;
@@ -603,6 +737,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             if (wk > 0) mbar_wait(empty_w + ws, (wk - 1) & 1);
             mbar_arrive_expect_tx(full_w + ws, w_slot_bytes);
             bulk_g2s(wbuf + (size_t)ws * a.w_slot_floats, wsrc + (size_t)c * a.w_slot_floats, w_slot_bytes, full_w + ws);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // =============================== input copy warp (TMA) ===============================
+    if (a.tma) {
+      const uint32_t row_bytes = (uint32_t)(a.cchunk * a.W) * 4u;
+      for (int it = it_begin; it < it_end; ++it) {
+        const int lit = it - it_begin;
+        const int n = it / a.ctas_per_sample, b = it - n * a.ctas_per_sample;
+        const int rbase = (b * a.ntile * 128) / a.pitch + a.min_ry;
+        const int row0 = a.row_mode == 1 ? (rbase >> 1) : (a.row_mode == 2 ? 2 * rbase : rbase);   // first source row (may be negative)
+        for (int cc = 0; cc < a.ncc; ++cc) {
+          const int rseq = lit * a.ncc + cc;
+          const int rs = rseq & 1, rk = rseq >> 1;
+          if (rk > 0) mbar_wait(raw_empty + rs, (rk - 1) & 1);
+          if (lane == 0) mbar_arrive_expect_tx(raw_full + rs, (uint32_t)a.RS * row_bytes);
+          __syncwarp();
+          float* dst = raw + (size_t)rs * a.raw_slot_floats;
+          for (int r = lane; r < a.RS; r += 32) {                    // one lane per source row; vertical wrap = row index mod H
+            int row = (row0 + r) % a.H; if (row < 0) row += a.H;
+            tma_load_4d(dst + (size_t)r * (a.cchunk * a.W), &tmap, 0, row, cc * a.cchunk, n, raw_full + rs);
           }
         }
       }
@@ -661,42 +819,49 @@ static bool tc_plan(const ConvDesc& d, ConvTcArgs& a, size_t* smem_out) {
   const int N2 = 2 * a.coutP;
   int ntile_max = 512 / N2; if (ntile_max > 4) ntile_max = 4;
   if (ntile_max > total_tiles) ntile_max = total_tiles;
-  const size_t budget = 225 * 1024;
-  // preference order: weights resident in shared memory (no re-streaming per item), then many M tiles per item (less halo,
-  // fewer weight passes), then wide channel chunks (fewer pipeline hand-offs), then wide tap chunks
+  const size_t budget = 226 * 1024;
+  a.row_mode = a.up_w ? 1 : (a.sx == 2 ? 2 : 0);
+  const bool tma_shape = (d.W % 4 == 0) && d.W <= 256 && ((long long)d.H * d.W) % 4 == 0;
+  // preference order: weights resident in shared memory (no re-streaming per item), double-buffered patch slots (staging overlaps
+  // the MMAs), then many M tiles per item (less halo, fewer weight passes), wide channel chunks (fewer pipeline hand-offs), wide tap chunks
   for (int resident = 1; resident >= 0; --resident)
-    for (int ntile = ntile_max; ntile >= 1; --ntile)
-      for (int cchunk = 32; cchunk >= 8; cchunk >>= 1) {
-        if (cchunk > 8 && cchunk > cin8) continue;
-        const int ncc = (d.cin + cchunk - 1) / cchunk;
-        const int rows = (a.pitch - 1 + ntile * 128 - 1) / a.pitch + 1 + span_y;
-        const int PHP = rows * a.pitch;
-        if (PHP > TC_STAGERS * TC_KP_MAX) continue;
-        int PP = a.pitch + ntile * 128 + max_off; if (PP < PHP) PP = PHP; PP = round_up(PP, 8);
-        if (PP > 16383) continue;
-        const size_t p_slot = (size_t)2 * a.nplanes * (cchunk / 4) * PP * 16;
-        for (int tchunk = a.ntaps; tchunk >= 1; --tchunk) {
-          if (a.ntaps % tchunk) continue;
-          const size_t w_slot = (size_t)tchunk * (cchunk / 4) * N2 * 16;
-          if (w_slot > 48 * 1024) continue;
-          const int ntc = a.ntaps / tchunk;
-          const size_t w_bytes = resident ? w_slot * ncc * ntc : 2 * w_slot;
-          const size_t smem = TC_SMEM_HEADER + 2 * p_slot + w_bytes;
-          if (smem > budget) continue;
-          a.resident = resident; a.ntile = ntile; a.cchunk = cchunk; a.nc4_shift = cchunk == 32 ? 3 : (cchunk == 16 ? 2 : 1);
-          a.ncc = ncc; a.tchunk = tchunk; a.ntc = ntc; a.PP = PP; a.PHP = PHP; a.nslot_p = 2;
-          a.kp = (PHP + TC_STAGERS - 1) / TC_STAGERS;
-          a.patch_slot_floats = (int)(p_slot / 4); a.w_slot_floats = (int)(w_slot / 4);
-          a.ctas_per_sample = (total_tiles + ntile - 1) / ntile; a.total_tiles = total_tiles;
-          for (int t = 0; t < a.ntaps; ++t) a.tap_aoff[t] = a.tap_plane[t] * (cchunk / 4) * PP + a.tap_off[t];
-          a.acc_cols = ntile * N2;
-          a.nacc = 2 * a.acc_cols <= 512 ? 2 : 1;
-          int p2 = 32; while (p2 < a.nacc * a.acc_cols) p2 <<= 1;
-          a.tmem_cols = p2;
-          *smem_out = smem;
-          return true;
+    for (int nslot_p = 2; nslot_p >= 1; --nslot_p)
+      for (int ntile = ntile_max; ntile >= 1; --ntile)
+        for (int cchunk = 32; cchunk >= 8; cchunk >>= 1) {
+          if (cchunk > 8 && cchunk > cin8) continue;
+          const int ncc = (d.cin + cchunk - 1) / cchunk;
+          if (nslot_p == 1 && ncc == 1 && ntile_max > 1) continue;      // a single slot only pays off for multi-chunk layers
+          const int rows = (a.pitch - 1 + ntile * 128 - 1) / a.pitch + 1 + span_y;
+          const int PHP = rows * a.pitch;
+          if (PHP > TC_STAGERS * TC_KP_MAX) continue;
+          int PP = a.pitch + ntile * 128 + max_off; if (PP < PHP) PP = PHP; PP = round_up(PP, 8);
+          if (PP > 16383) continue;
+          const size_t p_slot = (size_t)2 * a.nplanes * (cchunk / 4) * PP * 16;
+          const int RS = a.row_mode == 1 ? (rows >> 1) + 1 : (a.row_mode == 2 ? 2 * rows : rows);
+          const size_t raw_slot = tma_shape ? (size_t)RS * cchunk * d.W * 4 : 0;
+          for (int tchunk = a.ntaps; tchunk >= 1; --tchunk) {
+            if (a.ntaps % tchunk) continue;
+            const size_t w_slot = (size_t)tchunk * (cchunk / 4) * N2 * 16;
+            if (w_slot > 48 * 1024) continue;
+            const int ntc = a.ntaps / tchunk;
+            const size_t w_bytes = resident ? w_slot * ncc * ntc : 2 * w_slot;
+            const size_t smem = TC_SMEM_HEADER + 2 * raw_slot + nslot_p * p_slot + w_bytes;
+            if (smem > budget) continue;
+            a.resident = resident; a.ntile = ntile; a.cchunk = cchunk; a.nc4_shift = cchunk == 32 ? 3 : (cchunk == 16 ? 2 : 1);
+            a.ncc = ncc; a.tchunk = tchunk; a.ntc = ntc; a.PP = PP; a.PHP = PHP; a.nslot_p = nslot_p;
+            a.kp = (PHP + TC_STAGERS - 1) / TC_STAGERS;
+            a.patch_slot_floats = (int)(p_slot / 4); a.w_slot_floats = (int)(w_slot / 4);
+            a.tma = tma_shape ? 1 : 0; a.RS = RS; a.raw_slot_floats = (int)(raw_slot / 4);
+            a.ctas_per_sample = (total_tiles + ntile - 1) / ntile; a.total_tiles = total_tiles;
+            for (int t = 0; t < a.ntaps; ++t) a.tap_aoff[t] = a.tap_plane[t] * (cchunk / 4) * PP + a.tap_off[t];
+            a.acc_cols = ntile * N2;
+            a.nacc = 2 * a.acc_cols <= 512 ? 2 : 1;
+            int p2 = 32; while (p2 < a.nacc * a.acc_cols) p2 <<= 1;
+            a.tmem_cols = p2;
+            *smem_out = smem;
+            return true;
+          }
         }
-      }
   return false;
 }
 
@@ -728,6 +893,29 @@ int arpde_conv_tc_prep_launch(const ConvDesc& d, const float* w, long long w_gs,
   return ARPDE_OK;
 }
 
+// Tensor map of the input view [N][cin][H][W] (batch stride x_bs floats, channel stride H*W): box = one full-width row of
+// `cchunk` channels.  cuTensorMapEncodeTiled comes from the driver through the runtime (no link-time libcuda dependency).
+typedef CUresult (*tc_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                 const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static int tc_encode_input_map(CUtensorMap* map, const float* x, long long x_bs, int N, int cin, int H, int W, int cchunk) {
+  static tc_encode_fn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    ARPDE_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
+    ARPDE_CHECK_ARG(p != nullptr && qres == cudaDriverEntryPointSuccess, "conv_tc: cuTensorMapEncodeTiled not available from the driver");
+    fn = (tc_encode_fn)p;
+  }
+  const cuuint64_t gdim[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)cin, (cuuint64_t)N};
+  const cuuint64_t gstr[3] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4, (cuuint64_t)x_bs * 4};
+  const cuuint32_t box[4] = {(cuuint32_t)W, 1u, (cuuint32_t)cchunk, 1u};
+  const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { arpde_set_error("conv_tc: cuTensorMapEncodeTiled failed (%d) for [%d,%d,%d,%d] stride %lld", (int)r, N, cin, H, W, x_bs); return ARPDE_ERR_CUDA; }
+  return ARPDE_OK;
+}
+
 static long long* g_tc_dbg = nullptr;
 static int g_tc_dbg_flags = 0;
 extern "C" int arpde_conv_tc_set_debug_flags(int flags) { g_tc_dbg_flags = flags; return ARPDE_OK; }
@@ -745,21 +933,27 @@ int arpde_conv_tc_launch(const ConvDesc& d, const float* x, long long x_bs, cons
   a.x = x; a.x_bs = x_bs; a.scale = scale; a.shift = shift; a.ss_gs = ss_gs; a.wprep = wprep; a.wprep_gs = wprep_gs;
   a.y = y; a.stats = stats; a.relu_in = d.relu_in; a.act = d.act; a.y_ctot = d.y_ctot; a.y_coff = d.y_coff;
   a.n_per_group = d.n_per_group; a.dbg = g_tc_dbg; a.dbg_flags = g_tc_dbg_flags;
-  a.pair = (a.sx == 2 && !a.up_w && a.kp <= 4 && (a.W & 1) == 0 && (x_bs & 1) == 0 && (((uintptr_t)x) & 7) == 0 &&
+  a.N = d.N;
+  // TMA needs a 16-byte aligned base and 16-byte multiples for every global stride; otherwise the staging warps load with LDG
+  CUtensorMap tmap;
+  memset(&tmap, 0, sizeof(tmap));
+  if (a.tma && ((((uintptr_t)x) & 15) != 0 || (x_bs & 3) != 0 || getenv("ARPDE_TC_NO_TMA"))) a.tma = 0;
+  if (a.tma) {
+    int rc = tc_encode_input_map(&tmap, x, x_bs, d.N, d.cin, d.H, d.W, a.cchunk);
+    if (rc) return rc;
+  }
+  a.pair = (!a.tma && a.sx == 2 && !a.up_w && a.kp <= 4 && (a.W & 1) == 0 && (x_bs & 1) == 0 && (((uintptr_t)x) & 7) == 0 &&
             (((long long)a.H * a.W) & 1) == 0) ? 1 : 0;
   static thread_local size_t smem_set = 0;
   if (smem > smem_set) {
     ARPDE_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     smem_set = smem;
   }
-  a.N = d.N;
   const long long items = (long long)d.N * a.ctas_per_sample;
   ARPDE_CHECK_ARG(items < (1ll << 31), "conv_tc: too many work items");
-  // persistent CTAs: two per SM when shared memory and TMEM allow it (more loads in flight while staging)
-  const int per_sm = (smem <= 112 * 1024 && a.tmem_cols <= 256) ? 2 : 1;
-  long long blocks = (long long)arpde_num_sms() * per_sm;
+  long long blocks = (long long)arpde_num_sms();       // persistent CTAs, one per SM
   if (blocks > items) blocks = items;
-  conv_tc_kernel<<<(unsigned)blocks, TC_THREADS, smem, stream>>>(a);
+  conv_tc_kernel<<<(unsigned)blocks, TC_THREADS, smem, stream>>>(a, tmap);
   ARPDE_LAUNCH_CHECK();
   return ARPDE_OK;
 }

@@ -62,7 +62,8 @@ struct ConvTcArgs {
   int cchunk, nc4_shift, ncc, tchunk, ntc, ntaps, coutP, tmem_cols;
   int patch_slot_floats, w_slot_floats, nslot_p;
   int resident;              // 1: the whole split weight image of a group stays in shared memory
-  int nacc, acc_cols;        // accumulator ring in TMEM: nacc slots of acc_cols = ntile * 2 * coutP columns
+  int nacc, acc_cols;        // accumulator ring in TMEM: nacc slots of acc_cols = ntile * tile_cols columns
+  int split_terms, tile_cols; // 1: issuer 0 issues hi*[hi;lo], issuer 1 issues lo*hi into a third column range (tile_cols = 3*coutP)
   int kp;                    // patch positions per staging thread = ceil(PHP / 256)
   int pair;                  // stride-2 layer staged with float2 loads (both x parities at once)
   int tma;                   // 1: input rows arrive by TMA into the raw ring and the staging warps convert smem -> smem
@@ -581,7 +582,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         const int oy = q / a.pitch, ox = q - oy * a.pitch;
         const bool valid = oy < a.Ho && ox < a.Wo;
         float* yp = a.y + ((long long)n * a.y_ctot + a.y_coff) * HoWo + (long long)oy * a.Wo + ox;
-        const uint32_t trow = tmem + ((uint32_t)lanebase << 16) + (uint32_t)(as * a.acc_cols + t * N2);
+        const uint32_t trow = tmem + ((uint32_t)lanebase << 16) + (uint32_t)(as * a.acc_cols + t * a.tile_cols);
         if (plain) {
           // common case (no output activation, no batch statistics): 16 columns per TMEM round trip, straight stores.
           // (ncu on the first version: the per-element activation switch + statistics branches made the 4 epilogue warps
@@ -589,6 +590,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           for (int c0 = 0; c0 < a.cout; c0 += 16) {
             float v1[16], v2[16];
             DBG_T(1, tmem_ld16(trow + c0, v1); tmem_ld16(trow + a.coutP + c0, v2); tmem_ld_wait());
+            if (a.split_terms) {          // third column range: the lo*hi products of the second issuing warp
+              float v3[16];
+              tmem_ld16(trow + 2 * a.coutP + c0, v3);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v2[j] += v3[j];
+            }
             float* pc = yp + c0 * HoWo;
             if (valid) {
               if (c0 + 16 <= a.cout) {
@@ -609,6 +617,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             tmem_ld8(trow + c0, v1);
             tmem_ld8(trow + a.coutP + c0, v2);
             tmem_ld_wait();
+            if (a.split_terms) {
+              float v3[8];
+              tmem_ld8(trow + 2 * a.coutP + c0, v3);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v2[j] += v3[j];
+            }
             for (int j = 0; j < 8; ++j) {
               const int co = c0 + j;
               float val = apply_act(v1[j] + v2[j], a.act);
@@ -685,8 +700,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             // the 14-bit address field, which never overflows), so each MMA pair costs three 64-bit adds on top of the two UTCHMMA
             const uint64_t hi64 = (uint64_t)desc_hi << 32;
             const uint32_t first_chunk = chunk == 0 ? 0u : 1u;
+            if (a.split_terms) {
+              // issuer 0: A_hi * [W_hi;W_lo] into columns [0,2N); issuer 1: A_lo * W_hi into its own range [2N,3N) -- two
+              // independent accumulation chains, so the two warps never touch the same TMEM columns
+              for (int t = 0; t < nt_item; ++t) {
+                const uint32_t d_tmem = acc_base + (uint32_t)(t * a.tile_cols) + (issuer ? 2u * (uint32_t)a.coutP : 0u);
+                const uint32_t idesc = issuer ? idesc2 : idesc1;
+                uint64_t db = hi64 | wb;
+                for (int tl = 0; tl < a.tchunk; ++tl) {
+                  const uint32_t al = (uint32_t)a.tap_aoff[tc * a.tchunk + tl] + (uint32_t)(t * 128);
+                  uint64_t da = hi64 | ((issuer ? pa_lo : pa_hi) + al);
+                  uint32_t acc = (tl == 0) ? first_chunk : 1u;
+#pragma unroll 4
+                  for (int c8 = 0; c8 < nc8; ++c8) {
+                    umma_tf32(d_tmem, da, db, idesc, acc);
+                    acc = 1u;
+                    da += 2 * PP; db += 2 * (uint32_t)N2;
+                  }
+                }
+              }
+            } else {
             for (int t = issuer; t < nt_item; t += TC_ISSUERS) {
-              const uint32_t d_tmem = acc_base + (uint32_t)(t * N2);
+              const uint32_t d_tmem = acc_base + (uint32_t)(t * a.tile_cols);
               uint64_t db = hi64 | wb;
               for (int tl = 0; tl < a.tchunk; ++tl) {
                 const uint32_t al = (uint32_t)a.tap_aoff[tc * a.tchunk + tl] + (uint32_t)(t * 128);
@@ -700,6 +735,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                   da_h += 2 * PP; da_l += 2 * PP; db += 2 * (uint32_t)N2;
                 }
               }
+            }
             }
           }
           if (!a.resident && leader) umma_commit(empty_w + ws);
@@ -822,46 +858,52 @@ static bool tc_plan(const ConvDesc& d, ConvTcArgs& a, size_t* smem_out) {
   const size_t budget = 226 * 1024;
   a.row_mode = a.up_w ? 1 : (a.sx == 2 ? 2 : 0);
   const bool tma_shape = (d.W % 4 == 0) && d.W <= 256 && ((long long)d.H * d.W) % 4 == 0;
-  // preference order: weights resident in shared memory (no re-streaming per item), double-buffered patch slots (staging overlaps
-  // the MMAs), then many M tiles per item (less halo, fewer weight passes), wide channel chunks (fewer pipeline hand-offs), wide tap chunks
+  // preference order: weights resident in shared memory (no re-streaming per item), input rows by TMA, double-buffered patch
+  // slots (staging overlaps the MMAs), then many M tiles per item (less halo, fewer weight passes), wide channel chunks (fewer
+  // pipeline hand-offs), wide tap chunks
   for (int resident = 1; resident >= 0; --resident)
-    for (int nslot_p = 2; nslot_p >= 1; --nslot_p)
-      for (int ntile = ntile_max; ntile >= 1; --ntile)
-        for (int cchunk = 32; cchunk >= 8; cchunk >>= 1) {
-          if (cchunk > 8 && cchunk > cin8) continue;
-          const int ncc = (d.cin + cchunk - 1) / cchunk;
-          if (nslot_p == 1 && ncc == 1 && ntile_max > 1) continue;      // a single slot only pays off for multi-chunk layers
-          const int rows = (a.pitch - 1 + ntile * 128 - 1) / a.pitch + 1 + span_y;
-          const int PHP = rows * a.pitch;
-          if (PHP > TC_STAGERS * TC_KP_MAX) continue;
-          int PP = a.pitch + ntile * 128 + max_off; if (PP < PHP) PP = PHP; PP = round_up(PP, 8);
-          if (PP > 16383) continue;
-          const size_t p_slot = (size_t)2 * a.nplanes * (cchunk / 4) * PP * 16;
-          const int RS = a.row_mode == 1 ? (rows >> 1) + 1 : (a.row_mode == 2 ? 2 * rows : rows);
-          const size_t raw_slot = tma_shape ? (size_t)RS * cchunk * d.W * 4 : 0;
-          for (int tchunk = a.ntaps; tchunk >= 1; --tchunk) {
-            if (a.ntaps % tchunk) continue;
-            const size_t w_slot = (size_t)tchunk * (cchunk / 4) * N2 * 16;
-            if (w_slot > 48 * 1024) continue;
-            const int ntc = a.ntaps / tchunk;
-            const size_t w_bytes = resident ? w_slot * ncc * ntc : 2 * w_slot;
-            const size_t smem = TC_SMEM_HEADER + 2 * raw_slot + nslot_p * p_slot + w_bytes;
-            if (smem > budget) continue;
-            a.resident = resident; a.ntile = ntile; a.cchunk = cchunk; a.nc4_shift = cchunk == 32 ? 3 : (cchunk == 16 ? 2 : 1);
-            a.ncc = ncc; a.tchunk = tchunk; a.ntc = ntc; a.PP = PP; a.PHP = PHP; a.nslot_p = nslot_p;
-            a.kp = (PHP + TC_STAGERS - 1) / TC_STAGERS;
-            a.patch_slot_floats = (int)(p_slot / 4); a.w_slot_floats = (int)(w_slot / 4);
-            a.tma = tma_shape ? 1 : 0; a.RS = RS; a.raw_slot_floats = (int)(raw_slot / 4);
-            a.ctas_per_sample = (total_tiles + ntile - 1) / ntile; a.total_tiles = total_tiles;
-            for (int t = 0; t < a.ntaps; ++t) a.tap_aoff[t] = a.tap_plane[t] * (cchunk / 4) * PP + a.tap_off[t];
-            a.acc_cols = ntile * N2;
-            a.nacc = 2 * a.acc_cols <= 512 ? 2 : 1;
-            int p2 = 32; while (p2 < a.nacc * a.acc_cols) p2 <<= 1;
-            a.tmem_cols = p2;
-            *smem_out = smem;
-            return true;
+    for (int use_tma = tma_shape ? 1 : 0; use_tma >= 0; --use_tma)
+      for (int nslot_p = 2; nslot_p >= 1; --nslot_p)
+        for (int ntile = ntile_max; ntile >= 1; --ntile)
+          for (int cchunk = 32; cchunk >= 8; cchunk >>= 1) {
+            if (cchunk > 8 && cchunk > cin8) continue;
+            const int ncc = (d.cin + cchunk - 1) / cchunk;
+            if (nslot_p == 1 && ncc == 1 && ntile_max > 1) continue;      // a single slot only pays off for multi-chunk layers
+            const int rows = (a.pitch - 1 + ntile * 128 - 1) / a.pitch + 1 + span_y;
+            const int PHP = rows * a.pitch;
+            if (PHP > TC_STAGERS * TC_KP_MAX) continue;
+            int PP = a.pitch + ntile * 128 + max_off; if (PP < PHP) PP = PHP; PP = round_up(PP, 8);
+            if (PP > 16383) continue;
+            const size_t p_slot = (size_t)2 * a.nplanes * (cchunk / 4) * PP * 16;
+            const int RS = a.row_mode == 1 ? (rows >> 1) + 1 : (a.row_mode == 2 ? 2 * rows : rows);
+            const size_t raw_slot = use_tma ? (size_t)RS * cchunk * d.W * 4 : 0;
+            for (int tchunk = a.ntaps; tchunk >= 1; --tchunk) {
+              if (a.ntaps % tchunk) continue;
+              const size_t w_slot = (size_t)tchunk * (cchunk / 4) * N2 * 16;
+              if (w_slot > 48 * 1024) continue;
+              const int ntc = a.ntaps / tchunk;
+              const size_t w_bytes = resident ? w_slot * ncc * ntc : 2 * w_slot;
+              const size_t smem = TC_SMEM_HEADER + 2 * raw_slot + nslot_p * p_slot + w_bytes;
+              if (smem > budget) continue;
+              a.resident = resident; a.ntile = ntile; a.cchunk = cchunk; a.nc4_shift = cchunk == 32 ? 3 : (cchunk == 16 ? 2 : 1);
+              a.ncc = ncc; a.tchunk = tchunk; a.ntc = ntc; a.PP = PP; a.PHP = PHP; a.nslot_p = nslot_p;
+              a.kp = (PHP + TC_STAGERS - 1) / TC_STAGERS;
+              a.patch_slot_floats = (int)(p_slot / 4); a.w_slot_floats = (int)(w_slot / 4);
+              a.tma = use_tma; a.RS = RS; a.raw_slot_floats = (int)(raw_slot / 4);
+              a.ctas_per_sample = (total_tiles + ntile - 1) / ntile; a.total_tiles = total_tiles;
+              for (int t = 0; t < a.ntaps; ++t) a.tap_aoff[t] = a.tap_plane[t] * (cchunk / 4) * PP + a.tap_off[t];
+              // two issuing warps: split by M tile; single-tile items split by product term (separate column range for lo*hi) when a
+              // double-buffered accumulator of 3*coutP columns fits in TMEM (measured: splitting multi-tile items by term is slower)
+              a.split_terms = (ntile == 1 && 2 * 3 * a.coutP <= 512) ? 1 : 0;
+              a.tile_cols = a.split_terms ? 3 * a.coutP : N2;
+              a.acc_cols = ntile * a.tile_cols;
+              a.nacc = 2 * a.acc_cols <= 512 ? 2 : 1;
+              int p2 = 32; while (p2 < a.nacc * a.acc_cols) p2 <<= 1;
+              a.tmem_cols = p2;
+              *smem_out = smem;
+              return true;
+            }
           }
-        }
   return false;
 }
 

@@ -11,6 +11,7 @@
 // Layout: fp32, NCHW / NCL.  Inputs may be channel-slice views of a history tensor: each input
 // carries its own batch stride (elements); channel stride is H*W (resp. L).  Outputs are compact.
 #include "common.cuh"
+#include <stdlib.h>
 #include "../../include/arpde.h"
 
 // =====================================================================================
@@ -148,8 +149,8 @@ __device__ __forceinline__ void rhs_row4(const Row4& a, const Row4& b, const Row
   for (int j = 0; j < 4; ++j) rhs_point(q[j], q[j + 1], q[j + 2], b.u[j], b.v[j], k, Ru[j], Rv[j]);
 }
 
-template <int RY, bool EDGE>
-__global__ void __launch_bounds__(256) burgers2d_fwd_vec4(const float* __restrict__ up, int64_t up_bs,
+template <int RY, bool EDGE, int MINB>
+__global__ void __launch_bounds__(256, MINB) burgers2d_fwd_vec4(const float* __restrict__ up, int64_t up_bs,
                                                           const float* __restrict__ u0, int64_t u0_bs,
                                                           float* __restrict__ ustar, double* __restrict__ sse,
                                                           int N, int H, int W, int lx_log2, B2Coef k) {
@@ -231,6 +232,114 @@ __global__ void __launch_bounds__(256) burgers2d_fwd_vec4(const float* __restric
   }
 }
 
+// ---- shared-memory tiled path (alternative, see the dispatch note in arpde_cn_burgers2d_fwd): persistent CTAs, each walks (sample, strip of TY full-width rows)
+//      items.  The (TY+2)-row tiles of u, v, u0, v0 of the NEXT item are prefetched with 16-byte cp.async (coalesced, no register
+//      staging, periodic row wrap per chunk) into the second half of a double buffer while the current item is computed, so
+//      every CTA keeps a full tile (18 KB at 64x64) in flight all the time; three CTAs per SM hold ~55 KB in flight, above
+//      the ~40 KB/SM that 6.5 TB/s x ~0.9 us of HBM latency needs.  (The register-rolling kernel above -- 120 registers, two
+//      CTAs per SM, four float4 loads in flight per thread -- stops at 52% of the measured HBM peak; a first shared-memory
+//      version that loaded, synchronised and computed each tile in sequence reached only 37%.)  Every thread then computes one
+//      float4 of ustar_u and ustar_v: rows y-1, y, y+1 as one float4 plus two wrapped halo scalars per field.  The loss
+//      reduction is per-thread accumulation over all items, warp shuffles and one double atomic per CTA.
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N_> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N_) : "memory"); }
+
+template <bool CN>
+__global__ void __launch_bounds__(256) burgers2d_fwd_smem(const float* __restrict__ up, int64_t up_bs, const float* __restrict__ u0,
+                                                          int64_t u0_bs, float* __restrict__ ustar, double* __restrict__ sse, int N,
+                                                          int H, int W, int TY, B2Coef k) {
+  extern __shared__ __align__(16) float tile_all[];      // [2 buffers][4 fields][TY+2][W]
+  const int nstrips = (H + TY - 1) / TY;
+  const int items = N * nstrips;
+  const int rows = TY + 2, w4 = W >> 2;
+  const int HW = H * W;
+  const int per_field = rows * w4, total = 4 * per_field;
+  const int fstride = rows * W, tile_floats = 4 * fstride;
+
+  auto prefetch = [&](int it, float* tile) {
+    const int n = it / nstrips, y0 = (it - n * nstrips) * TY;
+    const float* up_n = up + (int64_t)n * up_bs;
+    const float* u0_n = u0 + (int64_t)n * u0_bs;
+    for (int i = threadIdx.x; i < total; i += 256) {
+      const int f = i / per_field, r = (i - f * per_field) / w4, c = i - f * per_field - r * w4;
+      const int y = wrap(y0 - 1 + r, H);                  // rows y0-1 .. y0+TY of the periodic field
+      const float* sp = (f < 2 ? up_n : u0_n) + (f & 1) * HW;
+      cp_async16(reinterpret_cast<float4*>(tile) + i, reinterpret_cast<const float4*>(sp + (size_t)y * W) + c);
+    }
+  };
+
+  float acc = 0.f;
+  int buf = 0;
+  int it = blockIdx.x;
+  if (it < items) prefetch(it, tile_all);
+  cp_async_commit();
+  for (; it < items; it += gridDim.x) {
+    const int nxt = it + gridDim.x;
+    if (nxt < items) prefetch(nxt, tile_all + (buf ^ 1) * tile_floats);
+    cp_async_commit();
+    cp_async_wait<1>();                                   // everything but the newest group (the next item) has landed
+    __syncthreads();
+    const float* tile = tile_all + buf * tile_floats;
+    const int n = it / nstrips, y0 = (it - n * nstrips) * TY;
+    for (int i = threadIdx.x; i < TY * w4; i += 256) {
+      const int r = i / w4, c = i - r * w4;
+      const int y = y0 + r;
+      if (y >= H) continue;
+      const int x0 = c << 2, xl = (x0 == 0 ? W : x0) - 1, xr = x0 + 4 == W ? 0 : x0 + 4;
+      float Ru[4], Rv[4], R0u[4] = {0, 0, 0, 0}, R0v[4] = {0, 0, 0, 0};
+      float ub[4], vb[4], u0b[4], v0b[4];
+#pragma unroll
+      for (int pass = 0; pass < (CN ? 2 : 1); ++pass) {
+        const float* tu = tile + (2 * pass) * fstride + r * W;     // rows r, r+1, r+2 of the tile = y-1, y, y+1
+        const float* tv = tu + fstride;
+        float U[3][6], V[3][6];
+#pragma unroll
+        for (int rr = 0; rr < 3; ++rr) {
+          const float4 a = *reinterpret_cast<const float4*>(tu + rr * W + x0);
+          const float4 b = *reinterpret_cast<const float4*>(tv + rr * W + x0);
+          U[rr][0] = tu[rr * W + xl]; U[rr][1] = a.x; U[rr][2] = a.y; U[rr][3] = a.z; U[rr][4] = a.w; U[rr][5] = tu[rr * W + xr];
+          V[rr][0] = tv[rr * W + xl]; V[rr][1] = b.x; V[rr][2] = b.y; V[rr][3] = b.z; V[rr][4] = b.w; V[rr][5] = tv[rr * W + xr];
+        }
+        Col6 q[6];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) q[j] = colq(U[0][j], U[1][j], U[2][j], V[0][j], V[1][j], V[2][j]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (pass == 0) { rhs_point(q[j], q[j + 1], q[j + 2], U[1][j + 1], V[1][j + 1], k, Ru[j], Rv[j]); ub[j] = U[1][j + 1]; vb[j] = V[1][j + 1]; }
+          else { rhs_point(q[j], q[j + 1], q[j + 2], U[1][j + 1], V[1][j + 1], k, R0u[j], R0v[j]); u0b[j] = U[1][j + 1]; v0b[j] = V[1][j + 1]; }
+        }
+      }
+      if (!CN) {
+        const float4 a = *reinterpret_cast<const float4*>(tile + 2 * fstride + (r + 1) * W + x0);
+        const float4 b = *reinterpret_cast<const float4*>(tile + 3 * fstride + (r + 1) * W + x0);
+        u0b[0] = a.x; u0b[1] = a.y; u0b[2] = a.z; u0b[3] = a.w; v0b[0] = b.x; v0b[1] = b.y; v0b[2] = b.z; v0b[3] = b.w;
+      }
+      float Su[4], Sv[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        Su[j] = fmaf(k.c, Ru[j] + R0u[j], u0b[j]); Sv[j] = fmaf(k.c, Rv[j] + R0v[j], v0b[j]);
+        const float du = Su[j] - ub[j], dv = Sv[j] - vb[j];
+        acc = fmaf(du, du, fmaf(dv, dv, acc));
+      }
+      if (ustar) {
+        float* o = ustar + (int64_t)n * 2 * HW + (size_t)y * W + x0;
+        *reinterpret_cast<float4*>(o) = make_float4(Su[0], Su[1], Su[2], Su[3]);
+        *reinterpret_cast<float4*>(o + HW) = make_float4(Sv[0], Sv[1], Sv[2], Sv[3]);
+      }
+    }
+    __syncthreads();                                      // the buffer is refilled by the prefetch of the next iteration
+    buf ^= 1;
+  }
+  cp_async_wait<0>();
+  if (sse) {
+    const double t = block_sum_d((double)acc);
+    if (threadIdx.x == 0) atomicAdd(sse, t);
+  }
+}
+
 // ---- adjoint, generic: one thread per point.  With G = dL/dustar (gu,gv):
 //   d/du = c [ u gh(gu) + gv(v gu) + nu L(gu) - gv_ gh(v) ],  d/dv = c [ -gu gv(u) + gh(u gv_) + v gv(gv_) + nu L(gv_) ]
 //   (gh, gv antisymmetric => adjoint = -gh, -gv; L symmetric), plus identity G onto uPred0.
@@ -299,15 +408,47 @@ extern "C" int arpde_cn_burgers2d_fwd(const float* uPred, int64_t up_bstride, co
   const bool pow2 = w4 > 0 && (w4 & (w4 - 1)) == 0;
   const bool vec_ok = (W % 4 == 0) && H >= 2 && aligned16(uPred) && aligned16(uPred0) && (!ustar || aligned16(ustar)) &&
                       up_bstride % 4 == 0 && u0_bstride % 4 == 0 && (pow2 || w4 % 32 == 0);
-  if (vec_ok) {
-    constexpr int RY = 8;
+  const bool base_ok = (W % 4 == 0) && aligned16(uPred) && aligned16(uPred0) && (!ustar || aligned16(ustar)) && up_bstride % 4 == 0 &&
+                       u0_bstride % 4 == 0 && (int64_t)H * W % 4 == 0;
+  int TY = W > 0 ? 1024 / W : 0; if (TY > H) TY = H;
+  const size_t tile_bytes = (size_t)2 * 4 * (TY + 2) * W * sizeof(float);   // double buffer
+  // Dispatch: the register-rolling kernel (RY = 4 rows per thread, 120 registers, no spills) is the measured best at 64x64
+  // (3.96 TB/s = 60% of the measured HBM peak; RY = 8: 3.4, RY = 2: 3.6; forcing 3 CTAs/SM spills and loses 6%); the
+  // shared-memory tiled kernel is issue-bound (ncu: 70% issue-active, 2.2x the instructions, 48% of its shared-memory wavefronts
+  // are bank conflicts of the halo scalars) and reaches 2.75 TB/s -- it serves widths the rolling kernel's lane mapping cannot
+  // (W/4 neither a power of two nor a multiple of 32) and is selectable with ARPDE_STENCIL_SMEM=1 for A/B runs.
+  static const bool force_smem = getenv("ARPDE_STENCIL_SMEM") != nullptr;
+  if (base_ok && TY >= 1 && tile_bytes <= 96 * 1024 && (force_smem || !vec_ok)) {
+    const int nstrips = (H + TY - 1) / TY;
+    const int64_t items = (int64_t)N * nstrips;
+    ARPDE_CHECK_ARG(items < (1ll << 31), "burgers2d_fwd: too many strips");
+    int per_sm = (int)((200 * 1024) / (tile_bytes + 1024)); if (per_sm > 4) per_sm = 4; if (per_sm < 1) per_sm = 1;
+    int64_t blocks = (int64_t)arpde_num_sms() * per_sm; if (blocks > items) blocks = items;
+    if (k.cn) {
+      if (tile_bytes > 40 * 1024) ARPDE_CUDA(cudaFuncSetAttribute(burgers2d_fwd_smem<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes));
+      burgers2d_fwd_smem<true><<<(unsigned)blocks, 256, tile_bytes, (cudaStream_t)stream_>>>(uPred, up_bstride, uPred0, u0_bstride, ustar, sse_out, N, H, W, TY, k);
+    } else {
+      if (tile_bytes > 40 * 1024) ARPDE_CUDA(cudaFuncSetAttribute(burgers2d_fwd_smem<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes));
+      burgers2d_fwd_smem<false><<<(unsigned)blocks, 256, tile_bytes, (cudaStream_t)stream_>>>(uPred, up_bstride, uPred0, u0_bstride, ustar, sse_out, N, H, W, TY, k);
+    }
+  } else if (vec_ok) {
+    static const int ry_env = getenv("ARPDE_STENCIL_RY") ? atoi(getenv("ARPDE_STENCIL_RY")) : 0;
+    const int RY = ry_env ? ry_env : 4;
+    static const int minb = getenv("ARPDE_STENCIL_MINB") ? atoi(getenv("ARPDE_STENCIL_MINB")) : 2;
     int lx_log2 = 0; while ((1 << lx_log2) < (w4 < 32 ? w4 : 32)) ++lx_log2;
     const bool edge = w4 > 32;
     const int G = 32 >> lx_log2, segs = w4 >> lx_log2, nstrips = (H + RY - 1) / RY;
     const int64_t ngroups = (int64_t)N * nstrips * segs, nwarps = ceil_div64(ngroups, G);
     const int64_t blocks = ceil_div64(nwarps, 8);
-    if (edge) burgers2d_fwd_vec4<RY, true><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream_>>>(uPred, up_bstride, uPred0, u0_bstride, ustar, sse_out, N, H, W, lx_log2, k);
-    else burgers2d_fwd_vec4<RY, false><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream_>>>(uPred, up_bstride, uPred0, u0_bstride, ustar, sse_out, N, H, W, lx_log2, k);
+#define LAUNCH_ROLL(RY_)                                                                                                                  \
+    do {                                                                                                                                  \
+      if (edge) burgers2d_fwd_vec4<RY_, true, 1><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream_>>>(uPred, up_bstride, uPred0, u0_bstride, ustar, sse_out, N, H, W, lx_log2, k); \
+      else if (minb == 2) burgers2d_fwd_vec4<RY_, false, 2><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream_>>>(uPred, up_bstride, uPred0, u0_bstride, ustar, sse_out, N, H, W, lx_log2, k);    \
+      else if (minb == 4) burgers2d_fwd_vec4<RY_, false, 4><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream_>>>(uPred, up_bstride, uPred0, u0_bstride, ustar, sse_out, N, H, W, lx_log2, k);    \
+      else burgers2d_fwd_vec4<RY_, false, 3><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream_>>>(uPred, up_bstride, uPred0, u0_bstride, ustar, sse_out, N, H, W, lx_log2, k);    \
+    } while (0)
+    if (RY == 2) LAUNCH_ROLL(2); else if (RY == 3) LAUNCH_ROLL(3); else if (RY == 4) LAUNCH_ROLL(4); else if (RY == 5) LAUNCH_ROLL(5); else if (RY == 6) LAUNCH_ROLL(6); else LAUNCH_ROLL(8);
+#undef LAUNCH_ROLL
   } else {
     const int64_t total = (int64_t)N * H * W;
     int64_t blocks = ceil_div64(total, 256); const int64_t cap = (int64_t)arpde_num_sms() * 32; if (blocks > cap) blocks = cap;

@@ -88,10 +88,17 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// Wait for the phase with the given parity.  A failed probe backs off with nanosleep: ncu showed 286 M SYNCS (try_wait)
+// warp-instructions against 3.7 M UTCHMMA in one In_conv3 launch -- sixteen spinning warps hammering the shared-memory
+// pipe that the tensor core's operand fetch and the staging warps are bound by.
+template <int SLEEP_NS = 32>
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   uint32_t done = 0;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+               : "=r"(done) : "r"(addr), "r"(parity) : "memory");
   while (!done) {
+    __nanosleep(SLEEP_NS);
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
                  : "=r"(done) : "r"(addr), "r"(parity) : "memory");
   }
@@ -574,7 +581,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       const int n = it / a.ctas_per_sample, b = it - n * a.ctas_per_sample;
       const int q0 = b * a.ntile * 128;
       const int as = lit % a.nacc, ak = lit / a.nacc;
-      DBG_T(0, mbar_wait(tmem_full + as, ak & 1));
+      DBG_T(0, mbar_wait<128>(tmem_full + as, ak & 1));
       tc_fence_after();
       const int nt_item = min(a.ntile, a.total_tiles - b * a.ntile);        // the last item of a sample may hold fewer M tiles
       for (int t = 0; t < ((a.dbg_flags & 2) ? 0 : nt_item); ++t) {
@@ -759,7 +766,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         if (a.resident) {
           // follow every accumulator hand-off in order (an mbarrier parity wait is only meaningful one phase behind), so that at a
           // group change all MMAs that read the old weight image are known to be complete
-          if (lit > 0) { const int pl_ = lit - 1; mbar_wait(tmem_full + (pl_ % a.nacc), (pl_ / a.nacc) & 1); }
+          if (lit > 0) { const int pl_ = lit - 1; mbar_wait<256>(tmem_full + (pl_ % a.nacc), (pl_ / a.nacc) & 1); }
           if (g != g_loaded) {
             mbar_arrive_expect_tx(wres_full, (uint32_t)nchunks * w_slot_bytes);
             for (int c = 0; c < nchunks; ++c)
@@ -770,7 +777,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           for (int c = 0; c < nchunks; ++c) {
             const int wseq = lit * nchunks + c;
             const int ws = wseq & 1, wk = wseq >> 1;
-            if (wk > 0) mbar_wait(empty_w + ws, (wk - 1) & 1);
+            if (wk > 0) mbar_wait<128>(empty_w + ws, (wk - 1) & 1);
             mbar_arrive_expect_tx(full_w + ws, w_slot_bytes);
             bulk_g2s(wbuf + (size_t)ws * a.w_slot_floats, wsrc + (size_t)c * a.w_slot_floats, w_slot_bytes, full_w + ws);
           }
@@ -790,7 +797,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         for (int cc = 0; cc < a.ncc; ++cc) {
           const int rseq = lit * a.ncc + cc;
           const int rs = rseq & 1, rk = rseq >> 1;
-          if (rk > 0) mbar_wait(raw_empty + rs, (rk - 1) & 1);
+          if (rk > 0) mbar_wait<128>(raw_empty + rs, (rk - 1) & 1);
           if (lane == 0) mbar_arrive_expect_tx(raw_full + rs, (uint32_t)a.RS * row_bytes);
           __syncwarp();
           float* dst = raw + (size_t)rs * a.raw_slot_floats;

@@ -136,8 +136,7 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t
   asm volatile(
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
-      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
-      : "memory");
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate));   // no "memory" clobber: it made ptxas reload every kernel parameter per MMA
 }
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
   uint32_t r[8];
@@ -668,32 +667,36 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     const uint32_t a_lo_base = (smem_u32(patch) >> 4) | (PP << 16);
     const uint32_t b_lo_base = (smem_u32(wbuf) >> 4) | ((uint32_t)N2 << 16);
     const uint32_t slot16 = (uint32_t)a.patch_slot_floats >> 2, w_slot16 = (uint32_t)a.w_slot_floats >> 2;
+    // loop-invariant parameters in registers (ncu: the per-tap loop spent most of its ~290 cycles re-reading them from the constant bank)
+    const int tchunk = a.tchunk, ntc = a.ntc, ncc = a.ncc, nslot_p = a.nslot_p, nacc = a.nacc, resident = a.resident, split_terms = a.split_terms;
+    const uint32_t coutP = (uint32_t)a.coutP, tile_cols = (uint32_t)a.tile_cols, acc_cols = (uint32_t)a.acc_cols, b_step = 2u * (uint32_t)N2;
     int g_loaded = -1, wgen = 0;
     const bool dbg_on = a.dbg != nullptr && blockIdx.x == 0 && leader && issuer == 0;
     long long dbg_acc[4] = {0, 0, 0, 0};
     const long long dbg_t0 = dbg_on ? clock64() : 0;
+    // item coordinates are advanced incrementally (five runtime integer divisions per item cost the single issuing lane ~10% of In_conv1)
+    const int cps = a.ctas_per_sample, npg = a.n_per_group, ntile = a.ntile, total_tiles = a.total_tiles, pitch = a.pitch;
+    int n = it_begin / cps, b = it_begin - n * cps, g = n / npg, n_in_g = n - g * npg;
+    int pseq = 0;
     for (int it = it_begin; it < it_end; ++it) {
       const int lit = it - it_begin;
-      const int n = it / a.ctas_per_sample, b = it - n * a.ctas_per_sample;
-      const int g = n / a.n_per_group;
-      const int q0 = b * a.ntile * 128;
-      const uint32_t qlocal0 = (uint32_t)(q0 - (q0 / a.pitch) * a.pitch);
-      const int nt_item = min(a.ntile, a.total_tiles - b * a.ntile);
-      const int as = lit % a.nacc, ak = lit / a.nacc;
+      const int q0 = b * ntile * 128;
+      const uint32_t qlocal0 = (uint32_t)(q0 % pitch);
+      const int nt_item = min(ntile, total_tiles - b * ntile);
+      const int as = nacc == 2 ? (lit & 1) : 0, ak = nacc == 2 ? (lit >> 1) : lit;
       if (ak > 0) DBG_T(0, mbar_wait(tmem_empty + as, (ak - 1) & 1));
-      if (a.resident && g != g_loaded) { DBG_T(2, mbar_wait(wres_full, wgen & 1)); ++wgen; g_loaded = g; }
+      if (resident && g != g_loaded) { DBG_T(2, mbar_wait(wres_full, wgen & 1)); ++wgen; g_loaded = g; }
       tc_fence_after();
-      const uint32_t acc_base = tmem + (uint32_t)(as * a.acc_cols);
-      for (int cc = 0; cc < a.ncc; ++cc) {
-        const int pseq = lit * a.ncc + cc;
-        const int ps = pseq % a.nslot_p, pk = pseq / a.nslot_p;
+      const uint32_t acc_base = tmem + (uint32_t)as * acc_cols;
+      for (int cc = 0; cc < ncc; ++cc, ++pseq) {
+        const int ps = nslot_p == 2 ? (pseq & 1) : 0, pk = nslot_p == 2 ? (pseq >> 1) : pseq;
         DBG_T(1, mbar_wait(full_p + ps, pk & 1));
         const uint32_t pa_hi = a_lo_base + (uint32_t)ps * slot16 + qlocal0, pa_lo = pa_hi + (slot16 >> 1);
-        for (int tc = 0; tc < a.ntc; ++tc) {
-          const int chunk = cc * a.ntc + tc;
+        for (int tc = 0; tc < ntc; ++tc) {
+          const int chunk = cc * ntc + tc;
           uint32_t wb;
           int ws = 0;
-          if (a.resident) {
+          if (resident) {
             wb = b_lo_base + (uint32_t)chunk * w_slot16;
           } else {
             const int wseq = lit * nchunks + chunk;
@@ -702,56 +705,64 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             wb = b_lo_base + (uint32_t)ws * w_slot16;
           }
           tc_fence_after();
+          const long long t_iss = dbg_on ? clock64() : 0;
           if (leader && !(a.dbg_flags & 4)) {
-            // one elected lane walks (tile, tap, 8-channel group); 64-bit descriptors are advanced in place (low word only carries
-            // the 14-bit address field, which never overflows), so each MMA pair costs three 64-bit adds on top of the two UTCHMMA
+            // one elected lane walks (tile, tap, 8-channel group); 64-bit descriptors are advanced in place (the low word only carries
+            // the 14-bit address field, which never overflows); the next tap's offset is fetched one iteration ahead
             const uint64_t hi64 = (uint64_t)desc_hi << 32;
             const uint32_t first_chunk = chunk == 0 ? 0u : 1u;
-            if (a.split_terms) {
+            const int tap0 = tc * tchunk;
+            if (split_terms) {
               // issuer 0: A_hi * [W_hi;W_lo] into columns [0,2N); issuer 1: A_lo * W_hi into its own range [2N,3N) -- two
               // independent accumulation chains, so the two warps never touch the same TMEM columns
+              const uint32_t idesc = issuer ? idesc2 : idesc1;
+              const uint32_t pa = issuer ? pa_lo : pa_hi;
               for (int t = 0; t < nt_item; ++t) {
-                const uint32_t d_tmem = acc_base + (uint32_t)(t * a.tile_cols) + (issuer ? 2u * (uint32_t)a.coutP : 0u);
-                const uint32_t idesc = issuer ? idesc2 : idesc1;
+                const uint32_t d_tmem = acc_base + (uint32_t)t * tile_cols + (issuer ? 2u * coutP : 0u);
                 uint64_t db = hi64 | wb;
-                for (int tl = 0; tl < a.tchunk; ++tl) {
-                  const uint32_t al = (uint32_t)a.tap_aoff[tc * a.tchunk + tl] + (uint32_t)(t * 128);
-                  uint64_t da = hi64 | ((issuer ? pa_lo : pa_hi) + al);
+                uint32_t al_next = (uint32_t)a.tap_aoff[tap0];
+                for (int tl = 0; tl < tchunk; ++tl) {
+                  uint64_t da = hi64 | (pa + al_next + (uint32_t)(t * 128));
+                  if (tl + 1 < tchunk) al_next = (uint32_t)a.tap_aoff[tap0 + tl + 1];
                   uint32_t acc = (tl == 0) ? first_chunk : 1u;
 #pragma unroll 4
                   for (int c8 = 0; c8 < nc8; ++c8) {
                     umma_tf32(d_tmem, da, db, idesc, acc);
                     acc = 1u;
-                    da += 2 * PP; db += 2 * (uint32_t)N2;
+                    da += 2 * PP; db += b_step;
                   }
                 }
               }
             } else {
-            for (int t = issuer; t < nt_item; t += TC_ISSUERS) {
-              const uint32_t d_tmem = acc_base + (uint32_t)(t * a.tile_cols);
-              uint64_t db = hi64 | wb;
-              for (int tl = 0; tl < a.tchunk; ++tl) {
-                const uint32_t al = (uint32_t)a.tap_aoff[tc * a.tchunk + tl] + (uint32_t)(t * 128);
-                uint64_t da_h = hi64 | (pa_hi + al), da_l = hi64 | (pa_lo + al);
-                uint32_t acc = (tl == 0) ? first_chunk : 1u;
+              for (int t = issuer; t < nt_item; t += TC_ISSUERS) {
+                const uint32_t d_tmem = acc_base + (uint32_t)t * tile_cols;
+                uint64_t db = hi64 | wb;
+                uint32_t al_next = (uint32_t)a.tap_aoff[tap0];
+                for (int tl = 0; tl < tchunk; ++tl) {
+                  const uint32_t al = al_next + (uint32_t)(t * 128);
+                  if (tl + 1 < tchunk) al_next = (uint32_t)a.tap_aoff[tap0 + tl + 1];
+                  uint64_t da_h = hi64 | (pa_hi + al), da_l = hi64 | (pa_lo + al);
+                  uint32_t acc = (tl == 0) ? first_chunk : 1u;
 #pragma unroll 2
-                for (int c8 = 0; c8 < nc8; ++c8) {
-                  umma_tf32(d_tmem, da_h, db, idesc1, acc);                            // hi * [hi;lo]
-                  umma_tf32(d_tmem + (uint32_t)a.coutP, da_l, db, idesc2, 1u);         // lo * hi -> correction half
-                  acc = 1u;
-                  da_h += 2 * PP; da_l += 2 * PP; db += 2 * (uint32_t)N2;
+                  for (int c8 = 0; c8 < nc8; ++c8) {
+                    umma_tf32(d_tmem, da_h, db, idesc1, acc);                  // hi * [hi;lo]
+                    umma_tf32(d_tmem + coutP, da_l, db, idesc2, 1u);           // lo * hi -> correction half
+                    acc = 1u;
+                    da_h += 2 * PP; da_l += 2 * PP; db += b_step;
+                  }
                 }
               }
             }
-            }
           }
-          if (!a.resident && leader) umma_commit(empty_w + ws);
+          if (dbg_on) dbg_acc[3] += clock64() - t_iss;
+          if (!resident && leader) umma_commit(empty_w + ws);
         }
         if (leader) umma_commit(empty_p + ps);
       }
       if (leader) umma_commit(tmem_full + as);
+      if (++b == cps) { b = 0; ++n; if (++n_in_g == npg) { n_in_g = 0; ++g; } }
     }
-    if (dbg_on) { a.dbg[8] = clock64() - dbg_t0; a.dbg[9] = dbg_acc[0]; a.dbg[10] = dbg_acc[1]; a.dbg[11] = dbg_acc[2]; a.dbg[12] = it_end - it_begin; }
+    if (dbg_on) { a.dbg[8] = clock64() - dbg_t0; a.dbg[9] = dbg_acc[0]; a.dbg[10] = dbg_acc[1]; a.dbg[11] = dbg_acc[2]; a.dbg[12] = it_end - it_begin; a.dbg[15] = dbg_acc[3]; }
     __syncwarp();
   } else if (warp == TC_WARP_WPROD) {
     // =============================== weight copy warp ===============================

@@ -354,16 +354,20 @@ def main():
                 'h2d_bytes_per_step': ic_host.numel() * 4, 'd2h_bytes_per_step': 2 * mean_host.numel() * 4},
         'roofline': {'kernel': 'conv_tc_kernel on In_conv3 (96->48, 3x3/s2, 1920 samples): tcgen05 implicit GEMM, 3xTF32 split (+ its weight-split launch)',
                      'bound': 'tensor', 'achieved': k1_tflops, 'peak': peaks['bf16_tflops'], 'unit': 'TFLOP/s', 'frac': k1_tflops / peaks['bf16_tflops'],
-                     'traffic': None, 'peak_source': peaks['source'] + ' bf16 dense (burst)',
+                     'traffic': 3.917e9, 'traffic_source': 'ncu --set full, profiles/r01b_conv_tc_ncu_full.md: dram read 3.542 GB + write 0.375 GB per launch '
+                                                           '(algorithmic input + output 3.40 GB; the excess is halo rows re-read past L2)',
+                     'peak_source': peaks['source'] + ' bf16 dense (burst)',
                      'note': 'achieved = algorithmic fp32 FLOPs (2*N*Ho*Wo*cout*cin*k^2) / CUDA-event time; the 1e-5 parity contract needs the 3-term '
                              'TF32 split (3 tensor MACs per algorithmic MAC) and TF32 runs at half the bf16 rate, so the attainable ceiling is '
                              'peak/6 = %.0f TFLOP/s -> frac_of_3xtf32_ceiling %.3f' % (peaks['bf16_tflops'] / 6, k1_tflops / (peaks['bf16_tflops'] / 6)),
                      'flops_per_launch': k1_flops, 'ms': k1_ms,
                      'ar_step': {'ms': step_ms, 'tflops': conv_tflops, 'flops': NT * MODEL_MFLOP * 1e6,
                                  'what': 'all 9 convs of one AR step (8 on conv_tc_kernel, the 16->2 output conv on the fp32 FFMA kernel)'}},
-        'roofline_stencil': {'kernel': 'burgers2d_fwd_vec4 (fused periodic stencil + Crank-Nicolson, API form)', 'bound': 'hbm',
+        'roofline_stencil': {'kernel': 'burgers2d_fwd_vec4<RY=4> (fused periodic stencil + Crank-Nicolson, API form: read uPred, uPred0, write ustar)', 'bound': 'hbm',
                              'achieved': k2_gbs, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': k2_gbs / peaks['hbm_gbs'],
-                             'traffic': None, 'bytes_per_launch': k2_bytes, 'ms': k2_ms, 'peak_source': peaks['source']},
+                             'traffic': 1.601e8, 'traffic_source': 'ncu --set full, profiles/r01b_stencil_ncu_full.md: dram read 125.9 MB + write 34.2 MB '
+                                                                   '(the rest of the 62.9 MB of ustar was still in L2 at kernel end)',
+                             'bytes_per_launch': k2_bytes, 'ms': k2_ms, 'peak_source': peaks['source']},
     }
     if not args.no_cpu_baseline:
         S, N, T = 2, 64, 4

@@ -56,8 +56,8 @@ for name, cin, cout, k, s, up, H, relu in LAYERS:
     run('arpde_conv_fwd_tc', x, w, sc, sh, y, NB, cin, H, cout, k, s, up, relu, scratch); torch.cuda.synchronize()
     L.lib.arpde_conv_tc_set_debug(0)
     d = dbg.cpu().tolist(); it = max(d[12], 1)
-    print('   per item (clk): stager total %d wait_empty %d store %d fence %d load_issue %d enter %d | epi total %d wait_full %d tmem_ld %d | issuer total %d wait_tmem_empty %d wait_full_p %d wait_w %d  (items %d)' % (
-        d[0] // it, d[1] // it, d[2] // it, d[3] // it, d[13] // it, d[14] // it, d[4] // it, d[5] // it, d[6] // it, d[8] // it, d[9] // it, d[10] // it, d[11] // it, d[12]))
+    print('   per item (clk): stager total %d wait_empty %d store %d fence %d load_issue %d enter %d | epi total %d wait_full %d tmem_ld %d | issuer total %d wait_tmem_empty %d wait_full_p %d wait_w %d issue_block %d (items %d)' % (
+        d[0] // it, d[1] // it, d[2] // it, d[3] // it, d[13] // it, d[14] // it, d[4] // it, d[5] // it, d[6] // it, d[8] // it, d[9] // it, d[10] // it, d[11] // it, d[15] // it, d[12]))
     print('%-9s N=%d  ffma %.3f ms (%.1f TF/s) err %.2e | tc %.3f ms (%.1f TF/s) err %.2e' % (
         name, NB, ms['arpde_conv_fwd'], fl / ms['arpde_conv_fwd'] / 1e9, errs['arpde_conv_fwd'],
         ms['arpde_conv_fwd_tc'], fl / ms['arpde_conv_fwd_tc'] / 1e9, errs['arpde_conv_fwd_tc']), flush=True)

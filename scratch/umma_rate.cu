@@ -5,7 +5,7 @@
 #include <cstdlib>
 #include <cstdint>
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__global__ void __launch_bounds__(512) rate(long long* out, int N, int n_mma, int layout, int distinct, int shiftA, int lboA) {
+__global__ void __launch_bounds__(512) rate(long long* out, int N, int n_mma, int layout, int distinct, int shiftA, int lboA, int boff) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(8) uint64_t mbar;
@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(512) rate(long long* out, int N, int n_mma, in
     else if (layout == 2) { lbo = 16; sbo = 512; }
     else { lbo = 16; sbo = 1024; }
     const uint32_t hi = ((sbo >> 4) & 0x3FFF) | (1u << 14) | (lt << 29);
-    const uint32_t a0 = smem_u32(smem) + (uint32_t)shiftA, b0 = smem_u32(smem) + 96 * 1024;
+    const uint32_t a0 = smem_u32(smem) + (uint32_t)shiftA, b0 = smem_u32(smem) + (uint32_t)boff;
     const uint64_t da = ((uint64_t)hi << 32) | ((a0 >> 4) & 0x3FFF) | ((((lboA ? (uint32_t)lboA : lbo) >> 4) & 0x3FFF) << 16);
     const uint64_t db = ((uint64_t)hi << 32) | ((b0 >> 4) & 0x3FFF) | (((lbo >> 4) & 0x3FFF) << 16);
     const uint64_t da2 = da + (distinct ? 512 : 0), db2 = db + (distinct ? 512 : 0);
@@ -96,7 +96,7 @@ int main(int argc, char** argv) {
   int nthreads = getenv("NT") ? atoi(getenv("NT")) : 128; int layout = atoi(argv[1]), N = atoi(argv[2]), n = atoi(argv[3]), distinct = argc > 4 ? atoi(argv[4]) : 1, shiftA = argc > 5 ? atoi(argv[5]) : 0, lboA = argc > 6 ? atoi(argv[6]) : 0;
   long long* d; cudaMalloc(&d, 8);
   cudaFuncSetAttribute(rate, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  for (int rep = 0; rep < 2; ++rep) rate<<<148, nthreads, 200 * 1024>>>(d, N, n, layout, distinct, shiftA, lboA);
+  for (int rep = 0; rep < 2; ++rep) rate<<<148, nthreads, 200 * 1024>>>(d, N, n, layout, distinct, shiftA, lboA, getenv("BOFF") ? atoi(getenv("BOFF")) : 96 * 1024);
   cudaError_t e = cudaDeviceSynchronize();
   long long h = 0; cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
   printf("shiftA=%d lboA=%d layout=%d N=%3d distinct=%d: %s  %.1f clk/MMA (floor %d)\n", shiftA, lboA, layout, N, distinct, cudaGetErrorString(e), (double)h / n, 128 * N / 256);

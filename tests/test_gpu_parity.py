@@ -217,6 +217,44 @@ def test_densed_generic_topology_vs_oracle():
             assert rel_err(v, sd['features.' + k]) < TOL, k
 
 
+def test_densed_wide_config_c5_vs_oracle():
+    """BASELINE.json configs[4] (C5): wide DenseED (growth 32, init_features 96) on a larger periodic grid -- every layer but the
+    output conv runs on the tensor-core kernel (N up to 96, K up to 1296).  128x128 instead of 256x256 keeps the fp32 CPU oracle
+    to a few seconds; eval and train mode (batch statistics from the tensor-core epilogue), plus backward through it."""
+    torch.manual_seed(5)
+    m = M.CLS['burgers2d'](6, 2, [4], growth_rate=32, init_features=96).to(DEV)
+    with torch.no_grad():
+        for mod in m.modules():
+            if hasattr(mod, 'running_var'):
+                mod.running_mean.uniform_(-0.2, 0.2); mod.running_var.uniform_(0.5, 1.5)
+                mod.weight.uniform_(0.5, 1.5); mod.bias.uniform_(-0.2, 0.2)
+    x = torch.randn(2, 6, 128, 128, device=DEV)
+    sd = {'features.' + k: v.detach().cpu().clone() for k, v in m.features.state_dict().items()}
+    for training in (False, True):
+        m.train(training)
+        with torch.no_grad():
+            y = m(x)
+        ref = O.densed_forward('burgers2d', sd, x.cpu(), [4], training=training)
+        assert y.shape == ref.shape == (2, 2, 128, 128)
+        assert rel_err(y, ref) < TOL
+    # gradients through the tensor-core forward (eval mode) against fp64 oracle autograd, on a 64x64 input: max-norm gradient
+    # comparisons are ReLU-kink sensitive (a 1e-6 forward difference flips the mask of a handful of the 3.1 M pre-activations at
+    # 128x128, each flip moves one pixel of dO by its full value), so the larger grid is checked in the forward direction only
+    m.eval()
+    xs = x[:, :, :64, :64].contiguous()
+    xg = xs.clone().requires_grad_(True)
+    (m(xg) ** 2).sum().backward()
+    sd64 = {k: v.double().requires_grad_(v.dtype.is_floating_point and 'running' not in k) if v.dtype.is_floating_point else v for k, v in sd.items()}
+    for k, v in m.features.state_dict().items():      # running stats were updated by the train-mode call above
+        if 'running' in k or 'num_batches' in k:
+            sd64['features.' + k] = v.detach().cpu().double() if v.dtype.is_floating_point else v.detach().cpu()
+    x64 = xs.cpu().double().requires_grad_(True)
+    (O.densed_forward('burgers2d', sd64, x64, [4], training=False) ** 2).sum().backward()
+    assert rel_err(xg.grad, x64.grad) < 2e-5
+    for name, p_ in m.features.named_parameters():
+        assert rel_err(p_.grad, sd64['features.' + name].grad) < 2e-5, name
+
+
 def test_forward_test_walks_modules():
     g, cfg, args, model, bayes, swag = M.build('burgers2d', DEV)
     M.load_golden_weights(bayes, g)

@@ -879,11 +879,15 @@ static bool tc_plan(const ConvDesc& d, ConvTcArgs& a, size_t* smem_out) {
   // preference order: weights resident in shared memory (no re-streaming per item), input rows by TMA, double-buffered patch
   // slots (staging overlaps the MMAs), then many M tiles per item (less halo, fewer weight passes), wide channel chunks (fewer
   // pipeline hand-offs), wide tap chunks
+  // experiment hook: ARPDE_TC_FORCE="nslot_p,ntile,cchunk" restricts the search (0 = free) -- used for A/B timing only
+  int f_slot = 0, f_ntile = 0, f_cchunk = 0;
+  if (const char* e = getenv("ARPDE_TC_FORCE")) sscanf(e, "%d,%d,%d", &f_slot, &f_ntile, &f_cchunk);
   for (int resident = 1; resident >= 0; --resident)
     for (int use_tma = tma_shape ? 1 : 0; use_tma >= 0; --use_tma)
       for (int nslot_p = 2; nslot_p >= 1; --nslot_p)
         for (int ntile = ntile_max; ntile >= 1; --ntile)
           for (int cchunk = 32; cchunk >= 8; cchunk >>= 1) {
+            if ((f_slot && nslot_p != f_slot) || (f_ntile && ntile != f_ntile) || (f_cchunk && cchunk != f_cchunk)) continue;
             if (cchunk > 8 && cchunk > cin8) continue;
             const int ncc = (d.cin + cchunk - 1) / cchunk;
             if (nslot_p == 1 && ncc == 1 && ntile_max > 1) continue;      // a single slot only pays off for multi-chunk layers

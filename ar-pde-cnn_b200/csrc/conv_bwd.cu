@@ -138,7 +138,7 @@ struct WgradArgs {
   const float* scale; const float* shift; int relu_in;
   const float* dO; long long dO_bs; int cout, Ho, Wo;
   double* dW;
-  int N, tiles_x, tiles_y, co_tiles, ci_chunks, TH, TW, pitch, plane, cic, ncg, dpitch;
+  int N, tiles_x, tiles_y, co_tiles, ci_chunks, TH, TW, pitch, plane, cic, ncg, dpitch, rgroups;
 };
 
 template <int KH, int KW, int S, int COT>
@@ -153,8 +153,9 @@ __global__ void __launch_bounds__(256) wgrad_kernel(WgradArgs a) {
   float* patch = smem + ((PH + PW + 3) & ~3);
   float* dsm = patch + a.cic * a.plane;                  // [TCO][TH][dpitch]
   const int tid = threadIdx.x, nthreads = blockDim.x;
-  const int ci_l = tid % a.cic, tc = tid / a.cic;        // ci lane, co group
-  const bool active = tc < a.ncg;
+  const int ci_l = tid % a.cic, tcr = tid / a.cic;       // ci lane, (co group, row group)
+  const int tc = tcr % a.ncg, rg = tcr / a.ncg;          // row group rg handles tile rows rg, rg + RG, ...
+  const bool active = rg < a.rgroups;
   const int bt = blockIdx.x;
   const int co_tile = bt % a.co_tiles, ci_chunk = bt / a.co_tiles;
   const int co0 = co_tile * TCO, ci0 = ci_chunk * a.cic;
@@ -179,30 +180,72 @@ __global__ void __launch_bounds__(256) wgrad_kernel(WgradArgs a) {
     for (int i = tid; i < PW; i += nthreads) { int ix = (ox0 * S - a.pad_x + i) % Wc; if (ix < 0) ix += Wc; colmap[i] = ix >> a.up; }
     __syncthreads();
     const float* xn = a.x + (long long)n * a.x_bs;
-    for (int r = warp; r < cic * PH; r += nwarps) {
-      const int ci = r / PH, py = r - ci * PH;
-      const float* src = xn + (ci0 + ci) * HW + (long long)rowmap[py] * a.W;
-      float sc = 1.f, sh = 0.f;
-      if (a.scale) { sc = a.scale[ci0 + ci]; sh = a.shift[ci0 + ci]; }
-      float* dst = patch + ci * a.plane + py * a.pitch;
-      for (int px = lane; px < a.pitch; px += 32) {
-        float v = 0.f;
-        if (px < PW) { v = fmaf(__ldg(src + colmap[px]), sc, sh); if (a.relu_in) v = fmaxf(v, 0.f); }
-        dst[px] = v;
+    // batched staging (all loads of 2 lines x 4 x 32 columns in flight before the first use; see conv_fwd.cu)
+    {
+      constexpr int RU = 2, PU = 4;
+      const int nlines = cic * PH;
+      for (int r0 = warp * RU; r0 < nlines; r0 += nwarps * RU) {
+        for (int px0 = 0; px0 < a.pitch; px0 += 32 * PU) {
+          float v[RU][PU], sc[RU], sh[RU];
+#pragma unroll
+          for (int u = 0; u < RU; ++u) {
+            const int r = r0 + u;
+            const bool rok = r < nlines;
+            const int ci = rok ? r / PH : 0, py = rok ? r - ci * PH : 0;
+            const float* src = xn + (ci0 + ci) * HW + (long long)rowmap[py] * a.W;
+            sc[u] = 1.f; sh[u] = 0.f;
+            if (a.scale && rok) { sc[u] = a.scale[ci0 + ci]; sh[u] = a.shift[ci0 + ci]; }
+#pragma unroll
+            for (int p = 0; p < PU; ++p) {
+              const int px = px0 + p * 32 + lane;
+              v[u][p] = (rok && px < PW) ? __ldg(src + colmap[px]) : 0.f;
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < RU; ++u) {
+            const int r = r0 + u;
+            if (r < nlines) {
+              const int ci = r / PH, py = r - ci * PH;
+              float* dst = patch + ci * a.plane + py * a.pitch;
+#pragma unroll
+              for (int p = 0; p < PU; ++p) {
+                const int px = px0 + p * 32 + lane;
+                if (px < a.pitch) {
+                  float t = 0.f;
+                  if (px < PW) { t = fmaf(v[u][p], sc[u], sh[u]); if (a.relu_in) t = fmaxf(t, 0.f); }
+                  dst[px] = t;
+                }
+              }
+            }
+          }
+        }
       }
     }
     const float* dn = a.dO + (long long)n * a.dO_bs;
-    for (int r = warp; r < TCO * a.TH; r += nwarps) {
-      const int co = r / a.TH, py = r - co * a.TH;
-      const bool ok = (co0 + co < a.cout) && (oy0 + py < a.Ho);
-      const float* src = dn + (long long)(co0 + co) * HoWo + (long long)(oy0 + py) * a.Wo + ox0;
-      float* dst = dsm + r * a.dpitch;
-      for (int px = lane; px < a.dpitch; px += 32) dst[px] = (ok && px < a.TW && ox0 + px < a.Wo) ? __ldg(src + px) : 0.f;
+    {
+      constexpr int RU = 4;
+      const int nlines = TCO * a.TH;
+      for (int r0 = warp * RU; r0 < nlines; r0 += nwarps * RU) {
+        for (int px0 = 0; px0 < a.dpitch; px0 += 32) {
+          float v[RU];
+          const int px = px0 + lane;
+#pragma unroll
+          for (int u = 0; u < RU; ++u) {
+            const int r = r0 + u;
+            const int co = r / a.TH, py = r - co * a.TH;
+            const bool ok = r < nlines && (co0 + co < a.cout) && (oy0 + py < a.Ho) && px < a.TW && ox0 + px < a.Wo;
+            v[u] = ok ? __ldg(dn + (long long)(co0 + co) * HoWo + (long long)(oy0 + py) * a.Wo + ox0 + px) : 0.f;
+          }
+#pragma unroll
+          for (int u = 0; u < RU; ++u)
+            if (r0 + u < nlines && px < a.dpitch) dsm[(r0 + u) * a.dpitch + px] = v[u];
+        }
+      }
     }
     __syncthreads();
     if (active && ci_l < cic) {
       const float* pbase = patch + ci_l * a.plane;
-      for (int py = 0; py < a.TH; ++py) {
+      for (int py = rg; py < a.TH; py += a.rgroups) {
         for (int xg = 0; xg < a.TW; xg += PXT) {
           float d[COT][PXT];
 #pragma unroll
@@ -249,14 +292,15 @@ __global__ void d2f_kernel(const double* __restrict__ src, float* __restrict__ d
 
 typedef void (*wgrad_fn)(WgradArgs);
 template <int KH, int KW, int S>
-static wgrad_fn pick_w(int* cot) {
+static wgrad_fn pick_w(int cout, int* cot) {
   constexpr int KK = KH * KW;
   constexpr int C = KK <= 9 ? 8 : (KK <= 25 ? 4 : 2);
+  if (C == 8 && cout <= 4) { *cot = 4; return wgrad_kernel<KH, KW, S, (C == 8 ? 4 : C)>; }   // dense layers (growth 4): no zero channels
   *cot = C;
   return wgrad_kernel<KH, KW, S, C>;
 }
-static wgrad_fn pick_wgrad(int kh, int kw, int s, int* cot) {
-#define PK(KH_, KW_, S_) if (kh == KH_ && kw == KW_ && s == S_) return pick_w<KH_, KW_, S_>(cot)
+static wgrad_fn pick_wgrad(int kh, int kw, int s, int cout, int* cot) {
+#define PK(KH_, KW_, S_) if (kh == KH_ && kw == KW_ && s == S_) return pick_w<KH_, KW_, S_>(cout, cot)
   PK(1, 1, 1); PK(3, 3, 1); PK(3, 3, 2); PK(5, 5, 1); PK(4, 4, 2); PK(7, 7, 2);
   PK(1, 3, 1); PK(1, 3, 2); PK(1, 5, 1); PK(1, 4, 2); PK(1, 7, 2);
 #undef PK
@@ -268,7 +312,7 @@ int arpde_conv_wgrad_launch(const ConvDesc& d, const float* x, long long x_bs, c
                             long long dO_bs, double* dW64, float* dW, cudaStream_t stream) {
   ARPDE_CHECK_ARG(x && dO && dW64 && dW, "conv_wgrad: null pointer");
   int cot = 8;
-  wgrad_fn fn = pick_wgrad(d.kh, d.kw, d.stride, &cot);
+  wgrad_fn fn = pick_wgrad(d.kh, d.kw, d.stride, d.cout, &cot);
   if (!fn) { arpde_set_error("conv_wgrad: kernel %dx%d stride %d not instantiated", d.kh, d.kw, d.stride); return ARPDE_ERR_UNSUPPORTED; }
   const int KK = d.kh * d.kw;
   const long long wn = (long long)d.cout * d.cin * KK;
@@ -286,6 +330,9 @@ int arpde_conv_wgrad_launch(const ConvDesc& d, const float* x, long long x_bs, c
   int ncg = (d.cout + cot - 1) / cot; if (ncg > 24) ncg = 24;
   int cic = 256 / ncg; if (cic > d.cin) cic = d.cin; if (cic < 1) cic = 1;
   a.ncg = ncg; a.cic = cic;
+  // few (co group, ci) pairs (small layers): several row groups share a tile so that the CTA still has ~256 busy threads
+  int rgroups = 256 / (ncg * cic); if (rgroups < 1) rgroups = 1; if (rgroups > 8) rgroups = 8;
+  a.rgroups = rgroups;
   const int TCO = ncg * cot;
   a.co_tiles = (d.cout + TCO - 1) / TCO; a.ci_chunks = (d.cin + cic - 1) / cic;
   int TW = ((Wo + 3) / 4) * 4; if (TW > 64) TW = 64;
@@ -310,7 +357,7 @@ int arpde_conv_wgrad_launch(const ConvDesc& d, const float* x, long long x_bs, c
   const long long items = (long long)d.N * a.tiles_x * a.tiles_y;
   const int gx = a.co_tiles * a.ci_chunks;
   long long split = (4ll * arpde_num_sms() + gx - 1) / gx; if (split > items) split = items; if (split < 1) split = 1; if (split > 65535) split = 65535;
-  int threads = ((ncg * cic + 31) / 32) * 32;
+  int threads = ((ncg * cic * rgroups + 31) / 32) * 32;
   fn<<<dim3(gx, (unsigned)split), threads, smem, stream>>>(a);
   ARPDE_LAUNCH_CHECK();
   d2f_kernel<<<(unsigned)ceil_div64(wn, 256), 256, 0, stream>>>(dW64, dW, wn);

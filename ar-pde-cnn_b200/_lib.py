@@ -56,7 +56,7 @@ _PROTOS = {
                              i32, f64p, i64, f32p, i32, f64, f64, f32p, i64, vp],
     'arpde_conv_fwd_tc': [f32p, i64, f32p, i64, f32p, f32p, i64, f32p, f64p] + [i32] * 14 + [f32p, i64, vp],
     'arpde_densed_backward': [vp, i32, vp, i32, vp, i32, f32p, i64, i32, i32, i32, f32p, f32p, f32p, f32p, i32, f32p,
-                              f32p, f32p, vp, f32p, f32p, f32p, f64p, i32, vp],
+                              f32p, f32p, vp, f32p, f32p, f32p, f64p, i32, f32p, i64, vp],
     'arpde_conv_tc_plan': [i32] * 8 + [vp],
     'arpde_conv_tc_set_debug': [vp],
     'arpde_conv_tc_set_debug_flags': [i32],

@@ -59,10 +59,13 @@ def densed_backward(ctx, gy):
     gwork = torch.empty((max(work_len, 1),), device=dev, dtype=torch.float32)
     gx = torch.empty((N, plan.c_in, H, W), device=dev, dtype=torch.float32) if need_x else None
     pp = L.ptr_array([t.data_ptr() for t in tensors])
+    # the data-gradient conv swaps cin/cout: size the tensor-core weight scratch for the largest transposed layer
+    tc_len = max([int(L.lib.arpde_conv_fwd_tc_scratch_floats(o['cout'], o['cin'], o['kh'], o['kw'], 1)) for o in plan.ops] + [1])
+    tc = torch.empty((tc_len,), device=dev, dtype=torch.float32)
     with torch.cuda.device(dev):
         L.call('arpde_densed_backward', ops_c, len(plan.ops), bufs_c, len(bufs), pp, len(tensors), L.ptr(x4), x_bs, N, H, W,
                L.ptr(gy4), L.ptr(y_saved), L.ptr(work), L.ptr(ss), plan.bn_total, L.ptr(saved), L.ptr(gwork), L.ptr(gx),
-               L.ptr_array(gptrs), L.ptr(T1), L.ptr(T2), L.ptr(wT), L.ptr(d64), 1 if training else 0, L.stream())
+               L.ptr_array(gptrs), L.ptr(T1), L.ptr(T2), L.ptr(wT), L.ptr(d64), 1 if training else 0, L.ptr(tc), tc_len, L.stream())
     grads, off = [], 0
     for i, t in enumerate(tensors):
         if i in slot_need:

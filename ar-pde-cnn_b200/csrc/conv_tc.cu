@@ -33,6 +33,7 @@
 #include "conv_common.cuh"
 #include "../../include/arpde.h"
 #include <stdlib.h>
+#include <mutex>
 #include <cuda.h>          // CUtensorMap + enums only; cuTensorMapEncodeTiled is resolved through cudaGetDriverEntryPoint
 
 #define TC_MAX_TAPS 49
@@ -1008,17 +1009,37 @@ int arpde_conv_tc_launch(const ConvDesc& d, const float* x, long long x_bs, cons
   }
   a.pair = (!a.tma && a.sx == 2 && !a.up_w && a.kp <= 4 && (a.W & 1) == 0 && (x_bs & 1) == 0 && (((uintptr_t)x) & 7) == 0 &&
             (((long long)a.H * a.W) & 1) == 0) ? 1 : 0;
-  static thread_local size_t smem_set = 0;
-  if (smem > smem_set) {
-    ARPDE_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set = smem;
+  // opt in to the device's full shared memory once per device.  (Not a thread_local high-water mark: autograd runs backward() on its
+  // own thread, whose first smaller request lowered the attribute under the forward thread's feet -> "invalid argument" launches.)
+  static std::mutex attr_mutex;
+  static bool attr_done[64] = {false};
+  size_t smem_set = 0;
+  {
+    int dev = 0;
+    ARPDE_CUDA(cudaGetDevice(&dev));
+    int optin = 0;
+    ARPDE_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    smem_set = (size_t)optin;
+    ARPDE_CHECK_ARG(smem <= smem_set, "conv_tc: plan needs %zu bytes of shared memory, device allows %zu", smem, smem_set);
+    std::lock_guard<std::mutex> lock(attr_mutex);
+    if (dev < 0 || dev >= 64 || !attr_done[dev]) {
+      ARPDE_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+      if (dev >= 0 && dev < 64) attr_done[dev] = true;
+    }
   }
   const long long items = (long long)d.N * a.ctas_per_sample;
   ARPDE_CHECK_ARG(items < (1ll << 31), "conv_tc: too many work items");
   long long blocks = (long long)arpde_num_sms();       // persistent CTAs, one per SM
   if (blocks > items) blocks = items;
   conv_tc_kernel<<<(unsigned)blocks, TC_THREADS, smem, stream>>>(a, tmap);
-  ARPDE_LAUNCH_CHECK();
+  {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+      arpde_set_error("conv_tc launch failed: %s (grid %lld, block %d, smem %zu (attribute set to %zu), N=%d cin=%d %dx%d cout=%d k=%dx%d s=%d up=%d tma=%d)",
+                      cudaGetErrorString(e), blocks, TC_THREADS, smem, smem_set, d.N, d.cin, d.H, d.W, d.cout, d.kh, d.kw, d.stride, d.up, a.tma);
+      return ARPDE_ERR_CUDA;
+    }
+  }
   return ARPDE_OK;
 }
 

@@ -205,7 +205,8 @@ extern "C" int arpde_densed_backward(const arpde_op_t* ops, int n_ops, const arp
                                      int n_params, const float* x, int64_t x_bstride, int N, int H, int W, const float* gy,
                                      const float* y, const float* workspace, const float* scale_shift, int bn_total,
                                      const float* saved_mean_invstd, float* gwork, float* gx, void* const* grads_host, float* T1,
-                                     float* T2, float* wT, double* d64, int training, arpde_stream_t stream_) {
+                                     float* T2, float* wT, double* d64, int training, float* tc_scratch, int64_t tc_scratch_floats,
+                                     arpde_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   int rc = check_program(ops, n_ops, bufs, n_bufs, n_params); if (rc) return rc;
   ARPDE_CHECK_ARG(params_host && grads_host && x && gy && T1 && T2 && wT && d64, "densed_backward: null pointer");
@@ -254,12 +255,21 @@ extern "C" int arpde_densed_backward(const arpde_op_t* ops, int n_ops, const arp
     float* dest; long long dest_bs; bool acc = false;
     if (o.in_buf < 0) { dest = gx; dest_bs = (long long)o.cin * Hin * Win; }
     else { const arpde_buf_t& b = bufs[o.in_buf]; dest = gwork + b.offset; dest_bs = (long long)b.ctot * b.h * b.w; acc = written[o.in_buf]; }
+    // the data-gradient conv of a stride-1 layer is an ordinary circular conv (pad k-1-p == p for odd k): tensor-core kernel
+    if (!g.dilate && g.pad_override == p) g.pad_override = -1;
+    const long long tc_need = arpde_conv_tc_wprep_floats(g.cin, g.cout, g.kh, g.kw);
+    const bool use_tc = tc_scratch && tc_need <= tc_scratch_floats && arpde_conv_tc_wanted(g);
+    if (use_tc) { rc = arpde_conv_tc_prep_launch(g, wT, 0, 1, tc_scratch, 0, stream); if (rc) return rc; }
     if (o.bn_param < 0 && !o.up && !acc) {
       g.y_ctot = (int)(dest_bs / ((long long)Hin * Win)); g.y_coff = 0;
-      rc = arpde_conv_fwd_launch(g, dO, dO_bs, wT, 0, nullptr, nullptr, 0, dest, nullptr, stream); if (rc) return rc;
+      rc = use_tc ? arpde_conv_tc_launch(g, dO, dO_bs, tc_scratch, 0, nullptr, nullptr, 0, dest, nullptr, stream)
+                  : arpde_conv_fwd_launch(g, dO, dO_bs, wT, 0, nullptr, nullptr, 0, dest, nullptr, stream);
+      if (rc) return rc;
     } else {
       g.y_ctot = o.cin; g.y_coff = 0;
-      rc = arpde_conv_fwd_launch(g, dO, dO_bs, wT, 0, nullptr, nullptr, 0, T1, nullptr, stream); if (rc) return rc;
+      rc = use_tc ? arpde_conv_tc_launch(g, dO, dO_bs, tc_scratch, 0, nullptr, nullptr, 0, T1, nullptr, stream)
+                  : arpde_conv_fwd_launch(g, dO, dO_bs, wT, 0, nullptr, nullptr, 0, T1, nullptr, stream);
+      if (rc) return rc;
       float* dgamma = o.bn_param >= 0 ? (float*)grads_host[o.bn_param] : nullptr;
       float* dbeta = o.bn_param >= 0 ? (float*)grads_host[o.bn_param + 1] : nullptr;
       rc = arpde_bn_relu_bwd_launch(T1, in, in_bs, scale, shift, mean, invstd, T2, d64, dest, dest_bs, dgamma, dbeta, N, o.cin, Hin, Win,

@@ -205,12 +205,13 @@ int64_t arpde_densed_tc_scratch_floats(const arpde_op_t* ops, int n_ops, int gro
  * workspace; gx (nullable): gradient of the input [N,cin,H,W] compact; grads_host: HOST array (n_params entries) of
  * device float* receiving each parameter's gradient (NULL = not needed; running-stat slots are ignored).
  * Scratch: T1 >= max N*cin*Hc*Wc floats over ops (conv-input resolution), T2 >= max(N*cin*H*W, N*cout_last*Ho*Wo) floats,
- * wT >= max weight numel floats, d64 >= max(weight numel, 2*max cin) doubles. */
+ * wT >= max weight numel floats, d64 >= max(weight numel, 2*max cin) doubles.  tc_scratch (nullable): arpde_densed_tc_scratch_floats(ops,
+ * n_ops, 1) floats; with it the data-gradient convolutions of the stride-1 layers run on the tensor-core kernel. */
 int arpde_densed_backward(const arpde_op_t* ops, int n_ops, const arpde_buf_t* bufs, int n_bufs, void* const* params_host,
                           int n_params, const float* x, int64_t x_bstride, int N, int H, int W, const float* gy, const float* y,
                           const float* workspace, const float* scale_shift, int bn_total, const float* saved_mean_invstd,
                           float* gwork, float* gx, void* const* grads_host, float* T1, float* T2, float* wT, double* d64,
-                          int training, arpde_stream_t stream);
+                          int training, float* tc_scratch, int64_t tc_scratch_floats, arpde_stream_t stream);
 
 /* Auto-regressive rollout in eval mode: the AR loops of main.py test()/testSample()
  * (2D-Burgers-SWAG/main.py:112-135,:160-179; 1D main.py :106-121,:148-163) without Python in the loop.

@@ -69,6 +69,7 @@ struct ConvTcArgs {
   int pair;                  // stride-2 layer staged with float2 loads (both x parities at once)
   int tma;                   // 1: input rows arrive by TMA into the raw ring and the staging warps convert smem -> smem
   int row_mode;              // 0: stride 1, 1: nearest x2 upsampled input, 2: stride 2 (parity planes)
+  int dilate;                // input is zero-inserted x2 (data gradient of a stride-2 layer): addressed like row_mode 1, odd rows/columns are 0
   int RS, raw_slot_floats;   // source rows per (item, channel chunk) and floats per raw ring slot [RS][cchunk][W]
   long long* dbg;            // optional cycle counters of CTA 0 (arpde_conv_tc_set_debug), else nullptr
   int dbg_flags;             // experiments: 1 = skip patch staging work, 2 = skip epilogue loads/stores, 4 = skip MMAs
@@ -408,7 +409,7 @@ __device__ __noinline__ void converter_loop(const ConvTcArgs& a, const float* ra
   const long long dbg_t0 = dbg_on ? clock64() : 0;
   // constant part of the raw offset of every owned position (plane (0,0), channel 0)
   int irow[KP], coff[KP];
-  uint32_t kmask = 0;
+  uint32_t kmask = 0, codd = 0;            // codd bit k: the position's column is odd in the zero-inserted (dilated) input space
 #pragma unroll
   for (int k = 0; k < KP; ++k) {
     irow[k] = 0; coff[k] = 0;
@@ -419,6 +420,7 @@ __device__ __noinline__ void converter_loop(const ConvTcArgs& a, const float* ra
       int C = (a.min_rx + j) % a.Wo; if (C < 0) C += a.Wo;
       irow[k] = i;
       coff[k] = (C * a.sx) >> a.up_w;
+      if (a.dilate && (C & 1)) codd |= 1u << k;
     }
   }
   int g_tab = -1;
@@ -439,10 +441,12 @@ __device__ __noinline__ void converter_loop(const ConvTcArgs& a, const float* ra
       g_tab = g;
     }
     int roff[KP];
+    uint32_t live = kmask;                 // positions that carry data (dilated input: even row and even column only)
 #pragma unroll
     for (int k = 0; k < KP; ++k) {
       const int rl = a.row_mode == 1 ? ((irow[k] + (rbase & 1)) >> 1) : (a.row_mode == 2 ? 2 * irow[k] : irow[k]);
       roff[k] = rl * rowf + coff[k];
+      if (a.dilate && (((rbase + irow[k]) & 1) || ((codd >> k) & 1u))) live &= ~(1u << k);
     }
     for (int cc = 0; cc < a.ncc; ++cc) {
       const int pseq = lit * a.ncc + cc;
@@ -471,7 +475,7 @@ __device__ __noinline__ void converter_loop(const ConvTcArgs& a, const float* ra
                 const float2 t2 = ((kmask >> k) & 1u) ? *reinterpret_cast<const float2*>(rw + roff[k] + uoff + e * a.W) : make_float2(0.f, 0.f);
                 v[k][e] = t2.x; v[k][4 + e] = t2.y;
               } else {
-                v[k][e] = ((kmask >> k) & 1u) ? rw[roff[k] + uoff + e * a.W] : 0.f;
+                v[k][e] = ((live >> k) & 1u) ? rw[roff[k] + uoff + e * a.W] : 0.f;
               }
             }
           }
@@ -841,12 +845,13 @@ int arpde_tc_enabled() {
 
 // Plan the tiling of one convolution for conv_tc_kernel.  Returns false if the layer is outside what the kernel covers.
 static bool tc_plan(const ConvDesc& d, ConvTcArgs& a, size_t* smem_out) {
-  if (d.dilate || d.pad_override >= 0) return false;
+  if (d.pad_override >= 0) return false;
+  if (d.dilate && (d.up || d.stride != 1 || (d.H == 1 && d.kh == 1))) return false;
   if (d.stride != 1 && d.stride != 2) return false;
   if (d.up && d.stride != 1) return false;
   const int one_d = (d.H == 1 && d.kh == 1);
   memset(&a, 0, sizeof(a));
-  a.cin = d.cin; a.H = d.H; a.W = d.W; a.up_w = d.up ? 1 : 0; a.up_h = one_d ? 0 : a.up_w;
+  a.cin = d.cin; a.H = d.H; a.W = d.W; a.up_w = (d.up || d.dilate) ? 1 : 0; a.up_h = one_d ? 0 : a.up_w; a.dilate = d.dilate ? 1 : 0;
   a.Hc = d.H << a.up_h; a.Wc = d.W << a.up_w; a.sy = one_d ? 1 : d.stride; a.sx = d.stride;
   if (a.Hc % a.sy || a.Wc % a.sx) return false;
   a.Ho = a.Hc / a.sy; a.Wo = a.Wc / a.sx;
@@ -884,7 +889,7 @@ static bool tc_plan(const ConvDesc& d, ConvTcArgs& a, size_t* smem_out) {
   int f_slot = 0, f_ntile = 0, f_cchunk = 0;
   if (const char* e = getenv("ARPDE_TC_FORCE")) sscanf(e, "%d,%d,%d", &f_slot, &f_ntile, &f_cchunk);
   for (int resident = 1; resident >= 0; --resident)
-    for (int use_tma = tma_shape ? 1 : 0; use_tma >= 0; --use_tma)
+    for (int use_tma = tma_shape ? 1 : 0; use_tma >= (d.dilate ? 1 : 0); --use_tma)
       for (int nslot_p = 2; nslot_p >= 1; --nslot_p)
         for (int ntile = ntile_max; ntile >= 1; --ntile)
           for (int cchunk = 32; cchunk >= 8; cchunk >>= 1) {
@@ -1003,6 +1008,8 @@ int arpde_conv_tc_launch(const ConvDesc& d, const float* x, long long x_bs, cons
   CUtensorMap tmap;
   memset(&tmap, 0, sizeof(tmap));
   if (a.tma && ((((uintptr_t)x) & 15) != 0 || (x_bs & 3) != 0 || getenv("ARPDE_TC_NO_TMA"))) a.tma = 0;
+  if (a.dilate && scale) { arpde_set_error("conv_tc: a zero-inserted input cannot carry a BatchNorm prologue"); return ARPDE_ERR_UNSUPPORTED; }
+  if (!a.tma && a.dilate) { arpde_set_error("conv_tc: zero-inserted input needs the TMA path (16-byte aligned input)"); return ARPDE_ERR_UNSUPPORTED; }
   if (a.tma) {
     int rc = tc_encode_input_map(&tmap, x, x_bs, d.N, d.cin, d.H, d.W, a.cchunk);
     if (rc) return rc;

@@ -264,7 +264,7 @@ extern "C" int arpde_densed_backward(const arpde_op_t* ops, int n_ops, const arp
     if (o.in_buf < 0) { dest = gx; dest_bs = (long long)o.cin * Hin * Win; }
     else { const arpde_buf_t& b = bufs[o.in_buf]; dest = gwork + b.offset; dest_bs = (long long)b.ctot * b.h * b.w; acc = written[o.in_buf]; }
     // the data-gradient conv of a stride-1 layer is an ordinary circular conv (pad k-1-p == p for odd k): tensor-core kernel
-    if (!g.dilate && g.pad_override == p) g.pad_override = -1;
+    if (g.pad_override == p) g.pad_override = -1;           // also for the zero-inserted input of a stride-2 layer
     const long long tc_need = arpde_conv_tc_wprep_floats(g.cin, g.cout, g.kh, g.kw);
     const bool use_tc = tc_scratch && tc_need <= tc_scratch_floats && arpde_conv_tc_wanted(g);
     if (use_tc) { rc = arpde_conv_tc_prep_launch(g, wT, 0, 1, tc_scratch, 0, stream); if (rc) return rc; }

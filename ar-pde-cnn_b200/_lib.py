@@ -58,6 +58,8 @@ _PROTOS = {
     'arpde_densed_backward': [vp, i32, vp, i32, vp, i32, f32p, i64, i32, i32, i32, f32p, f32p, f32p, f32p, i32, f32p,
                               f32p, f32p, vp, f32p, f32p, f32p, f64p, i32, f32p, i64, vp],
     'arpde_conv_tc_plan': [i32] * 8 + [vp],
+    'arpde_conv_wgrad_tc': [vp, i64, vp, vp, vp, i64, vp, vp] + [i32] * 10 + [vp, i64, vp],
+    'arpde_conv_wgrad_tc_plan': [i32] * 8 + [vp],
     'arpde_conv_tc_set_debug': [vp],
     'arpde_conv_tc_set_debug_flags': [i32],
     'arpde_rollout': [vp, i32, vp, i32, vp, vp, i32, f32p, i32, i32, i32, i32, i32, i32, i32, i32, i32, f32p, f32p,
@@ -76,8 +78,11 @@ lib.arpde_densed_tc_scratch_floats.argtypes = [vp, i32, i32]
 lib.arpde_densed_tc_scratch_floats.restype = C.c_int64
 lib.arpde_conv_fwd_tc_scratch_floats.argtypes = [i32, i32, i32, i32, i32]
 lib.arpde_conv_fwd_tc_scratch_floats.restype = C.c_int64
+lib.arpde_conv_wgrad_tc_scratch.argtypes = [i32] * 9
+lib.arpde_conv_wgrad_tc_scratch.restype = C.c_int64
 
-EXPORTS = sorted(list(_PROTOS) + ['arpde_last_error', 'arpde_densed_tc_scratch_floats', 'arpde_conv_fwd_tc_scratch_floats'])
+EXPORTS = sorted(list(_PROTOS) + ['arpde_last_error', 'arpde_densed_tc_scratch_floats', 'arpde_conv_fwd_tc_scratch_floats',
+                                   'arpde_conv_wgrad_tc_scratch'])
 
 
 def check(rc, what=''):

@@ -60,7 +60,11 @@ def densed_backward(ctx, gy):
     gx = torch.empty((N, plan.c_in, H, W), device=dev, dtype=torch.float32) if need_x else None
     pp = L.ptr_array([t.data_ptr() for t in tensors])
     # the data-gradient conv swaps cin/cout: size the tensor-core weight scratch for the largest transposed layer
+    # (the tensor-core weight gradient keeps its per-CTA partial sums in the same scratch, earlier on the stream)
     tc_len = max([int(L.lib.arpde_conv_fwd_tc_scratch_floats(o['cout'], o['cin'], o['kh'], o['kw'], 1)) for o in plan.ops] + [1])
+    for o in plan.ops:
+        hin, win = (H, W) if o['in_buf'] < 0 else bufs[o['in_buf']][3:5]
+        tc_len = max(tc_len, int(L.lib.arpde_conv_wgrad_tc_scratch(N, o['cin'], hin, win, o['cout'], o['kh'], o['kw'], o['stride'], o['up'])))
     tc = torch.empty((tc_len,), device=dev, dtype=torch.float32)
     with torch.cuda.device(dev):
         L.call('arpde_densed_backward', ops_c, len(plan.ops), bufs_c, len(bufs), pp, len(tensors), L.ptr(x4), x_bs, N, H, W,

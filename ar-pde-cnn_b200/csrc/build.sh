@@ -9,7 +9,7 @@ FLAGS=(-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompil
 pids=()
 for f in "$HERE"/*.cu; do
   o="$HERE/_obj/$(basename "${f%.cu}").o"
-  if [[ ! -f "$o" || "$f" -nt "$o" || "$HERE/common.cuh" -nt "$o" || "$HERE/../../include/arpde.h" -nt "$o" ]]; then
+  if [[ ! -f "$o" || "$f" -nt "$o" || "$HERE/common.cuh" -nt "$o" || "$HERE/tc_ptx.cuh" -nt "$o" || "$HERE/conv_common.cuh" -nt "$o" || "$HERE/../../include/arpde.h" -nt "$o" ]]; then
     ( "$NVCC" "${FLAGS[@]}" -c "$f" -o "$o" > "$o.log" 2>&1 || { cat "$o.log"; rm -f "$o"; exit 1; } ) &
     pids+=($!)
   fi

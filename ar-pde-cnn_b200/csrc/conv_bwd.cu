@@ -290,6 +290,12 @@ __global__ void d2f_kernel(const double* __restrict__ src, float* __restrict__ d
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) dst[i] = (float)src[i];
 }
 
+int arpde_d2f_launch(const double* src, float* dst, long long n, cudaStream_t stream) {
+  d2f_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, stream>>>(src, dst, n);
+  ARPDE_LAUNCH_CHECK();
+  return ARPDE_OK;
+}
+
 typedef void (*wgrad_fn)(WgradArgs);
 template <int KH, int KW, int S>
 static wgrad_fn pick_w(int cout, int* cot) {

@@ -141,6 +141,20 @@ int arpde_conv_fwd_tc(const float* x, int64_t x_bstride, const float* w, int64_t
  * at least 130 int32).  Used by the CPU tests to check the shifted-window index arithmetic without a GPU. */
 int arpde_conv_tc_plan(int cin, int H, int W, int cout, int kh, int kw, int stride, int up, int32_t* out);
 
+/* Weight gradient of one circular convolution on the tensor cores (conv_wgrad_tc.cu): the dW that torch autograd derives for
+ * nn.Conv2d(padding_mode='circular') under loss.backward() (2D-Burgers-SWAG/main.py:81), with the same fused prologue as the
+ * forward op: a = up2?(relu?(scale*x + shift)), dW[co][ci][ky][kx] = sum_{n,oy,ox} dO[n][co][oy][ox] * a_wrapped[n][ci][oy*s+ky-p][ox*s+kx-p].
+ * dW64: scratch of cout*cin*kh*kw doubles (fp64 accumulation across CTAs), dW: float result [cout][cin][kh][kw];
+ * scratch: arpde_conv_wgrad_tc_scratch(...) floats of device memory (per-CTA fp32 partial sums; 0 = layer not covered).
+ * Returns ARPDE_ERR_UNSUPPORTED for layers the kernel does not cover (1D, cout < 16 or > 128, too few taps); the fused backward
+ * (arpde_densed_backward) then uses the fp32 FFMA kernel.  arpde_conv_wgrad_tc_plan: host-only diagnostic of the tiling
+ * (field list in conv_wgrad_tc.cu; out holds at least 200 int32). */
+int64_t arpde_conv_wgrad_tc_scratch(int N, int cin, int H, int W, int cout, int kh, int kw, int stride, int up);
+int arpde_conv_wgrad_tc(const float* x, int64_t x_bstride, const float* scale, const float* shift, const float* dO,
+                        int64_t dO_bstride, double* dW64, float* dW, int N, int cin, int H, int W, int cout, int kh, int kw,
+                        int stride, int up, int relu_in, float* scratch, int64_t scratch_floats, arpde_stream_t stream);
+int arpde_conv_wgrad_tc_plan(int cin, int H, int W, int cout, int kh, int kw, int stride, int up, int32_t* out);
+
 /* Profiling hooks of the tensor-core kernel (development only; both default to off).  set_debug: per-role cycle counters of
  * CTA 0 of every following arpde_conv_fwd_tc / program launch are written to dev_buf (16 device int64; NULL = off).
  * set_debug_flags: ablation switches (1 = skip patch staging, 2 = skip the epilogue, 4 = skip the MMAs; results are garbage). */

@@ -56,6 +56,7 @@ int arpde_conv_wgrad_tc_launch(const ConvDesc& d, const float* x, long long x_bs
                                long long dO_bs, double* dW64, float* dW, float* scratch, long long scratch_floats, cudaStream_t stream);
 
 // tensor-core (tcgen05) implicit-GEMM path, conv_tc.cu
+long long* arpde_tc_debug_buffer();                              // arpde_conv_tc_set_debug's buffer (nullptr = off)
 int arpde_tc_enabled();                                          // ARPDE_TC=0 in the environment disables it
 bool arpde_conv_tc_wanted(const ConvDesc& d);                    // layer heuristics + plannability
 long long arpde_conv_tc_wprep_floats(int cin, int cout, int kh, int kw);   // prepared-weight floats per weight group

@@ -903,6 +903,7 @@ extern "C" int arpde_conv_tc_set_debug_flags(int flags) { g_tc_dbg_flags = flags
 // [0..3] stager: total, wait empty_p, staging, fence+arrive; [4,5] epilogue: total, wait tmem_full;
 // [8..12] issuer: total, wait tmem_empty, wait full_p, wait weights, items
 extern "C" int arpde_conv_tc_set_debug(long long* dev_buf) { g_tc_dbg = dev_buf; return ARPDE_OK; }
+long long* arpde_tc_debug_buffer() { return g_tc_dbg; }
 
 int arpde_conv_tc_launch(const ConvDesc& d, const float* x, long long x_bs, const float* wprep, long long wprep_gs, const float* scale,
                          const float* shift, long long ss_gs, float* y, double* stats, cudaStream_t stream) {

@@ -60,6 +60,8 @@ struct WgTcArgs {
   int RB, RBH, nch_u, lead, pcu, NR, ring;     // row blocks per sample, rows per block, MMA chunks / patch chunks per unit, ring chunks / rows
   int npl, NC, ncc, cchunk, packed, ntaps;     // planes, MMA N, channel chunks (grid split), channels per chunk, (kx,ci) packing, MMA taps
   int M, mrows, tmem_cols, slices, units, cols, nacc;   // cols = ntaps * NC accumulator columns per set, nacc sets
+  long long* dbg;                              // cycle counters of CTA 0 (arpde_conv_tc_set_debug), else nullptr
+  int dbg_flags;                               // experiments (ARPDE_WG_DBG): 1 = converters skip loads and stores, 4 = skip the MMAs
   int plane_floats, gy_slot_floats;            // one ring plane (hi or lo) incl. mirror; one dO slot (hi + lo)
   int tap_plane[WG_MAX_TAPS];
   int tap_off[WG_MAX_TAPS];
@@ -119,7 +121,6 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __gr
 
   if (warp < WG_CONV_WARPS) {
     // =============================== converter warps ===============================
-    const long long HW = (long long)a.H * a.W, HoWo = (long long)a.Ho * a.Wo;
     // the four columns this thread fills in every patch row (one 16-byte store per plane and part)
     const int e0 = 4 * warp;
     int cch[4], cdx[4]; float csc[4], csh[4];
@@ -135,49 +136,68 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __gr
     const bool any_col = cch[0] >= 0 || cch[1] >= 0 || cch[2] >= 0 || cch[3] >= 0;
     const int gy_units = a.cout * 8;                   // (co, group of 4 positions) per dO chunk
     int pg = 0, hg = 0;                                // running patch-chunk / dO-chunk counters of this CTA
+    const bool dbg_on = a.dbg != nullptr && blockIdx.x == 0 && tid == 0;
+    long long d_wait_p = 0, d_wait_g = 0, d_load = 0;
+    const long long d_t0 = dbg_on ? clock64() : 0;
+    // loop-invariant geometry in registers; every per-step index is advanced incrementally (the first version recomputed two integer
+    // divisions and 64-bit address products per load and spent ~1500 cycles per 32-position step on index arithmetic alone)
+    const int pitch = a.pitch, Ho = a.Ho, Wo = a.Wo, Wsrc = a.W, sy = a.sy, sx = a.sx, up_h = a.up_h, up_w = a.up_w, npl = a.npl;
+    const int HWi = a.H * a.W, HoWoi = a.Ho * a.Wo;
+    int coff[4];                                       // channel offset of each column inside the sample
+#pragma unroll
+    for (int k = 0; k < 4; ++k) coff[k] = (cch[k] < 0 ? 0 : cch[k]) * HWi;
+    int gco[4], gq4[4];                                // dO unit of this thread: channel offset, first position inside the chunk
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { const int uu = tid + k * WG_CONVERTERS; gco[k] = (uu >> 3) * HoWoi; gq4[k] = (uu & 7) << 2; }
+    const bool no_load = (a.dbg_flags & 1) != 0;
     for (int u = u_begin; u < u_end; ++u) {
       const int n = u / a.RB, rb = u - n * a.RB;
       const int R0 = rb * a.RBH;
       const float* xn = a.x + (long long)n * a.x_bs;
       const float* gn = a.dO + (long long)n * a.dO_bs + (long long)R0 * a.Wo;
+      int pi = 0, pj = lane;                           // (row, column) of this thread's patch position in the padded row pitch
+      while (pj >= pitch) { pj -= pitch; ++pi; }
+      int goy[4], gox[4];                              // (row, column) of the dO positions
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { goy[k] = 0; gox[k] = gq4[k]; while (gox[k] >= pitch) { gox[k] -= pitch; ++goy[k]; } }
       for (int t = 0; t < a.pcu; ++t, ++pg) {
         // ---- loads of patch chunk t (32 positions, this thread: position `lane`, 4 columns, every plane)
+        const long long d_t1 = dbg_on ? clock64() : 0;
         float xv[4][4];
-        {
-          const int p = t * WG_CK + lane;
-          const int i = p / a.pitch, j = p - i * a.pitch;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            int jj = j + cdx[k], ii = i;
-            if (jj >= a.pitch) { jj -= a.pitch; ++ii; }
-            int R = R0 + a.min_ry + ii; if (R < 0) R += a.Ho; else if (R >= a.Ho) R -= a.Ho; if (R >= a.Ho) R -= a.Ho;
-            int C = a.min_rx + jj; if (C < 0) C += a.Wo; else if (C >= a.Wo) C -= a.Wo;
-            const float* src = xn + (long long)(cch[k] < 0 ? 0 : cch[k]) * HW + (long long)((R * a.sy) >> a.up_h) * a.W + ((C * a.sx) >> a.up_w);
+        for (int k = 0; k < 4; ++k) {
+          int jj = pj + cdx[k], ii = pi;
+          if (jj >= pitch) { jj -= pitch; ++ii; }
+          int R = R0 + a.min_ry + ii; if (R < 0) R += Ho; else if (R >= Ho) R -= Ho; if (R >= Ho) R -= Ho;
+          int C = a.min_rx + jj; if (C < 0) C += Wo; else if (C >= Wo) C -= Wo;
+          const float* src = xn + (coff[k] + ((R * sy) >> up_h) * Wsrc + ((C * sx) >> up_w));
+          const bool ok = cch[k] >= 0 && !no_load;
 #pragma unroll
-            for (int pl = 0; pl < 4; ++pl)
-              xv[k][pl] = (pl < a.npl && cch[k] >= 0) ? __ldg(src + (pl >> 1) * a.W + (pl & 1)) : 0.f;
-          }
+          for (int pl = 0; pl < 4; ++pl) xv[k][pl] = (pl < npl && ok) ? __ldg(src + (pl >> 1) * Wsrc + (pl & 1)) : 0.f;
         }
+        pj += WG_CK;
+        while (pj >= pitch) { pj -= pitch; ++pi; }
         // ---- loads of dO chunk t - lead
         const int jg = t - a.lead;
         float4 gv[4];
         if (jg >= 0) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const int uu = tid + k * WG_CONVERTERS;
             gv[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (uu < gy_units) {
-              const int co = uu >> 3, q = jg * WG_CK + ((uu & 7) << 2);
-              const int oy = q / a.pitch, ox = q - oy * a.pitch;
-              if (ox < a.Wo) gv[k] = __ldg(reinterpret_cast<const float4*>(gn + (long long)co * HoWo + (long long)oy * a.Wo + ox));
+            if (tid + k * WG_CONVERTERS < gy_units) {
+              if (gox[k] < Wo && !no_load) gv[k] = __ldg(reinterpret_cast<const float4*>(gn + (gco[k] + goy[k] * Wo + gox[k])));
+              gox[k] += WG_CK;
+              while (gox[k] >= pitch) { gox[k] -= pitch; ++goy[k]; }
             }
           }
         }
         // ---- patch chunk: convert + store
         {
           const int s = pg % a.NR, pk = pg / a.NR;
+          const long long d_t2 = dbg_on ? clock64() : 0;
           if (pk > 0) mbar_wait(patch_empty + s, (pk - 1) & 1);
-          if (any_col) {
+          if (dbg_on) { d_load += d_t2 - d_t1; d_wait_p += clock64() - d_t2; }
+          if (any_col && !(a.dbg_flags & 2)) {
             const int rr = s * WG_CK + lane;
             const int fo = rr * 32 + ((((e0 >> 3) ^ (rr & 3)) << 3) | (e0 & 7));
 #pragma unroll
@@ -208,7 +228,9 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __gr
         // ---- dO chunk: split + store
         if (jg >= 0) {
           const int s = hg % WG_NG, hk = hg / WG_NG;
+          const long long d_t3 = dbg_on ? clock64() : 0;
           if (hk > 0) mbar_wait(gy_empty + s, (hk - 1) & 1);
+          if (dbg_on) d_wait_g += clock64() - d_t3;
           float* gh = gyb + (size_t)s * a.gy_slot_floats;
           float* gl = gh + (a.gy_slot_floats >> 1);
 #pragma unroll
@@ -230,6 +252,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __gr
         }
       }
     }
+    if (dbg_on) { a.dbg[0] = clock64() - d_t0; a.dbg[1] = d_wait_p; a.dbg[2] = d_wait_g; a.dbg[3] = d_load; a.dbg[4] = pg; }
   } else if (warp == WG_WARP_MMA) {
     // =============================== MMA issuing warp ===============================
     const bool leader = elect_one();
@@ -240,12 +263,17 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __gr
     const uint32_t a_lbo = (uint32_t)a.mrows * 16u;
     const int ring_rows = a.ring, ntaps = a.ntaps, NC = a.NC, NR = a.NR, lead = a.lead, nch_u = a.nch_u, pcu = a.pcu;
     const int nacc = a.nacc, cols = a.cols;
+    const bool dbg_on = a.dbg != nullptr && blockIdx.x == 0 && leader;
+    long long d_wait_f = 0, d_wait_a = 0, d_iss = 0;
+    const long long d_t0 = dbg_on ? clock64() : 0;
     int pg = 0, hg = 0;
     for (int u = u_begin; u < u_end; ++u) {
       for (int j = 0; j < nch_u; ++j, ++hg) {
         const int sg = hg / WG_FC, sc = hg - sg * WG_FC;          // accumulation segment and chunk inside it
         const int as = nacc == 2 ? (sg & 1) : 0, ak = nacc == 2 ? (sg >> 1) : sg;
+        const long long d_t1 = dbg_on ? clock64() : 0;
         if (sc == 0 && ak > 0) mbar_wait(acc_free + as, (ak - 1) & 1);
+        const long long d_t2 = dbg_on ? clock64() : 0;
         const bool first = sc == 0;
         const uint32_t acc_base = tmem + (uint32_t)(as * cols);
         const int pneed = pg + j + lead;
@@ -253,8 +281,9 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __gr
         const int gs = hg % WG_NG;
         mbar_wait(gy_full + gs, (hg / WG_NG) & 1);
         tc_fence_after();
+        const long long d_t3 = dbg_on ? clock64() : 0;
         const int base_row = ((pg + j) % NR) * WG_CK;
-        if (leader) {
+        if (leader && !(a.dbg_flags & 4)) {
           const uint32_t ga_hi = gy_base + (uint32_t)gs * gy_slot_bytes, ga_lo = ga_hi + gy_lo_bytes;
 #pragma unroll 1
           for (int k8 = 0; k8 < 4; ++k8) {
@@ -273,16 +302,20 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __gr
               umma_tf32(d, da_lo, db_hi, idesc, 1u);
             }
           }
+        }
+        if (leader) {
           umma_commit(gy_empty + gs);
           umma_commit(patch_empty + (pg + j) % NR);
           if (j == nch_u - 1)
             for (int t = 1; t <= lead; ++t) umma_commit(patch_empty + (pg + j + t) % NR);
           if (sc == WG_FC - 1 || hg == nchunks_cta - 1) umma_commit(acc_full + as);
         }
+        if (dbg_on) { d_wait_a += d_t2 - d_t1; d_wait_f += d_t3 - d_t2; d_iss += clock64() - d_t3; }
         __syncwarp();
       }
       pg += pcu;
     }
+    if (dbg_on) { a.dbg[8] = clock64() - d_t0; a.dbg[9] = d_wait_a; a.dbg[10] = d_wait_f; a.dbg[11] = d_iss; a.dbg[12] = hg; }
     __syncwarp();
   } else {
     // =============================== drain warps ===============================
@@ -291,29 +324,35 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __gr
     const int co = a.M == 128 ? q * 32 + lane : (lane < 16 ? q * 16 + lane : -1);
     const bool row_ok = co >= 0 && co < a.cout;
     float* slab = a.slab + (size_t)blockIdx.x * a.cols * 128 + q * 32 + lane;
+    const bool dbg_on = a.dbg != nullptr && blockIdx.x == 0 && q == 0 && lane == 0;
+    long long d_wait = 0;
+    const long long d_t0 = dbg_on ? clock64() : 0;
     for (int sg = 0; sg < nseg; ++sg) {
       const int as = a.nacc == 2 ? (sg & 1) : 0, ak = a.nacc == 2 ? (sg >> 1) : sg;
+      const long long d_t1 = dbg_on ? clock64() : 0;
       mbar_wait<128>(acc_full + as, ak & 1);
+      if (dbg_on) d_wait += clock64() - d_t1;
       tc_fence_after();
       const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * a.cols);
       const bool last = sg == nseg - 1;
       for (int c0 = 0; c0 < a.cols; c0 += 16) {
-        float v[16], o[16];
-        if (sg > 0) {
-#pragma unroll
-          for (int k = 0; k < 16; ++k) o[k] = slab[(size_t)(c0 + k) * 128];
-        }
+        float v[16];
         tmem_ld16(trow + (uint32_t)c0, v);
         tmem_ld_wait();
-        if (sg > 0) {
-#pragma unroll
-          for (int k = 0; k < 16; ++k) v[k] += o[k];
-        }
         if (!last) {
+          // fire-and-forget: plain stores for the first segment, RED.ADD.F32 (round-to-nearest, no load round trip) afterwards
+          if (sg == 0) {
 #pragma unroll
-          for (int k = 0; k < 16; ++k) slab[(size_t)(c0 + k) * 128] = v[k];
+            for (int k = 0; k < 16; ++k) slab[(size_t)(c0 + k) * 128] = v[k];
+          } else {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) atomicAdd(slab + (size_t)(c0 + k) * 128, v[k]);
+          }
         } else if (row_ok) {
           const int t = c0 / a.NC, eb = c0 - t * a.NC;           // NC is a multiple of 8; a 16-column batch may span two taps
+          float o[16];
+#pragma unroll
+          for (int k = 0; k < 16; ++k) o[k] = sg > 0 ? __ldcg(slab + (size_t)(c0 + k) * 128) : 0.f;
 #pragma unroll
           for (int k = 0; k < 16; ++k) {
             int tt = t, e = eb + k;
@@ -322,7 +361,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __gr
             const int ci = cil < 0 ? -1 : cc * a.cchunk + cil;
             if (ci >= 0 && ci < a.cin && tt < a.ntaps) {
               const int tap = a.packed ? tt * a.kw + a.col_dx[e] : tt;
-              atomicAdd(a.dW + ((long long)co * a.cin + ci) * (a.kh * a.kw) + tap, (double)v[k]);
+              atomicAdd(a.dW + ((long long)co * a.cin + ci) * (a.kh * a.kw) + tap, (double)v[k] + (double)o[k]);
             }
           }
         }
@@ -331,6 +370,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __gr
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_free + as);
     }
+    if (dbg_on) { a.dbg[5] = clock64() - d_t0; a.dbg[6] = d_wait; a.dbg[7] = nseg; }
   }
   tc_fence_before();
   __syncthreads();
@@ -429,6 +469,9 @@ static bool wg_plan(const ConvDesc& d, WgTcArgs& a, size_t* smem_out) {
 bool arpde_conv_wgrad_tc_wanted(const ConvDesc& d) {
   if (!arpde_tc_enabled()) return false;
   if (const char* e = getenv("ARPDE_WGRAD_TC")) if (e[0] == '0') return false;
+  // an MMA costs ~40 cycles whatever M is: with cout < 32 most of the 64 accumulator rows are padding and the FFMA kernel wins
+  // (measured, N = 128: LastTransUp conv3x3 32->16 at 64x64: tensor core 0.41 ms, FFMA 0.375 ms)
+  if (d.cout < 32) return false;
   WgTcArgs a; size_t smem;
   return wg_plan(d, a, &smem);
 }
@@ -449,7 +492,8 @@ int arpde_conv_wgrad_tc_launch(const ConvDesc& d, const float* x, long long x_bs
   ARPDE_CHECK_ARG((((uintptr_t)dO) & 15) == 0 && (dO_bs & 3) == 0, "conv_wgrad_tc: output gradient must be 16-byte aligned");
   const long long need = (long long)a.ncc * a.slices * a.cols * 128;
   ARPDE_CHECK_ARG(scratch_floats >= need, "conv_wgrad_tc: scratch too small (%lld < %lld floats)", scratch_floats, need);
-  a.slab = scratch;
+  a.slab = scratch; a.dbg = arpde_tc_debug_buffer();
+  if (const char* e = getenv("ARPDE_WG_DBG")) a.dbg_flags = atoi(e);
   a.x = x; a.x_bs = x_bs; a.scale = scale; a.shift = shift; a.relu_in = d.relu_in; a.dO = dO; a.dO_bs = dO_bs; a.dW = dW64;
   const long long wn = (long long)d.cout * d.cin * d.kh * d.kw;
   ARPDE_CUDA(cudaMemsetAsync(dW64, 0, sizeof(double) * wn, stream));

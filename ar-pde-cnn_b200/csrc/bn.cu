@@ -78,11 +78,44 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__
   if (threadIdx.x == 0) { atomicAdd(stats + 2 * c, d1); atomicAdd(stats + 2 * c + 1, d2); }
 }
 
+// vectorised variant (16-byte aligned rows): CTA (chunk, channel) sums `per4` consecutive float4 of the channel's N x HW/4 elements;
+// (sample, offset) advance incrementally.  The scalar kernel above took 39 us for a 2 MB dense-layer output (8 CTAs per channel, a
+// 64-bit division per element); 16 such launches per training step were 8% of it.
+__global__ void __launch_bounds__(256) bn_stats_v_kernel(const float* __restrict__ x, long long x_bs, int N, int HW4, double* __restrict__ stats,
+                                                         int per4) {
+  const int c = blockIdx.y;
+  const long long total4 = (long long)N * HW4;
+  const long long lo = (long long)blockIdx.x * per4, hi = lo + per4 < total4 ? lo + per4 : total4;
+  long long i4 = lo + threadIdx.x;
+  int n = (int)(i4 / HW4), r4 = (int)(i4 - (long long)n * HW4);
+  float s1 = 0.f, s2 = 0.f;
+  const float* xc = x + (long long)c * HW4 * 4;
+  for (; i4 < hi; i4 += 256) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(xc + n * x_bs) + r4);
+    s1 += (v.x + v.y) + (v.z + v.w);
+    s2 = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, s2))));
+    r4 += 256;
+    while (r4 >= HW4) { r4 -= HW4; ++n; }
+  }
+  const double d1 = block_sum_d((double)s1);
+  const double d2 = block_sum_d((double)s2);
+  if (threadIdx.x == 0) { atomicAdd(stats + 2 * c, d1); atomicAdd(stats + 2 * c + 1, d2); }
+}
+
 extern "C" int arpde_bn_stats(const float* x, int64_t x_bstride, int N, int C, int64_t HW, double* stats, arpde_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   ARPDE_CHECK_ARG(x && stats && N > 0 && C > 0 && HW > 0, "bn_stats: bad args");
   ARPDE_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * C, stream));
   const long long total = (long long)N * HW;
+  if ((HW & 3) == 0 && (x_bstride & 3) == 0 && (((uintptr_t)x) & 15) == 0 && HW / 4 < (1ll << 30)) {
+    const long long total4 = total / 4;
+    const int per4 = 1024;                             // 4 float4 per thread: short fp32 partial sums, then fp64
+    const long long chunks = (total4 + per4 - 1) / per4;
+    ARPDE_CHECK_ARG(chunks < (1ll << 31) && C <= 65535, "bn_stats: tensor too large");
+    bn_stats_v_kernel<<<dim3((unsigned)chunks, (unsigned)C), 256, 0, stream>>>(x, x_bstride, N, (int)(HW / 4), stats, per4);
+    ARPDE_LAUNCH_CHECK();
+    return ARPDE_OK;
+  }
   int chunks = (int)ceil_div64(total, 256 * 64); if (chunks < 1) chunks = 1; if (chunks > 64) chunks = 64;
   bn_stats_kernel<<<C * chunks, 256, 0, stream>>>(x, x_bstride, N, C, HW, stats, chunks);
   ARPDE_LAUNCH_CHECK();

@@ -22,6 +22,9 @@
 //     stride 2: one ring per input parity plane (tap -> plane, offset), as conv_tc.cu;
 //     narrow-cin layers (cin * kw <= 32, e.g. the 6-channel stem): the 32 columns of a row hold (kx, ci) pairs, i.e.
 //     the x taps are unrolled into the MMA's N and only kh taps remain -- N = 32 instead of 8 per instruction.
+//     small-cout layers (dense layers, cout = growth rate <= 8): roles swapped -- the patch ring is the M operand (MN-major A: up to
+//     128 channels = four 32-channel blocks at LBO stride), dO the K-major N operand (N = 8), D[ci][(tap, co)]; otherwise 60 of the
+//     64 accumulator rows would be padding (an MMA costs ~40 cycles whatever M and N <= 64 are).
 //   3xTF32: hi*hi + hi*lo + lo*hi into the same fp32 accumulator (lo*lo ~ 2^-22 dropped).
 //   The tensor core TRUNCATES when it adds into the fp32 accumulator (measured: one 1100-step accumulation chain over a
 //   training batch was off by 2.3e-5 relative, always towards zero), so a chain is cut after WG_FC chunks (96 adds):
@@ -58,15 +61,16 @@ struct WgTcArgs {
   int N, cin, H, W, up_h, up_w, sy, sx, Ho, Wo, cout, kh, kw;
   int pitch, min_ry, min_rx;
   int RB, RBH, nch_u, lead, pcu, NR, ring;     // row blocks per sample, rows per block, MMA chunks / patch chunks per unit, ring chunks / rows
-  int npl, NC, ncc, cchunk, packed, ntaps;     // planes, MMA N, channel chunks (grid split), channels per chunk, (kx,ci) packing, MMA taps
+  int npl, NC, ncc, cchunk, packed, ntaps;     // planes, columns per tap (MMA N), channel chunks (grid split), channels per chunk, (kx,ci) packing, MMA taps
+  int swap, nblk;                              // swap = 1: ring is the M operand (nblk blocks of 32 channels), dO the N operand (NC = cout padded)
   int M, mrows, tmem_cols, slices, units, cols, nacc;   // cols = ntaps * NC accumulator columns per set, nacc sets
   long long* dbg;                              // cycle counters of CTA 0 (arpde_conv_tc_set_debug), else nullptr
   int dbg_flags;                               // experiments (ARPDE_WG_DBG): 1 = converters skip loads and stores, 4 = skip the MMAs
   int plane_floats, gy_slot_floats;            // one ring plane (hi or lo) incl. mirror; one dO slot (hi + lo)
   int tap_plane[WG_MAX_TAPS];
   int tap_off[WG_MAX_TAPS];
-  signed char col_ci[32];                      // column -> channel inside the chunk (-1: padding)
-  signed char col_dx[32];                      // column -> x-tap index folded into the column (packed layers), else 0
+  signed char col_ci[32];                      // ring column (block 0) -> channel inside the chunk (-1: padding); block b adds 32 b
+  signed char col_dx[32];                      // ring column -> x-tap index folded into the column (packed layers), else 0
 };
 
 __device__ __forceinline__ uint64_t wg_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
@@ -79,6 +83,45 @@ __device__ __forceinline__ void wg_split(float t, float& hi, float& lo) {
   lo = t - hi;
 }
 
+// MMAs of one 32-position chunk, issued by the elected lane: 4 K steps x taps x 3 split terms.  Descriptor high words are constants
+// (dO: K-major no-swizzle, SBO 128 B; ring: MN-major layout type 1, SBO 512 B, LBO = one ring plane between 32-channel blocks); only the
+// 14-bit start-address field of the low word changes.  (The first version rebuilt four 64-bit descriptors per tap and branched on the
+// role inside the loop: 60-80 cycles per MMA instead of the tensor core's ~40.)
+template <bool SWAP>
+__device__ __forceinline__ void wg_issue_chunk(const WgTcArgs& a, uint32_t gy_lo, uint32_t ring_lo, int base_row, uint32_t acc_base,
+                                               uint32_t idesc, bool first) {
+  const uint64_t gy_hi64 = (uint64_t)((128u >> 4) | (1u << 14)) << 32;
+  const uint64_t ring_hi64 = (uint64_t)((512u >> 4) | (1u << 14) | (1u << 29)) << 32;
+  const uint32_t gy_part16 = (uint32_t)a.gy_slot_floats >> 3;                           // hi -> lo part of a dO slot, 16-byte units
+  const uint32_t ring_part16 = (uint32_t)(a.npl * a.nblk) * ((uint32_t)a.plane_floats >> 2);
+  const uint32_t plane16 = (uint32_t)a.nblk * ((uint32_t)a.plane_floats >> 2);        // parity planes are nblk ring planes apart
+  const uint32_t k8_step16 = 2u * (uint32_t)a.mrows;                                    // two 16-byte K planes per K = 8 step
+  const int ntaps = a.ntaps, ring_rows = a.ring;
+  const uint32_t NC = (uint32_t)a.NC;
+#pragma unroll 1
+  for (int k8 = 0; k8 < 4; ++k8) {
+    const uint64_t dg_hi = gy_hi64 | (gy_lo + (uint32_t)k8 * k8_step16), dg_lo = dg_hi + gy_part16;
+    const uint32_t acc0 = (first && k8 == 0) ? 0u : 1u;
+    const int row0 = base_row + k8 * 8;
+    uint32_t d = acc_base;
+#pragma unroll 1
+    for (int t = 0; t < ntaps; ++t, d += NC) {
+      int rr = row0 + a.tap_off[t];
+      if (rr >= ring_rows) rr -= ring_rows;
+      const uint64_t dr_hi = ring_hi64 | (ring_lo + (uint32_t)a.tap_plane[t] * plane16 + (uint32_t)rr * 8u), dr_lo = dr_hi + ring_part16;
+      if (!SWAP) {
+        umma_tf32(d, dg_hi, dr_hi, idesc, acc0);
+        umma_tf32(d, dg_hi, dr_lo, idesc, 1u);
+        umma_tf32(d, dg_lo, dr_hi, idesc, 1u);
+      } else {
+        umma_tf32(d, dr_hi, dg_hi, idesc, acc0);
+        umma_tf32(d, dr_lo, dg_hi, idesc, 1u);
+        umma_tf32(d, dr_hi, dg_lo, idesc, 1u);
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __grid_constant__ WgTcArgs a) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   uint64_t* patch_full = reinterpret_cast<uint64_t*>(smem_raw);        // [NR] ring chunk converted (one arrival per converter warp)
@@ -89,8 +132,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __gr
   uint64_t* acc_free = acc_full + 2;                                    // [2] accumulator set drained (one arrival per drain warp)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + 512);
   float* ss_tab = reinterpret_cast<float*>(smem_raw + 1024);            // [scale | shift][WG_MAX_CIN]
-  float* ring = reinterpret_cast<float*>(smem_raw + WG_HEADER);         // [hi | lo][npl][ring + 8 rows][32]
-  float* gyb = ring + (size_t)2 * a.npl * a.plane_floats;               // [NG][hi | lo][8][mrows][4]
+  float* ring = reinterpret_cast<float*>(smem_raw + WG_HEADER);         // [hi | lo][npl * nblk][ring + 8 rows][32]
+  float* gyb = ring + (size_t)2 * a.npl * a.nblk * a.plane_floats;      // [NG][hi | lo][8][mrows][4]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int cc = (int)blockIdx.x % a.ncc, slice = (int)blockIdx.x / a.ncc;
@@ -142,7 +185,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __gr
     // loop-invariant geometry in registers; every per-step index is advanced incrementally (the first version recomputed two integer
     // divisions and 64-bit address products per load and spent ~1500 cycles per 32-position step on index arithmetic alone)
     const int pitch = a.pitch, Ho = a.Ho, Wo = a.Wo, Wsrc = a.W, sy = a.sy, sx = a.sx, up_h = a.up_h, up_w = a.up_w, npl = a.npl;
-    const int HWi = a.H * a.W, HoWoi = a.Ho * a.Wo;
+    const int HWi = a.H * a.W, HoWoi = a.Ho * a.Wo, nblk = a.nblk, nslot = a.npl * a.nblk;
+    const int climit = min(a.cin, (cc + 1) * a.cchunk);           // channels of this CTA's chunk end here
     int coff[4];                                       // channel offset of each column inside the sample
 #pragma unroll
     for (int k = 0; k < 4; ++k) coff[k] = (cch[k] < 0 ? 0 : cch[k]) * HWi;
@@ -163,7 +207,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __gr
       for (int t = 0; t < a.pcu; ++t, ++pg) {
         // ---- loads of patch chunk t (32 positions, this thread: position `lane`, 4 columns, every plane)
         const long long d_t1 = dbg_on ? clock64() : 0;
-        float xv[4][4];
+        float xv[4][4];                                  // [column][slot], slot = plane (stride 2) or 32-channel block (swapped roles)
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           int jj = pj + cdx[k], ii = pi;
@@ -172,8 +216,13 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __gr
           int C = a.min_rx + jj; if (C < 0) C += Wo; else if (C >= Wo) C -= Wo;
           const float* src = xn + (coff[k] + ((R * sy) >> up_h) * Wsrc + ((C * sx) >> up_w));
           const bool ok = cch[k] >= 0 && !no_load;
+          if (nblk == 1) {
 #pragma unroll
-          for (int pl = 0; pl < 4; ++pl) xv[k][pl] = (pl < npl && ok) ? __ldg(src + (pl >> 1) * Wsrc + (pl & 1)) : 0.f;
+            for (int pl = 0; pl < 4; ++pl) xv[k][pl] = (pl < npl && ok) ? __ldg(src + (pl >> 1) * Wsrc + (pl & 1)) : 0.f;
+          } else {
+#pragma unroll
+            for (int b = 0; b < 4; ++b) xv[k][b] = (b < nblk && ok && cch[k] + 32 * b < climit) ? __ldg(src + b * 32 * HWi) : 0.f;
+          }
         }
         pj += WG_CK;
         while (pj >= pitch) { pj -= pitch; ++pi; }
@@ -201,17 +250,23 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __gr
             const int rr = s * WG_CK + lane;
             const int fo = rr * 32 + ((((e0 >> 3) ^ (rr & 3)) << 3) | (e0 & 7));
 #pragma unroll
-            for (int pl = 0; pl < 4; ++pl) {
-              if (pl < a.npl) {
+            for (int sl = 0; sl < 4; ++sl) {
+              if (sl < nslot) {
                 float hi[4], lo[4];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                  float v = fmaf(xv[k][pl], csc[k], csh[k]);
+                  float sc_ = csc[k], sh_ = csh[k];
+                  if (nblk > 1 && sl > 0) {              // block sl of the same column: channel + 32 sl
+                    const int c = cch[k] + 32 * sl;
+                    const bool okc = cch[k] >= 0 && c < climit;
+                    sc_ = okc ? ss_tab[c] : 0.f; sh_ = okc ? ss_tab[WG_MAX_CIN + c] : 0.f;
+                  }
+                  float v = fmaf(xv[k][sl], sc_, sh_);
                   if (a.relu_in) v = fmaxf(v, 0.f);
                   wg_split(v, hi[k], lo[k]);
                 }
-                float* ph = ring + (size_t)pl * a.plane_floats + fo;
-                float* plo = ph + (size_t)a.npl * a.plane_floats;
+                float* ph = ring + (size_t)sl * a.plane_floats + fo;
+                float* plo = ph + (size_t)nslot * a.plane_floats;
                 *reinterpret_cast<float4*>(ph) = make_float4(hi[0], hi[1], hi[2], hi[3]);
                 *reinterpret_cast<float4*>(plo) = make_float4(lo[0], lo[1], lo[2], lo[3]);
                 if (s == 0 && lane < 8) {              // mirror of the first 8 ring rows behind the ring end
@@ -256,11 +311,17 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __gr
   } else if (warp == WG_WARP_MMA) {
     // =============================== MMA issuing warp ===============================
     const bool leader = elect_one();
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((uint32_t)(a.NC >> 3) << 17) | ((uint32_t)(a.M >> 4) << 24);
+    // D = f32, A = B = tf32; the patch ring is the MN-major operand: B (bit 16) normally, A (bit 15) with swapped roles
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (a.swap ? (1u << 15) : (1u << 16)) | ((uint32_t)(a.NC >> 3) << 17) | ((uint32_t)(a.M >> 4) << 24);
+    const int swap = a.swap;
     const uint32_t ring_base = smem_u32(ring), gy_base = smem_u32(gyb);
-    const uint32_t plane_bytes = (uint32_t)a.plane_floats * 4u, lo_bytes = (uint32_t)a.npl * plane_bytes;
+    const uint32_t plane_bytes = (uint32_t)a.plane_floats * 4u, lo_bytes = (uint32_t)(a.npl * a.nblk) * plane_bytes;
+    const uint32_t tap_plane_bytes = (uint32_t)a.nblk * plane_bytes;      // parity planes are nblk slots apart
     const uint32_t gy_slot_bytes = (uint32_t)a.gy_slot_floats * 4u, gy_lo_bytes = gy_slot_bytes >> 1;
-    const uint32_t a_lbo = (uint32_t)a.mrows * 16u;
+    // low descriptor words (start address >> 4 | LBO >> 4 << 16) of dO slot 0 / ring plane 0; every operand lies below 256 KB, so adding
+    // 16-byte offsets to the low word never carries into the LBO field
+    const uint32_t gy_lo0 = (gy_base >> 4) | ((uint32_t)a.mrows << 16);
+    const uint32_t ring_lo0 = (ring_base >> 4) | ((plane_bytes >> 4) << 16);
     const int ring_rows = a.ring, ntaps = a.ntaps, NC = a.NC, NR = a.NR, lead = a.lead, nch_u = a.nch_u, pcu = a.pcu;
     const int nacc = a.nacc, cols = a.cols;
     const bool dbg_on = a.dbg != nullptr && blockIdx.x == 0 && leader;
@@ -284,24 +345,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __gr
         const long long d_t3 = dbg_on ? clock64() : 0;
         const int base_row = ((pg + j) % NR) * WG_CK;
         if (leader && !(a.dbg_flags & 4)) {
-          const uint32_t ga_hi = gy_base + (uint32_t)gs * gy_slot_bytes, ga_lo = ga_hi + gy_lo_bytes;
-#pragma unroll 1
-          for (int k8 = 0; k8 < 4; ++k8) {
-            const uint64_t da_hi = wg_desc(ga_hi + (uint32_t)k8 * 2u * a_lbo, a_lbo, 128u, 0u);
-            const uint64_t da_lo = wg_desc(ga_lo + (uint32_t)k8 * 2u * a_lbo, a_lbo, 128u, 0u);
-            const uint32_t acc0 = (first && k8 == 0) ? 0u : 1u;
-#pragma unroll 1
-            for (int t = 0; t < ntaps; ++t) {
-              int rr = base_row + k8 * 8 + a.tap_off[t];
-              if (rr >= ring_rows) rr -= ring_rows;
-              const uint32_t b_hi = ring_base + (uint32_t)a.tap_plane[t] * plane_bytes + (uint32_t)rr * 128u;
-              const uint64_t db_hi = wg_desc(b_hi, 0u, 512u, 1u), db_lo = wg_desc(b_hi + lo_bytes, 0u, 512u, 1u);
-              const uint32_t d = acc_base + (uint32_t)(t * NC);
-              umma_tf32(d, da_hi, db_hi, idesc, acc0);
-              umma_tf32(d, da_hi, db_lo, idesc, 1u);
-              umma_tf32(d, da_lo, db_hi, idesc, 1u);
-            }
-          }
+          if (swap) wg_issue_chunk<true>(a, gy_lo0 + (uint32_t)gs * (gy_slot_bytes >> 4), ring_lo0, base_row, acc_base, idesc, first);
+          else wg_issue_chunk<false>(a, gy_lo0 + (uint32_t)gs * (gy_slot_bytes >> 4), ring_lo0, base_row, acc_base, idesc, first);
         }
         if (leader) {
           umma_commit(gy_empty + gs);
@@ -321,8 +366,10 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __gr
     // =============================== drain warps ===============================
     // TMEM lane quarter = warp % 4.  Segment sg: slab (+)= accumulators; the last segment adds slab + accumulators into dW64.
     const int q = warp & 3;
-    const int co = a.M == 128 ? q * 32 + lane : (lane < 16 ? q * 16 + lane : -1);
-    const bool row_ok = co >= 0 && co < a.cout;
+    const int row = a.M == 128 ? q * 32 + lane : (lane < 16 ? q * 16 + lane : -1);     // accumulator row of this TMEM lane
+    // normal roles: row = output channel, column = (tap, ring column); swapped: row = input channel of the chunk, column = (tap, co)
+    const int co = row, ci_row = cc * a.cchunk + row;
+    const bool row_ok = row >= 0 && (a.swap ? (row < a.cchunk && ci_row < a.cin) : row < a.cout);
     float* slab = a.slab + (size_t)blockIdx.x * a.cols * 128 + q * 32 + lane;
     const bool dbg_on = a.dbg != nullptr && blockIdx.x == 0 && q == 0 && lane == 0;
     long long d_wait = 0;
@@ -357,11 +404,16 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __gr
           for (int k = 0; k < 16; ++k) {
             int tt = t, e = eb + k;
             if (e >= a.NC) { e -= a.NC; ++tt; }
-            const int cil = a.col_ci[e];
-            const int ci = cil < 0 ? -1 : cc * a.cchunk + cil;
-            if (ci >= 0 && ci < a.cin && tt < a.ntaps) {
-              const int tap = a.packed ? tt * a.kw + a.col_dx[e] : tt;
-              atomicAdd(a.dW + ((long long)co * a.cin + ci) * (a.kh * a.kw) + tap, (double)v[k] + (double)o[k]);
+            if (a.swap) {
+              if (e < a.cout && tt < a.ntaps)
+                atomicAdd(a.dW + ((long long)e * a.cin + ci_row) * (a.kh * a.kw) + tt, (double)v[k] + (double)o[k]);
+            } else {
+              const int cil = a.col_ci[e];
+              const int ci = cil < 0 ? -1 : cc * a.cchunk + cil;
+              if (ci >= 0 && ci < a.cin && tt < a.ntaps) {
+                const int tap = a.packed ? tt * a.kw + a.col_dx[e] : tt;
+                atomicAdd(a.dW + ((long long)co * a.cin + ci) * (a.kh * a.kw) + tap, (double)v[k] + (double)o[k]);
+              }
             }
           }
         }
@@ -386,7 +438,7 @@ static bool wg_plan(const ConvDesc& d, WgTcArgs& a, size_t* smem_out) {
   if (d.H == 1 && d.kh == 1) return false;                       // 1D nets stay on the FFMA kernel
   if (d.stride != 1 && d.stride != 2) return false;
   if (d.up && d.stride != 1) return false;
-  if (d.cout < 16 || d.cout > 128 || d.cin > WG_MAX_CIN) return false;
+  if (d.cout > 128 || d.cin > WG_MAX_CIN) return false;
   if (d.kh > 7 || d.kw > 7) return false;
   memset(&a, 0, sizeof(a));
   a.N = d.N; a.cin = d.cin; a.H = d.H; a.W = d.W; a.up_w = d.up ? 1 : 0; a.up_h = a.up_w; a.sy = a.sx = d.stride;
@@ -402,8 +454,21 @@ static bool wg_plan(const ConvDesc& d, WgTcArgs& a, size_t* smem_out) {
   for (int k = 0; k < d.kw; ++k) { const int dx = k - pad_x; px[k] = ((dx % a.sx) + a.sx) % a.sx; rx[k] = wg_floor_div(dx - px[k], a.sx); if (rx[k] < min_rx) min_rx = rx[k]; if (rx[k] > max_rx) max_rx = rx[k]; }
   a.min_ry = min_ry; a.min_rx = min_rx;
   const int span_y = max_ry - min_ry, span_x = max_rx - min_rx;
+  (void)span_y;
   a.pitch = wg_round_up(a.Wo + span_x, 4);
   a.npl = a.sy * a.sx;
+  a.nblk = 1;
+  // roles: cout on the accumulator rows (M) unless it is tiny -- then the input channels go there and cout becomes the MMA's N
+  a.swap = (d.cout <= 8 && d.cin >= 32 && a.sx == 1) ? 1 : 0;
+  if (!a.swap && d.cout < 16) return false;
+  if (a.swap) {
+    a.cchunk = d.cin < 128 ? d.cin : 128; a.ncc = (d.cin + a.cchunk - 1) / a.cchunk;
+    a.M = a.cchunk <= 64 ? 64 : 128; a.nblk = a.M / 32;
+    a.NC = wg_round_up(d.cout, a.M == 128 ? 16 : 8); a.ntaps = d.kh * d.kw;
+    for (int e = 0; e < 32; ++e) { a.col_ci[e] = (signed char)e; a.col_dx[e] = 0; }
+    for (int ky = 0; ky < d.kh; ++ky)
+      for (int kx = 0; kx < d.kw; ++kx) { a.tap_plane[ky * d.kw + kx] = 0; a.tap_off[ky * d.kw + kx] = (ry[ky] - min_ry) * a.pitch + (rx[kx] - min_rx); }
+  } else {
   a.M = d.cout <= 64 ? 64 : 128;
   const int nmult = a.M == 128 ? 16 : 8;
   a.packed = (a.sx == 1 && d.kw > 1 && d.cin * d.kw <= 32) ? 1 : 0;
@@ -423,6 +488,7 @@ static bool wg_plan(const ConvDesc& d, WgTcArgs& a, size_t* smem_out) {
         a.tap_off[ky * d.kw + kx] = (ry[ky] - min_ry) * a.pitch + (rx[kx] - min_rx);
       }
   }
+  }
   if (a.ntaps > WG_MAX_TAPS || a.ntaps * a.NC > 512) return false;
   if (4 * a.ntaps * 3 < 48) return false;                        // too few MMAs per chunk to hide the staging: FFMA kernel
   int max_off = 0;
@@ -440,7 +506,7 @@ static bool wg_plan(const ConvDesc& d, WgTcArgs& a, size_t* smem_out) {
   a.RBH = a.Ho / a.RB;
   if ((a.RBH * a.pitch) % WG_CK) return false;
   a.nch_u = a.RBH * a.pitch / WG_CK; a.pcu = a.nch_u + a.lead;
-  a.mrows = d.cout | 1;                                          // odd row count: the 8 position groups of a dO chunk hit distinct banks
+  a.mrows = (a.swap ? a.NC : d.cout) | 1;                                          // odd row count: the 8 position groups of a dO chunk hit distinct banks
   a.gy_slot_floats = 2 * 8 * a.mrows * 4;
   // an M-row MMA reads rows [0, M) of every 16-byte K plane: the over-read of the last plane must stay inside the slot ring
   const size_t gy_bytes = (size_t)WG_NG * a.gy_slot_floats * 4 + (size_t)a.M * 16;
@@ -449,7 +515,7 @@ static bool wg_plan(const ConvDesc& d, WgTcArgs& a, size_t* smem_out) {
   for (int nr = a.lead + 6; nr >= a.lead + 2; --nr) {
     if (nr > WG_MAX_NR) continue;
     const size_t plane = (size_t)(nr * WG_CK + 8) * 128;
-    if (WG_HEADER + 2 * a.npl * plane + gy_bytes <= budget) { a.NR = nr; break; }
+    if (WG_HEADER + 2 * a.npl * a.nblk * plane + gy_bytes <= budget) { a.NR = nr; break; }
   }
   if (!a.NR) return false;
   a.ring = a.NR * WG_CK;
@@ -462,7 +528,7 @@ static bool wg_plan(const ConvDesc& d, WgTcArgs& a, size_t* smem_out) {
   a.units = d.N * a.RB;
   int slices = arpde_num_sms() / a.ncc; if (slices < 1) slices = 1; if (slices > a.units) slices = a.units;
   a.slices = slices;
-  *smem_out = WG_HEADER + (size_t)2 * a.npl * a.plane_floats * 4 + gy_bytes;
+  *smem_out = WG_HEADER + (size_t)2 * a.npl * a.nblk * a.plane_floats * 4 + gy_bytes;
   return true;
 }
 
@@ -471,7 +537,7 @@ bool arpde_conv_wgrad_tc_wanted(const ConvDesc& d) {
   if (const char* e = getenv("ARPDE_WGRAD_TC")) if (e[0] == '0') return false;
   // an MMA costs ~40 cycles whatever M is: with cout < 32 most of the 64 accumulator rows are padding and the FFMA kernel wins
   // (measured, N = 128: LastTransUp conv3x3 32->16 at 64x64: tensor core 0.41 ms, FFMA 0.375 ms)
-  if (d.cout < 32) return false;
+  if (d.cout < 32 && d.cout > 8) return false;
   WgTcArgs a; size_t smem;
   return wg_plan(d, a, &smem);
 }
@@ -517,8 +583,8 @@ int arpde_conv_wgrad_tc_launch(const ConvDesc& d, const float* x, long long x_bs
   return arpde_d2f_launch(dW64, dW, wn, stream);
 }
 
-// Diagnostic (host only): the tiling conv_wgrad_tc_kernel would use.  out[0..23] = pitch, min_ry, min_rx, RB, RBH, nch_u, lead, pcu, NR,
-// npl, NC, ncc, cchunk, packed, ntaps, M, mrows, tmem_cols, slices(N=1), smem bytes, Ho, Wo, sy, sx; out[32+t] = tap plane,
+// Diagnostic (host only): the tiling conv_wgrad_tc_kernel would use.  out[0..25] = pitch, min_ry, min_rx, RB, RBH, nch_u, lead, pcu, NR,
+// npl, NC, ncc, cchunk, packed, ntaps, M, mrows, tmem_cols, slices(N=1), smem bytes, Ho, Wo, sy, sx, swap, nblk; out[32+t] = tap plane,
 // out[81+t] = tap offset, out[130+e] = column channel, out[162+e] = column x-tap.
 extern "C" int arpde_conv_wgrad_tc_plan(int cin, int H, int W, int cout, int kh, int kw, int stride, int up, int32_t* out) {
   ARPDE_CHECK_ARG(out, "conv_wgrad_tc_plan: null output");
@@ -527,9 +593,9 @@ extern "C" int arpde_conv_wgrad_tc_plan(int cin, int H, int W, int cout, int kh,
   d.up = up; d.relu_in = 0; d.act = 0; d.y_ctot = cout; d.y_coff = 0; d.n_per_group = 1;
   WgTcArgs a; size_t smem = 0;
   if (!wg_plan(d, a, &smem)) { arpde_set_error("conv_wgrad_tc_plan: layer not supported"); return ARPDE_ERR_UNSUPPORTED; }
-  const int v[24] = {a.pitch, a.min_ry, a.min_rx, a.RB, a.RBH, a.nch_u, a.lead, a.pcu, a.NR, a.npl, a.NC, a.ncc, a.cchunk, a.packed, a.ntaps,
-                     a.M, a.mrows, a.tmem_cols, a.slices, (int)smem, a.Ho, a.Wo, a.sy, a.sx};
-  for (int i = 0; i < 24; ++i) out[i] = v[i];
+  const int v[26] = {a.pitch, a.min_ry, a.min_rx, a.RB, a.RBH, a.nch_u, a.lead, a.pcu, a.NR, a.npl, a.NC, a.ncc, a.cchunk, a.packed, a.ntaps,
+                     a.M, a.mrows, a.tmem_cols, a.slices, (int)smem, a.Ho, a.Wo, a.sy, a.sx, a.swap, a.nblk};
+  for (int i = 0; i < 26; ++i) out[i] = v[i];
   for (int t = 0; t < WG_MAX_TAPS; ++t) { out[32 + t] = t < a.ntaps ? a.tap_plane[t] : 0; out[81 + t] = t < a.ntaps ? a.tap_off[t] : 0; }
   for (int e = 0; e < 32; ++e) { out[130 + e] = a.col_ci[e]; out[162 + e] = a.col_dx[e]; }
   return ARPDE_OK;

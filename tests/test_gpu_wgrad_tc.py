@@ -50,6 +50,10 @@ LAYERS = [
     (3, 20, 7, 1, 0, 32, 32, 3),         # k7, packed (21 columns)
     (20, 128, 3, 1, 0, 16, 16, 7),       # cout = 128
     (40, 64, 5, 1, 0, 16, 16, 2),        # 25 taps x 16 columns, M = 64
+    (48, 4, 3, 1, 0, 32, 32, 5),         # denselayer1: swapped roles (channels on the accumulator rows, N = 8)
+    (60, 4, 3, 1, 0, 32, 32, 5),         # denselayer4
+    (150, 8, 3, 1, 0, 16, 16, 4),        # swapped, M = 128 (four channel blocks), two channel chunks
+    (64, 5, 5, 1, 0, 16, 16, 3),         # swapped, 25 taps
 ]
 
 
@@ -93,7 +97,7 @@ def test_wgrad_tc_training_batch():
 
 
 def test_wgrad_tc_unsupported_layer_reports_error():
-    x = torch.randn(2, 48, 32, 32, device=DEV)
-    gy = torch.randn(2, 4, 32, 32, device=DEV)
+    x = torch.randn(2, 16, 32, 32, device=DEV)
+    gy = torch.randn(2, 12, 32, 32, device=DEV)
     with pytest.raises(RuntimeError, match='not supported'):
-        wgrad_tc(x, 48 * 32 * 32, None, None, gy, 4 * 32 * 32, 2, 48, 32, 32, 4, 3, 3, 1, 0, 0)
+        wgrad_tc(x, 16 * 32 * 32, None, None, gy, 12 * 32 * 32, 2, 16, 32, 32, 12, 3, 3, 1, 0, 0)

@@ -12,7 +12,7 @@ import torch
 from oracle import arpde_oracle as O
 from arpde_b200 import _lib as L
 
-NAMES = 'pitch min_ry min_rx RB RBH nch_u lead pcu NR npl NC ncc cchunk packed ntaps M mrows tmem slices smem Ho Wo sy sx'.split()
+NAMES = 'pitch min_ry min_rx RB RBH nch_u lead pcu NR npl NC ncc cchunk packed ntaps M mrows tmem slices smem Ho Wo sy sx swap nblk'.split()
 
 
 def plan(cin, H, W, cout, kh, kw, s, up):
@@ -35,8 +35,10 @@ def replay(x, gy, up, kh, kw, p, ahead):
     ring = NR * 32
     dW = np.zeros((cout, cin, kh, kw))
     for cc in range(p['ncc']):
-        D = np.zeros((cout, p['ntaps'], p['NC']))
-        patch = np.full((p['npl'], ring + 8, 32), np.nan)
+        nblk, swap = p['nblk'], p['swap']
+        climit = min(cin, (cc + 1) * p['cchunk'])
+        D = np.zeros((p['M'] if swap else cout, p['ntaps'], p['NC']))
+        patch = np.full((p['npl'] * nblk, ring + 8, 32), np.nan)       # slot = plane * nblk + 32-channel block
         units = [(n, rb) for n in range(N) for rb in range(p['RB'])]
 
         def produce(g):      # global patch chunk g -> ring slot
@@ -47,10 +49,11 @@ def replay(x, gy, up, kh, kw, p, ahead):
             for lane in range(32):
                 pos = t * 32 + lane
                 i, j = divmod(pos, pitch)
-                for e in range(p['NC']):
+                for e in range(32 if swap else p['NC']):
+                  for blk in range(nblk):
                     ci = p['col_ci'][e]
-                    c = cc * p['cchunk'] + ci if ci >= 0 else -1
-                    if c < 0 or c >= cin:
+                    c = cc * p['cchunk'] + ci + 32 * blk if ci >= 0 else -1
+                    if c < 0 or c >= climit:
                         val = np.zeros(p['npl'])
                     else:
                         jj, ii = j + p['col_dx'][e], i
@@ -62,9 +65,10 @@ def replay(x, gy, up, kh, kw, p, ahead):
                         sr, sc = (R * p['sy']) >> up, (Cc * p['sx']) >> up
                         val = np.array([x[n, c, sr + (pl >> 1), sc + (pl & 1)] for pl in range(p['npl'])])
                     rr = s * 32 + lane
-                    patch[:, rr, e] = val
+                    sl = slice(blk, None, nblk) if nblk == 1 else slice(blk, blk + 1)
+                    patch[sl, rr, e] = val
                     if s == 0 and lane < 8:
-                        patch[:, ring + lane, e] = val
+                        patch[sl, ring + lane, e] = val
         produced = 0
         total_chunks = len(units) * pcu
         released = 0          # chunks [0, released) have been released by the MMAs
@@ -88,6 +92,11 @@ def replay(x, gy, up, kh, kw, p, ahead):
                         if rr >= ring:
                             rr -= ring
                         assert rr + 8 <= ring + 8
+                        if swap:      # ring = M operand: rows = channels of the nblk blocks, columns = cout (padded)
+                            xa = np.concatenate([patch[p['tap_plane'][t] * nblk + blk, rr:rr + 8, :] for blk in range(nblk)], axis=1)   # [8, M]
+                            assert not np.isnan(xa[:, :climit - cc * p['cchunk']]).any(), (lu, j, k8, t)
+                            D[:, t, :cout] += np.nan_to_num(xa).T @ g8.T
+                            continue
                         b = patch[p['tap_plane'][t], rr:rr + 8, :p['NC']]                               # [8, NC]
                         assert not np.isnan(b).any(), (lu, j, k8, t)
                         D[:, t, :] += g8 @ b
@@ -95,6 +104,11 @@ def replay(x, gy, up, kh, kw, p, ahead):
                 if j == nch_u - 1:
                     released = pg + pcu
             pg += pcu
+        if swap:
+            for row in range(min(p['cchunk'], climit - cc * p['cchunk'])):
+                for t in range(p['ntaps']):
+                    dW[:, cc * p['cchunk'] + row, t // kw, t % kw] += D[row, t, :cout]
+            continue
         for t in range(p['ntaps']):
             for e in range(p['NC']):
                 ci = p['col_ci'][e]
@@ -107,7 +121,7 @@ def replay(x, gy, up, kh, kw, p, ahead):
 
 CASES = [  # cin, cout, kh, kw, stride, up, H, W
     (6, 16, 5, 5, 1, 0, 16, 16), (40, 16, 3, 3, 2, 0, 16, 32), (12, 16, 3, 3, 1, 1, 8, 8), (3, 20, 7, 7, 1, 0, 16, 16),
-    (12, 16, 4, 4, 2, 0, 32, 32), (33, 17, 3, 3, 1, 0, 8, 16)]
+    (12, 16, 4, 4, 2, 0, 32, 32), (33, 17, 3, 3, 1, 0, 8, 16), (48, 4, 3, 3, 1, 0, 8, 16), (150, 8, 3, 3, 1, 0, 8, 16)]
 
 
 @pytest.mark.parametrize('ahead', [False, True])
@@ -135,10 +149,12 @@ def test_wgrad_plan_of_the_c4_layers():
     p3 = plan(96, 64, 64, 48, 3, 3, 2, 0)           # stride 2: four parity planes, three channel chunks
     assert p3['npl'] == 4 and p3['ncc'] == 3 and p3['M'] == 64 and p3['ntaps'] * p3['NC'] <= 512 and p3['smem'] <= 227 * 1024
     assert p3['NR'] >= p3['lead'] + 2
+    pd = plan(60, 32, 32, 4, 3, 3, 1, 0)            # dense layer: roles swapped, 64 accumulator rows = two channel blocks, N = 8
+    assert pd['swap'] == 1 and pd['M'] == 64 and pd['nblk'] == 2 and pd['NC'] == 8 and pd['ncc'] == 1
 
 
 def test_wgrad_unsupported_layers_fall_back():
     out = (C.c_int32 * 200)()
-    for args in [(48, 32, 32, 4, 3, 3, 1, 0), (16, 64, 64, 2, 5, 5, 1, 0), (64, 32, 32, 32, 1, 1, 1, 0), (16, 1, 512, 32, 1, 5, 1, 0)]:
+    for args in [(16, 32, 32, 12, 3, 3, 1, 0), (16, 64, 64, 2, 5, 5, 1, 0), (64, 32, 32, 32, 1, 1, 1, 0), (16, 1, 512, 32, 1, 5, 1, 0)]:
         rc = L.lib.arpde_conv_wgrad_tc_plan(*args, C.addressof(out))
         assert rc != 0, args

@@ -20,8 +20,9 @@
 //         streams through whole row blocks -- the halo (span_y rows) is paid once per row block, not per K tile; the
 //         first 8 rows are mirrored behind the ring end so that an 8-position K step never wraps;
 //     stride 2: one ring per input parity plane (tap -> plane, offset), as conv_tc.cu;
-//     narrow-cin layers (cin * kw <= 32, e.g. the 6-channel stem): the 32 columns of a row hold (kx, ci) pairs, i.e.
-//     the x taps are unrolled into the MMA's N and only kh taps remain -- N = 32 instead of 8 per instruction.
+//     narrow-cin layers (cin * kh <= 32, e.g. the 6-channel stem): the 32 columns of a row hold (ky, ci) pairs, i.e.
+//     the y taps are unrolled into the MMA's N and only the kw x-taps remain (offsets < kw: a one-chunk halo) -- N = 32
+//     instead of 8 per instruction; with swapped roles up to 128 (ky, ci) rows (LastTransUp's 16 -> 2 5x5 conv).
 //     small-cout layers (dense layers, cout = growth rate <= 8): roles swapped -- the patch ring is the M operand (MN-major A: up to
 //     128 channels = four 32-channel blocks at LBO stride), dO the K-major N operand (N = 8), D[ci][(tap, co)]; otherwise 60 of the
 //     64 accumulator rows would be padding (an MMA costs ~40 cycles whatever M and N <= 64 are).
@@ -69,8 +70,8 @@ struct WgTcArgs {
   int plane_floats, gy_slot_floats;            // one ring plane (hi or lo) incl. mirror; one dO slot (hi + lo)
   int tap_plane[WG_MAX_TAPS];
   int tap_off[WG_MAX_TAPS];
-  signed char col_ci[32];                      // ring column (block 0) -> channel inside the chunk (-1: padding); block b adds 32 b
-  signed char col_dx[32];                      // ring column -> x-tap index folded into the column (packed layers), else 0
+  signed char col_ci[128];                     // ring column (32 per channel block) -> channel inside the chunk (-1: padding)
+  signed char col_dy[128];                     // ring column -> y-tap index folded into the column (packed layers), else 0
 };
 
 __device__ __forceinline__ uint64_t wg_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
@@ -166,17 +167,17 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __gr
     // =============================== converter warps ===============================
     // the four columns this thread fills in every patch row (one 16-byte store per plane and part)
     const int e0 = 4 * warp;
-    int cch[4], cdx[4]; float csc[4], csh[4];
+    int cch[4], cdy[4]; float csc[4], csh[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int ci = a.col_ci[e0 + k];
       const int c = ci < 0 ? -1 : cc * a.cchunk + ci;
       cch[k] = (c >= 0 && c < a.cin) ? c : -1;
-      cdx[k] = a.col_dx[e0 + k];
+      cdy[k] = a.col_dy[e0 + k];
       csc[k] = cch[k] >= 0 ? ss_tab[cch[k]] : 0.f;
       csh[k] = cch[k] >= 0 ? ss_tab[WG_MAX_CIN + cch[k]] : 0.f;
     }
-    const bool any_col = cch[0] >= 0 || cch[1] >= 0 || cch[2] >= 0 || cch[3] >= 0;
+    const bool any_col = cch[0] >= 0 || cch[1] >= 0 || cch[2] >= 0 || cch[3] >= 0 || a.nblk > 1;
     const int gy_units = a.cout * 8;                   // (co, group of 4 positions) per dO chunk
     int pg = 0, hg = 0;                                // running patch-chunk / dO-chunk counters of this CTA
     const bool dbg_on = a.dbg != nullptr && blockIdx.x == 0 && tid == 0;
@@ -208,20 +209,35 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __gr
         // ---- loads of patch chunk t (32 positions, this thread: position `lane`, 4 columns, every plane)
         const long long d_t1 = dbg_on ? clock64() : 0;
         float xv[4][4];                                  // [column][slot], slot = plane (stride 2) or 32-channel block (swapped roles)
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          int jj = pj + cdx[k], ii = pi;
-          if (jj >= pitch) { jj -= pitch; ++ii; }
-          int R = R0 + a.min_ry + ii; if (R < 0) R += Ho; else if (R >= Ho) R -= Ho; if (R >= Ho) R -= Ho;
-          int C = a.min_rx + jj; if (C < 0) C += Wo; else if (C >= Wo) C -= Wo;
-          const float* src = xn + (coff[k] + ((R * sy) >> up_h) * Wsrc + ((C * sx) >> up_w));
-          const bool ok = cch[k] >= 0 && !no_load;
+        {
+          int C = a.min_rx + pj; if (C < 0) C += Wo; else if (C >= Wo) C -= Wo;
+          const int col_off = (C * sx) >> up_w;
+          const int Rb = R0 + a.min_ry + pi;             // row before the folded y tap; in [-Ho, 2 Ho)
           if (nblk == 1) {
 #pragma unroll
-            for (int pl = 0; pl < 4; ++pl) xv[k][pl] = (pl < npl && ok) ? __ldg(src + (pl >> 1) * Wsrc + (pl & 1)) : 0.f;
-          } else {
+            for (int k = 0; k < 4; ++k) {
+              int R = Rb + cdy[k]; if (R < 0) R += Ho; else if (R >= Ho) R -= Ho; if (R >= Ho) R -= Ho;
+              const float* src = xn + (coff[k] + ((R * sy) >> up_h) * Wsrc + col_off);
+              const bool ok = cch[k] >= 0 && !no_load;
 #pragma unroll
-            for (int b = 0; b < 4; ++b) xv[k][b] = (b < nblk && ok && cch[k] + 32 * b < climit) ? __ldg(src + b * 32 * HWi) : 0.f;
+              for (int pl = 0; pl < 4; ++pl) xv[k][pl] = (pl < npl && ok) ? __ldg(src + (pl >> 1) * Wsrc + (pl & 1)) : 0.f;
+            }
+          } else {                                       // swapped roles: up to four 32-row blocks, rows looked up in the tables
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                xv[k][b] = 0.f;
+                if (b < nblk) {
+                  const int r = 32 * b + e0 + k;
+                  const int ci = a.col_ci[r], c = cc * a.cchunk + ci;
+                  if (ci >= 0 && c < climit && !no_load) {
+                    int R = Rb + a.col_dy[r]; if (R < 0) R += Ho; else if (R >= Ho) R -= Ho; if (R >= Ho) R -= Ho;
+                    xv[k][b] = __ldg(xn + (c * HWi + ((R * sy) >> up_h) * Wsrc + col_off));
+                  }
+                }
+              }
+            }
           }
         }
         pj += WG_CK;
@@ -256,9 +272,9 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __gr
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                   float sc_ = csc[k], sh_ = csh[k];
-                  if (nblk > 1 && sl > 0) {              // block sl of the same column: channel + 32 sl
-                    const int c = cch[k] + 32 * sl;
-                    const bool okc = cch[k] >= 0 && c < climit;
+                  if (nblk > 1 && sl > 0) {              // row of block sl: its own channel
+                    const int ci = a.col_ci[32 * sl + e0 + k], c = cc * a.cchunk + ci;
+                    const bool okc = ci >= 0 && c < climit;
                     sc_ = okc ? ss_tab[c] : 0.f; sh_ = okc ? ss_tab[WG_MAX_CIN + c] : 0.f;
                   }
                   float v = fmaf(xv[k][sl], sc_, sh_);
@@ -368,8 +384,9 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __gr
     const int q = warp & 3;
     const int row = a.M == 128 ? q * 32 + lane : (lane < 16 ? q * 16 + lane : -1);     // accumulator row of this TMEM lane
     // normal roles: row = output channel, column = (tap, ring column); swapped: row = input channel of the chunk, column = (tap, co)
-    const int co = row, ci_row = cc * a.cchunk + row;
-    const bool row_ok = row >= 0 && (a.swap ? (row < a.cchunk && ci_row < a.cin) : row < a.cout);
+    const int co = row;
+    const int ci_row = (a.swap && row >= 0 && a.col_ci[row] >= 0) ? cc * a.cchunk + a.col_ci[row] : -1, ky_row = (a.swap && row >= 0) ? a.col_dy[row] : 0;
+    const bool row_ok = row >= 0 && (a.swap ? (ci_row >= 0 && ci_row < a.cin) : row < a.cout);
     float* slab = a.slab + (size_t)blockIdx.x * a.cols * 128 + q * 32 + lane;
     const bool dbg_on = a.dbg != nullptr && blockIdx.x == 0 && q == 0 && lane == 0;
     long long d_wait = 0;
@@ -406,12 +423,12 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __gr
             if (e >= a.NC) { e -= a.NC; ++tt; }
             if (a.swap) {
               if (e < a.cout && tt < a.ntaps)
-                atomicAdd(a.dW + ((long long)e * a.cin + ci_row) * (a.kh * a.kw) + tt, (double)v[k] + (double)o[k]);
+                atomicAdd(a.dW + ((long long)e * a.cin + ci_row) * (a.kh * a.kw) + (a.packed ? ky_row * a.kw + tt : tt), (double)v[k] + (double)o[k]);
             } else {
               const int cil = a.col_ci[e];
               const int ci = cil < 0 ? -1 : cc * a.cchunk + cil;
               if (ci >= 0 && ci < a.cin && tt < a.ntaps) {
-                const int tap = a.packed ? tt * a.kw + a.col_dx[e] : tt;
+                const int tap = a.packed ? a.col_dy[e] * a.kw + tt : tt;
                 atomicAdd(a.dW + ((long long)co * a.cin + ci) * (a.kh * a.kw) + tap, (double)v[k] + (double)o[k]);
               }
             }
@@ -459,38 +476,44 @@ static bool wg_plan(const ConvDesc& d, WgTcArgs& a, size_t* smem_out) {
   a.npl = a.sy * a.sx;
   a.nblk = 1;
   // roles: cout on the accumulator rows (M) unless it is tiny -- then the input channels go there and cout becomes the MMA's N
-  a.swap = (d.cout <= 8 && d.cin >= 32 && a.sx == 1) ? 1 : 0;
+  for (int e = 0; e < 128; ++e) { a.col_ci[e] = -1; a.col_dy[e] = 0; }
+  const bool can_pack = a.sx == 1 && d.kh > 1;
+  a.swap = (d.cout <= 8 && a.sx == 1 && (d.cin >= 32 || (can_pack && d.cin * d.kh >= 32 && d.cin * d.kh <= 128))) ? 1 : 0;
   if (!a.swap && d.cout < 16) return false;
   if (a.swap) {
-    a.cchunk = d.cin < 128 ? d.cin : 128; a.ncc = (d.cin + a.cchunk - 1) / a.cchunk;
-    a.M = a.cchunk <= 64 ? 64 : 128; a.nblk = a.M / 32;
-    a.NC = wg_round_up(d.cout, a.M == 128 ? 16 : 8); a.ntaps = d.kh * d.kw;
-    for (int e = 0; e < 32; ++e) { a.col_ci[e] = (signed char)e; a.col_dx[e] = 0; }
-    for (int ky = 0; ky < d.kh; ++ky)
-      for (int kx = 0; kx < d.kw; ++kx) { a.tap_plane[ky * d.kw + kx] = 0; a.tap_off[ky * d.kw + kx] = (ry[ky] - min_ry) * a.pitch + (rx[kx] - min_rx); }
+    a.packed = (d.cin < 32) ? 1 : 0;
+    int rows;
+    if (a.packed) { a.cchunk = d.cin; a.ncc = 1; rows = d.cin * d.kh; a.ntaps = d.kw; }
+    else { a.cchunk = d.cin < 128 ? d.cin : 128; a.ncc = (d.cin + a.cchunk - 1) / a.cchunk; rows = a.cchunk; a.ntaps = d.kh * d.kw; }
+    a.M = rows <= 64 ? 64 : 128; a.nblk = a.M / 32;
+    a.NC = wg_round_up(d.cout, a.M == 128 ? 16 : 8);
+    for (int r = 0; r < rows; ++r) { a.col_ci[r] = (signed char)(a.packed ? r % d.cin : r); a.col_dy[r] = (signed char)(a.packed ? r / d.cin : 0); }
   } else {
-  a.M = d.cout <= 64 ? 64 : 128;
-  const int nmult = a.M == 128 ? 16 : 8;
-  a.packed = (a.sx == 1 && d.kw > 1 && d.cin * d.kw <= 32) ? 1 : 0;
+    a.M = d.cout <= 64 ? 64 : 128;
+    const int nmult = a.M == 128 ? 16 : 8;
+    a.packed = (can_pack && d.cin * d.kh <= 32) ? 1 : 0;
+    if (a.packed) {
+      a.ncc = 1; a.cchunk = d.cin; a.NC = wg_round_up(d.cin * d.kh, nmult); a.ntaps = d.kw;
+      for (int e = 0; e < d.cin * d.kh; ++e) { a.col_ci[e] = (signed char)(e % d.cin); a.col_dy[e] = (signed char)(e / d.cin); }
+    } else {
+      a.ntaps = d.kh * d.kw;
+      a.cchunk = d.cin < 32 ? d.cin : 32;
+      while (a.cchunk > 8 && a.ntaps * wg_round_up(a.cchunk, nmult) > 512) a.cchunk = wg_round_up(a.cchunk, 16) / 2;   // every tap keeps its own TMEM columns
+      a.ncc = (d.cin + a.cchunk - 1) / a.cchunk; a.NC = wg_round_up(a.cchunk, nmult);
+      for (int e = 0; e < a.cchunk; ++e) a.col_ci[e] = (signed char)e;
+    }
+  }
+  // MMA taps: packed layers keep the x taps only (the y taps are rows/columns of the ring), the others all kh*kw
   if (a.packed) {
-    a.ncc = 1; a.cchunk = d.cin; a.NC = wg_round_up(d.cin * d.kw, nmult); a.ntaps = d.kh;
-    for (int e = 0; e < 32; ++e) { a.col_ci[e] = e < d.cin * d.kw ? (signed char)(e % d.cin) : (signed char)-1; a.col_dx[e] = e < d.cin * d.kw ? (signed char)(e / d.cin) : (signed char)0; }
-    for (int ky = 0; ky < d.kh; ++ky) { a.tap_plane[ky] = 0; a.tap_off[ky] = (ry[ky] - min_ry) * a.pitch; }
+    for (int kx = 0; kx < d.kw; ++kx) { a.tap_plane[kx] = 0; a.tap_off[kx] = rx[kx] - min_rx; }
   } else {
-    a.ntaps = d.kh * d.kw;
-    a.cchunk = d.cin < 32 ? d.cin : 32;
-    while (a.cchunk > 8 && a.ntaps * wg_round_up(a.cchunk, nmult) > 512) a.cchunk = wg_round_up(a.cchunk, 16) / 2;   // every tap keeps its own TMEM columns
-    a.ncc = (d.cin + a.cchunk - 1) / a.cchunk; a.NC = wg_round_up(a.cchunk, nmult);
-    for (int e = 0; e < 32; ++e) { a.col_ci[e] = e < a.cchunk ? (signed char)e : (signed char)-1; a.col_dx[e] = 0; }
     for (int ky = 0; ky < d.kh; ++ky)
       for (int kx = 0; kx < d.kw; ++kx) {
         a.tap_plane[ky * d.kw + kx] = py[ky] * a.sx + px[kx];
         a.tap_off[ky * d.kw + kx] = (ry[ky] - min_ry) * a.pitch + (rx[kx] - min_rx);
       }
   }
-  }
   if (a.ntaps > WG_MAX_TAPS || a.ntaps * a.NC > 512) return false;
-  if (4 * a.ntaps * 3 < 48) return false;                        // too few MMAs per chunk to hide the staging: FFMA kernel
   int max_off = 0;
   for (int t = 0; t < a.ntaps; ++t) if (a.tap_off[t] > max_off) max_off = a.tap_off[t];
   a.lead = (WG_CK - 1 + max_off) / WG_CK;
@@ -539,7 +562,11 @@ bool arpde_conv_wgrad_tc_wanted(const ConvDesc& d) {
   // (measured, N = 128: LastTransUp conv3x3 32->16 at 64x64: tensor core 0.41 ms, FFMA 0.375 ms)
   if (d.cout < 32 && d.cout > 8) return false;
   WgTcArgs a; size_t smem;
-  return wg_plan(d, a, &smem);
+  if (!wg_plan(d, a, &smem)) return false;
+  // swapped + packed with four row blocks (LastTransUp's 16 -> 2 5x5 conv: 80 (ky, ci) rows): the converters stage 16 table-driven
+  // rows per thread and step and become the bottleneck -- measured 0.43 ms against 0.37 ms for the FFMA kernel (N = 128)
+  if (a.swap && a.packed && a.nblk > 2) return false;
+  return true;
 }
 
 long long arpde_conv_wgrad_tc_scratch_floats(const ConvDesc& d) {
@@ -585,7 +612,7 @@ int arpde_conv_wgrad_tc_launch(const ConvDesc& d, const float* x, long long x_bs
 
 // Diagnostic (host only): the tiling conv_wgrad_tc_kernel would use.  out[0..25] = pitch, min_ry, min_rx, RB, RBH, nch_u, lead, pcu, NR,
 // npl, NC, ncc, cchunk, packed, ntaps, M, mrows, tmem_cols, slices(N=1), smem bytes, Ho, Wo, sy, sx, swap, nblk; out[32+t] = tap plane,
-// out[81+t] = tap offset, out[130+e] = column channel, out[162+e] = column x-tap.
+// out[81+t] = tap offset, out[130+e] = column channel, out[258+e] = column y-tap (e < 128).
 extern "C" int arpde_conv_wgrad_tc_plan(int cin, int H, int W, int cout, int kh, int kw, int stride, int up, int32_t* out) {
   ARPDE_CHECK_ARG(out, "conv_wgrad_tc_plan: null output");
   ConvDesc d;
@@ -597,7 +624,7 @@ extern "C" int arpde_conv_wgrad_tc_plan(int cin, int H, int W, int cout, int kh,
                      a.M, a.mrows, a.tmem_cols, a.slices, (int)smem, a.Ho, a.Wo, a.sy, a.sx, a.swap, a.nblk};
   for (int i = 0; i < 26; ++i) out[i] = v[i];
   for (int t = 0; t < WG_MAX_TAPS; ++t) { out[32 + t] = t < a.ntaps ? a.tap_plane[t] : 0; out[81 + t] = t < a.ntaps ? a.tap_off[t] : 0; }
-  for (int e = 0; e < 32; ++e) { out[130 + e] = a.col_ci[e]; out[162 + e] = a.col_dx[e]; }
+  for (int e = 0; e < 128; ++e) { out[130 + e] = a.col_ci[e]; out[258 + e] = a.col_dy[e]; }
   return ARPDE_OK;
 }
 

@@ -148,7 +148,7 @@ int arpde_conv_tc_plan(int cin, int H, int W, int cout, int kh, int kw, int stri
  * scratch: arpde_conv_wgrad_tc_scratch(...) floats of device memory (per-CTA fp32 partial sums; 0 = layer not covered).
  * Returns ARPDE_ERR_UNSUPPORTED for layers the kernel does not cover (1D, cout < 16 or > 128, too few taps); the fused backward
  * (arpde_densed_backward) then uses the fp32 FFMA kernel.  arpde_conv_wgrad_tc_plan: host-only diagnostic of the tiling
- * (field list in conv_wgrad_tc.cu; out holds at least 200 int32). */
+ * (field list in conv_wgrad_tc.cu; out holds at least 400 int32). */
 int64_t arpde_conv_wgrad_tc_scratch(int N, int cin, int H, int W, int cout, int kh, int kw, int stride, int up);
 int arpde_conv_wgrad_tc(const float* x, int64_t x_bstride, const float* scale, const float* shift, const float* dO,
                         int64_t dO_bstride, double* dW64, float* dW, int N, int cin, int H, int W, int cout, int kh, int kw,

@@ -40,7 +40,7 @@ def oracle_wgrad(x, sc, sh, relu_in, up, gy, cout, kh, kw, s):
 
 LAYERS = [
     # cin, cout, k, s, up, H, W, N
-    (6, 96, 5, 1, 0, 64, 64, 5),         # In_conv1: (kx, ci) packed columns, M = 128, two row blocks per sample
+    (6, 96, 5, 1, 0, 64, 64, 5),         # In_conv1: (ky, ci) packed columns, M = 128
     (96, 48, 3, 2, 0, 64, 64, 5),        # In_conv3: stride 2 (four parity planes), three channel chunks, M = 64
     (32, 16, 3, 1, 1, 32, 32, 5),        # LastTransUp conv3x3 on the nearest-upsampled input
     (48, 32, 3, 1, 0, 32, 32, 4),        # wide dense layer
@@ -54,6 +54,9 @@ LAYERS = [
     (60, 4, 3, 1, 0, 32, 32, 5),         # denselayer4
     (150, 8, 3, 1, 0, 16, 16, 4),        # swapped, M = 128 (four channel blocks), two channel chunks
     (64, 5, 5, 1, 0, 16, 16, 3),         # swapped, 25 taps
+    (16, 2, 5, 1, 0, 64, 64, 5),         # LastTransUp conv5x5: swapped and (ky, ci) packed, 80 rows in three channel blocks
+    (64, 32, 1, 1, 0, 32, 32, 5),        # 1x1 conv: a single tap, two channel chunks
+    (8, 4, 5, 1, 0, 32, 32, 3),          # swapped + packed with M = 64 (40 rows)
 ]
 
 

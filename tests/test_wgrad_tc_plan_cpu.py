@@ -16,13 +16,13 @@ NAMES = 'pitch min_ry min_rx RB RBH nch_u lead pcu NR npl NC ncc cchunk packed n
 
 
 def plan(cin, H, W, cout, kh, kw, s, up):
-    out = (C.c_int32 * 200)()
+    out = (C.c_int32 * 400)()
     L.call('arpde_conv_wgrad_tc_plan', cin, H, W, cout, kh, kw, s, up, C.addressof(out))
     p = dict(zip(NAMES, out[:len(NAMES)]))
     p['tap_plane'] = list(out[32:32 + p['ntaps']])
     p['tap_off'] = list(out[81:81 + p['ntaps']])
-    p['col_ci'] = list(out[130:162])
-    p['col_dx'] = list(out[162:194])
+    p['col_ci'] = list(out[130:258])
+    p['col_dy'] = list(out[258:386])
     return p
 
 
@@ -51,17 +51,13 @@ def replay(x, gy, up, kh, kw, p, ahead):
                 i, j = divmod(pos, pitch)
                 for e in range(32 if swap else p['NC']):
                   for blk in range(nblk):
-                    ci = p['col_ci'][e]
-                    c = cc * p['cchunk'] + ci + 32 * blk if ci >= 0 else -1
+                    ci = p['col_ci'][32 * blk + e]
+                    c = cc * p['cchunk'] + ci if ci >= 0 else -1
                     if c < 0 or c >= climit:
                         val = np.zeros(p['npl'])
                     else:
-                        jj, ii = j + p['col_dx'][e], i
-                        if jj >= pitch:
-                            jj -= pitch
-                            ii += 1
-                        R = (R0 + p['min_ry'] + ii) % Ho
-                        Cc = (p['min_rx'] + jj) % Wo
+                        R = (R0 + p['min_ry'] + i + p['col_dy'][32 * blk + e]) % Ho
+                        Cc = (p['min_rx'] + j) % Wo
                         sr, sc = (R * p['sy']) >> up, (Cc * p['sx']) >> up
                         val = np.array([x[n, c, sr + (pl >> 1), sc + (pl & 1)] for pl in range(p['npl'])])
                     rr = s * 32 + lane
@@ -94,7 +90,7 @@ def replay(x, gy, up, kh, kw, p, ahead):
                         assert rr + 8 <= ring + 8
                         if swap:      # ring = M operand: rows = channels of the nblk blocks, columns = cout (padded)
                             xa = np.concatenate([patch[p['tap_plane'][t] * nblk + blk, rr:rr + 8, :] for blk in range(nblk)], axis=1)   # [8, M]
-                            assert not np.isnan(xa[:, :climit - cc * p['cchunk']]).any(), (lu, j, k8, t)
+                            assert not np.isnan(xa[:, [r for r in range(p['M']) if p['col_ci'][r] >= 0 and cc * p['cchunk'] + p['col_ci'][r] < climit]]).any()
                             D[:, t, :cout] += np.nan_to_num(xa).T @ g8.T
                             continue
                         b = patch[p['tap_plane'][t], rr:rr + 8, :p['NC']]                               # [8, NC]
@@ -105,23 +101,28 @@ def replay(x, gy, up, kh, kw, p, ahead):
                     released = pg + pcu
             pg += pcu
         if swap:
-            for row in range(min(p['cchunk'], climit - cc * p['cchunk'])):
+            for row in range(p['M']):
+                ci = p['col_ci'][row]
+                c = cc * p['cchunk'] + ci
+                if ci < 0 or c >= climit:
+                    continue
                 for t in range(p['ntaps']):
-                    dW[:, cc * p['cchunk'] + row, t // kw, t % kw] += D[row, t, :cout]
+                    tap = p['col_dy'][row] * kw + t if p['packed'] else t
+                    dW[:, c, tap // kw, tap % kw] += D[row, t, :cout]
             continue
         for t in range(p['ntaps']):
             for e in range(p['NC']):
                 ci = p['col_ci'][e]
                 c = cc * p['cchunk'] + ci if ci >= 0 else -1
                 if 0 <= c < cin:
-                    tap = t * kw + p['col_dx'][e] if p['packed'] else t
+                    tap = p['col_dy'][e] * kw + t if p['packed'] else t
                     dW[:, c, tap // kw, tap % kw] += D[:, t, e]
     return dW
 
 
 CASES = [  # cin, cout, kh, kw, stride, up, H, W
     (6, 16, 5, 5, 1, 0, 16, 16), (40, 16, 3, 3, 2, 0, 16, 32), (12, 16, 3, 3, 1, 1, 8, 8), (3, 20, 7, 7, 1, 0, 16, 16),
-    (12, 16, 4, 4, 2, 0, 32, 32), (33, 17, 3, 3, 1, 0, 8, 16), (48, 4, 3, 3, 1, 0, 8, 16), (150, 8, 3, 3, 1, 0, 8, 16)]
+    (12, 16, 4, 4, 2, 0, 32, 32), (33, 17, 3, 3, 1, 0, 8, 16), (48, 4, 3, 3, 1, 0, 8, 16), (150, 8, 3, 3, 1, 0, 8, 16), (16, 2, 5, 5, 1, 0, 16, 16), (64, 32, 1, 1, 1, 0, 8, 16)]
 
 
 @pytest.mark.parametrize('ahead', [False, True])
@@ -144,17 +145,19 @@ def test_wgrad_ring_index_arithmetic(cin, cout, kh, kw, s, up, H, W, ahead):
 
 
 def test_wgrad_plan_of_the_c4_layers():
-    p1 = plan(6, 64, 64, 96, 5, 5, 1, 0)            # stem: (kx, ci) packed into the MMA's N, 5 taps left
-    assert p1['packed'] == 1 and p1['NC'] == 32 and p1['ntaps'] == 5 and p1['M'] == 128 and p1['smem'] <= 227 * 1024
+    p1 = plan(6, 64, 64, 96, 5, 5, 1, 0)            # stem: (ky, ci) packed into the MMA's N, the 5 x-taps left (one-chunk halo)
+    assert p1['packed'] == 1 and p1['NC'] == 32 and p1['ntaps'] == 5 and p1['M'] == 128 and p1['lead'] == 1 and p1['smem'] <= 227 * 1024
     p3 = plan(96, 64, 64, 48, 3, 3, 2, 0)           # stride 2: four parity planes, three channel chunks
     assert p3['npl'] == 4 and p3['ncc'] == 3 and p3['M'] == 64 and p3['ntaps'] * p3['NC'] <= 512 and p3['smem'] <= 227 * 1024
     assert p3['NR'] >= p3['lead'] + 2
     pd = plan(60, 32, 32, 4, 3, 3, 1, 0)            # dense layer: roles swapped, 64 accumulator rows = two channel blocks, N = 8
     assert pd['swap'] == 1 and pd['M'] == 64 and pd['nblk'] == 2 and pd['NC'] == 8 and pd['ncc'] == 1
+    pl = plan(16, 64, 64, 2, 5, 5, 1, 0)            # LastTransUp 5x5 16 -> 2: swapped and packed, 80 (ky, ci) rows in three blocks
+    assert pl['swap'] == 1 and pl['packed'] == 1 and pl['M'] == 128 and pl['nblk'] == 4 and pl['ntaps'] == 5 and pl['smem'] <= 227 * 1024
 
 
 def test_wgrad_unsupported_layers_fall_back():
-    out = (C.c_int32 * 200)()
-    for args in [(16, 32, 32, 12, 3, 3, 1, 0), (16, 64, 64, 2, 5, 5, 1, 0), (64, 32, 32, 32, 1, 1, 1, 0), (16, 1, 512, 32, 1, 5, 1, 0)]:
+    out = (C.c_int32 * 400)()
+    for args in [(16, 32, 32, 12, 3, 3, 1, 0), (4, 64, 64, 2, 3, 3, 1, 0), (96, 256, 256, 48, 3, 3, 2, 0), (16, 1, 512, 32, 1, 5, 1, 0)]:
         rc = L.lib.arpde_conv_wgrad_tc_plan(*args, C.addressof(out))
         assert rc != 0, args

@@ -22,13 +22,14 @@ for name, cin, cout, k, s, up, H, W in LAYERS:
     def run():
         L.call('arpde_conv_wgrad_tc', L.ptr(x), cin * H * W, L.ptr(sc), L.ptr(sh), L.ptr(gy), cout * Ho * Wo, L.ptr(d64), L.ptr(dW), N, cin, H, W,
                cout, k, k, s, up, 1, L.ptr(scratch), n, L.stream())
-    for _ in range(3): run()
+    for _ in range(int(os.environ.get('WG_WARM', '3'))): run()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(10): run()
+    reps = int(os.environ.get('WG_REPS', '10'))
+    for _ in range(reps): run()
     e1.record(); torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / 10
+    ms = e0.elapsed_time(e1) / reps
     fl = 2.0 * N * Ho * Wo * cout * cin * k * k
     print('%-9s %7.3f ms  %6.1f TFLOP/s (fp32-equivalent)  scratch %.1f MB' % (name, ms, fl / ms / 1e9, n * 4 / 1e6))
     d = dbg.tolist()

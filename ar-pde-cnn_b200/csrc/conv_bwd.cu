@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
 // ---- vectorised variants (16-byte aligned tensors, W % 4 == 0): one CTA per (channel, group of samples), float4 along the row,
 // no integer division per element, and no dz round trip -- the apply pass recomputes the masked (pooled) gradient from da and x.
 // Traffic per element: reduce reads da + x; apply reads da + x and writes gx (was: +1 write and +1 read of dz).  At the training batch
-// (N = 128) the old pair ran at ~2 TB/s on the 96-channel 64x64 tensor; see DESIGN.md 4.4.
+// (N = 128) the old pair ran at ~2 TB/s on the 96-channel 64x64 tensor; see DESIGN.md 4.5.
 template <int UP>
 __device__ __forceinline__ float4 bnb_load_g(const float* __restrict__ da_nc, int r, int W) {
   if (UP == 0) return __ldg(reinterpret_cast<const float4*>(da_nc + r));

@@ -183,6 +183,50 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def train_step_probe(dev, B=128, tback=2, nwarm=3, nrep=10):
+    """Training-step timing (SURVEY.md 8 row M5 + P1 + L1): C3-shaped mini-batch of B random Fourier ICs, a tback-step BPTT window
+    (DenseED forward with batch-statistics BatchNorm, Crank-Nicolson target, negative log joint), loss.backward(), Adam step
+    (2D-Burgers-SWAG/main.py:61-91).  Reported next to the headline; not part of the timed rollout."""
+    import contextlib, io, types
+    import numpy as np
+    import torch
+    from arpde_b200.nn.densed import DenseED2d
+    from arpde_b200.nn.bayesnn import BayesNN
+    from arpde_b200.nn.swag import SwagNN
+    from arpde_b200.nn.integrators import Burger2DIntegrate
+    torch.manual_seed(0); np.random.seed(0)
+    a = types.SimpleNamespace(dt=0.005, device=dev, nic=3)
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = DenseED2d(6, 2, [4], growth_rate=4, init_features=96).to(dev)
+        bayes = BayesNN(a, model); swag = SwagNN(a, bayes, full_cov=True, max_models=30)
+        integ = Burger2DIntegrate(1.0 / NEL, nu=0.005, grad_kernels=[3, 3], device=dev)
+    opt = torch.optim.Adam([{'params': [bayes.model.log_beta], 'lr': 1e-3}, {'params': bayes.model.features.parameters()}], lr=1e-3)
+    ic = make_ics(B).to(dev)
+    swag.train()
+
+    def step():
+        inp = ic.repeat(1, 3, 1, 1)
+        loss = 0
+        for _ in range(tback):
+            u_pred = swag(inp[:, -6:])
+            ustar = integ.crankNicolson(u_pred, inp[:, -2:], 0.003)
+            loss = loss + swag.calc_neg_log_joint(u_pred, ustar, 10)
+            inp = torch.cat([inp, u_pred], 1)
+        loss.backward(); opt.step(); opt.zero_grad()
+    for _ in range(nwarm):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(nrep):
+        step()
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / nrep
+    return {'ms': ms, 'value': tback * B / ms * 1e3, 'unit': 'sample-steps/s', 'batch': B, 'tback': tback,
+            'what': 'forward (batch-stat BN) + Crank-Nicolson + neg log joint + backward (tensor-core data and weight gradients) + torch Adam, '
+                    'mean of %d steps after %d warm-up (CUDA events)' % (nrep, nwarm)}
+
+
 def workload_config(n_gpus):
     return {'workload': 'C4: 2D coupled Burgers SWAG inference, %d weight samples x %d ICs/GPU x %d AR steps, %dx%d grid, DenseED blocks=[4] growth=4 init_features=96'
                         % (S_SAMPLES, N_IC, T_STEPS, NEL, NEL),
@@ -199,6 +243,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-train-probe', action='store_true', help='skip the (untimed, rank-0) training-step measurement')
     ap.add_argument('--tsteps', type=int, default=T_STEPS, help='debug: shorter rollouts (the JSON line then names the reduced config)')
     args = ap.parse_args()
     if args.impl == 'reference':
@@ -371,6 +416,8 @@ def main():
                                                                    '(the rest of the 62.9 MB of ustar was still in L2 at kernel end)',
                              'bytes_per_launch': k2_bytes, 'ms': k2_ms, 'peak_source': peaks['source']},
     }
+    if not args.no_train_probe:
+        line['train_step'] = train_step_probe(dev)
     if not args.no_cpu_baseline:
         S, N, T = 2, 64, 4
         rate, dt = cpu_reference_rate(S, N, T)

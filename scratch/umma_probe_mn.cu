@@ -1,5 +1,5 @@
 // umma_probe_mn.cu -- tcgen05 kind::tf32 with an MN-major B operand, as the tensor-core weight gradient needs (K = positions).
-// Findings on B200 (see DESIGN.md 4.5): for tf32, MN-major operands only work with descriptor layout type 1
+// Findings on B200 (see DESIGN.md 4.4): for tf32, MN-major operands only work with descriptor layout type 1
 // (SWIZZLE_128B_BASE32B); the other layout types silently produce zeros.  Layout validated here:
 //   B element (k, n): byte = (n/32)*LBO + (k/4)*SBO + (k%4)*128 + (n%32)*4, then bits[5,7) ^= bits[7,9) (32-byte chunks XOR row&3)
 //   A stays K-major, no swizzle: [K/4][M][4 floats] (rows 16 B apart, SBO = 128, LBO = plane).

@@ -798,11 +798,16 @@ static bool tc_plan(const ConvDesc& d, ConvTcArgs& a, size_t* smem_out) {
   // experiment hook: ARPDE_TC_FORCE="nslot_p,ntile,cchunk" restricts the search (0 = free) -- used for A/B timing only
   int f_slot = 0, f_ntile = 0, f_cchunk = 0;
   if (const char* e = getenv("ARPDE_TC_FORCE")) sscanf(e, "%d,%d,%d", &f_slot, &f_ntile, &f_cchunk);
+  // (streamed weights, stride 2, all taps in one weight slot -- pass 0: two M tiles sharing one patch slot halve the weight streaming
+  //  and the halo per tile; measured on In_conv3 at N = 1920: 2.10 ms against 2.22 ms for one tile with two patch slots, 2.31 / 3.75 ms
+  //  for three / four tiles.  Stride-1 layers and split tap chunks lose with it: 144->32 3x3 at 16x16 0.70 vs 0.47 ms.)
   for (int resident = 1; resident >= 0; --resident)
+   for (int pass = resident ? 1 : 0; pass <= 1; ++pass)
     for (int use_tma = tma_shape ? 1 : 0; use_tma >= (d.dilate ? 1 : 0); --use_tma)
       for (int nslot_p = 2; nslot_p >= 1; --nslot_p)
         for (int ntile = ntile_max; ntile >= 1; --ntile)
           for (int cchunk = 32; cchunk >= 8; cchunk >>= 1) {
+            if (pass == 0 && (!use_tma || a.nplanes != 4 || nslot_p != 1 || ntile != 2 || 2 * 2 * N2 > 512 || f_slot || f_ntile || f_cchunk)) continue;
             if ((f_slot && nslot_p != f_slot) || (f_ntile && ntile != f_ntile) || (f_cchunk && cchunk != f_cchunk)) continue;
             if (cchunk > 8 && cchunk > cin8) continue;
             const int ncc = (d.cin + cchunk - 1) / cchunk;
@@ -817,6 +822,7 @@ static bool tc_plan(const ConvDesc& d, ConvTcArgs& a, size_t* smem_out) {
             const size_t raw_slot = use_tma ? (size_t)RS * cchunk * d.W * 4 : 0;
             for (int tchunk = a.ntaps; tchunk >= 1; --tchunk) {
               if (a.ntaps % tchunk) continue;
+              if (pass == 0 && tchunk != a.ntaps) continue;
               const size_t w_slot = (size_t)tchunk * (cchunk / 4) * N2 * 16;
               if (w_slot > 48 * 1024) continue;
               const int ntc = a.ntaps / tchunk;

@@ -4,7 +4,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from arpde_b200 import _lib as L
 DEV = 'cuda:0'
 LAYERS = [('In_conv1', 6, 96, 5, 1, 0, 64, 0), ('In_conv3', 96, 48, 3, 2, 0, 64, 0), ('dense1', 48, 4, 3, 1, 0, 32, 1), ('dense4', 60, 4, 3, 1, 0, 32, 1),
-          ('conv1x1', 64, 32, 1, 1, 0, 32, 1), ('conv2up', 32, 16, 3, 1, 1, 32, 1), ('conv3', 16, 2, 5, 1, 0, 64, 1)]
+          ('conv1x1', 64, 32, 1, 1, 0, 32, 1), ('conv2up', 32, 16, 3, 1, 1, 32, 1), ('conv3', 16, 2, 5, 1, 0, 64, 1),
+          ('wide144', 144, 32, 3, 1, 0, 16, 1), ('wide_in3_128', 96, 48, 3, 2, 0, 128, 1), ('dgrad_like', 48, 96, 3, 1, 0, 32, 0)]
 name, cin, cout, k, s, up, H, relu = LAYERS[int(sys.argv[1])]
 NB = int(sys.argv[2]) if len(sys.argv) > 2 else 1920
 out = (ctypes.c_int32 * 160)()

@@ -161,6 +161,12 @@ int arpde_conv_wgrad_tc_plan(int cin, int H, int W, int cout, int kh, int kw, in
 int arpde_conv_tc_set_debug(long long* dev_buf);
 int arpde_conv_tc_set_debug_flags(int flags);
 
+/* Random periodic initial conditions of the 2D Burgers data set on the device (InitPeriodicCond2d.__getitem__,
+ * 2D-Burgers-SWAG/utils/burgerLoader2D.py:99-112): u[b][comp] = 2 f / max|f| + c[b][comp] with
+ * f = sum_m lam[b][0][comp][m] cos(2 pi k_m.x) + lam[b][1][comp][m] sin(2 pi k_m.x) over the (2*order+1)^2 modes, evaluated in fp64.
+ * lam [B][2][2][(2*order+1)^2] and c [B][2] are DEVICE doubles (the host draws them from numpy's per-index stream); out [B][2][n][n]. */
+int arpde_fourier_ic2d(const double* lam, const double* c, float* out, int B, int ncells, int order, arpde_stream_t stream);
+
 /* BatchNorm bookkeeping (nn.BatchNorm{1,2}d, eps 1e-5, momentum 0.1): per-channel sums of x[N,C(+),HW],
  * train-mode finalize (scale/shift, saved mean/invstd, running-stat update, num_batches_tracked += 1),
  * eval-mode fold of the running statistics. */

@@ -12,7 +12,7 @@ Shims applied (none edits a reference file):
   3. noise draws of SwagNN.sample are recorded by wrapping torch.randn_like / Tensor.normal_.
 
 Outputs: tests/golden/{burgers2d,burgers1d,ks1d}.npz (+ *_ckpt200.npz for the shipped 1D
-checkpoints).  The npz files are committed; this script documents how they were made.
+checkpoints) and ic2d.npz (`make_golden.py ic2d`: samples of the on-the-fly initial-condition data set).  The npz files are committed; this script documents how they were made.
 """
 import os
 import subprocess
@@ -296,11 +296,29 @@ def gen(system):
         print(system, 'checkpoint fixture keys:', len(ck))
 
 
+def gen_ic2d():
+    """Initial conditions of the reference's on-the-fly data set (2D-Burgers-SWAG/utils/burgerLoader2D.py:80-116)."""
+    import numpy as np
+    install_shims()
+    sys.path.insert(0, os.path.join(REF, PROJ['burgers2d']))
+    from utils.burgerLoader2D import InitPeriodicCond2d
+    out = {}
+    for ncells, idx in [(16, [0, 1, 7]), (64, [3, 12345])]:
+        ds = InitPeriodicCond2d(ncells, 100000)
+        out['ic/%d/index' % ncells] = np.array(idx)
+        out['ic/%d/u' % ncells] = np.stack([ds[i].numpy() for i in idx], 0)
+    np.savez_compressed(os.path.join(HERE, 'ic2d.npz'), **out)
+    print('wrote ic2d.npz', {k: v.shape for k, v in out.items()})
+
+
 if __name__ == '__main__':
-    if len(sys.argv) > 1:
+    if len(sys.argv) > 1 and sys.argv[1] == 'ic2d':
+        gen_ic2d()
+    elif len(sys.argv) > 1:
         gen(sys.argv[1])
     else:
         for s in PROJ:
             cwd = '/tmp/arpde_golden_' + s
             os.makedirs(cwd, exist_ok=True)
             subprocess.check_call([sys.executable, os.path.abspath(__file__), s], cwd=cwd)
+        subprocess.check_call([sys.executable, os.path.abspath(__file__), 'ic2d'], cwd='/tmp')

@@ -182,3 +182,12 @@ def test_ic_generator_2d_is_deterministic():
     a = O.ic_burgers2d(16, [0, 1]); b = O.ic_burgers2d(16, [1])
     assert a.shape == (2, 2, 16, 16) and torch.equal(a[1], b[0])
     assert float(a.abs().max()) <= 3.0 + 1e-6
+
+
+def test_ic_generator_2d_vs_reference_golden():
+    """oracle.ic_burgers2d == the reference's InitPeriodicCond2d (tests/golden/ic2d.npz, made by make_golden.py ic2d)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'ic2d.npz'))
+    for ncells in (16, 64):
+        got = O.ic_burgers2d(ncells, [int(i) for i in g['ic/%d/index' % ncells]]).numpy()
+        assert np.abs(got - g['ic/%d/u' % ncells]).max() <= 1e-6

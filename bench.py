@@ -200,7 +200,8 @@ def train_step_probe(dev, B=128, tback=2, nwarm=3, nrep=10):
         model = DenseED2d(6, 2, [4], growth_rate=4, init_features=96).to(dev)
         bayes = BayesNN(a, model); swag = SwagNN(a, bayes, full_cov=True, max_models=30)
         integ = Burger2DIntegrate(1.0 / NEL, nu=0.005, grad_kernels=[3, 3], device=dev)
-    opt = torch.optim.Adam([{'params': [bayes.model.log_beta], 'lr': 1e-3}, {'params': bayes.model.features.parameters()}], lr=1e-3)
+    from arpde_b200.optim import Adam
+    opt = Adam([{'params': [bayes.model.log_beta], 'lr': 1e-3}, {'params': bayes.model.features.parameters()}], lr=1e-3)
     ic = make_ics(B).to(dev)
     swag.train()
 
@@ -223,7 +224,7 @@ def train_step_probe(dev, B=128, tback=2, nwarm=3, nrep=10):
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / nrep
     return {'ms': ms, 'value': tback * B / ms * 1e3, 'unit': 'sample-steps/s', 'batch': B, 'tback': tback,
-            'what': 'forward (batch-stat BN) + Crank-Nicolson + neg log joint + backward (tensor-core data and weight gradients) + torch Adam, '
+            'what': 'forward (batch-stat BN) + Crank-Nicolson + neg log joint + backward (tensor-core data and weight gradients) + one-launch Adam, '
                     'mean of %d steps after %d warm-up (CUDA events)' % (nrep, nwarm)}
 
 

@@ -167,6 +167,14 @@ int arpde_conv_tc_set_debug_flags(int flags);
  * lam [B][2][2][(2*order+1)^2] and c [B][2] are DEVICE doubles (the host draws them from numpy's per-index stream); out [B][2][n][n]. */
 int arpde_fourier_ic2d(const double* lam, const double* c, float* out, int B, int ncells, int order, arpde_stream_t stream);
 
+/* One-launch Adam step over n fp32 tensors (torch.optim.Adam.step of 2D-Burgers-SWAG/main.py:221-222,84; non-amsgrad):
+ * host arrays of DEVICE pointers (param, grad, exp_avg, exp_avg_sq) and element counts; per tensor step_size = lr / (1 - beta1^t),
+ * bias_correction2_sqrt = sqrt(1 - beta2^t) and L2 weight decay (NULL = 0), computed by the caller in double as torch does.
+ * The state tensors are torch.optim.Adam's own, so optimizer checkpoints interchange. */
+int arpde_adam_step(void* const* params, void* const* grads, void* const* exp_avg, void* const* exp_avg_sq, const int64_t* numel,
+                    const double* step_size, const double* bias_correction2_sqrt, const double* weight_decay, int n, double beta1,
+                    double beta2, double eps, arpde_stream_t stream);
+
 /* BatchNorm bookkeeping (nn.BatchNorm{1,2}d, eps 1e-5, momentum 0.1): per-channel sums of x[N,C(+),HW],
  * train-mode finalize (scale/shift, saved mean/invstd, running-stat update, num_batches_tracked += 1),
  * eval-mode fold of the running statistics. */

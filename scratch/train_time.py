@@ -14,7 +14,8 @@ with contextlib.redirect_stdout(io.StringIO()):
     model = DenseED2d(6, 2, [4], growth_rate=4, init_features=96).to(dev)
     bayes = BayesNN(args, model); swag = SwagNN(args, bayes, full_cov=True, max_models=30)
     integ = Burger2DIntegrate(1.0 / 64, nu=0.005, grad_kernels=[3, 3], device=dev)
-opt = torch.optim.Adam([{'params': [bayes.model.log_beta], 'lr': 1e-3}, {'params': bayes.model.features.parameters()}], lr=1e-3)
+from arpde_b200.optim import Adam as _A
+opt = (torch.optim.Adam if os.environ.get('TORCH_ADAM') else _A)([{'params': [bayes.model.log_beta], 'lr': 1e-3}, {'params': bayes.model.features.parameters()}], lr=1e-3)
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 128
 ic = Bn.make_ics(B).to(dev)
 swag.train()

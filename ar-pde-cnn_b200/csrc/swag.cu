@@ -101,3 +101,42 @@ extern "C" int arpde_predictive_moments(const float* traj, int64_t bstride, int6
   ARPDE_LAUNCH_CHECK();
   return ARPDE_OK;
 }
+
+// ------------------------------------------------------------------ error metrics of a rollout against a target trajectory
+// testMSE / testBayesianMSE of 2D-Burgers-SWAG/post/plotMSE.py:78-85,133-137 (and the 1D twins): per (case n, saved time t)
+//   mse = mean_f (pred - target)^2,   ese = ( sum_f pred^2 / 2 / points  -  sum_f target^2 / 2 / points )^2
+// over the F = components x grid values of one state; pred is the (sample-mean) prediction.  The reference moves the whole
+// [N, S, T+1, 2, H, W] prediction tensor to the host first; here the rows are reduced where the rollout left them (row strides
+// select every test_every-th step), fp64 accumulation, one CTA per (n, t).
+__global__ void __launch_bounds__(256) error_metrics_kernel(const float* __restrict__ pred, long long pred_ns, long long pred_ts,
+                                                            const float* __restrict__ target, long long tgt_ns, long long tgt_ts, int Tp,
+                                                            long long F, double inv_points, double* __restrict__ mse, double* __restrict__ ese) {
+  const int n = blockIdx.x / Tp, t = blockIdx.x - n * Tp;
+  const float* p = pred + n * pred_ns + t * pred_ts;
+  const float* q = target + n * tgt_ns + t * tgt_ts;
+  double s_d = 0.0, s_p = 0.0, s_q = 0.0;
+  for (long long i = threadIdx.x; i < F; i += blockDim.x) {
+    const double a = (double)p[i], b = (double)q[i];
+    s_d += (a - b) * (a - b); s_p += a * a; s_q += b * b;
+  }
+  s_d = block_sum_d(s_d);
+  s_p = block_sum_d(s_p);
+  s_q = block_sum_d(s_q);
+  if (threadIdx.x == 0) {
+    mse[blockIdx.x] = s_d / (double)F;
+    const double e = 0.5 * s_p * inv_points - 0.5 * s_q * inv_points;
+    ese[blockIdx.x] = e * e;
+  }
+}
+
+extern "C" int arpde_error_metrics(const float* pred, int64_t pred_nstride, int64_t pred_tstride, const float* target, int64_t tgt_nstride,
+                                   int64_t tgt_tstride, int N, int Tp, int64_t F, int64_t points, double* mse, double* ese,
+                                   arpde_stream_t stream_) {
+  ARPDE_CHECK_ARG(pred && target && mse && ese && N >= 0 && Tp > 0 && F > 0 && points > 0, "error_metrics: bad args");
+  if (N == 0) return ARPDE_OK;
+  ARPDE_CHECK_ARG((long long)N * Tp < (1ll << 31), "error_metrics: too many rows");
+  error_metrics_kernel<<<(unsigned)(N * Tp), 256, 0, (cudaStream_t)stream_>>>(pred, pred_nstride, pred_tstride, target, tgt_nstride, tgt_tstride, Tp, F,
+                                                                              1.0 / (double)points, mse, ese);
+  ARPDE_LAUNCH_CHECK();
+  return ARPDE_OK;
+}

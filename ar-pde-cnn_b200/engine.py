@@ -143,3 +143,30 @@ def swag_rollout(swag_nn, ic, tsteps, n_samples, diagCov=False, scale=1.0, gener
         betas = flat[:, off].exp()
     mean, var = predictive_moments(traj, n_samples, betas, formula)
     return traj, mean, var, betas
+
+
+@torch.no_grad()
+def error_metrics(pred, target, test_every=1, points=None):
+    """MSE and energy-squared error of a (sample-mean) trajectory against a target, per case and saved step.
+
+    pred [N, T+1, ...state...] (e.g. the `mean` of `swag_rollout`), target [N, Tp, ...state...] with Tp <= T // test_every + 1;
+    step t of the target is compared with step t * test_every of the prediction (testMSE / testBayesianMSE of
+    2D-Burgers-SWAG/post/plotMSE.py:78-85,133-137).  points = grid values per component (nel**2; default: state size / channels).
+    Returns (mse, ese) as float64 CUDA tensors [N, Tp]."""
+    L.require_cuda(pred); L.require_cuda(target)
+    if pred.dtype != torch.float32 or target.dtype != torch.float32:
+        raise TypeError('error_metrics: float32 tensors expected')
+    N, Tp = target.shape[0], target.shape[1]
+    F = target[0, 0].numel()
+    if pred.shape[0] != N or pred[0, 0].numel() != F or (Tp - 1) * test_every >= pred.shape[1]:
+        raise ValueError('error_metrics: prediction %s does not cover target %s with test_every=%d' % (tuple(pred.shape), tuple(target.shape), test_every))
+    if points is None:
+        points = F // target.shape[2] if target.dim() > 3 else F
+    p = pred if pred[0, 0].is_contiguous() else pred.contiguous()
+    q = target if target[0, 0].is_contiguous() else target.contiguous()
+    mse = torch.empty((N, Tp), device=pred.device, dtype=torch.float64)
+    ese = torch.empty_like(mse)
+    with torch.cuda.device(pred.device):
+        L.call('arpde_error_metrics', L.ptr(p), p.stride(0), p.stride(1) * test_every, L.ptr(q), q.stride(0), q.stride(1), N, Tp, F, points,
+               L.ptr(mse), L.ptr(ese), L.stream())
+    return mse, ese

@@ -167,6 +167,13 @@ int arpde_conv_tc_set_debug_flags(int flags);
  * lam [B][2][2][(2*order+1)^2] and c [B][2] are DEVICE doubles (the host draws them from numpy's per-index stream); out [B][2][n][n]. */
 int arpde_fourier_ic2d(const double* lam, const double* c, float* out, int B, int ncells, int order, arpde_stream_t stream);
 
+/* Error metrics of a (sample-mean) rollout against a target trajectory, on the device (testMSE / testBayesianMSE,
+ * 2D-Burgers-SWAG/post/plotMSE.py:78-85,133-137): for every case n < N and saved step t < Tp over the F values of one state
+ *   mse[n*Tp+t] = mean_f (pred - target)^2,  ese[n*Tp+t] = (sum_f pred^2 / (2*points) - sum_f target^2 / (2*points))^2   (fp64).
+ * Row (n, t) of pred / target starts at n*nstride + t*tstride floats (tstride = test_every * state size selects every k-th step). */
+int arpde_error_metrics(const float* pred, int64_t pred_nstride, int64_t pred_tstride, const float* target, int64_t tgt_nstride,
+                        int64_t tgt_tstride, int N, int Tp, int64_t F, int64_t points, double* mse, double* ese, arpde_stream_t stream);
+
 /* One-launch Adam step over n fp32 tensors (torch.optim.Adam.step of 2D-Burgers-SWAG/main.py:221-222,84; non-amsgrad):
  * host arrays of DEVICE pointers (param, grad, exp_avg, exp_avg_sq) and element counts; per tensor step_size = lr / (1 - beta1^t),
  * bias_correction2_sqrt = sqrt(1 - beta2^t) and L2 weight decay (NULL = 0), computed by the caller in double as torch does.

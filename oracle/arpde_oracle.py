@@ -368,6 +368,16 @@ def ic_burgers2d(ncells, indices, order=4):
     return torch.stack(out, 0)
 
 
+def error_metrics(mean_pred, target, nel, test_every=1):
+    """testBayesianMSE's error curves (2D-Burgers-SWAG/post/plotMSE.py:131-137): mean_pred [N, T+1, 2, H, W], target [N, Tp, 2, H, W]."""
+    n, tp = target.shape[0], target.shape[1]
+    u_out = mean_pred.reshape(n, mean_pred.shape[1], -1)[:, ::test_every][:, :tp]
+    u_target = target.reshape(n, tp, -1)
+    mse_error = torch.mean(torch.pow(u_out.double() - u_target.double(), 2), dim=-1)
+    ese_error = torch.pow(torch.sum(torch.pow(u_out, 2) / 2.0, dim=-1) / (nel ** 2) - torch.sum(torch.pow(u_target, 2) / 2.0, dim=-1) / (nel ** 2), 2)
+    return mse_error, ese_error
+
+
 def mse(a, b):
     return float(((a - b) ** 2).mean())
 

@@ -36,3 +36,18 @@ def test_ic_vs_reference_golden():
 def test_ic_needs_cuda_device():
     with pytest.raises(RuntimeError, match='no CPU path'):
         InitPeriodicCond2d(16, 10, device='cpu')
+
+
+def test_error_metrics_vs_oracle():
+    """arpde_error_metrics == testBayesianMSE's MSE / ESE curves (post/plotMSE.py:131-137), incl. test_every sub-sampling and strided rows."""
+    from arpde_b200 import engine
+    torch.manual_seed(5)
+    N, T, nel, every = 3, 10, 32, 2
+    buf = torch.randn(N, T + 1, 5, nel, nel)                       # prediction rows are channel-slice views of a larger buffer
+    pred = buf[:, :, 1:3]
+    target = pred[:, ::every][:, :5] + 0.05 * torch.randn(N, 5, 2, nel, nel)
+    mse_ref, ese_ref = O.error_metrics(pred, target, nel, test_every=every)
+    mse, ese = engine.error_metrics(buf.to('cuda:0')[:, :, 1:3], target.to('cuda:0'), test_every=every, points=nel * nel)
+    assert mse.shape == (N, 5) and mse.dtype == torch.float64
+    assert float((mse.cpu() - mse_ref).abs().max() / mse_ref.abs().max()) < 1e-6
+    assert float((ese.cpu() - ese_ref.double()).abs().max() / ese_ref.abs().max()) < 1e-4      # the reference sums 2048 squares in fp32

@@ -201,6 +201,156 @@ __global__ void __launch_bounds__(256) conv_fwd_kernel(ConvFwdArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------
+// Row-tiled variant for the narrow output layers (cout <= 4, stride 1, 2D, no upsampling; e.g. LastTransUp's 5x5 16 -> 2).
+// ncu on the generic kernel for that layer (N = 1920): FMA pipe 23 % active, 52 % issue-active -- a thread owned 2 x 8 outputs,
+// re-read its weights from shared memory for every (ci, ky) and the 8-row tiles staged a 50 % halo.  Here a thread owns
+// COT x RY x 8 outputs (RY rows), keeps the KH*KW*COT weights of the current input channel in registers and walks the
+// KH + RY - 1 patch rows once: 43 shared loads per 800 FMAs (5x5, COT = 2, RY = 2) instead of 65 per 400; tiles are up to 64 rows.
+template <int KH, int KW, int COT, int RY, int PXT>
+__global__ void __launch_bounds__(256) conv_fwd_rt_kernel(ConvFwdArgs a) {
+  constexpr int KK = KH * KW;
+  constexpr int SEG = (PXT + KW - 1 + 3) & ~3;
+  extern __shared__ __align__(16) float smem[];
+  const int PH = a.TH + KH - 1, PW = a.TW + KW - 1;
+  const int PITCH = a.pitch;
+  int* rowmap = reinterpret_cast<int*>(smem);
+  int* colmap = rowmap + PH;
+  float* patch = smem + ((PH + PW + 3) & ~3);
+  float* wsm = patch + a.ci_chunk * PH * PITCH;            // [ci][kk][COT]
+
+  int t = blockIdx.x;
+  const int tx_tile = t % a.tiles_x; t /= a.tiles_x;
+  const int ty_tile = t % a.tiles_y; t /= a.tiles_y;
+  const int n = t;
+  const int g = n / a.n_per_group;
+  const int oy0 = ty_tile * a.TH, ox0 = tx_tile * a.TW;
+  const int tid = threadIdx.x, nthreads = blockDim.x;
+  for (int i = tid; i < PH; i += nthreads) { int iy = (oy0 - a.pad_y + i) % a.H; if (iy < 0) iy += a.H; rowmap[i] = iy; }
+  for (int i = tid; i < PW; i += nthreads) { int ix = (ox0 - a.pad_x + i) % a.W; if (ix < 0) ix += a.W; colmap[i] = ix; }
+
+  const int nxt = a.TW / PXT;
+  const int trow = tid / nxt, pcol = (tid - trow * nxt) * PXT;
+  const int prow = trow * RY;
+  const bool px_valid = prow < a.TH;
+
+  float acc[COT][RY][PXT];
+#pragma unroll
+  for (int c = 0; c < COT; ++c)
+#pragma unroll
+    for (int r = 0; r < RY; ++r)
+#pragma unroll
+      for (int p = 0; p < PXT; ++p) acc[c][r][p] = 0.f;
+
+  const float* xn = a.x + (long long)n * a.x_bs;
+  const float* wg = a.w + (long long)g * a.w_gs;
+  const float* scale = a.scale ? a.scale + (long long)g * a.ss_gs : nullptr;
+  const float* shift = a.scale ? a.shift + (long long)g * a.ss_gs : nullptr;
+  const long long HW = (long long)a.H * a.W;
+  const int warp = tid >> 5, lane = tid & 31, nwarps = nthreads >> 5;
+
+  for (int ci0 = 0; ci0 < a.cin; ci0 += a.ci_chunk) {
+    const int cic = min(a.ci_chunk, a.cin - ci0);
+    __syncthreads();
+    {   // stage the patch.  The tile spans the full width (TW == W, checked by the launcher): a patch line is one contiguous, 16-byte
+        // aligned input row plus the wrap halo, so lanes 0..W/4-1 move one float4 each and a few lanes the halo columns; four lines
+        // per warp are in flight.  (First version: per-element column-map lookups and a division per line -- 17 integer instructions
+        // per load, as many as the FFMAs of the whole kernel.)
+      constexpr int RU = 4;
+      const int nlines = cic * PH, W4 = a.W >> 2, nhalo = PW - a.W;
+      for (int r0 = warp * RU; r0 < nlines; r0 += nwarps * RU) {
+        float4 v[RU]; float hv[RU]; float sc[RU], sh[RU];
+        int ci = r0 / PH, py = r0 - ci * PH;
+#pragma unroll
+        for (int u = 0; u < RU; ++u) {
+          const bool rok = r0 + u < nlines;
+          const float* src = xn + (ci0 + (rok ? ci : 0)) * HW + (long long)rowmap[rok ? py : 0] * a.W;
+          sc[u] = 1.f; sh[u] = 0.f;
+          if (scale && rok) { sc[u] = scale[ci0 + ci]; sh[u] = shift[ci0 + ci]; }
+          v[u] = (rok && lane < W4) ? __ldg(reinterpret_cast<const float4*>(src) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+          // halo column h (lane h): patch column h < pad_x -> input column W - pad_x + h, else patch column W + h -> input column h - pad_x
+          hv[u] = (rok && lane < nhalo) ? __ldg(src + (lane < a.pad_x ? a.W - a.pad_x + lane : lane - a.pad_x)) : 0.f;
+          if (++py == PH) { py = 0; ++ci; }
+        }
+#pragma unroll
+        for (int u = 0; u < RU; ++u) {
+          if (r0 + u < nlines) {
+            float* dst = patch + (r0 + u) * PITCH;
+            float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { e[k] = fmaf(e[k], sc[u], sh[u]); if (a.relu_in) e[k] = fmaxf(e[k], 0.f); }
+            if (lane < W4) {
+              float* d4 = dst + a.pad_x + 4 * lane;           // 8-byte aligned for even pads, else scalar stores
+              if ((a.pad_x & 1) == 0) { *reinterpret_cast<float2*>(d4) = make_float2(e[0], e[1]); *reinterpret_cast<float2*>(d4 + 2) = make_float2(e[2], e[3]); }
+              else { d4[0] = e[0]; d4[1] = e[1]; d4[2] = e[2]; d4[3] = e[3]; }
+            }
+            if (lane < nhalo) {
+              float tv = fmaf(hv[u], sc[u], sh[u]); if (a.relu_in) tv = fmaxf(tv, 0.f);
+              dst[lane < a.pad_x ? lane : a.W + lane] = tv;
+            }
+          }
+        }
+      }
+    }
+    for (int i = tid; i < cic * KK * COT; i += nthreads) {          // weights: global [co][ci][kk] -> smem [ci][kk][COT]
+      const int c = i % COT, j = i / COT;                          // j = ci * KK + kk
+      wsm[i] = c < a.cout ? __ldg(wg + ((long long)c * a.cin + ci0) * KK + j) : 0.f;
+    }
+    __syncthreads();
+    if (px_valid) {
+      for (int ci = 0; ci < cic; ++ci) {
+        float w[KK][COT];
+        const float* wp = wsm + ci * KK * COT;
+#pragma unroll
+        for (int k = 0; k < KK; ++k)
+#pragma unroll
+          for (int c = 0; c < COT; ++c) w[k][c] = wp[k * COT + c];
+        const float* base = patch + (ci * PH + prow) * PITCH + pcol;
+#pragma unroll
+        for (int pr = 0; pr < KH + RY - 1; ++pr) {
+          float in[SEG];
+#pragma unroll
+          for (int q = 0; q < SEG / 4; ++q) {
+            const float4 v4 = *reinterpret_cast<const float4*>(base + pr * PITCH + 4 * q);
+            in[4 * q] = v4.x; in[4 * q + 1] = v4.y; in[4 * q + 2] = v4.z; in[4 * q + 3] = v4.w;
+          }
+#pragma unroll
+          for (int r = 0; r < RY; ++r) {
+            const int ky = pr - r;
+            if (ky >= 0 && ky < KH) {
+#pragma unroll
+              for (int kx = 0; kx < KW; ++kx)
+#pragma unroll
+                for (int c = 0; c < COT; ++c)
+#pragma unroll
+                  for (int p = 0; p < PXT; ++p) acc[c][r][p] = fmaf(w[ky * KW + kx][c], in[p + kx], acc[c][r][p]);
+            }
+          }
+        }
+      }
+    }
+  }
+
+  const long long HoWo = (long long)a.Ho * a.Wo;
+#pragma unroll
+  for (int c = 0; c < COT; ++c) {
+    if (px_valid && c < a.cout) {
+#pragma unroll
+      for (int r = 0; r < RY; ++r) {
+        const int oy = oy0 + prow + r;
+        if (oy < a.Ho && prow + r < a.TH) {
+          float* yp = a.y + ((long long)n * a.y_ctot + a.y_coff + c) * HoWo + (long long)oy * a.Wo + ox0 + pcol;
+          float v[PXT];
+#pragma unroll
+          for (int p = 0; p < PXT; ++p) v[p] = apply_act(acc[c][r][p], a.act);
+#pragma unroll
+          for (int q = 0; q < PXT / 4; ++q) *reinterpret_cast<float4*>(yp + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // host-side dispatch
 // ------------------------------------------------------------------------------------------
 typedef void (*conv_fwd_fn)(ConvFwdArgs);
@@ -239,6 +389,51 @@ int arpde_conv_fwd_launch(const ConvDesc& d, const float* x, long long x_bs, con
   const int sh = (d.H == 1 && d.kh == 1) ? 1 : d.stride;
   ARPDE_CHECK_ARG(Hc % sh == 0 && Wc % d.stride == 0, "conv_fwd: spatial size %dx%d not divisible by stride %d", Hc, Wc, d.stride);
   const int Ho = Hc / sh, Wo = Wc / d.stride;
+  // narrow output layers: row-tiled kernel (see conv_fwd_rt_kernel)
+  if (!getenv("ARPDE_CONV_RT_OFF") && d.stride == 1 && !d.up && !d.dilate && d.pad_override < 0 && d.H > 1 && d.cout <= 4 && stats == nullptr &&
+      (Wo & 7) == 0 && (((uintptr_t)y) & 15) == 0) {
+    conv_fwd_fn rt = nullptr;
+    const int cot = d.cout <= 2 ? 2 : 4;
+    // 8 columns per thread on wide rows, 4 on narrow ones (a 32x32 image then still fills 128 threads)
+    const int PXT = Wo >= 64 ? 8 : 4;
+    if (d.kh == 5 && d.kw == 5) rt = PXT == 8 ? (cot == 2 ? conv_fwd_rt_kernel<5, 5, 2, 2, 8> : conv_fwd_rt_kernel<5, 5, 4, 2, 8>)
+                                              : (cot == 2 ? conv_fwd_rt_kernel<5, 5, 2, 2, 4> : conv_fwd_rt_kernel<5, 5, 4, 2, 4>);
+    else if (d.kh == 3 && d.kw == 3) rt = PXT == 8 ? (cot == 2 ? conv_fwd_rt_kernel<3, 3, 2, 2, 8> : conv_fwd_rt_kernel<3, 3, 4, 2, 8>)
+                                                   : (cot == 2 ? conv_fwd_rt_kernel<3, 3, 2, 2, 4> : conv_fwd_rt_kernel<3, 3, 4, 2, 4>);
+    if (rt) {
+      constexpr int RY = 2;
+      ConvFwdArgs a;
+      memset(&a, 0, sizeof(a));
+      a.x = x; a.x_bs = x_bs; a.cin = d.cin; a.H = d.H; a.W = d.W;
+      a.pad_y = (d.kh - 1) / 2; a.pad_x = (d.kw - 1) / 2;
+      a.w = w; a.w_gs = w_gs; a.scale = scale; a.shift = shift; a.ss_gs = ss_gs; a.relu_in = d.relu_in;
+      a.y = y; a.y_ctot = d.y_ctot; a.y_coff = d.y_coff; a.cout = d.cout; a.Ho = Ho; a.Wo = Wo; a.act = d.act;
+      a.n_per_group = d.n_per_group; a.N = d.N;
+      int TW = Wo < 64 ? Wo : 64;
+      const int nxt = TW / PXT;
+      int TH = (256 / nxt) * RY; if (TH > Ho) TH = (Ho + RY - 1) / RY * RY;
+      a.TH = TH; a.TW = TW; a.tiles_x = (Wo + TW - 1) / TW; a.tiles_y = (Ho + TH - 1) / TH; a.co_tiles = 1;
+      const int PH = TH + d.kh - 1, PW = TW + d.kw - 1;
+      a.pitch = (TW + ((d.kw - 1 + 3) & ~3) + 3) & ~3;
+      const int KK = d.kh * d.kw;
+      const size_t fixed = (size_t)(((PH + PW + 3) & ~3)) * 4;
+      const size_t per_ci = (size_t)PH * a.pitch * 4 + (size_t)KK * cot * 4;
+      const size_t budget = (size_t)(getenv("ARPDE_RT_SMEM_KB") ? atoi(getenv("ARPDE_RT_SMEM_KB")) : (Wo >= 64 ? 100 : 56)) * 1024;   // 2 CTAs per SM on 64-wide rows, 4 of the smaller ones
+      int cic = (int)((budget - fixed) / per_ci); if (cic < 1) cic = 1; if (cic > d.cin) cic = d.cin;
+      cic = (d.cin + ((d.cin + cic - 1) / cic) - 1) / ((d.cin + cic - 1) / cic);
+      a.ci_chunk = cic;
+      const size_t smem = fixed + per_ci * cic;
+      const int threads = ((nxt * ((TH + RY - 1) / RY) + 31) / 32) * 32;
+      if (smem <= 200 * 1024 && threads <= 256 && threads >= 128 && TW == Wo && (d.W & 3) == 0 && (x_bs & 3) == 0 && (((uintptr_t)x) & 15) == 0) {
+        if (smem > 48 * 1024) ARPDE_CUDA(cudaFuncSetAttribute(rt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const long long blocks = (long long)d.N * a.tiles_y * a.tiles_x;
+        ARPDE_CHECK_ARG(blocks < (1ll << 31), "conv_fwd: grid too large");
+        rt<<<(unsigned)blocks, threads, smem, stream>>>(a);
+        ARPDE_LAUNCH_CHECK();
+        return ARPDE_OK;
+      }
+    }
+  }
   const int cot = d.cout > 4 ? 8 : (d.cout > 2 ? 4 : 2);
   int pxt = 8;
   conv_fwd_fn fn = pick_kernel(d.kh, d.kw, d.stride, cot, &pxt);

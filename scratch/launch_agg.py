@@ -11,7 +11,7 @@ for r in rows[hi + 1:]:
     if r[mu] == 'ns': v /= 1e3
     elif r[mu] == 'ms': v *= 1e3
     L.append((re.sub(r'\(.*', '', r[kn])[:60], r[gs], v))
-idx = [i for i, (n, g, v) in enumerate(L) if 'multi_tensor' in n]
+idx = [i for i, (n, g, v) in enumerate(L) if 'multi_tensor' in n or 'adam_step' in n]
 # two training steps were captured (1 warm-up + 1 timed): the second one starts after the first half of the Adam launches
 S = L[idx[len(idx) // 2 - 1] + 1:idx[-1] + 1]
 agg = collections.defaultdict(lambda: [0, 0.0]); tot = 0

@@ -410,7 +410,12 @@ extern "C" int arpde_cn_burgers2d_fwd(const float* uPred, int64_t up_bstride, co
                       up_bstride % 4 == 0 && u0_bstride % 4 == 0 && (pow2 || w4 % 32 == 0);
   const bool base_ok = (W % 4 == 0) && aligned16(uPred) && aligned16(uPred0) && (!ustar || aligned16(ustar)) && up_bstride % 4 == 0 &&
                        u0_bstride % 4 == 0 && (int64_t)H * W % 4 == 0;
-  int TY = W > 0 ? 1024 / W : 0; if (TY > H) TY = H;
+  static const int ty_env = getenv("ARPDE_STENCIL_TY") ? atoi(getenv("ARPDE_STENCIL_TY")) : 0;
+  // rows wider than one warp's 128 columns: the rolling kernel needs its EDGE variant (halo scalars from global memory, 152 registers,
+  // one CTA per SM: 2.3-2.4 TB/s at 256x256); the tiled kernel with the tallest tile that fits 96 KB reaches 2.9 TB/s there
+  // (TY = 4 / 6 / 8 / 10 rows: 2.58 / 2.86 / 2.88 / 2.94 TB/s)
+  const bool wide = W > 128;
+  int TY = ty_env ? ty_env : (W > 0 ? (wide ? 3072 / W - 2 : 1024 / W) : 0); if (TY > H) TY = H;
   const size_t tile_bytes = (size_t)2 * 4 * (TY + 2) * W * sizeof(float);   // double buffer
   // Dispatch: the register-rolling kernel (RY = 4 rows per thread, 120 registers, no spills) is the measured best at 64x64
   // (3.96 TB/s = 60% of the measured HBM peak; RY = 8: 3.4, RY = 2: 3.6; forcing 3 CTAs/SM spills and loses 6%); the
@@ -418,7 +423,7 @@ extern "C" int arpde_cn_burgers2d_fwd(const float* uPred, int64_t up_bstride, co
   // are bank conflicts of the halo scalars) and reaches 2.75 TB/s -- it serves widths the rolling kernel's lane mapping cannot
   // (W/4 neither a power of two nor a multiple of 32) and is selectable with ARPDE_STENCIL_SMEM=1 for A/B runs.
   static const bool force_smem = getenv("ARPDE_STENCIL_SMEM") != nullptr;
-  if (base_ok && TY >= 1 && tile_bytes <= 96 * 1024 && (force_smem || !vec_ok)) {
+  if (base_ok && TY >= 1 && tile_bytes <= 96 * 1024 && (force_smem || !vec_ok || (wide && TY >= 4))) {
     const int nstrips = (H + TY - 1) / TY;
     const int64_t items = (int64_t)N * nstrips;
     ARPDE_CHECK_ARG(items < (1ll << 31), "burgers2d_fwd: too many strips");

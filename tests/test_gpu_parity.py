@@ -38,10 +38,10 @@ def test_integrator_fwd_bwd_vs_reference(system, meth):
     assert rel_err(b.grad, g['integ/%s/g_uPred0' % meth]) < TOL
 
 
-@pytest.mark.parametrize('shape', [(3, 64, 64), (2, 32, 32), (1, 256, 256), (2, 8, 4), (2, 17, 23), (3, 6, 12), (1, 24, 128)])
+@pytest.mark.parametrize('shape', [(3, 64, 64), (2, 32, 32), (1, 256, 256), (2, 8, 4), (2, 17, 23), (3, 6, 12), (1, 24, 128), (1, 8, 1024)])
 @pytest.mark.parametrize('mode', [0, 1])
 def test_burgers2d_fast_vs_generic_vs_oracle(shape, mode):
-    """vectorised kernel (incl. the multi-warp-row EDGE variant at W=256), generic kernel and oracle agree;
+    """vectorised kernel (incl. the multi-warp-row EDGE variant at W=1024), tiled kernel (W=256), generic kernel and oracle agree;
     inputs are channel-slice views of a longer history, as main.py passes them."""
     N, H, W = shape
     torch.manual_seed(3)

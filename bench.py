@@ -183,9 +183,10 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def train_step_probe(dev, B=128, tback=2, nwarm=3, nrep=10):
-    """Training-step timing (SURVEY.md 8 row M5 + P1 + L1): C3-shaped mini-batch of B random Fourier ICs, a tback-step BPTT window
-    (DenseED forward with batch-statistics BatchNorm, Crank-Nicolson target, negative log joint), loss.backward(), Adam step
+def train_step_probe(dev, B=128, tback=2, nwarm=3, nrep=10, rank=0, world=1):
+    """Training-step timing (SURVEY.md 8 row M5 + P1 + L1; BASELINE config C2): every rank takes its own mini-batch of B random Fourier
+    ICs (weak scaling), runs a tback-step BPTT window (DenseED forward with batch-statistics BatchNorm, Crank-Nicolson target, negative
+    log joint), loss.backward(), ONE flat-bucket gradient all-reduce over NCCL when world > 1, and the Adam step
     (2D-Burgers-SWAG/main.py:61-91).  Reported next to the headline; not part of the timed rollout."""
     import contextlib, io, types
     import numpy as np
@@ -202,8 +203,14 @@ def train_step_probe(dev, B=128, tback=2, nwarm=3, nrep=10):
         integ = Burger2DIntegrate(1.0 / NEL, nu=0.005, grad_kernels=[3, 3], device=dev)
     from arpde_b200.optim import Adam
     opt = Adam([{'params': [bayes.model.log_beta], 'lr': 1e-3}, {'params': bayes.model.features.parameters()}], lr=1e-3)
-    ic = make_ics(B).to(dev)
+    from arpde_b200.data import InitPeriodicCond2d
+    ic = InitPeriodicCond2d(NEL, 1 << 30, device=dev).batch(range(rank * B, rank * B + B))      # synthesised on the device (csrc/ic.cu)
     swag.train()
+    bucket = None
+    if world > 1:
+        import torch.distributed as dist
+        from arpde_b200.parallel import FlatGradBucket
+        bucket = FlatGradBucket([bayes.model.log_beta] + list(bayes.model.features.parameters()))
 
     def step():
         inp = ic.repeat(1, 3, 1, 1)
@@ -213,19 +220,29 @@ def train_step_probe(dev, B=128, tback=2, nwarm=3, nrep=10):
             ustar = integ.crankNicolson(u_pred, inp[:, -2:], 0.003)
             loss = loss + swag.calc_neg_log_joint(u_pred, ustar, 10)
             inp = torch.cat([inp, u_pred], 1)
-        loss.backward(); opt.step(); opt.zero_grad()
+        loss.backward()
+        if bucket is not None:
+            bucket.all_reduce_(average=True)
+        opt.step(); opt.zero_grad()
     for _ in range(nwarm):
         step()
     torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(nrep):
         step()
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / nrep
-    return {'ms': ms, 'value': tback * B / ms * 1e3, 'unit': 'sample-steps/s', 'batch': B, 'tback': tback,
+    if world > 1:                                   # slowest rank
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return {'ms': ms, 'value': world * tback * B / ms * 1e3, 'unit': 'sample-steps/s', 'batch_per_gpu': B, 'n_gpus': world, 'tback': tback,
+            'scaling': 'weak', 'parallelism': 'mini-batch sharded x%d, one flat-bucket gradient all-reduce (NCCL) per optimizer step' % world,
             'what': 'forward (batch-stat BN) + Crank-Nicolson + neg log joint + backward (tensor-core data and weight gradients) + one-launch Adam, '
-                    'mean of %d steps after %d warm-up (CUDA events)' % (nrep, nwarm)}
+                    'mean of %d steps after %d warm-up (CUDA events, max over ranks)' % (nrep, nwarm)}
 
 
 def workload_config(n_gpus):
@@ -387,6 +404,9 @@ def main():
     k2_bytes = NT * NEL * NEL * STENCIL_BYTES_PT
     k2_gbs = k2_bytes / (k2_ms * 1e-3) / 1e9
 
+    train = None
+    if not args.no_train_probe:
+        train = train_step_probe(dev, rank=rank, world=world)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -417,8 +437,8 @@ def main():
                                                                    '(the rest of the 62.9 MB of ustar was still in L2 at kernel end)',
                              'bytes_per_launch': k2_bytes, 'ms': k2_ms, 'peak_source': peaks['source']},
     }
-    if not args.no_train_probe:
-        line['train_step'] = train_step_probe(dev)
+    if train is not None:
+        line['train_step'] = train
     if not args.no_cpu_baseline:
         S, N, T = 2, 64, 4
         rate, dt = cpu_reference_rate(S, N, T)

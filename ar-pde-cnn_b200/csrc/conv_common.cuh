@@ -23,6 +23,7 @@ struct ConvFwdArgs {
   double* stats;
   int n_per_group, N;
   int tiles_x, tiles_y, co_tiles, TH, TW, pitch, ci_chunk;
+  int rows_are_samples;    // 1D signals: the TH rows of a tile are TH consecutive samples (no vertical coupling), see conv_fwd.cu
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {

@@ -23,7 +23,9 @@ __global__ void __launch_bounds__(256) conv_fwd_kernel(ConvFwdArgs a) {
   constexpr int KK = KH * KW;
   constexpr int SEG = ((PXT - 1) * S + KW + 3) & ~3;      // input floats a thread reads per (ci,ky), as float4s
   extern __shared__ __align__(16) float smem[];
-  const int PH = (a.TH - 1) * S + KH, PW = (a.TW - 1) * S + KW;
+  // 1D signals (rows_are_samples): a tile row is a sample, rows are independent (KH == 1) and never strided
+  const int SV = a.rows_are_samples ? 1 : S;
+  const int PH = (a.TH - 1) * SV + KH, PW = (a.TW - 1) * S + KW;
   const int PITCH = a.pitch;
   const int TCO = blockDim.y * COT;
   int* rowmap = reinterpret_cast<int*>(smem);
@@ -36,14 +38,15 @@ __global__ void __launch_bounds__(256) conv_fwd_kernel(ConvFwdArgs a) {
   const int tx_tile = t % a.tiles_x; t /= a.tiles_x;
   const int ty_tile = t % a.tiles_y; t /= a.tiles_y;
   const int co_tile = t % a.co_tiles; t /= a.co_tiles;
-  const int n = t;
+  const int n = a.rows_are_samples ? ty_tile * a.TH : t;          // (first) sample of the tile
   const int g = n / a.n_per_group;
-  const int oy0 = ty_tile * a.TH, ox0 = tx_tile * a.TW, co0 = co_tile * TCO;
+  const int oy0 = a.rows_are_samples ? 0 : ty_tile * a.TH, ox0 = tx_tile * a.TW, co0 = co_tile * TCO;
   const int Hc = a.H << a.up_h, Wc = a.W << a.up;
   const int pad_y = a.pad_y, pad_x = a.pad_x;
 
   const int tid = threadIdx.y * blockDim.x + threadIdx.x, nthreads = blockDim.x * blockDim.y;
   for (int i = tid; i < PH; i += nthreads) {
+    if (a.rows_are_samples) { rowmap[i] = n + i < a.N ? i : -1; continue; }      // row i = sample n + i
     int iy = (oy0 * S - pad_y + i) % Hc; if (iy < 0) iy += Hc;
     rowmap[i] = (a.dilate && a.up_h && (iy & 1)) ? -1 : (iy >> a.up_h);     // zero-inserted rows read as 0
   }
@@ -90,7 +93,8 @@ __global__ void __launch_bounds__(256) conv_fwd_kernel(ConvFwdArgs a) {
             const bool rok = r < nlines;
             const int ci = rok ? r / PH : 0, py = rok ? r - ci * PH : 0;
             const int rm = rok ? rowmap[py] : -1;
-            const float* src = xn + (ci0 + ci) * HW + (long long)(rm < 0 ? 0 : rm) * a.W;
+            const float* src = a.rows_are_samples ? xn + (long long)(rm < 0 ? 0 : rm) * a.x_bs + (ci0 + ci) * HW
+                                                  : xn + (ci0 + ci) * HW + (long long)(rm < 0 ? 0 : rm) * a.W;
             sc[u] = 1.f; sh[u] = 0.f;
             if (scale && rok) { sc[u] = scale[ci0 + ci]; sh[u] = shift[ci0 + ci]; }
 #pragma unroll
@@ -134,7 +138,7 @@ __global__ void __launch_bounds__(256) conv_fwd_kernel(ConvFwdArgs a) {
       for (int ci = 0; ci < cic; ++ci) {
 #pragma unroll
         for (int ky = 0; ky < KH; ++ky) {
-          const float* rowp = patch + (ci * PH + prow * S + ky) * PITCH + pcol * S;
+          const float* rowp = patch + (ci * PH + prow * SV + ky) * PITCH + pcol * S;
           float in[SEG];
 #pragma unroll
           for (int q = 0; q < SEG / 4; ++q) {
@@ -166,15 +170,16 @@ __global__ void __launch_bounds__(256) conv_fwd_kernel(ConvFwdArgs a) {
   }
 
   // ---- epilogue: activation, masked store at the channel offset, optional batch-stat sums
-  const int oy = oy0 + prow;
-  const bool row_ok = px_valid && oy < a.Ho;
+  const int oy = a.rows_are_samples ? 0 : oy0 + prow;
+  const int ns = a.rows_are_samples ? n + prow : n;           // sample of this thread's output row
+  const bool row_ok = px_valid && oy < a.Ho && ns < a.N;
   const long long HoWo = (long long)a.Ho * a.Wo;
 #pragma unroll
   for (int c = 0; c < COT; ++c) {
     const int co = co0 + tc * COT + c;
     float s1 = 0.f, s2 = 0.f;
     if (row_ok && co < a.cout) {
-      float* yp = a.y + ((long long)n * a.y_ctot + a.y_coff + co) * HoWo + (long long)oy * a.Wo + ox0 + pcol;
+      float* yp = a.y + ((long long)ns * a.y_ctot + a.y_coff + co) * HoWo + (long long)oy * a.Wo + ox0 + pcol;
       float v[PXT];
 #pragma unroll
       for (int p = 0; p < PXT; ++p) v[p] = apply_act(acc[c][p], a.act);
@@ -456,14 +461,23 @@ int arpde_conv_fwd_launch(const ConvDesc& d, const float* x, long long x_bs, con
   const int tw_cap = (Ho == 1 ? 32 * npw_max : 16) * pxt;
   if (TW > tw_cap) TW = tw_cap;
   const int nxt = TW / pxt;
-  int TH = (32 * npw_max) / nxt; if (TH < 1) TH = 1; if (TH > Ho) TH = Ho;
+  int TH = (32 * npw_max) / nxt; if (TH < 1) TH = 1;
+  // 1D signals: fill the CTA with consecutive samples as tile rows (they must share a weight group).  A 96-point KS layer used 6 or 12
+  // of its 32+ px-threads with one sample per CTA (C1 rollout: 433 us per AR step of 1920 samples)
+  const bool one_d_rows = Ho == 1 && d.kh == 1 && !getenv("ARPDE_CONV_1D_ROWS_OFF");
+  if (one_d_rows) {
+    // ... but keep at least ~3 CTAs per SM in the grid (1920 samples in tiles of 32 would be 60 CTAs on 148 SMs)
+    const long long per_row_ctas = (long long)((d.cout + ncg * cot - 1) / (ncg * cot)) * ((Wo + TW - 1) / TW);
+    while (TH > 1 && (d.n_per_group % TH != 0 || TH > d.N || ((d.N + TH - 1) / TH) * per_row_ctas < 3ll * arpde_num_sms())) --TH;
+  }
+  else if (TH > Ho) TH = Ho;
   const int npw = (nxt * TH + 31) / 32;
   ARPDE_CHECK_ARG(npw >= 1 && npw <= npw_max, "conv_fwd: internal tiling error (npw=%d)", npw);
-  a.TH = TH; a.TW = TW;
-  a.tiles_x = (Wo + TW - 1) / TW; a.tiles_y = (Ho + TH - 1) / TH;
+  a.TH = TH; a.TW = TW; a.rows_are_samples = one_d_rows ? 1 : 0;
+  a.tiles_x = (Wo + TW - 1) / TW; a.tiles_y = one_d_rows ? (d.N + TH - 1) / TH : (Ho + TH - 1) / TH;
   const int TCO = ncg * cot;
   a.co_tiles = (d.cout + TCO - 1) / TCO;
-  const int PH = (TH - 1) * d.stride + d.kh, PW = (TW - 1) * d.stride + d.kw;
+  const int PH = one_d_rows ? TH : (TH - 1) * d.stride + d.kh, PW = (TW - 1) * d.stride + d.kw;
   const int seg = (((pxt - 1) * d.stride + d.kw) + 3) & ~3;
   // a thread reads SEG floats from column pcol*S; the last thread starts at (TW-PXT)*S
   int pitch = (TW - pxt) * d.stride + seg; if (pitch < PW) pitch = PW; pitch = (pitch + 3) & ~3;
@@ -478,7 +492,7 @@ int arpde_conv_fwd_launch(const ConvDesc& d, const float* x, long long x_bs, con
   const size_t smem = fixed + per_ci * cic;
   ARPDE_CHECK_ARG(smem <= 200 * 1024, "conv_fwd: tile needs %zu bytes of shared memory", smem);
   if (smem > 48 * 1024) ARPDE_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const long long blocks = (long long)d.N * a.co_tiles * a.tiles_y * a.tiles_x;
+  const long long blocks = (long long)(one_d_rows ? 1 : d.N) * a.co_tiles * a.tiles_y * a.tiles_x;
   ARPDE_CHECK_ARG(blocks < (1ll << 31), "conv_fwd: grid too large");
   fn<<<(unsigned)blocks, dim3(32 * npw, ncg), smem, stream>>>(a);
   ARPDE_LAUNCH_CHECK();

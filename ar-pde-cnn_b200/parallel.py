@@ -70,12 +70,9 @@ class FlatGradBucket:
         if ws == 1 or not self.params:
             return
         dev = self.params[0].device
-        flat = torch.zeros((self.numel,), dtype=torch.float32, device=dev)
-        off = 0
-        for p in self.params:
-            if p.grad is not None:
-                flat[off:off + p.numel()] = p.grad.reshape(-1)
-            off += p.numel()
+        # one concatenation kernel instead of one copy per tensor (25 tensors for the default 2D net)
+        flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1).to(torch.float32) for p in self.params])
+        assert flat.device == dev and flat.numel() == self.numel
         dist.all_reduce(flat, op=dist.ReduceOp.SUM)
         if average:
             flat /= ws

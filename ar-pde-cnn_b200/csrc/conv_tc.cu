@@ -29,6 +29,11 @@
 //     shared memory, reloaded only when the weight group (SWAG sample) changes;
 //   * weights arrive pre-split (hi/lo) and pre-arranged in the UMMA layout by conv_tc_wprep_kernel.
 // M tiles that straddle image rows waste only the (pitch - Wo)/pitch halo positions.
+// Nearest x2 upsampling followed by a 3x3 conv is folded ("upfold"): an output pixel of parity (py, px) only sees a 2x2 block of
+// distinct low-resolution pixels, so the layer is computed as ONE 3x3 conv on the low-resolution grid with 4*cout output channels
+// (parity-major) whose weights are sums of the original taps (row offsets: py = 0: {w0 | w1+w2 | -}, py = 1: {- | w0+w1 | w2}); the
+// epilogue scatters channel (parity, co) to pixel (2y+py, 2x+px).  4x fewer M tiles, N 4x larger: 2.7x fewer tensor-core cycles for
+// LastTransUp's 32->16 layer and a 4x smaller patch to stage.
 #include "common.cuh"
 #include "conv_common.cuh"
 #include "../../include/arpde.h"
@@ -71,6 +76,7 @@ struct ConvTcArgs {
   int row_mode;              // 0: stride 1, 1: nearest x2 upsampled input, 2: stride 2 (parity planes)
   int dilate;                // input is zero-inserted x2 (data gradient of a stride-2 layer): addressed like row_mode 1, odd rows/columns are 0
   int RS, raw_slot_floats;   // source rows per (item, channel chunk) and floats per raw ring slot [RS][cchunk][W]
+  int upfold, cout_fold;     // upfold: `cout` = 4 * cout_fold parity-major channels on the low-resolution grid, scattered by the epilogue
   long long* dbg;            // optional cycle counters of CTA 0 (arpde_conv_tc_set_debug), else nullptr
   int dbg_flags;             // experiments: 1 = skip patch staging work, 2 = skip epilogue loads/stores, 4 = skip MMAs
   int tap_plane[TC_MAX_TAPS];
@@ -93,7 +99,7 @@ struct ConvTcArgs {
 // of every (channel chunk, tap chunk) weight slot: rows [0,coutP) = tf32 hi part, rows [coutP,2coutP) = lo part.
 __global__ void __launch_bounds__(256) conv_tc_wprep_kernel(const float* __restrict__ w, long long w_gs, float* __restrict__ out,
                                                             long long out_gs, int groups, int cout, int cin, int ntaps,
-                                                            int cchunk, int ncc, int tchunk, int ntc, int coutP) {
+                                                            int cchunk, int ncc, int tchunk, int ntc, int coutP, int cout_fold) {
   const int nc4 = cchunk >> 2, rows = 2 * coutP;
   const long long per_group = (long long)ncc * ntc * tchunk * nc4 * rows * 4;
   const long long total = per_group * groups;
@@ -107,7 +113,22 @@ __global__ void __launch_bounds__(256) conv_tc_wprep_kernel(const float* __restr
     const int tc = (int)(r % ntc); const int cc = (int)(r / ntc);
     const int tap = tc * tchunk + tl, c = cc * cchunk + c4 * 4 + e, co = row < coutP ? row : row - coutP;
     float v = 0.f;
-    if (co < cout && c < cin) v = __ldg(w + (long long)g * w_gs + ((long long)co * cin + c) * ntaps + tap);
+    if (co < cout && c < cin) {
+      if (cout_fold == 0) {
+        v = __ldg(w + (long long)g * w_gs + ((long long)co * cin + c) * ntaps + tap);
+      } else {
+        // upfold: channel co = parity * cout_fold + cr, low-resolution tap (ty, tx) = sum of the 3x3 taps that land on it
+        const int par = co / cout_fold, cr = co - par * cout_fold, py = par >> 1, px = par & 1, ty = tap / 3, tx = tap - ty * 3;
+        const float* wp = w + (long long)g * w_gs + ((long long)cr * cin + c) * 9;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+          if (((py + ky + 1) >> 1) != ty) continue;           // low-res row offset of original tap ky: floor((py + ky - 1) / 2) + 1
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx)
+            if (((px + kx + 1) >> 1) == tx) v += __ldg(wp + ky * 3 + kx);
+        }
+      }
+    }
     const float hi = tf32_rna(v);
     out[(long long)g * out_gs + (idx - (long long)g * per_group)] = row < coutP ? hi : tf32_rna(v - hi);
   }
@@ -503,11 +524,40 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         const int oy = q / a.pitch, ox = q - oy * a.pitch;
         const bool valid = oy < a.Ho && ox < a.Wo;
         float* yp = a.y + ((long long)n * a.y_ctot + a.y_coff) * HoWo + (long long)oy * a.Wo + ox;
+        // upfold: channel c = parity * cout_fold + co goes to pixel (2 oy + py, 2 ox + px) of the 2Ho x 2Wo output
+        const long long HoWo4 = 4 * HoWo;
+        float* ypf = a.y + ((long long)n * a.y_ctot + a.y_coff) * HoWo4 + (long long)(2 * oy) * (2 * a.Wo) + 2 * ox;
         const uint32_t trow = tmem + ((uint32_t)lanebase << 16) + (uint32_t)(as * a.acc_cols + t * a.tile_cols);
         if (plain) {
           // common case (no output activation, no batch statistics): 16 columns per TMEM round trip, straight stores.
           // (ncu on the first version: the per-element activation switch + statistics branches made the 4 epilogue warps
           //  the critical path -- ~95% busy, half of their stalls branch_resolving / instruction-cache misses.)
+          if (a.upfold && (a.cout_fold & 15) == 0) {
+            // folded upsampling, 16 | cout_fold: the two x-parities of a (row parity, channel) are adjacent pixels -> one float2 store each,
+            // a warp writes 256 contiguous bytes per instruction.  (First version: 64 scalar stride-2 stores per thread with a runtime
+            // division per column -- the epilogue took 0.7 of the layer's 1.1 ms.)
+            const int cf = a.cout_fold;
+            for (int py = 0; py < 2; ++py) {
+              for (int cr0 = 0; cr0 < cf; cr0 += 16) {
+                const int ca = 2 * py * cf + cr0, cb = ca + cf;
+                float a1[16], a2[16], b1[16], b2[16];
+                tmem_ld16(trow + ca, a1); tmem_ld16(trow + a.coutP + ca, a2); tmem_ld16(trow + cb, b1); tmem_ld16(trow + a.coutP + cb, b2);
+                tmem_ld_wait();
+                if (a.split_terms) {
+                  float a3[16], b3[16];
+                  tmem_ld16(trow + 2 * a.coutP + ca, a3); tmem_ld16(trow + 2 * a.coutP + cb, b3);
+                  tmem_ld_wait();
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) { a2[j] += a3[j]; b2[j] += b3[j]; }
+                }
+                if (valid) {
+                  float* d = ypf + (long long)py * (2 * a.Wo) + (long long)cr0 * HoWo4;
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) { *reinterpret_cast<float2*>(d) = make_float2(a1[j] + a2[j], b1[j] + b2[j]); d += HoWo4; }
+                }
+              }
+            }
+          } else
           for (int c0 = 0; c0 < a.cout; c0 += 16) {
             float v1[16], v2[16];
             DBG_T(1, tmem_ld16(trow + c0, v1); tmem_ld16(trow + a.coutP + c0, v2); tmem_ld_wait());
@@ -519,7 +569,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
               for (int j = 0; j < 16; ++j) v2[j] += v3[j];
             }
             float* pc = yp + c0 * HoWo;
-            if (valid) {
+            if (valid && a.upfold) {       // generic folded store (cout_fold not a multiple of 16): parity / channel advanced incrementally
+              int par = c0 / a.cout_fold, cr = c0 - par * a.cout_fold;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                if (c0 + j < a.cout) ypf[cr * HoWo4 + (par >> 1) * (2 * a.Wo) + (par & 1)] = v1[j] + v2[j];
+                if (++cr == a.cout_fold) { cr = 0; ++par; }
+              }
+            } else if (valid) {
               if (c0 + 16 <= a.cout) {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) { *pc = v1[j] + v2[j]; pc += HoWo; }
@@ -549,12 +606,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
               const int co = c0 + j;
               float val = apply_act(v1[j] + v2[j], a.act);
               const bool st = valid && co < a.cout;
-              if (st) yp[co * HoWo] = val;
+              const int par = a.upfold ? co / a.cout_fold : 0, cr = a.upfold ? co - par * a.cout_fold : co;     // real output channel
+              if (st) { if (a.upfold) ypf[cr * HoWo4 + (par >> 1) * (2 * a.Wo) + (par & 1)] = val; else yp[co * HoWo] = val; }
               if (a.stats) {
                 if (!st) val = 0.f;
                 const float s1 = warp_sum(val), s2 = warp_sum(val * val);
                 if (lane == 0 && co < a.cout) {
-                  double* sp = a.stats + 2 * (a.y_coff + co);
+                  double* sp = a.stats + 2 * (a.y_coff + cr);
                   atomicAdd(sp, (double)s1); atomicAdd(sp + 1, (double)s2);
                 }
               }
@@ -756,6 +814,11 @@ int arpde_tc_enabled() {
 // Plan the tiling of one convolution for conv_tc_kernel.  Returns false if the layer is outside what the kernel covers.
 static bool tc_plan(const ConvDesc& d, ConvTcArgs& a, size_t* smem_out) {
   if (d.pad_override >= 0) return false;
+  // nearest x2 + 3x3: plan the equivalent low-resolution conv with 4*cout parity-major channels (see the header comment)
+  if (d.up && !d.dilate && d.stride == 1 && d.kh == 3 && d.kw == 3 && d.H > 1 && 4 * d.cout <= 128 && !getenv("ARPDE_TC_NO_UPFOLD")) {
+    ConvDesc e = d; e.up = 0; e.cout = 4 * d.cout;
+    if (tc_plan(e, a, smem_out)) { a.upfold = 1; a.cout_fold = d.cout; return true; }
+  }
   if (d.dilate && (d.up || d.stride != 1 || (d.H == 1 && d.kh == 1))) return false;
   if (d.stride != 1 && d.stride != 2) return false;
   if (d.up && d.stride != 1) return false;
@@ -853,7 +916,8 @@ static bool tc_plan(const ConvDesc& d, ConvTcArgs& a, size_t* smem_out) {
 
 // floats of prepared weights one group needs for this layer (upper bound over every plan tc_plan may pick)
 long long arpde_conv_tc_wprep_floats(int cin, int cout, int kh, int kw) {
-  return (long long)kh * kw * round_up(cin, 32) * 2 * round_up(cout, 16);
+  const int cout_eff = (kh == 3 && kw == 3 && 4 * cout <= 128) ? 4 * cout : cout;      // the layer may be an upsampling one (upfold)
+  return (long long)kh * kw * round_up(cin, 32) * 2 * round_up(cout_eff, 16);
 }
 
 // heuristic: which layers go to the tensor cores (the rest stay on the fp32 FFMA kernel)
@@ -873,8 +937,8 @@ int arpde_conv_tc_prep_launch(const ConvDesc& d, const float* w, long long w_gs,
   ARPDE_CHECK_ARG(groups == 1 || wprep_gs >= per_group, "conv_tc: wprep group stride too small");
   const long long total = per_group * groups;
   const int blocks = (int)((total + 255) / 256 < 2048 ? (total + 255) / 256 : 2048);
-  conv_tc_wprep_kernel<<<blocks, 256, 0, stream>>>(w, w_gs, wprep, wprep_gs, groups, d.cout, d.cin, a.ntaps, a.cchunk, a.ncc, a.tchunk,
-                                                   a.ntc, a.coutP);
+  conv_tc_wprep_kernel<<<blocks, 256, 0, stream>>>(w, w_gs, wprep, wprep_gs, groups, a.cout, d.cin, a.ntaps, a.cchunk, a.ncc, a.tchunk,
+                                                   a.ntc, a.coutP, a.upfold ? a.cout_fold : 0);
   ARPDE_LAUNCH_CHECK();
   return ARPDE_OK;
 }
@@ -998,7 +1062,7 @@ extern "C" int arpde_conv_fwd_tc(const float* x, int64_t x_bstride, const float*
 
 // Diagnostic (host only, no GPU needed): the tiling conv_tc_kernel would use for a layer.  out[0..26] = pitch, min_ry, min_rx, ntile,
 // ctas_per_sample, PP, PHP, nplanes, cchunk, ncc, tchunk, ntc, ntaps, coutP, tmem_cols, nslot_p, smem bytes, Ho, Wo, Hc, Wc, sy, sx,
-// wanted-by-heuristic, resident, nacc, kp; out[32+t] = tap plane, out[32+49+t] = tap offset.  Returns ARPDE_ERR_UNSUPPORTED if not plannable.
+// wanted-by-heuristic, resident, nacc, kp, upfold, cout_fold; out[32+t] = tap plane, out[32+49+t] = tap offset.  Returns ARPDE_ERR_UNSUPPORTED if not plannable.
 extern "C" int arpde_conv_tc_plan(int cin, int H, int W, int cout, int kh, int kw, int stride, int up, int32_t* out) {
   ARPDE_CHECK_ARG(out, "conv_tc_plan: null output");
   ConvDesc d;
@@ -1006,6 +1070,7 @@ extern "C" int arpde_conv_tc_plan(int cin, int H, int W, int cout, int kh, int k
   d.up = up; d.relu_in = 0; d.act = 0; d.y_ctot = cout; d.y_coff = 0; d.n_per_group = 1;
   ConvTcArgs a; size_t smem = 0;
   if (!tc_plan(d, a, &smem)) { arpde_set_error("conv_tc_plan: layer not supported"); return ARPDE_ERR_UNSUPPORTED; }
+  out[27] = a.upfold; out[28] = a.cout_fold;
   const int v[27] = {a.pitch, a.min_ry, a.min_rx, a.ntile, a.ctas_per_sample, a.PP, a.PHP, a.nplanes, a.cchunk, a.ncc, a.tchunk, a.ntc,
                      a.ntaps, a.coutP, a.tmem_cols, a.nslot_p, (int)smem, a.Ho, a.Wo, a.Hc, a.Wc, a.sy, a.sx, arpde_conv_tc_wanted(d) ? 1 : 0,
                      a.resident, a.nacc, a.kp};

@@ -18,6 +18,7 @@ def plan(cin, H, W, cout, kh, kw, s, up):
     out = (C.c_int32 * 160)()
     L.call('arpde_conv_tc_plan', cin, H, W, cout, kh, kw, s, up, C.addressof(out))
     p = dict(zip(NAMES, out[:len(NAMES)]))
+    p['upfold'], p['cout_fold'] = out[27], out[28]
     p['tap_plane'] = list(out[32:32 + kh * kw])
     p['tap_off'] = list(out[81:81 + kh * kw])
     return p
@@ -71,7 +72,23 @@ def test_shifted_window_index_arithmetic(cin, cout, kh, kw, s, up, H, W):
     p = plan(cin, H, W, cout, kh, kw, s, up)
     rng = np.random.default_rng(cin * 100 + kh)
     x, w = rng.standard_normal((cin, H, W)), rng.standard_normal((cout, cin, kh, kw))
-    y = replay(x, w, up, p)
+    if p['upfold']:
+        # nearest x2 + 3x3 folded into a 3x3 conv on the low-resolution grid with 4*cout parity-major channels (conv_tc.cu header):
+        # low-res tap t of parity p collects the original taps k with (p + k + 1) >> 1 == t; channel (py, px, co) -> pixel (2y+py, 2x+px)
+        assert p['cout_fold'] == cout and up == 1 and kh == 3 and kw == 3
+        wf = np.zeros((4 * cout, cin, 3, 3))
+        for py in range(2):
+            for px in range(2):
+                for ky in range(3):
+                    for kx in range(3):
+                        wf[(py * 2 + px) * cout:(py * 2 + px + 1) * cout, :, (py + ky + 1) >> 1, (px + kx + 1) >> 1] += w[:, :, ky, kx]
+        yl = replay(x, wf, 0, p)
+        y = np.zeros((cout, 2 * H, 2 * W))
+        for py in range(2):
+            for px in range(2):
+                y[:, py::2, px::2] = yl[(py * 2 + px) * cout:(py * 2 + px + 1) * cout]
+    else:
+        y = replay(x, w, up, p)
     xt = torch.from_numpy(x)[None]
     if up:
         xt = O._up2(xt) if H > 1 else xt.repeat_interleave(2, -1)
@@ -87,6 +104,7 @@ def test_plans_of_the_default_network_fit_the_sm():
                                      (32, 16, 3, 1, 1, 32), (176, 88, 1, 1, 0, 128), (88, 44, 3, 1, 1, 128), (6, 96, 5, 1, 0, 256)):
         p = plan(cin, H, H, cout, k, k, s, up)
         assert p['smem'] <= 227 * 1024 and p['tmem'] <= 512 and p['nacc'] * p['ntile'] * 2 * p['coutP'] <= p['tmem']
+        assert p['upfold'] == (1 if (up and k == 3 and 4 * cout <= 128) else 0)
         assert p['PHP'] <= 2048 and p['kp'] == -(-p['PHP'] // 256)
         assert p['wanted'] == 1
 

@@ -61,6 +61,7 @@ _PROTOS = {
     'arpde_error_metrics': [vp, i64, i64, vp, i64, i64, i32, i32, i64, i64, vp, vp, vp],
     'arpde_adam_step': [vp, vp, vp, vp, vp, vp, vp, vp, i32, f64, f64, f64, vp],
     'arpde_fourier_ic2d': [vp, vp, vp, i32, i32, i32, vp],
+    'arpde_conv_wgrad': [vp, i64, vp, vp, vp, i64, vp, vp] + [i32] * 10 + [vp, i64, i32, vp],
     'arpde_conv_wgrad_tc': [vp, i64, vp, vp, vp, i64, vp, vp] + [i32] * 10 + [vp, i64, vp],
     'arpde_conv_wgrad_tc_plan': [i32] * 8 + [vp],
     'arpde_conv_tc_set_debug': [vp],

@@ -403,6 +403,179 @@ int arpde_d2f_launch(const double* src, float* dst, long long n, cudaStream_t st
   return ARPDE_OK;
 }
 
+// ------------------------------------------------------------------ weight gradient of narrow layers (cout <= 4, stride 1, 2D)
+// dW has only cout*cin*k^2 entries (800 for the 16 -> 2 5x5 output conv, 2160 for a 60 -> 4 dense layer) while the sum runs over
+// N*H*W positions: the work is ~10 us of FMAs, and both other kernels are ~30x off (generic wgrad_kernel: 0.42 ms, 0.2 ms; the
+// tensor core pays ~40 cycles per MMA for 4 useful accumulator rows: 0.13 ms).  Here a thread owns one (input channel, ky) pair and
+// all KW x CO accumulators of it; it slides along the rows of a tile: per 8 positions three float4 of the input row and the 8 x CO
+// output-gradient values (broadcast) feed 8*KW*CO FMAs.  Persistent CTAs keep the accumulators across tiles; one block-level
+// reduction over the row groups and cin*KH*KW*CO fp64 atomics per CTA at the end.
+struct WgradSmallArgs {
+  const float* x; long long x_bs; const float* scale; const float* shift; int relu_in;
+  const float* dO; long long dO_bs; double* dW;
+  int N, cin, H, W, cout, TH, tiles_y, pitch, gpitch;
+};
+
+template <int KH, int KW, int CO>
+__global__ void __launch_bounds__(256) wgrad_small_kernel(WgradSmallArgs a) {
+  constexpr int PXB = 8, SEG = (PXB + KW - 1 + 3) & ~3;
+  extern __shared__ __align__(16) float smem[];
+  const int PH = a.TH + KH - 1, PW = a.W + KW - 1;
+  const int pad_y = (KH - 1) / 2, pad_x = (KW - 1) / 2;
+  float* patch = smem;                                   // [cin][PH][pitch]
+  float* gys = patch + (size_t)a.cin * PH * a.pitch;     // [TH][gpitch]: CO values per position, interleaved
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+  const int npairs = a.cin * KH;
+  const int rgroups = blockDim.x / npairs;               // row groups; threads beyond npairs * rgroups only help staging
+  const int pr = tid % npairs, rg = tid / npairs;
+  const bool worker = rg < rgroups;
+  const int ci = pr / KH, ky = pr - ci * KH;
+  const long long HW = (long long)a.H * a.W;
+  float acc[KW][CO];
+#pragma unroll
+  for (int k = 0; k < KW; ++k)
+#pragma unroll
+    for (int c = 0; c < CO; ++c) acc[k][c] = 0.f;
+
+  const int W4 = a.W >> 2, nhalo = PW - a.W;
+  for (int t = blockIdx.x; t < a.N * a.tiles_y; t += gridDim.x) {
+    const int n = t / a.tiles_y, y0 = (t - n * a.tiles_y) * a.TH;
+    const float* xn = a.x + (long long)n * a.x_bs;
+    const float* gn = a.dO + (long long)n * a.dO_bs;
+    __syncthreads();
+    // ---- input patch: whole rows as float4 + wrap halo lanes, BN/ReLU applied (as conv_fwd_rt_kernel), four lines per warp in flight
+    {
+      constexpr int RU = 4;
+      const int nlines = a.cin * PH;
+      for (int r0 = warp * RU; r0 < nlines; r0 += nwarps * RU) {
+        float4 v[RU]; float hv[RU], sc[RU], sh[RU];
+        int c = r0 / PH, py = r0 - c * PH;
+#pragma unroll
+        for (int u = 0; u < RU; ++u) {
+          const bool rok = r0 + u < nlines;
+          int iy = y0 - pad_y + (rok ? py : 0); if (iy < 0) iy += a.H; else if (iy >= a.H) iy -= a.H;
+          const float* src = xn + (long long)(rok ? c : 0) * HW + (long long)iy * a.W;
+          sc[u] = 1.f; sh[u] = 0.f;
+          if (a.scale && rok) { sc[u] = a.scale[c]; sh[u] = a.shift[c]; }
+          v[u] = (rok && lane < W4) ? __ldg(reinterpret_cast<const float4*>(src) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+          hv[u] = (rok && lane < nhalo) ? __ldg(src + (lane < pad_x ? a.W - pad_x + lane : lane - pad_x)) : 0.f;
+          if (++py == PH) { py = 0; ++c; }
+        }
+#pragma unroll
+        for (int u = 0; u < RU; ++u) {
+          if (r0 + u < nlines) {
+            float* dst = patch + (size_t)(r0 + u) * a.pitch;
+            float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { e[k] = fmaf(e[k], sc[u], sh[u]); if (a.relu_in) e[k] = fmaxf(e[k], 0.f); }
+            if (lane < W4) {
+              float* d4 = dst + pad_x + 4 * lane;
+              if ((pad_x & 1) == 0) { *reinterpret_cast<float2*>(d4) = make_float2(e[0], e[1]); *reinterpret_cast<float2*>(d4 + 2) = make_float2(e[2], e[3]); }
+              else { d4[0] = e[0]; d4[1] = e[1]; d4[2] = e[2]; d4[3] = e[3]; }
+            }
+            if (lane < nhalo) {
+              float tv = fmaf(hv[u], sc[u], sh[u]); if (a.relu_in) tv = fmaxf(tv, 0.f);
+              dst[lane < pad_x ? lane : a.W + lane] = tv;
+            }
+          }
+        }
+      }
+    }
+    // ---- output gradient: [TH][W][CO] interleaved (rows past the image: zeros)
+    for (int i = tid; i < a.TH * CO * W4; i += blockDim.x) {
+      const int x4 = i % W4, rc = i / W4, c = rc % CO, r = rc / CO;
+      float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c < a.cout && y0 + r < a.H) g4 = __ldg(reinterpret_cast<const float4*>(gn + (long long)c * HW + (long long)(y0 + r) * a.W) + x4);
+      float* d = gys + (size_t)r * a.gpitch + (size_t)(4 * x4) * CO + c;
+      d[0] = g4.x; d[CO] = g4.y; d[2 * CO] = g4.z; d[3 * CO] = g4.w;
+    }
+    __syncthreads();
+    if (worker) {
+      for (int r = rg; r < a.TH; r += rgroups) {
+        const float* ap = patch + (size_t)(ci * PH + r + ky) * a.pitch;
+        const float* gp = gys + (size_t)r * a.gpitch;
+        for (int x0 = 0; x0 < a.W; x0 += PXB) {
+          float in[SEG], g[PXB][CO];
+#pragma unroll
+          for (int q = 0; q < SEG / 4; ++q) {
+            const float4 v4 = *reinterpret_cast<const float4*>(ap + x0 + 4 * q);
+            in[4 * q] = v4.x; in[4 * q + 1] = v4.y; in[4 * q + 2] = v4.z; in[4 * q + 3] = v4.w;
+          }
+#pragma unroll
+          for (int q = 0; q < PXB * CO / 4; ++q) {
+            const float4 v4 = *reinterpret_cast<const float4*>(gp + (size_t)x0 * CO + 4 * q);
+            (&g[0][0])[4 * q] = v4.x; (&g[0][0])[4 * q + 1] = v4.y; (&g[0][0])[4 * q + 2] = v4.z; (&g[0][0])[4 * q + 3] = v4.w;
+          }
+#pragma unroll
+          for (int p = 0; p < PXB; ++p)
+#pragma unroll
+            for (int k = 0; k < KW; ++k)
+#pragma unroll
+              for (int c = 0; c < CO; ++c) acc[k][c] = fmaf(g[p][c], in[p + k], acc[k][c]);
+        }
+      }
+    }
+  }
+  // ---- reduce the row groups in shared memory, then fp64 atomics (one per weight and CTA)
+  __syncthreads();
+  float* red = smem;                                     // [npairs][KW * CO]
+  for (int g = 0; g < rgroups; ++g) {
+    if (worker && rg == g) {
+#pragma unroll
+      for (int k = 0; k < KW; ++k)
+#pragma unroll
+        for (int c = 0; c < CO; ++c) {
+          float* d = red + (size_t)pr * (KW * CO) + k * CO + c;
+          *d = g == 0 ? acc[k][c] : *d + acc[k][c];
+        }
+    }
+    __syncthreads();
+  }
+  for (int i = tid; i < npairs * KW * CO; i += blockDim.x) {
+    const int c = i % CO, k = (i / CO) % KW, p2 = i / (CO * KW);
+    const int ci2 = p2 / KH, ky2 = p2 - ci2 * KH;
+    if (c < a.cout) atomicAdd(a.dW + (((long long)c * a.cin + ci2) * KH + ky2) * KW + k, (double)red[i]);
+  }
+}
+
+typedef void (*wgrad_small_fn)(WgradSmallArgs);
+
+// returns ARPDE_OK if the narrow-layer kernel took the job, ARPDE_ERR_UNSUPPORTED if the layer is not its kind (caller falls back)
+static int wgrad_small_launch(const ConvDesc& d, const float* x, long long x_bs, const float* scale, const float* shift, const float* dO,
+                              long long dO_bs, double* dW64, cudaStream_t stream) {
+  if (getenv("ARPDE_WGRAD_SMALL_OFF")) return ARPDE_ERR_UNSUPPORTED;
+  if (d.stride != 1 || d.up || d.dilate || d.pad_override >= 0 || d.H < 2 || d.cout > 4 || d.kh != d.kw) return ARPDE_ERR_UNSUPPORTED;
+  if ((d.W & 7) || d.W > 128 || (x_bs & 3) || (dO_bs & 3) || (((uintptr_t)x | (uintptr_t)dO) & 15)) return ARPDE_ERR_UNSUPPORTED;
+  const int CO = d.cout <= 2 ? 2 : 4;
+  wgrad_small_fn fn = nullptr;
+  if (d.kh == 3) fn = CO == 2 ? wgrad_small_kernel<3, 3, 2> : wgrad_small_kernel<3, 3, 4>;
+  else if (d.kh == 5) fn = CO == 2 ? wgrad_small_kernel<5, 5, 2> : wgrad_small_kernel<5, 5, 4>;
+  if (!fn) return ARPDE_ERR_UNSUPPORTED;
+  const int npairs = d.cin * d.kh;
+  if (npairs > 256) return ARPDE_ERR_UNSUPPORTED;
+  WgradSmallArgs a; memset(&a, 0, sizeof(a));
+  a.x = x; a.x_bs = x_bs; a.scale = scale; a.shift = shift; a.relu_in = d.relu_in; a.dO = dO; a.dO_bs = dO_bs; a.dW = dW64;
+  a.N = d.N; a.cin = d.cin; a.H = d.H; a.W = d.W; a.cout = d.cout;
+  a.pitch = ((d.W + d.kw - 1 + 3) & ~3) + 4;                 // room for the 12-float window of the last 8 columns
+  a.gpitch = d.W * CO;
+  // tile height: the tallest that keeps the patch + gradient tile under ~100 KB (two CTAs per SM), whole tiles preferred
+  int TH = d.H < 16 ? d.H : 16;
+  size_t smem = 0;
+  for (;; --TH) {
+    smem = ((size_t)d.cin * (TH + d.kh - 1) * a.pitch + (size_t)TH * a.gpitch) * 4;
+    if (smem <= 100 * 1024 || TH == 1) break;
+  }
+  if (smem > 200 * 1024) return ARPDE_ERR_UNSUPPORTED;
+  const size_t red_bytes = (size_t)npairs * d.kw * CO * 4;
+  if (red_bytes > smem) smem = red_bytes;
+  a.TH = TH; a.tiles_y = (d.H + TH - 1) / TH;
+  if (smem > 48 * 1024) ARPDE_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  long long blocks = (long long)d.N * a.tiles_y; const long long cap = 2ll * arpde_num_sms(); if (blocks > cap) blocks = cap;
+  fn<<<(unsigned)blocks, 256, smem, stream>>>(a);
+  ARPDE_LAUNCH_CHECK();
+  return ARPDE_OK;
+}
+
 typedef void (*wgrad_fn)(WgradArgs);
 template <int KH, int KW, int S>
 static wgrad_fn pick_w(int cout, int* cot) {
@@ -430,6 +603,8 @@ int arpde_conv_wgrad_launch(const ConvDesc& d, const float* x, long long x_bs, c
   const int KK = d.kh * d.kw;
   const long long wn = (long long)d.cout * d.cin * KK;
   ARPDE_CUDA(cudaMemsetAsync(dW64, 0, sizeof(double) * wn, stream));
+  if (d.N > 0 && wgrad_small_launch(d, x, x_bs, scale, shift, dO, dO_bs, dW64, stream) == ARPDE_OK)
+    return arpde_d2f_launch(dW64, dW, wn, stream);
   const int one_d = (d.H == 1 && d.kh == 1);
   const int up_h = one_d ? 0 : d.up;
   const int Hc = d.H << up_h, Wc = d.W << d.up;
@@ -476,4 +651,44 @@ int arpde_conv_wgrad_launch(const ConvDesc& d, const float* x, long long x_bs, c
   d2f_kernel<<<(unsigned)ceil_div64(wn, 256), 256, 0, stream>>>(dW64, dW, wn);
   ARPDE_LAUNCH_CHECK();
   return ARPDE_OK;
+}
+
+// narrow layers first (sliding-window kernel, inside arpde_conv_wgrad_launch), then the tensor core, then the generic fp32 kernel
+static bool wgrad_small_eligible(const ConvDesc& d, const float* x, long long x_bs, const float* dO, long long dO_bs) {
+  if (getenv("ARPDE_WGRAD_SMALL_OFF")) return false;
+  if (d.stride != 1 || d.up || d.dilate || d.pad_override >= 0 || d.H < 2 || d.cout > 4 || d.kh != d.kw || (d.kh != 3 && d.kh != 5)) return false;
+  if ((d.W & 7) || d.W > 128 || (x_bs & 3) || (dO_bs & 3) || (((uintptr_t)x | (uintptr_t)dO) & 15) || d.cin * d.kh > 256) return false;
+  return true;
+}
+
+int arpde_conv_wgrad_best_launch(const ConvDesc& d, const float* x, long long x_bs, const float* scale, const float* shift, const float* dO,
+                                 long long dO_bs, double* dW64, float* dW, float* tc_scratch, long long tc_scratch_floats, cudaStream_t stream) {
+  if (!wgrad_small_eligible(d, x, x_bs, dO, dO_bs) && tc_scratch) {
+    const long long need = arpde_conv_wgrad_tc_scratch_floats(d);
+    if (need > 0 && need <= tc_scratch_floats && arpde_conv_wgrad_tc_wanted(d) && (((uintptr_t)dO) & 15) == 0 && (dO_bs & 3) == 0)
+      return arpde_conv_wgrad_tc_launch(d, x, x_bs, scale, shift, dO, dO_bs, dW64, dW, tc_scratch, tc_scratch_floats, stream);
+  }
+  return arpde_conv_wgrad_launch(d, x, x_bs, scale, shift, dO, dO_bs, dW64, dW, stream);
+}
+
+// C ABI: weight gradient of one circular convolution, best available kernel (narrow-layer sliding window, tensor core when a scratch of
+// arpde_conv_wgrad_tc_scratch(...) floats is given and the layer is covered, else the generic fp32 kernel).  Same contract as
+// arpde_conv_wgrad_tc; path = 0 auto, 1 generic FFMA only (cross-check).
+extern "C" int arpde_conv_wgrad(const float* x, int64_t x_bstride, const float* scale, const float* shift, const float* dO,
+                                int64_t dO_bstride, double* dW64, float* dW, int N, int cin, int H, int W, int cout, int kh, int kw,
+                                int stride, int up, int relu_in, float* scratch, int64_t scratch_floats, int path, arpde_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  ConvDesc d;
+  d.dilate = 0; d.pad_override = -1; d.N = N; d.cin = cin; d.H = H; d.W = W; d.cout = cout; d.kh = kh; d.kw = kw; d.stride = stride;
+  d.up = up; d.relu_in = relu_in; d.act = 0; d.y_ctot = cout; d.y_coff = 0; d.n_per_group = N > 0 ? N : 1;
+  ARPDE_CHECK_ARG((scale == nullptr) == (shift == nullptr), "conv_wgrad: scale/shift must both be given or both be null");
+  ARPDE_CHECK_ARG(x && dO && dW64 && dW, "conv_wgrad: null pointer");
+  if (path == 1) {
+    // generic kernel only
+    setenv("ARPDE_WGRAD_SMALL_OFF", "1", 1);
+    int rc = arpde_conv_wgrad_launch(d, x, x_bstride, scale, shift, dO, dO_bstride, dW64, dW, stream);
+    unsetenv("ARPDE_WGRAD_SMALL_OFF");
+    return rc;
+  }
+  return arpde_conv_wgrad_best_launch(d, x, x_bstride, scale, shift, dO, dO_bstride, dW64, dW, scratch, scratch_floats, stream);
 }

@@ -49,6 +49,8 @@ int arpde_act_bwd_launch(const float* gy, const float* y, float* out, long long 
 int arpde_conv_wgrad_launch(const ConvDesc& d, const float* x, long long x_bs, const float* scale, const float* shift, const float* dO,
                             long long dO_bs, double* dW64, float* dW, cudaStream_t stream);
 
+int arpde_conv_wgrad_best_launch(const ConvDesc& d, const float* x, long long x_bs, const float* scale, const float* shift, const float* dO,
+                                 long long dO_bs, double* dW64, float* dW, float* tc_scratch, long long tc_scratch_floats, cudaStream_t stream);
 int arpde_d2f_launch(const double* src, float* dst, long long n, cudaStream_t stream);
 // tensor-core weight gradient, conv_wgrad_tc.cu (ARPDE_WGRAD_TC=0 disables it)
 bool arpde_conv_wgrad_tc_wanted(const ConvDesc& d);

@@ -252,13 +252,9 @@ extern "C" int arpde_densed_backward(const arpde_op_t* ops, int n_ops, const arp
     d.relu_in = o.bn_param >= 0; d.act = 0; d.y_ctot = o.cout; d.y_coff = 0; d.n_per_group = N;
     float* gw = (float*)grads_host[o.w_param];
     if (gw) {
-      // wide layers: tensor-core kernel (conv_wgrad_tc.cu) with its partial-sum slabs in the tensor-core scratch (free until the data
-      // gradient below prepares its weights there, later on the same stream); needs a 16-byte aligned output gradient
-      const long long wg_need = tc_scratch ? arpde_conv_wgrad_tc_scratch_floats(d) : 0;
-      if (wg_need > 0 && wg_need <= tc_scratch_floats && arpde_conv_wgrad_tc_wanted(d) && (((uintptr_t)dO) & 15) == 0 && (dO_bs & 3) == 0)
-        rc = arpde_conv_wgrad_tc_launch(d, in, in_bs, scale, shift, dO, dO_bs, d64, gw, tc_scratch, tc_scratch_floats, stream);
-      else
-        rc = arpde_conv_wgrad_launch(d, in, in_bs, scale, shift, dO, dO_bs, d64, gw, stream);
+      // narrow layers: sliding-window kernel; wide layers: tensor-core kernel (conv_wgrad_tc.cu) with its partial-sum slabs in the
+      // tensor-core scratch (free until the data gradient below prepares its weights there, later on the same stream); else generic
+      rc = arpde_conv_wgrad_best_launch(d, in, in_bs, scale, shift, dO, dO_bs, d64, gw, tc_scratch, tc_scratch_floats, stream);
       if (rc) return rc;
     }
     const bool need_dx = o.in_buf >= 0 || gx != nullptr;

@@ -153,6 +153,11 @@ int64_t arpde_conv_wgrad_tc_scratch(int N, int cin, int H, int W, int cout, int 
 int arpde_conv_wgrad_tc(const float* x, int64_t x_bstride, const float* scale, const float* shift, const float* dO,
                         int64_t dO_bstride, double* dW64, float* dW, int N, int cin, int H, int W, int cout, int kh, int kw,
                         int stride, int up, int relu_in, float* scratch, int64_t scratch_floats, arpde_stream_t stream);
+/* Same contract, best available kernel: the sliding-window kernel for narrow layers (cout <= 4, stride 1), the tensor core when
+ * `scratch` is given and covers the layer, else the generic fp32 kernel.  path = 0 auto, 1 generic kernel only (cross-check). */
+int arpde_conv_wgrad(const float* x, int64_t x_bstride, const float* scale, const float* shift, const float* dO, int64_t dO_bstride,
+                     double* dW64, float* dW, int N, int cin, int H, int W, int cout, int kh, int kw, int stride, int up, int relu_in,
+                     float* scratch, int64_t scratch_floats, int path, arpde_stream_t stream);
 int arpde_conv_wgrad_tc_plan(int cin, int H, int W, int cout, int kh, int kw, int stride, int up, int32_t* out);
 
 /* Profiling hooks of the tensor-core kernel (development only; both default to off).  set_debug: per-role cycle counters of

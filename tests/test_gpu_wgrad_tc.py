@@ -104,3 +104,30 @@ def test_wgrad_tc_unsupported_layer_reports_error():
     gy = torch.randn(2, 12, 32, 32, device=DEV)
     with pytest.raises(RuntimeError, match='not supported'):
         wgrad_tc(x, 16 * 32 * 32, None, None, gy, 12 * 32 * 32, 2, 16, 32, 32, 12, 3, 3, 1, 0, 0)
+
+
+NARROW = [  # cin, cout, k, H, W, N
+    (16, 2, 5, 64, 64, 5),       # LastTransUp conv5x5
+    (60, 4, 3, 32, 32, 5),       # denselayer4
+    (7, 3, 3, 20, 24, 3),        # odd channel counts, image height not a multiple of the tile height
+    (12, 1, 5, 16, 40, 2),
+]
+
+
+@pytest.mark.parametrize('cin,cout,k,H,W,N', NARROW)
+def test_wgrad_narrow_layers_vs_oracle(cin, cout, k, H, W, N):
+    """arpde_conv_wgrad picks the sliding-window kernel for cout <= 4 (path 0); path 1 = generic FFMA kernel as cross-check."""
+    torch.manual_seed(cin + 100 * cout)
+    xbuf = torch.randn(N, cin + 4, H, W)
+    x = xbuf[:, 4:]                                               # channel-slice view (dense-block layout)
+    gy = torch.randn(N, cout, H, W)
+    sc, sh = torch.rand(cin) + 0.5, torch.randn(cin) * 0.3
+    ref = oracle_wgrad(x, sc, sh, 1, 0, gy, cout, k, k, 1)
+    xd, gd, scd, shd = xbuf.to(DEV), gy.to(DEV), sc.to(DEV), sh.to(DEV)
+    d64 = torch.empty((cout * cin * k * k,), device=DEV, dtype=torch.float64)
+    for path in (0, 1):
+        dW = torch.full((cout, cin, k, k), 5.0, device=DEV)
+        L.call('arpde_conv_wgrad', L.ptr(xd[:, 4:]), (cin + 4) * H * W, L.ptr(scd), L.ptr(shd), L.ptr(gd), cout * H * W, L.ptr(d64), L.ptr(dW),
+               N, cin, H, W, cout, k, k, 1, 0, 1, 0, 0, path, L.stream())
+        torch.cuda.synchronize()
+        assert rel_err(dW, ref) < TOL, path

@@ -424,6 +424,7 @@ __global__ void __launch_bounds__(256) wgrad_small_kernel(WgradSmallArgs a) {
   const int pad_y = (KH - 1) / 2, pad_x = (KW - 1) / 2;
   float* patch = smem;                                   // [cin][PH][pitch]
   float* gys = patch + (size_t)a.cin * PH * a.pitch;     // [TH][gpitch]: CO values per position, interleaved
+  int* rowmap = reinterpret_cast<int*>(gys + (size_t)a.TH * a.gpitch);   // [PH]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
   const int npairs = a.cin * KH;
   const int rgroups = blockDim.x / npairs;               // row groups; threads beyond npairs * rgroups only help staging
@@ -437,50 +438,16 @@ __global__ void __launch_bounds__(256) wgrad_small_kernel(WgradSmallArgs a) {
 #pragma unroll
     for (int c = 0; c < CO; ++c) acc[k][c] = 0.f;
 
-  const int W4 = a.W >> 2, nhalo = PW - a.W;
+  const int W4 = a.W >> 2;
   for (int t = blockIdx.x; t < a.N * a.tiles_y; t += gridDim.x) {
     const int n = t / a.tiles_y, y0 = (t - n * a.tiles_y) * a.TH;
     const float* xn = a.x + (long long)n * a.x_bs;
     const float* gn = a.dO + (long long)n * a.dO_bs;
     __syncthreads();
-    // ---- input patch: whole rows as float4 + wrap halo lanes, BN/ReLU applied (as conv_fwd_rt_kernel), four lines per warp in flight
-    {
-      constexpr int RU = 4;
-      const int nlines = a.cin * PH;
-      for (int r0 = warp * RU; r0 < nlines; r0 += nwarps * RU) {
-        float4 v[RU]; float hv[RU], sc[RU], sh[RU];
-        int c = r0 / PH, py = r0 - c * PH;
-#pragma unroll
-        for (int u = 0; u < RU; ++u) {
-          const bool rok = r0 + u < nlines;
-          int iy = y0 - pad_y + (rok ? py : 0); if (iy < 0) iy += a.H; else if (iy >= a.H) iy -= a.H;
-          const float* src = xn + (long long)(rok ? c : 0) * HW + (long long)iy * a.W;
-          sc[u] = 1.f; sh[u] = 0.f;
-          if (a.scale && rok) { sc[u] = a.scale[c]; sh[u] = a.shift[c]; }
-          v[u] = (rok && lane < W4) ? __ldg(reinterpret_cast<const float4*>(src) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
-          hv[u] = (rok && lane < nhalo) ? __ldg(src + (lane < pad_x ? a.W - pad_x + lane : lane - pad_x)) : 0.f;
-          if (++py == PH) { py = 0; ++c; }
-        }
-#pragma unroll
-        for (int u = 0; u < RU; ++u) {
-          if (r0 + u < nlines) {
-            float* dst = patch + (size_t)(r0 + u) * a.pitch;
-            float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
-#pragma unroll
-            for (int k = 0; k < 4; ++k) { e[k] = fmaf(e[k], sc[u], sh[u]); if (a.relu_in) e[k] = fmaxf(e[k], 0.f); }
-            if (lane < W4) {
-              float* d4 = dst + pad_x + 4 * lane;
-              if ((pad_x & 1) == 0) { *reinterpret_cast<float2*>(d4) = make_float2(e[0], e[1]); *reinterpret_cast<float2*>(d4 + 2) = make_float2(e[2], e[3]); }
-              else { d4[0] = e[0]; d4[1] = e[1]; d4[2] = e[2]; d4[3] = e[3]; }
-            }
-            if (lane < nhalo) {
-              float tv = fmaf(hv[u], sc[u], sh[u]); if (a.relu_in) tv = fmaxf(tv, 0.f);
-              dst[lane < pad_x ? lane : a.W + lane] = tv;
-            }
-          }
-        }
-      }
-    }
+    // ---- input patch: whole rows + wrap halo, BN/ReLU applied (stage_full_rows)
+    for (int i = tid; i < PH; i += blockDim.x) { int iy = y0 - pad_y + i; if (iy < 0) iy += a.H; else if (iy >= a.H) iy -= a.H; if (iy >= a.H) iy -= a.H; rowmap[i] = iy; }
+    __syncthreads();
+    stage_full_rows(patch, a.pitch, xn, (int)HW, 0, a.cin * PH, PH, rowmap, a.W, pad_x, PW - a.W, a.scale, a.shift, a.relu_in, tid, blockDim.x);
     // ---- output gradient: [TH][W][CO] interleaved (rows past the image: zeros)
     for (int i = tid; i < a.TH * CO * W4; i += blockDim.x) {
       const int x4 = i % W4, rc = i / W4, c = rc % CO, r = rc / CO;
@@ -562,7 +529,7 @@ static int wgrad_small_launch(const ConvDesc& d, const float* x, long long x_bs,
   int TH = d.H < 16 ? d.H : 16;
   size_t smem = 0;
   for (;; --TH) {
-    smem = ((size_t)d.cin * (TH + d.kh - 1) * a.pitch + (size_t)TH * a.gpitch) * 4;
+    smem = ((size_t)d.cin * (TH + d.kh - 1) * a.pitch + (size_t)TH * a.gpitch + (TH + d.kh - 1)) * 4;
     if (smem <= 100 * 1024 || TH == 1) break;
   }
   if (smem > 200 * 1024) return ARPDE_ERR_UNSUPPORTED;

@@ -37,6 +37,57 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   }
 }
 
+
+// Stage `nlines` = nch x PH full-width patch lines (stride-1, full-width tiles: a line is one input row plus the circular halo) into
+// shared memory with the per-channel affine + ReLU prologue applied.  Lanes are packed as (row, float4 column): a 32-wide row uses 8
+// lanes, so one warp instruction moves 4 rows (the first version moved one row per instruction: for W = 32 the staging of a dense layer
+// issued twice as many instructions as its FFMAs).  rowmap[py] = source row of patch row py; the caller synchronises afterwards.
+__device__ __forceinline__ void stage_full_rows(float* __restrict__ patch, int pitch, const float* __restrict__ xn, int HWi, int c0, int nlines,
+                                                int PH, const int* __restrict__ rowmap, int W, int pad_x, int nhalo,
+                                                const float* __restrict__ scale, const float* __restrict__ shift, int relu, int tid,
+                                                int nthreads) {
+  const int W4 = W >> 2;
+  const int G = W4 >= 32 ? 1 : 32 / W4;                // rows per warp pass
+  const int warp = tid >> 5, lane = tid & 31, nwarps = nthreads >> 5;
+  const int g = lane / W4, x4 = lane - g * W4;
+  const bool lane_on = g < G;
+  constexpr int RU = 2;
+  for (int base = warp * G * RU; base < nlines; base += nwarps * G * RU) {
+    float4 v[RU]; float sc[RU], sh[RU]; int rr[RU];
+#pragma unroll
+    for (int u = 0; u < RU; ++u) {
+      const int r = base + u * G + g;
+      const bool ok = lane_on && r < nlines;
+      rr[u] = ok ? r : -1;
+      const int ci = ok ? r / PH : 0, py = ok ? r - ci * PH : 0;
+      sc[u] = 1.f; sh[u] = 0.f;
+      if (scale && ok) { sc[u] = scale[c0 + ci]; sh[u] = shift[c0 + ci]; }
+      v[u] = ok ? __ldg(reinterpret_cast<const float4*>(xn + (c0 + ci) * HWi + rowmap[py] * W) + x4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < RU; ++u) {
+      if (rr[u] >= 0) {
+        float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { e[k] = fmaf(e[k], sc[u], sh[u]); if (relu) e[k] = fmaxf(e[k], 0.f); }
+        float* d4 = patch + rr[u] * pitch + pad_x + 4 * x4;
+        if ((pad_x & 1) == 0) { *reinterpret_cast<float2*>(d4) = make_float2(e[0], e[1]); *reinterpret_cast<float2*>(d4 + 2) = make_float2(e[2], e[3]); }
+        else { d4[0] = e[0]; d4[1] = e[1]; d4[2] = e[2]; d4[3] = e[3]; }
+      }
+    }
+  }
+  // halo columns: patch column h < pad_x <- input column W - pad_x + h, patch column W + h (h >= pad_x) <- input column h - pad_x
+  for (int i = tid; i < nlines * nhalo; i += nthreads) {
+    const int r = i / nhalo, h = i - r * nhalo;
+    const int ci = r / PH, py = r - ci * PH;
+    float tv = __ldg(xn + (c0 + ci) * HWi + rowmap[py] * W + (h < pad_x ? W - pad_x + h : h - pad_x));
+    if (scale) tv = fmaf(tv, scale[c0 + ci], shift[c0 + ci]);
+    if (relu) tv = fmaxf(tv, 0.f);
+    patch[r * pitch + (h < pad_x ? h : W + h)] = tv;
+  }
+}
+
+bool arpde_conv_fwd_rt_shape_ok(const ConvDesc& d);      // the row-tiled FFMA kernel covers (and wins on) this layer shape
 int arpde_conv_fwd_launch(const ConvDesc& d, const float* x, long long x_bs, const float* w, long long w_gs,
                           const float* scale, const float* shift, long long ss_gs, float* y, double* stats,
                           cudaStream_t stream);

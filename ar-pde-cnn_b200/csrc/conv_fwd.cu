@@ -256,46 +256,8 @@ __global__ void __launch_bounds__(256) conv_fwd_rt_kernel(ConvFwdArgs a) {
   for (int ci0 = 0; ci0 < a.cin; ci0 += a.ci_chunk) {
     const int cic = min(a.ci_chunk, a.cin - ci0);
     __syncthreads();
-    {   // stage the patch.  The tile spans the full width (TW == W, checked by the launcher): a patch line is one contiguous, 16-byte
-        // aligned input row plus the wrap halo, so lanes 0..W/4-1 move one float4 each and a few lanes the halo columns; four lines
-        // per warp are in flight.  (First version: per-element column-map lookups and a division per line -- 17 integer instructions
-        // per load, as many as the FFMAs of the whole kernel.)
-      constexpr int RU = 4;
-      const int nlines = cic * PH, W4 = a.W >> 2, nhalo = PW - a.W;
-      for (int r0 = warp * RU; r0 < nlines; r0 += nwarps * RU) {
-        float4 v[RU]; float hv[RU]; float sc[RU], sh[RU];
-        int ci = r0 / PH, py = r0 - ci * PH;
-#pragma unroll
-        for (int u = 0; u < RU; ++u) {
-          const bool rok = r0 + u < nlines;
-          const float* src = xn + (ci0 + (rok ? ci : 0)) * HW + (long long)rowmap[rok ? py : 0] * a.W;
-          sc[u] = 1.f; sh[u] = 0.f;
-          if (scale && rok) { sc[u] = scale[ci0 + ci]; sh[u] = shift[ci0 + ci]; }
-          v[u] = (rok && lane < W4) ? __ldg(reinterpret_cast<const float4*>(src) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
-          // halo column h (lane h): patch column h < pad_x -> input column W - pad_x + h, else patch column W + h -> input column h - pad_x
-          hv[u] = (rok && lane < nhalo) ? __ldg(src + (lane < a.pad_x ? a.W - a.pad_x + lane : lane - a.pad_x)) : 0.f;
-          if (++py == PH) { py = 0; ++ci; }
-        }
-#pragma unroll
-        for (int u = 0; u < RU; ++u) {
-          if (r0 + u < nlines) {
-            float* dst = patch + (r0 + u) * PITCH;
-            float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
-#pragma unroll
-            for (int k = 0; k < 4; ++k) { e[k] = fmaf(e[k], sc[u], sh[u]); if (a.relu_in) e[k] = fmaxf(e[k], 0.f); }
-            if (lane < W4) {
-              float* d4 = dst + a.pad_x + 4 * lane;           // 8-byte aligned for even pads, else scalar stores
-              if ((a.pad_x & 1) == 0) { *reinterpret_cast<float2*>(d4) = make_float2(e[0], e[1]); *reinterpret_cast<float2*>(d4 + 2) = make_float2(e[2], e[3]); }
-              else { d4[0] = e[0]; d4[1] = e[1]; d4[2] = e[2]; d4[3] = e[3]; }
-            }
-            if (lane < nhalo) {
-              float tv = fmaf(hv[u], sc[u], sh[u]); if (a.relu_in) tv = fmaxf(tv, 0.f);
-              dst[lane < a.pad_x ? lane : a.W + lane] = tv;
-            }
-          }
-        }
-      }
-    }
+    // stage the patch: the tile spans the full width (TW == W, checked by the launcher), see stage_full_rows
+    stage_full_rows(patch, PITCH, xn, (int)HW, ci0, cic * PH, PH, rowmap, a.W, a.pad_x, PW - a.W, scale, shift, a.relu_in, tid, nthreads);
     for (int i = tid; i < cic * KK * COT; i += nthreads) {          // weights: global [co][ci][kk] -> smem [ci][kk][COT]
       const int c = i % COT, j = i / COT;                          // j = ci * KK + kk
       wsm[i] = c < a.cout ? __ldg(wg + ((long long)c * a.cin + ci0) * KK + j) : 0.f;
@@ -377,6 +339,19 @@ static conv_fwd_fn pick_kernel(int kh, int kw, int s, int cot, int* pxt) {
   PK(1, 3, 1); PK(1, 3, 2); PK(1, 5, 1); PK(1, 4, 2); PK(1, 7, 2); PK(1, 7, 1); PK(7, 7, 1);
 #undef PK
   return nullptr;
+}
+
+// shape part of the row-tiled kernel's eligibility (pointer alignment is checked at launch): the narrow layers it is faster on than
+// the tensor-core kernel (measured at N = 1920: dense 52->4 3x3 at 32x32 0.44 vs 0.52 ms, 16->2 5x5 at 64x64 0.56 vs 1.1 ms)
+bool arpde_conv_fwd_rt_shape_ok(const ConvDesc& d) {
+  if (getenv("ARPDE_CONV_RT_OFF")) return false;
+  if (d.stride != 1 || d.up || d.dilate || d.pad_override >= 0 || d.H <= 1 || d.cout > 4) return false;
+  if (!((d.kh == 3 && d.kw == 3) || (d.kh == 5 && d.kw == 5))) return false;
+  if ((d.W & 7) || d.W > 64 || (d.W & 3)) return false;
+  const int pxt = d.W >= 64 ? 8 : 4, nxt = d.W / pxt;
+  int TH = (256 / nxt) * 2; if (TH > d.H) TH = (d.H + 1) / 2 * 2;
+  const int threads = ((nxt * ((TH + 1) / 2) + 31) / 32) * 32;
+  return threads >= 128 && threads <= 256;
 }
 
 int arpde_conv_fwd_launch(const ConvDesc& d, const float* x, long long x_bs, const float* w, long long w_gs,

@@ -925,6 +925,7 @@ bool arpde_conv_tc_wanted(const ConvDesc& d) {
   if (!arpde_tc_enabled()) return false;
   if (d.H == 1 && d.kh == 1) return false;                 // 1D nets: tiles of 128 positions are mostly halo
   if (d.cout < 4 || d.cin * d.kh * d.kw < 32) return false;
+  if (arpde_conv_fwd_rt_shape_ok(d) && !getenv("ARPDE_TC_DENSE")) return false;     // narrow layers: the row-tiled FFMA kernel is faster
   ConvTcArgs a; size_t smem;
   return tc_plan(d, a, &smem);
 }

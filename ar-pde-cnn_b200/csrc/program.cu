@@ -123,6 +123,11 @@ static int run_ops(const RunCtx& c, const float* x, long long x_bs, float* y, in
         const long long Ho = one_d ? 1 : ((long long)(d.H << (d.up ? 1 : 0)) / d.stride), Wo = ((long long)(d.W << (d.up ? 1 : 0)) / d.stride);
         rc = arpde_bn_stats(out + (long long)d.y_coff * Ho * Wo, (long long)d.y_ctot * Ho * Wo, d.N, d.cout, Ho * Wo, st + 2 * d.y_coff, c.stream);
       }
+    } else if (st && arpde_conv_fwd_rt_shape_ok(d)) {
+      // train mode, narrow layer: the row-tiled kernel has no statistics epilogue -- same separate streaming pass as above
+      const long long Ho = d.H, Wo = d.W;
+      rc = arpde_conv_fwd_launch(d, in, in_bs, (const float*)c.params[o.w_param], c.gstride[o.w_param], scale, shift, c.bn_total, out, nullptr, c.stream);
+      if (!rc) rc = arpde_bn_stats(out + (long long)d.y_coff * Ho * Wo, (long long)d.y_ctot * Ho * Wo, d.N, d.cout, Ho * Wo, st + 2 * d.y_coff, c.stream);
     } else
       rc = arpde_conv_fwd_launch(d, in, in_bs, (const float*)c.params[o.w_param], c.gstride[o.w_param], scale, shift,
                                  c.bn_total, out, st, c.stream);

@@ -447,7 +447,7 @@ __global__ void __launch_bounds__(256) wgrad_small_kernel(WgradSmallArgs a) {
     // ---- input patch: whole rows + wrap halo, BN/ReLU applied (stage_full_rows)
     for (int i = tid; i < PH; i += blockDim.x) { int iy = y0 - pad_y + i; if (iy < 0) iy += a.H; else if (iy >= a.H) iy -= a.H; if (iy >= a.H) iy -= a.H; rowmap[i] = iy; }
     __syncthreads();
-    stage_full_rows(patch, a.pitch, xn, (int)HW, 0, a.cin * PH, PH, rowmap, a.W, pad_x, PW - a.W, a.scale, a.shift, a.relu_in, tid, blockDim.x);
+    stage_full_rows<4>(patch, a.pitch, xn, (int)HW, 0, a.cin * PH, PH, rowmap, a.W, pad_x, PW - a.W, a.scale, a.shift, a.relu_in, tid, blockDim.x);
     // ---- output gradient: [TH][W][CO] interleaved (rows past the image: zeros)
     for (int i = tid; i < a.TH * CO * W4; i += blockDim.x) {
       const int x4 = i % W4, rc = i / W4, c = rc % CO, r = rc / CO;

@@ -42,6 +42,7 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 // shared memory with the per-channel affine + ReLU prologue applied.  Lanes are packed as (row, float4 column): a 32-wide row uses 8
 // lanes, so one warp instruction moves 4 rows (the first version moved one row per instruction: for W = 32 the staging of a dense layer
 // issued twice as many instructions as its FFMAs).  rowmap[py] = source row of patch row py; the caller synchronises afterwards.
+template <int RU = 2>
 __device__ __forceinline__ void stage_full_rows(float* __restrict__ patch, int pitch, const float* __restrict__ xn, int HWi, int c0, int nlines,
                                                 int PH, const int* __restrict__ rowmap, int W, int pad_x, int nhalo,
                                                 const float* __restrict__ scale, const float* __restrict__ shift, int relu, int tid,
@@ -51,7 +52,6 @@ __device__ __forceinline__ void stage_full_rows(float* __restrict__ patch, int p
   const int warp = tid >> 5, lane = tid & 31, nwarps = nthreads >> 5;
   const int g = lane / W4, x4 = lane - g * W4;
   const bool lane_on = g < G;
-  constexpr int RU = 2;
   for (int base = warp * G * RU; base < nlines; base += nwarps * G * RU) {
     float4 v[RU]; float sc[RU], sh[RU]; int rr[RU];
 #pragma unroll

@@ -257,7 +257,10 @@ __global__ void __launch_bounds__(256) conv_fwd_rt_kernel(ConvFwdArgs a) {
     const int cic = min(a.ci_chunk, a.cin - ci0);
     __syncthreads();
     // stage the patch: the tile spans the full width (TW == W, checked by the launcher), see stage_full_rows
-    stage_full_rows(patch, PITCH, xn, (int)HW, ci0, cic * PH, PH, rowmap, a.W, a.pad_x, PW - a.W, scale, shift, a.relu_in, tid, nthreads);
+    // 8 row groups in flight per lane: with 4 warps per CTA the staging phase is otherwise a chain of exposed global-load latencies
+    // (0.44 -> 0.39 ms on a dense layer; a cp.async double buffer with the prologue applied at compute time and an aligned patch
+    //  layout with float4 stores were both tried and were no faster: 0.40 / 0.44 ms)
+    stage_full_rows<8>(patch, PITCH, xn, (int)HW, ci0, cic * PH, PH, rowmap, a.W, a.pad_x, PW - a.W, scale, shift, a.relu_in, tid, nthreads);
     for (int i = tid; i < cic * KK * COT; i += nthreads) {          // weights: global [co][ci][kk] -> smem [ci][kk][COT]
       const int c = i % COT, j = i / COT;                          // j = ci * KK + kk
       wsm[i] = c < a.cout ? __ldg(wg + ((long long)c * a.cin + ci0) * KK + j) : 0.f;

@@ -26,6 +26,9 @@
 //     small-cout layers (dense layers, cout = growth rate <= 8): roles swapped -- the patch ring is the M operand (MN-major A: up to
 //     128 channels = four 32-channel blocks at LBO stride), dO the K-major N operand (N = 8), D[ci][(tap, co)]; otherwise 60 of the
 //     64 accumulator rows would be padding (an MMA costs ~40 cycles whatever M and N <= 64 are).
+//     nearest x2 + 3x3 (LastTransUp conv2): folded like the forward (conv_tc.cu "upfold") -- the gradient of the equivalent
+//     low-resolution conv with 4*cout parity channels is accumulated (dO gathered with stride 2 at staging time, 4x fewer positions,
+//     all 64 accumulator rows real) and the drain adds every folded tap into the original taps it is the sum of.
 //   3xTF32: hi*hi + hi*lo + lo*hi into the same fp32 accumulator (lo*lo ~ 2^-22 dropped).
 //   The tensor core TRUNCATES when it adds into the fp32 accumulator (measured: one 1100-step accumulation chain over a
 //   training batch was off by 2.3e-5 relative, always towards zero), so a chain is cut after WG_FC chunks (96 adds):
@@ -63,6 +66,7 @@ struct WgTcArgs {
   int pitch, min_ry, min_rx;
   int RB, RBH, nch_u, lead, pcu, NR, ring;     // row blocks per sample, rows per block, MMA chunks / patch chunks per unit, ring chunks / rows
   int npl, NC, ncc, cchunk, packed, ntaps;     // planes, columns per tap (MMA N), channel chunks (grid split), channels per chunk, (kx,ci) packing, MMA taps
+  int fold, cout_fold;                         // folded upsampling: cout = 4 * cout_fold parity-major channels on the low-resolution grid
   int swap, nblk;                              // swap = 1: ring is the M operand (nblk blocks of 32 channels), dO the N operand (NC = cout padded)
   int M, mrows, tmem_cols, slices, units, cols, nacc;   // cols = ntaps * NC accumulator columns per set, nacc sets
   long long* dbg;                              // cycle counters of CTA 0 (arpde_conv_tc_set_debug), else nullptr
@@ -123,6 +127,8 @@ __device__ __forceinline__ void wg_issue_chunk(const WgTcArgs& a, uint32_t gy_lo
   }
 }
 
+// FOLD (folded upsampling) is a template parameter: as a run-time branch in the dO staging it cost the other layers 5-35 %
+template <bool FOLD>
 __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __grid_constant__ WgTcArgs a) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   uint64_t* patch_full = reinterpret_cast<uint64_t*>(smem_raw);        // [NR] ring chunk converted (one arrival per converter warp)
@@ -191,15 +197,22 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __gr
     int coff[4];                                       // channel offset of each column inside the sample
 #pragma unroll
     for (int k = 0; k < 4; ++k) coff[k] = (cch[k] < 0 ? 0 : cch[k]) * HWi;
-    int gco[4], gq4[4];                                // dO unit of this thread: channel offset, first position inside the chunk
+    int gco[4], gq4[4], gpx[4];                                // dO unit of this thread: channel offset, first position inside the chunk
 #pragma unroll
-    for (int k = 0; k < 4; ++k) { const int uu = tid + k * WG_CONVERTERS; gco[k] = (uu >> 3) * HoWoi; gq4[k] = (uu & 7) << 2; }
+    for (int k = 0; k < 4; ++k) {
+      const int uu = tid + k * WG_CONVERTERS, ch = uu >> 3;
+      gq4[k] = (uu & 7) << 2;
+      if (FOLD) {      // channel ch = parity * cout_fold + co reads dO[co][2 oy + py][2 ox + px]: offset of (co, row parity), px kept apart
+        const int par = ch / a.cout_fold, co = ch - par * a.cout_fold;
+        gco[k] = co * 4 * HoWoi + (par >> 1) * 2 * a.Wo; gpx[k] = par & 1;
+      } else { gco[k] = ch * HoWoi; gpx[k] = 0; }
+    }
     const bool no_load = (a.dbg_flags & 1) != 0;
     for (int u = u_begin; u < u_end; ++u) {
       const int n = u / a.RB, rb = u - n * a.RB;
       const int R0 = rb * a.RBH;
       const float* xn = a.x + (long long)n * a.x_bs;
-      const float* gn = a.dO + (long long)n * a.dO_bs + (long long)R0 * a.Wo;
+      const float* gn = a.dO + (long long)n * a.dO_bs + (long long)R0 * a.Wo * (FOLD ? 4 : 1);     // folded: row 2 R0 of the 2Wo-wide gradient
       int pi = 0, pj = lane;                           // (row, column) of this thread's patch position in the padded row pitch
       while (pj >= pitch) { pj -= pitch; ++pi; }
       int goy[4], gox[4];                              // (row, column) of the dO positions
@@ -250,7 +263,14 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __gr
           for (int k = 0; k < 4; ++k) {
             gv[k] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (tid + k * WG_CONVERTERS < gy_units) {
-              if (gox[k] < Wo && !no_load) gv[k] = __ldg(reinterpret_cast<const float4*>(gn + (gco[k] + goy[k] * Wo + gox[k])));
+              if (gox[k] < Wo && !no_load) {
+                if (!FOLD) gv[k] = __ldg(reinterpret_cast<const float4*>(gn + (gco[k] + goy[k] * Wo + gox[k])));
+                else {     // 8 consecutive full-resolution columns from 2 ox: every other one belongs to this x parity
+                  const float4* p8 = reinterpret_cast<const float4*>(gn + (gco[k] + goy[k] * 4 * Wo + 2 * gox[k]));
+                  const float4 lo4 = __ldg(p8), hi4 = __ldg(p8 + 1);
+                  gv[k] = gpx[k] ? make_float4(lo4.y, lo4.w, hi4.y, hi4.w) : make_float4(lo4.x, lo4.z, hi4.x, hi4.z);
+                }
+              }
               gox[k] += WG_CK;
               while (gox[k] >= pitch) { gox[k] -= pitch; ++goy[k]; }
             }
@@ -428,8 +448,19 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __gr
               const int cil = a.col_ci[e];
               const int ci = cil < 0 ? -1 : cc * a.cchunk + cil;
               if (ci >= 0 && ci < a.cin && tt < a.ntaps) {
-                const int tap = a.packed ? a.col_dy[e] * a.kw + tt : tt;
-                atomicAdd(a.dW + ((long long)co * a.cin + ci) * (a.kh * a.kw) + tap, (double)v[k] + (double)o[k]);
+                if (FOLD) {
+                  // folded tap (ty, tx) of parity (py, px) is the sum of the original taps with (py + ky + 1) >> 1 == ty, (px + kx + 1) >> 1 == tx
+                  const int par = co / a.cout_fold, cr = co - par * a.cout_fold, py = par >> 1, px = par & 1, ty = tt / 3, tx = tt - ty * 3;
+                  const double val = (double)v[k] + (double)o[k];
+                  for (int ky = 0; ky < 3; ++ky) {
+                    if (((py + ky + 1) >> 1) != ty) continue;
+                    for (int kx = 0; kx < 3; ++kx)
+                      if (((px + kx + 1) >> 1) == tx) atomicAdd(a.dW + ((long long)cr * a.cin + ci) * 9 + ky * 3 + kx, val);
+                  }
+                } else {
+                  const int tap = a.packed ? a.col_dy[e] * a.kw + tt : tt;
+                  atomicAdd(a.dW + ((long long)co * a.cin + ci) * (a.kh * a.kw) + tap, (double)v[k] + (double)o[k]);
+                }
               }
             }
           }
@@ -452,6 +483,10 @@ static int wg_floor_div(int a, int b) { int q = a / b, r = a % b; return (r != 0
 
 static bool wg_plan(const ConvDesc& d, WgTcArgs& a, size_t* smem_out) {
   if (d.dilate || d.pad_override >= 0) return false;
+  if (d.up && d.stride == 1 && d.kh == 3 && d.kw == 3 && d.H > 1 && 4 * d.cout <= 128 && 4 * d.cout > 8 && !getenv("ARPDE_WG_NO_FOLD")) {
+    ConvDesc e = d; e.up = 0; e.cout = 4 * d.cout;         // equivalent low-resolution conv, parity-major channels (conv_tc.cu upfold)
+    if (wg_plan(e, a, smem_out) && !a.swap) { a.fold = 1; a.cout_fold = d.cout; return true; }
+  }
   if (d.H == 1 && d.kh == 1) return false;                       // 1D nets stay on the FFMA kernel
   if (d.stride != 1 && d.stride != 2) return false;
   if (d.up && d.stride != 1) return false;
@@ -560,9 +595,9 @@ bool arpde_conv_wgrad_tc_wanted(const ConvDesc& d) {
   if (const char* e = getenv("ARPDE_WGRAD_TC")) if (e[0] == '0') return false;
   // an MMA costs ~40 cycles whatever M is: with cout < 32 most of the 64 accumulator rows are padding and the FFMA kernel wins
   // (measured, N = 128: LastTransUp conv3x3 32->16 at 64x64: tensor core 0.41 ms, FFMA 0.375 ms)
-  if (d.cout < 32 && d.cout > 8) return false;
   WgTcArgs a; size_t smem;
   if (!wg_plan(d, a, &smem)) return false;
+  if (!a.fold && d.cout < 32 && d.cout > 8) return false;      // (a folded upsampling layer has 4 * cout real accumulator rows)
   // swapped + packed with four row blocks (LastTransUp's 16 -> 2 5x5 conv: 80 (ky, ci) rows): the converters stage 16 table-driven
   // rows per thread and step and become the bottleneck -- measured 0.43 ms against 0.37 ms for the FFMA kernel (N = 128)
   if (a.swap && a.packed && a.nblk > 2) return false;
@@ -600,18 +635,20 @@ int arpde_conv_wgrad_tc_launch(const ConvDesc& d, const float* x, long long x_bs
     {
       std::lock_guard<std::mutex> lock(attr_mutex);
       if (dev < 0 || dev >= 64 || !attr_done[dev]) {
-        ARPDE_CUDA(cudaFuncSetAttribute(conv_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+        ARPDE_CUDA(cudaFuncSetAttribute(conv_wgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+        ARPDE_CUDA(cudaFuncSetAttribute(conv_wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
         if (dev >= 0 && dev < 64) attr_done[dev] = true;
       }
     }
-    conv_wgrad_tc_kernel<<<(unsigned)(a.ncc * a.slices), WG_THREADS, smem, stream>>>(a);
+    if (a.fold) conv_wgrad_tc_kernel<true><<<(unsigned)(a.ncc * a.slices), WG_THREADS, smem, stream>>>(a);
+    else conv_wgrad_tc_kernel<false><<<(unsigned)(a.ncc * a.slices), WG_THREADS, smem, stream>>>(a);
     ARPDE_LAUNCH_CHECK();
   }
   return arpde_d2f_launch(dW64, dW, wn, stream);
 }
 
 // Diagnostic (host only): the tiling conv_wgrad_tc_kernel would use.  out[0..25] = pitch, min_ry, min_rx, RB, RBH, nch_u, lead, pcu, NR,
-// npl, NC, ncc, cchunk, packed, ntaps, M, mrows, tmem_cols, slices(N=1), smem bytes, Ho, Wo, sy, sx, swap, nblk; out[32+t] = tap plane,
+// npl, NC, ncc, cchunk, packed, ntaps, M, mrows, tmem_cols, slices(N=1), smem bytes, Ho, Wo, sy, sx, swap, nblk, fold, cout_fold; out[32+t] = tap plane,
 // out[81+t] = tap offset, out[130+e] = column channel, out[258+e] = column y-tap (e < 128).
 extern "C" int arpde_conv_wgrad_tc_plan(int cin, int H, int W, int cout, int kh, int kw, int stride, int up, int32_t* out) {
   ARPDE_CHECK_ARG(out, "conv_wgrad_tc_plan: null output");
@@ -620,6 +657,7 @@ extern "C" int arpde_conv_wgrad_tc_plan(int cin, int H, int W, int cout, int kh,
   d.up = up; d.relu_in = 0; d.act = 0; d.y_ctot = cout; d.y_coff = 0; d.n_per_group = 1;
   WgTcArgs a; size_t smem = 0;
   if (!wg_plan(d, a, &smem)) { arpde_set_error("conv_wgrad_tc_plan: layer not supported"); return ARPDE_ERR_UNSUPPORTED; }
+  out[26] = a.fold; out[27] = a.cout_fold;
   const int v[26] = {a.pitch, a.min_ry, a.min_rx, a.RB, a.RBH, a.nch_u, a.lead, a.pcu, a.NR, a.npl, a.NC, a.ncc, a.cchunk, a.packed, a.ntaps,
                      a.M, a.mrows, a.tmem_cols, a.slices, (int)smem, a.Ho, a.Wo, a.sy, a.sx, a.swap, a.nblk};
   for (int i = 0; i < 26; ++i) out[i] = v[i];

@@ -19,6 +19,7 @@ def plan(cin, H, W, cout, kh, kw, s, up):
     out = (C.c_int32 * 400)()
     L.call('arpde_conv_wgrad_tc_plan', cin, H, W, cout, kh, kw, s, up, C.addressof(out))
     p = dict(zip(NAMES, out[:len(NAMES)]))
+    p['fold'], p['cout_fold'] = out[26], out[27]
     p['tap_plane'] = list(out[32:32 + p['ntaps']])
     p['tap_off'] = list(out[81:81 + p['ntaps']])
     p['col_ci'] = list(out[130:258])
@@ -133,7 +134,20 @@ def test_wgrad_ring_index_arithmetic(cin, cout, kh, kw, s, up, H, W, ahead):
     N = 2
     x = rng.standard_normal((N, cin, H, W))
     gy = rng.standard_normal((N, cout, p['Ho'], p['Wo']))
-    dW = replay(x, gy, up, kh, kw, p, ahead)
+    if p['fold']:
+        # nearest x2 + 3x3 folded: gradient of the low-resolution conv with 4*cout parity-major channels, then every folded tap
+        # (ty, tx) of parity (py, px) is added into the original taps with (py + ky + 1) >> 1 == ty and (px + kx + 1) >> 1 == tx
+        assert up == 1 and kh == 3 and kw == 3 and p['cout_fold'] == cout
+        gyf = np.concatenate([gy[:, :, py::2, px::2] for py in range(2) for px in range(2)], axis=1)       # [N, 4*cout, H, W]
+        dWf = replay(x, gyf, 0, 3, 3, p, ahead)
+        dW = np.zeros((cout, cin, 3, 3))
+        for py in range(2):
+            for px in range(2):
+                for ky in range(3):
+                    for kx in range(3):
+                        dW[:, :, ky, kx] += dWf[(py * 2 + px) * cout:(py * 2 + px + 1) * cout, :, (py + ky + 1) >> 1, (px + kx + 1) >> 1]
+    else:
+        dW = replay(x, gy, up, kh, kw, p, ahead)
     xt = torch.from_numpy(x)
     if up:
         xt = O._up2(xt)

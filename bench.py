@@ -425,7 +425,7 @@ def main():
                 'h2d_bytes_per_step': ic_host.numel() * 4, 'd2h_bytes_per_step': 2 * mean_host.numel() * 4},
         'roofline': {'kernel': 'conv_tc_kernel on In_conv3 (96->48, 3x3/s2, 1920 samples): tcgen05 implicit GEMM, 3xTF32 split (+ its weight-split launch)',
                      'bound': 'tensor', 'achieved': k1_tflops, 'peak': peaks['bf16_tflops'], 'unit': 'TFLOP/s', 'frac': k1_tflops / peaks['bf16_tflops'],
-                     'traffic': 3.917e9, 'traffic_source': 'ncu --set full, profiles/r01b_conv_tc_ncu_full.md: dram read 3.542 GB + write 0.375 GB per launch '
+                     'traffic': 4.486e9, 'traffic_source': 'ncu --set full, profiles/r01d_conv_tc_in3_ncu_full.md: dram read 4.108 GB + write 0.377 GB per launch '
                                                            '(algorithmic input + output 3.40 GB; the excess is halo rows re-read past L2)',
                      'peak_source': peaks['source'] + ' bf16 dense (burst)',
                      'note': 'achieved = algorithmic fp32 FLOPs (2*N*Ho*Wo*cout*cin*k^2) / CUDA-event time; the 1e-5 parity contract needs the 3-term '

@@ -143,6 +143,28 @@ def test_circular_conv_semantics(k, s, nd):
         assert rel_err(got, ref) < TOL, (k, s, nd, cin, cout, size)
 
 
+@pytest.mark.parametrize('cin,cout,k,H,W', [(7, 3, 3, 40, 24), (5, 4, 5, 64, 48), (16, 2, 5, 64, 64), (52, 4, 3, 32, 32), (9, 1, 3, 48, 40)])
+def test_conv_row_tiled_kernel_narrow_layers(cin, cout, k, H, W):
+    """conv_fwd_rt_kernel (cout <= 4, stride 1, full-width tiles): BN+ReLU prologue, per-group weights, channel-offset output, input as a
+    channel-slice view; row widths that pack 2, 4 or 5 rows per staging instruction."""
+    torch.manual_seed(cin * 3 + cout)
+    G, npg = 2, 3
+    N = G * npg
+    xbuf = torch.randn(N, cin + 2, H, W)
+    w = torch.randn(G, cout, cin, k, k) / (cin * k * k) ** 0.5
+    sc, sh = torch.rand(G, cin) + 0.5, torch.randn(G, cin) * 0.3
+    xd, wd, scd, shd = xbuf.to(DEV), w.to(DEV), sc.to(DEV), sh.to(DEV)
+    ybuf = torch.full((N, cout + 4, H, W), 7.0, device=DEV)
+    L.call('arpde_conv_fwd', L.ptr(xd[:, 2:]), (cin + 2) * H * W, L.ptr(wd), cout * cin * k * k, L.ptr(scd), L.ptr(shd), cin, L.ptr(ybuf), 0,
+           N, cin, H, W, cout, k, k, 1, 0, 1, 0, cout + 4, 4, npg, L.stream())
+    torch.cuda.synchronize()
+    assert float((ybuf[:, :4] - 7.0).abs().max()) == 0.0                      # channels outside the window untouched
+    for g in range(G):
+        a = torch.relu(xbuf[g * npg:(g + 1) * npg, 2:].double() * sc[g].double().view(1, -1, 1, 1) + sh[g].double().view(1, -1, 1, 1))
+        ref = O.conv_circ(a, w[g].double(), stride=1)
+        assert rel_err(ybuf[g * npg:(g + 1) * npg, 4:], ref) < TOL, g
+
+
 def test_conv_prologue_upsample_concat_groups():
     torch.manual_seed(0)
     N, cin, cout, H, W = 6, 10, 12, 8, 16

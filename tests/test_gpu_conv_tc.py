@@ -66,6 +66,24 @@ def test_conv_tc_1d_vs_oracle(k, s, L_):
     assert rel_err(y.squeeze(2), ref) < TOL
 
 
+@pytest.mark.parametrize('cin,cout,H,W', [(32, 16, 32, 32), (20, 8, 16, 24), (24, 32, 16, 16), (36, 5, 12, 16)])
+def test_conv_tc_upsample_fold(cin, cout, H, W):
+    """nearest x2 + 3x3 folded into a low-resolution conv with 4*cout parity channels: float2 epilogue (16 | cout), generic folded
+    stores (cout = 8, 5), N' = 256 (cout = 32); BN+ReLU prologue, output written at a channel offset."""
+    torch.manual_seed(cin + cout)
+    N = 3
+    x = torch.randn(N, cin, H, W)
+    w = torch.randn(cout, cin, 3, 3) / (cin * 9) ** 0.5
+    sc, sh = torch.rand(cin) + 0.5, torch.randn(cin) * 0.3
+    a = torch.relu(x.double() * sc.double().view(1, -1, 1, 1) + sh.double().view(1, -1, 1, 1))
+    ref = O.conv_circ(O._up2(a), w.double(), stride=1)
+    xd, wd, scd, shd = x.to(DEV), w.to(DEV), sc.to(DEV), sh.to(DEV)
+    ybuf = torch.full((N, cout + 4, 2 * H, 2 * W), 7.0, device=DEV)
+    conv_tc(xd, cin * H * W, wd, 0, scd, shd, 0, ybuf, None, N, cin, H, W, cout, 3, 3, 1, 1, 1, 0, cout + 4, 4, N)
+    assert float((ybuf[:, :4] - 7.0).abs().max()) == 0.0
+    assert rel_err(ybuf[:, 4:], ref) < TOL
+
+
 def test_conv_tc_prologue_upsample_concat_groups_stats():
     """BN+ReLU prologue, nearest x2, channel-offset output, per-group weights, tanh, batch statistics."""
     torch.manual_seed(0)

@@ -57,6 +57,10 @@ _PROTOS = {
     'arpde_conv_fwd_tc': [f32p, i64, f32p, i64, f32p, f32p, i64, f32p, f64p] + [i32] * 14 + [f32p, i64, vp],
     'arpde_densed_backward': [vp, i32, vp, i32, vp, i32, f32p, i64, i32, i32, i32, f32p, f32p, f32p, f32p, i32, f32p,
                               f32p, f32p, vp, f32p, f32p, f32p, f64p, i32, f32p, i64, vp],
+    'arpde_densed_forward_dp': [vp, i32, vp, i32, vp, vp, i32, f32p, i64, i32, i32, i32, i32, f32p, i32, i32, f32p, f32p,
+                                i32, f64p, i64, f32p, i32, f64, f64, f32p, i64, vp, vp, i32, vp],
+    'arpde_densed_backward_dp': [vp, i32, vp, i32, vp, i32, f32p, i64, i32, i32, i32, f32p, f32p, f32p, f32p, i32, f32p,
+                                 f32p, f32p, vp, f32p, f32p, f32p, f64p, i32, f32p, i64, vp, vp, i32, vp],
     'arpde_conv_tc_plan': [i32] * 8 + [vp],
     'arpde_error_metrics': [vp, i64, i64, vp, i64, i64, i32, i32, i64, i64, vp, vp, vp],
     'arpde_adam_step': [vp, vp, vp, vp, vp, vp, vp, vp, i32, f64, f64, f64, vp],
@@ -64,8 +68,6 @@ _PROTOS = {
     'arpde_conv_wgrad': [vp, i64, vp, vp, vp, i64, vp, vp] + [i32] * 10 + [vp, i64, i32, vp],
     'arpde_conv_wgrad_tc': [vp, i64, vp, vp, vp, i64, vp, vp] + [i32] * 10 + [vp, i64, vp],
     'arpde_conv_wgrad_tc_plan': [i32] * 8 + [vp],
-    'arpde_conv_tc_set_debug': [vp],
-    'arpde_conv_tc_set_debug_flags': [i32],
     'arpde_rollout': [vp, i32, vp, i32, vp, vp, i32, f32p, i32, i32, i32, i32, i32, i32, i32, i32, i32, f32p, f32p,
                       i32, f64, f32p, i64, vp],
     'arpde_swag_sample': [vp, vp, vp, vp, i32, f32p, f32p, f32p, i32, i32, i32, f64, f64, i32, vp],
@@ -110,6 +112,29 @@ def stream():
 
 def call(name, *args):
     check(getattr(lib, name)(*args), name)
+
+
+ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64)     # arpde_allreduce_fn
+
+
+def allreduce_callback(sync, *tensors):
+    """ctypes callback for arpde_densed_*_dp: `sync.all_reduce(view)` on the float64 slice of one of `tensors` that the
+    library points at (the library only ever hands back addresses inside the scratch tensors it was given)."""
+    spans = [(t.data_ptr(), t.data_ptr() + t.numel() * t.element_size(), t) for t in tensors if t is not None and t.dtype == torch.float64]
+
+    def cb(user, buf, n):
+        try:
+            for lo, hi, t in spans:
+                if lo <= buf and buf + 8 * n <= hi:
+                    off = (buf - lo) // 8
+                    sync.all_reduce(t.view(-1)[off:off + n])
+                    return 0
+            return 1
+        except Exception:          # never let an exception cross the C boundary
+            import traceback
+            traceback.print_exc()
+            return 2
+    return ALLREDUCE_FN(cb)
 
 
 def ptr_array(ptrs):

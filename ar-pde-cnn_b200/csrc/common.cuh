@@ -32,6 +32,16 @@ void arpde_set_error(const char* fmt, ...);
 
 #define ARPDE_LAUNCH_CHECK() ARPDE_CUDA(cudaGetLastError())
 
+// Development switches (kernel ablations, tile-size overrides).  They read the environment ONLY in a library built with
+// -DARPDE_DEV (`ARPDE_DEV=1 bash build.sh`); the shipped library reads no environment variable and keeps no state but the
+// thread-local error string, as include/arpde.h promises.
+#ifdef ARPDE_DEV
+#include <stdlib.h>
+static inline const char* arpde_dev_env(const char* key) { return getenv(key); }
+#else
+static inline const char* arpde_dev_env(const char*) { return nullptr; }
+#endif
+
 int arpde_num_sms();   // cached cudaDevAttrMultiProcessorCount of the current device
 
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }

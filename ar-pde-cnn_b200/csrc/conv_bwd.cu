@@ -71,9 +71,9 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
                                                            const float* __restrict__ invstd, const double* __restrict__ sums,
                                                            float* __restrict__ gx, long long gx_bs, float* __restrict__ dgamma,
                                                            float* __restrict__ dbeta, int N, int C, long long HW, int training,
-                                                           int accumulate) {
+                                                           int accumulate, int dp_world) {
   const long long total = (long long)N * C * HW;
-  const double invM = 1.0 / ((double)N * (double)HW);
+  const double invM = 1.0 / ((double)N * (double)HW * (double)dp_world);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long r = i % HW; const int c = (int)((i / HW) % C); const long long n = i / (HW * C);
     float g = dz[i];
@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_v_kernel(const float* __rest
                                                              const float* __restrict__ mean, const float* __restrict__ invstd,
                                                              const double* __restrict__ sums, float* __restrict__ gx, long long gx_bs,
                                                              float* __restrict__ dgamma, float* __restrict__ dbeta, int N, int C, int H,
-                                                             int W, int nper, int training, int accumulate) {
+                                                             int W, int nper, int training, int accumulate, int dp_world) {
   const int c = blockIdx.y;
   const int n_lo = blockIdx.x * nper, n_hi = min(N, n_lo + nper);
   const int HW = H * W, HW4 = HW >> 2;
@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_v_kernel(const float* __rest
   const bool bn = scale != nullptr;
   const float sc = bn ? scale[c] : 1.f, sh = bn ? shift[c] : 0.f;
   const float mu = (bn && mean) ? mean[c] : 0.f, is = (bn && invstd) ? invstd[c] : 1.f;
-  const double invM = 1.0 / ((double)N * (double)HW);
+  const double invM = 1.0 / ((double)N * (double)HW * (double)dp_world);
   const float m1 = (bn && training) ? (float)(sums[2 * c] * invM) : 0.f, m2 = (bn && training) ? (float)(sums[2 * c + 1] * invM) : 0.f;
   for (int n = n_lo; n < n_hi; ++n) {
     const float* xn = x + n * x_bs + (long long)c * HW;
@@ -182,14 +182,32 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_v_kernel(const float* __rest
   if (bn && dgamma && blockIdx.x == 0 && threadIdx.x == 0) { dgamma[c] = (float)sums[2 * c + 1]; dbeta[c] = (float)sums[2 * c]; }
 }
 
+// dgamma = sum dz*xhat, dbeta = sum dz of THIS rank's samples (data-parallel BatchNorm: written before the sums are all-reduced, the
+// gradient all-reduce adds the ranks up)
+__global__ void bn_dparam_kernel(const double* __restrict__ sums, float* __restrict__ dgamma, float* __restrict__ dbeta, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) { dgamma[c] = (float)sums[2 * c + 1]; dbeta[c] = (float)sums[2 * c]; }
+}
+
+// dp: optional data-parallel hook -- between the reduction and the apply pass the (sum dz, sum dz*xhat) pairs are all-reduced over the
+// ranks (global-batch BatchNorm backward), the element count is N*HW*dp->world
 int arpde_bn_relu_bwd_launch(const float* da, const float* x, long long x_bs, const float* scale, const float* shift, const float* mean,
                              const float* invstd, float* dz, double* sums, float* gx, long long gx_bs, float* dgamma, float* dbeta, int N,
-                             int C, int H, int W, int up_h, int up_w, int training, int accumulate, cudaStream_t stream) {
+                             int C, int H, int W, int up_h, int up_w, int training, int accumulate, cudaStream_t stream, const DpHook* dp) {
   const long long HW = (long long)H * W, total = (long long)N * HW;
+  const bool sync = dp && dp->allreduce && dp->world > 1 && scale && training;
+  const int dpw = sync ? dp->world : 1;
+  auto sync_sums = [&]() -> int {
+    if (!sync) return ARPDE_OK;
+    if (dgamma) { bn_dparam_kernel<<<(C + 127) / 128, 128, 0, stream>>>(sums, dgamma, dbeta, C); ARPDE_LAUNCH_CHECK(); }
+    if (dp->allreduce(dp->user, sums, 2ll * C)) { arpde_set_error("bn backward: the all-reduce callback failed"); return ARPDE_ERR_CUDA; }
+    return ARPDE_OK;
+  };
+  float* dgamma_k = sync ? nullptr : dgamma;      // the apply kernels write dgamma / dbeta from the (then global) sums otherwise
   if (scale) ARPDE_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, stream));
   // vector path: full 2D pooling (or none), rows of whole float4s, every base and stride 16-byte aligned; dz is not used
   const bool vec = up_h == up_w && (W & 3) == 0 && (x_bs & 3) == 0 && (gx_bs & 3) == 0 && (((uintptr_t)da | (uintptr_t)x | (uintptr_t)gx) & 15) == 0 &&
-                   !getenv("ARPDE_BN_BWD_SCALAR");
+                   !arpde_dev_env("ARPDE_BN_BWD_SCALAR");
   if (vec) {
     // samples per CTA: enough CTAs to fill the machine a few times over, at least ~2k float4 per CTA
     int nper = 1;
@@ -200,17 +218,19 @@ int arpde_bn_relu_bwd_launch(const float* da, const float* x, long long x_bs, co
       if (up_w) bn_relu_bwd_reduce_v_kernel<1><<<grid, 256, 0, stream>>>(da, x, x_bs, scale, shift, mean, invstd, sums, N, C, H, W, nper);
       else bn_relu_bwd_reduce_v_kernel<0><<<grid, 256, 0, stream>>>(da, x, x_bs, scale, shift, mean, invstd, sums, N, C, H, W, nper);
       ARPDE_LAUNCH_CHECK();
+      if (int rc = sync_sums()) return rc;
     }
-    if (up_w) bn_bwd_apply_v_kernel<1><<<grid, 256, 0, stream>>>(da, x, x_bs, scale, shift, mean, invstd, sums, gx, gx_bs, dgamma, dbeta, N, C, H, W, nper, training, accumulate);
-    else bn_bwd_apply_v_kernel<0><<<grid, 256, 0, stream>>>(da, x, x_bs, scale, shift, mean, invstd, sums, gx, gx_bs, dgamma, dbeta, N, C, H, W, nper, training, accumulate);
+    if (up_w) bn_bwd_apply_v_kernel<1><<<grid, 256, 0, stream>>>(da, x, x_bs, scale, shift, mean, invstd, sums, gx, gx_bs, dgamma_k, dbeta, N, C, H, W, nper, training, accumulate, dpw);
+    else bn_bwd_apply_v_kernel<0><<<grid, 256, 0, stream>>>(da, x, x_bs, scale, shift, mean, invstd, sums, gx, gx_bs, dgamma_k, dbeta, N, C, H, W, nper, training, accumulate, dpw);
     ARPDE_LAUNCH_CHECK();
     return ARPDE_OK;
   }
   int chunks = (int)ceil_div64(total, 256 * 32); if (chunks < 1) chunks = 1; if (chunks > 128) chunks = 128;
   bn_relu_bwd_reduce_kernel<<<C * chunks, 256, 0, stream>>>(da, x, x_bs, scale, shift, mean, invstd, dz, sums, N, C, H, W, up_h, up_w, chunks);
   ARPDE_LAUNCH_CHECK();
+  if (int rc = sync_sums()) return rc;
   int64_t blocks = ceil_div64(total * C, 256 * 4); const int64_t cap = (int64_t)arpde_num_sms() * 16; if (blocks > cap) blocks = cap; if (blocks < 1) blocks = 1;
-  bn_bwd_apply_kernel<<<(unsigned)blocks, 256, 0, stream>>>(dz, x, x_bs, scale, mean, invstd, sums, gx, gx_bs, dgamma, dbeta, N, C, HW, training, accumulate);
+  bn_bwd_apply_kernel<<<(unsigned)blocks, 256, 0, stream>>>(dz, x, x_bs, scale, mean, invstd, sums, gx, gx_bs, dgamma_k, dbeta, N, C, HW, training, accumulate, dpw);
   ARPDE_LAUNCH_CHECK();
   return ARPDE_OK;
 }
@@ -510,7 +530,6 @@ typedef void (*wgrad_small_fn)(WgradSmallArgs);
 // returns ARPDE_OK if the narrow-layer kernel took the job, ARPDE_ERR_UNSUPPORTED if the layer is not its kind (caller falls back)
 static int wgrad_small_launch(const ConvDesc& d, const float* x, long long x_bs, const float* scale, const float* shift, const float* dO,
                               long long dO_bs, double* dW64, cudaStream_t stream) {
-  if (getenv("ARPDE_WGRAD_SMALL_OFF")) return ARPDE_ERR_UNSUPPORTED;
   if (d.stride != 1 || d.up || d.dilate || d.pad_override >= 0 || d.H < 2 || d.cout > 4 || d.kh != d.kw) return ARPDE_ERR_UNSUPPORTED;
   if ((d.W & 7) || d.W > 128 || (x_bs & 3) || (dO_bs & 3) || (((uintptr_t)x | (uintptr_t)dO) & 15)) return ARPDE_ERR_UNSUPPORTED;
   const int CO = d.cout <= 2 ? 2 : 4;
@@ -562,7 +581,7 @@ static wgrad_fn pick_wgrad(int kh, int kw, int s, int cout, int* cot) {
 
 // dW (float, [cout][cin][kh][kw]) = sum over batch; dW64 scratch: cout*cin*kh*kw doubles
 int arpde_conv_wgrad_launch(const ConvDesc& d, const float* x, long long x_bs, const float* scale, const float* shift, const float* dO,
-                            long long dO_bs, double* dW64, float* dW, cudaStream_t stream) {
+                            long long dO_bs, double* dW64, float* dW, cudaStream_t stream, bool generic_only) {
   ARPDE_CHECK_ARG(x && dO && dW64 && dW, "conv_wgrad: null pointer");
   int cot = 8;
   wgrad_fn fn = pick_wgrad(d.kh, d.kw, d.stride, d.cout, &cot);
@@ -570,7 +589,7 @@ int arpde_conv_wgrad_launch(const ConvDesc& d, const float* x, long long x_bs, c
   const int KK = d.kh * d.kw;
   const long long wn = (long long)d.cout * d.cin * KK;
   ARPDE_CUDA(cudaMemsetAsync(dW64, 0, sizeof(double) * wn, stream));
-  if (d.N > 0 && wgrad_small_launch(d, x, x_bs, scale, shift, dO, dO_bs, dW64, stream) == ARPDE_OK)
+  if (d.N > 0 && !generic_only && wgrad_small_launch(d, x, x_bs, scale, shift, dO, dO_bs, dW64, stream) == ARPDE_OK)
     return arpde_d2f_launch(dW64, dW, wn, stream);
   const int one_d = (d.H == 1 && d.kh == 1);
   const int up_h = one_d ? 0 : d.up;
@@ -622,7 +641,6 @@ int arpde_conv_wgrad_launch(const ConvDesc& d, const float* x, long long x_bs, c
 
 // narrow layers first (sliding-window kernel, inside arpde_conv_wgrad_launch), then the tensor core, then the generic fp32 kernel
 static bool wgrad_small_eligible(const ConvDesc& d, const float* x, long long x_bs, const float* dO, long long dO_bs) {
-  if (getenv("ARPDE_WGRAD_SMALL_OFF")) return false;
   if (d.stride != 1 || d.up || d.dilate || d.pad_override >= 0 || d.H < 2 || d.cout > 4 || d.kh != d.kw || (d.kh != 3 && d.kh != 5)) return false;
   if ((d.W & 7) || d.W > 128 || (x_bs & 3) || (dO_bs & 3) || (((uintptr_t)x | (uintptr_t)dO) & 15) || d.cin * d.kh > 256) return false;
   return true;
@@ -652,10 +670,7 @@ extern "C" int arpde_conv_wgrad(const float* x, int64_t x_bstride, const float* 
   ARPDE_CHECK_ARG(x && dO && dW64 && dW, "conv_wgrad: null pointer");
   if (path == 1) {
     // generic kernel only
-    setenv("ARPDE_WGRAD_SMALL_OFF", "1", 1);
-    int rc = arpde_conv_wgrad_launch(d, x, x_bstride, scale, shift, dO, dO_bstride, dW64, dW, stream);
-    unsetenv("ARPDE_WGRAD_SMALL_OFF");
-    return rc;
+    return arpde_conv_wgrad_launch(d, x, x_bstride, scale, shift, dO, dO_bstride, dW64, dW, stream, true);
   }
   return arpde_conv_wgrad_best_launch(d, x, x_bstride, scale, shift, dO, dO_bstride, dW64, dW, scratch, scratch_floats, stream);
 }

@@ -93,12 +93,16 @@ int arpde_conv_fwd_launch(const ConvDesc& d, const float* x, long long x_bs, con
                           cudaStream_t stream);
 
 int arpde_weight_flip_transpose_launch(const float* w, float* wt, int cout, int cin, int kh, int kw, cudaStream_t stream);
+// data-parallel hook of the program runner (arpde_densed_forward_dp / _backward_dp): in-place SUM over the ranks of n device doubles,
+// enqueued by the callback on the calling stream (or ordered against it); world = number of ranks, every rank holds the same N
+struct DpHook { int (*allreduce)(void* user, double* buf, long long n); void* user; int world; };
 int arpde_bn_relu_bwd_launch(const float* da, const float* x, long long x_bs, const float* scale, const float* shift, const float* mean,
                              const float* invstd, float* dz, double* sums, float* gx, long long gx_bs, float* dgamma, float* dbeta, int N,
-                             int C, int H, int W, int up_h, int up_w, int training, int accumulate, cudaStream_t stream);
+                             int C, int H, int W, int up_h, int up_w, int training, int accumulate, cudaStream_t stream,
+                             const DpHook* dp = nullptr);
 int arpde_act_bwd_launch(const float* gy, const float* y, float* out, long long n, int act, cudaStream_t stream);
 int arpde_conv_wgrad_launch(const ConvDesc& d, const float* x, long long x_bs, const float* scale, const float* shift, const float* dO,
-                            long long dO_bs, double* dW64, float* dW, cudaStream_t stream);
+                            long long dO_bs, double* dW64, float* dW, cudaStream_t stream, bool generic_only = false);
 
 int arpde_conv_wgrad_best_launch(const ConvDesc& d, const float* x, long long x_bs, const float* scale, const float* shift, const float* dO,
                                  long long dO_bs, double* dW64, float* dW, float* tc_scratch, long long tc_scratch_floats, cudaStream_t stream);

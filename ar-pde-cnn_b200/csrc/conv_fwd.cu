@@ -347,7 +347,7 @@ static conv_fwd_fn pick_kernel(int kh, int kw, int s, int cot, int* pxt) {
 // shape part of the row-tiled kernel's eligibility (pointer alignment is checked at launch): the narrow layers it is faster on than
 // the tensor-core kernel (measured at N = 1920: dense 52->4 3x3 at 32x32 0.44 vs 0.52 ms, 16->2 5x5 at 64x64 0.56 vs 1.1 ms)
 bool arpde_conv_fwd_rt_shape_ok(const ConvDesc& d) {
-  if (getenv("ARPDE_CONV_RT_OFF")) return false;
+  if (arpde_dev_env("ARPDE_CONV_RT_OFF")) return false;
   if (d.stride != 1 || d.up || d.dilate || d.pad_override >= 0 || d.H <= 1 || d.cout > 4) return false;
   if (!((d.kh == 3 && d.kw == 3) || (d.kh == 5 && d.kw == 5))) return false;
   if ((d.W & 7) || d.W > 64 || (d.W & 3)) return false;
@@ -376,7 +376,7 @@ int arpde_conv_fwd_launch(const ConvDesc& d, const float* x, long long x_bs, con
   ARPDE_CHECK_ARG(Hc % sh == 0 && Wc % d.stride == 0, "conv_fwd: spatial size %dx%d not divisible by stride %d", Hc, Wc, d.stride);
   const int Ho = Hc / sh, Wo = Wc / d.stride;
   // narrow output layers: row-tiled kernel (see conv_fwd_rt_kernel)
-  if (!getenv("ARPDE_CONV_RT_OFF") && d.stride == 1 && !d.up && !d.dilate && d.pad_override < 0 && d.H > 1 && d.cout <= 4 && stats == nullptr &&
+  if (!arpde_dev_env("ARPDE_CONV_RT_OFF") && d.stride == 1 && !d.up && !d.dilate && d.pad_override < 0 && d.H > 1 && d.cout <= 4 && stats == nullptr &&
       (Wo & 7) == 0 && (((uintptr_t)y) & 15) == 0) {
     conv_fwd_fn rt = nullptr;
     const int cot = d.cout <= 2 ? 2 : 4;
@@ -404,7 +404,7 @@ int arpde_conv_fwd_launch(const ConvDesc& d, const float* x, long long x_bs, con
       const int KK = d.kh * d.kw;
       const size_t fixed = (size_t)(((PH + PW + 3) & ~3)) * 4;
       const size_t per_ci = (size_t)PH * a.pitch * 4 + (size_t)KK * cot * 4;
-      const size_t budget = (size_t)(getenv("ARPDE_RT_SMEM_KB") ? atoi(getenv("ARPDE_RT_SMEM_KB")) : (Wo >= 64 ? 100 : 56)) * 1024;   // 2 CTAs per SM on 64-wide rows, 4 of the smaller ones
+      const size_t budget = (size_t)(arpde_dev_env("ARPDE_RT_SMEM_KB") ? atoi(arpde_dev_env("ARPDE_RT_SMEM_KB")) : (Wo >= 64 ? 100 : 56)) * 1024;   // 2 CTAs per SM on 64-wide rows, 4 of the smaller ones
       int cic = (int)((budget - fixed) / per_ci); if (cic < 1) cic = 1; if (cic > d.cin) cic = d.cin;
       cic = (d.cin + ((d.cin + cic - 1) / cic) - 1) / ((d.cin + cic - 1) / cic);
       a.ci_chunk = cic;
@@ -445,7 +445,7 @@ int arpde_conv_fwd_launch(const ConvDesc& d, const float* x, long long x_bs, con
   int TH = (32 * npw_max) / nxt; if (TH < 1) TH = 1;
   // 1D signals: fill the CTA with consecutive samples as tile rows (they must share a weight group).  A 96-point KS layer used 6 or 12
   // of its 32+ px-threads with one sample per CTA (C1 rollout: 433 us per AR step of 1920 samples)
-  const bool one_d_rows = Ho == 1 && d.kh == 1 && !getenv("ARPDE_CONV_1D_ROWS_OFF");
+  const bool one_d_rows = Ho == 1 && d.kh == 1 && !arpde_dev_env("ARPDE_CONV_1D_ROWS_OFF");
   if (one_d_rows) {
     // ... but keep at least ~3 CTAs per SM in the grid (1920 samples in tiles of 32 would be 60 CTAs on 148 SMs)
     const long long per_row_ctas = (long long)((d.cout + ncg * cot - 1) / (ncg * cot)) * ((Wo + TW - 1) / TW);

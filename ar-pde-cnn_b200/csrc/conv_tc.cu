@@ -807,7 +807,7 @@ static int floor_div(int a, int b) { int q = a / b, r = a % b; return (r != 0 &&
 
 int arpde_tc_enabled() {
   static int cached = -1;
-  if (cached < 0) { const char* e = getenv("ARPDE_TC"); cached = (e && e[0] == '0') ? 0 : 1; }
+  if (cached < 0) { const char* e = arpde_dev_env("ARPDE_TC"); cached = (e && e[0] == '0') ? 0 : 1; }
   return cached;
 }
 
@@ -815,7 +815,7 @@ int arpde_tc_enabled() {
 static bool tc_plan(const ConvDesc& d, ConvTcArgs& a, size_t* smem_out) {
   if (d.pad_override >= 0) return false;
   // nearest x2 + 3x3: plan the equivalent low-resolution conv with 4*cout parity-major channels (see the header comment)
-  if (d.up && !d.dilate && d.stride == 1 && d.kh == 3 && d.kw == 3 && d.H > 1 && 4 * d.cout <= 128 && !getenv("ARPDE_TC_NO_UPFOLD")) {
+  if (d.up && !d.dilate && d.stride == 1 && d.kh == 3 && d.kw == 3 && d.H > 1 && 4 * d.cout <= 128 && !arpde_dev_env("ARPDE_TC_NO_UPFOLD")) {
     ConvDesc e = d; e.up = 0; e.cout = 4 * d.cout;
     if (tc_plan(e, a, smem_out)) { a.upfold = 1; a.cout_fold = d.cout; return true; }
   }
@@ -860,7 +860,7 @@ static bool tc_plan(const ConvDesc& d, ConvTcArgs& a, size_t* smem_out) {
   // pipeline hand-offs), wide tap chunks
   // experiment hook: ARPDE_TC_FORCE="nslot_p,ntile,cchunk" restricts the search (0 = free) -- used for A/B timing only
   int f_slot = 0, f_ntile = 0, f_cchunk = 0;
-  if (const char* e = getenv("ARPDE_TC_FORCE")) sscanf(e, "%d,%d,%d", &f_slot, &f_ntile, &f_cchunk);
+  if (const char* e = arpde_dev_env("ARPDE_TC_FORCE")) sscanf(e, "%d,%d,%d", &f_slot, &f_ntile, &f_cchunk);
   // (streamed weights, stride 2, all taps in one weight slot -- pass 0: two M tiles sharing one patch slot halve the weight streaming
   //  and the halo per tile; measured on In_conv3 at N = 1920: 2.10 ms against 2.22 ms for one tile with two patch slots, 2.31 / 3.75 ms
   //  for three / four tiles.  Stride-1 layers and split tap chunks lose with it: 144->32 3x3 at 16x16 0.70 vs 0.47 ms.)
@@ -925,7 +925,7 @@ bool arpde_conv_tc_wanted(const ConvDesc& d) {
   if (!arpde_tc_enabled()) return false;
   if (d.H == 1 && d.kh == 1) return false;                 // 1D nets: tiles of 128 positions are mostly halo
   if (d.cout < 4 || d.cin * d.kh * d.kw < 32) return false;
-  if (arpde_conv_fwd_rt_shape_ok(d) && !getenv("ARPDE_TC_DENSE")) return false;     // narrow layers: the row-tiled FFMA kernel is faster
+  if (arpde_conv_fwd_rt_shape_ok(d) && !arpde_dev_env("ARPDE_TC_DENSE")) return false;     // narrow layers: the row-tiled FFMA kernel is faster
   ConvTcArgs a; size_t smem;
   return tc_plan(d, a, &smem);
 }
@@ -967,6 +967,9 @@ static int tc_encode_input_map(CUtensorMap* map, const float* x, long long x_bs,
   return ARPDE_OK;
 }
 
+// Profiling hooks: only a development build (-DARPDE_DEV) keeps this process-global state and exports the two setters; in the
+// shipped library the buffer is always null and the flags always 0.
+#ifdef ARPDE_DEV
 static long long* g_tc_dbg = nullptr;
 static int g_tc_dbg_flags = 0;
 extern "C" int arpde_conv_tc_set_debug_flags(int flags) { g_tc_dbg_flags = flags; return ARPDE_OK; }
@@ -975,6 +978,11 @@ extern "C" int arpde_conv_tc_set_debug_flags(int flags) { g_tc_dbg_flags = flags
 // [8..12] issuer: total, wait tmem_empty, wait full_p, wait weights, items
 extern "C" int arpde_conv_tc_set_debug(long long* dev_buf) { g_tc_dbg = dev_buf; return ARPDE_OK; }
 long long* arpde_tc_debug_buffer() { return g_tc_dbg; }
+#else
+static constexpr long long* g_tc_dbg = nullptr;
+static constexpr int g_tc_dbg_flags = 0;
+long long* arpde_tc_debug_buffer() { return nullptr; }
+#endif
 
 int arpde_conv_tc_launch(const ConvDesc& d, const float* x, long long x_bs, const float* wprep, long long wprep_gs, const float* scale,
                          const float* shift, long long ss_gs, float* y, double* stats, cudaStream_t stream) {
@@ -989,7 +997,7 @@ int arpde_conv_tc_launch(const ConvDesc& d, const float* x, long long x_bs, cons
   // TMA needs a 16-byte aligned base and 16-byte multiples for every global stride; otherwise the staging warps load with LDG
   CUtensorMap tmap;
   memset(&tmap, 0, sizeof(tmap));
-  if (a.tma && ((((uintptr_t)x) & 15) != 0 || (x_bs & 3) != 0 || getenv("ARPDE_TC_NO_TMA"))) a.tma = 0;
+  if (a.tma && ((((uintptr_t)x) & 15) != 0 || (x_bs & 3) != 0 || arpde_dev_env("ARPDE_TC_NO_TMA"))) a.tma = 0;
   if (a.dilate && scale) { arpde_set_error("conv_tc: a zero-inserted input cannot carry a BatchNorm prologue"); return ARPDE_ERR_UNSUPPORTED; }
   if (!a.tma && a.dilate) { arpde_set_error("conv_tc: zero-inserted input needs the TMA path (16-byte aligned input)"); return ARPDE_ERR_UNSUPPORTED; }
   if (a.tma) {

@@ -483,7 +483,7 @@ static int wg_floor_div(int a, int b) { int q = a / b, r = a % b; return (r != 0
 
 static bool wg_plan(const ConvDesc& d, WgTcArgs& a, size_t* smem_out) {
   if (d.dilate || d.pad_override >= 0) return false;
-  if (d.up && d.stride == 1 && d.kh == 3 && d.kw == 3 && d.H > 1 && 4 * d.cout <= 128 && 4 * d.cout > 8 && !getenv("ARPDE_WG_NO_FOLD")) {
+  if (d.up && d.stride == 1 && d.kh == 3 && d.kw == 3 && d.H > 1 && 4 * d.cout <= 128 && 4 * d.cout > 8 && !arpde_dev_env("ARPDE_WG_NO_FOLD")) {
     ConvDesc e = d; e.up = 0; e.cout = 4 * d.cout;         // equivalent low-resolution conv, parity-major channels (conv_tc.cu upfold)
     if (wg_plan(e, a, smem_out) && !a.swap) { a.fold = 1; a.cout_fold = d.cout; return true; }
   }
@@ -592,7 +592,7 @@ static bool wg_plan(const ConvDesc& d, WgTcArgs& a, size_t* smem_out) {
 
 bool arpde_conv_wgrad_tc_wanted(const ConvDesc& d) {
   if (!arpde_tc_enabled()) return false;
-  if (const char* e = getenv("ARPDE_WGRAD_TC")) if (e[0] == '0') return false;
+  if (const char* e = arpde_dev_env("ARPDE_WGRAD_TC")) if (e[0] == '0') return false;
   // an MMA costs ~40 cycles whatever M is: with cout < 32 most of the 64 accumulator rows are padding and the FFMA kernel wins
   // (measured, N = 128: LastTransUp conv3x3 32->16 at 64x64: tensor core 0.41 ms, FFMA 0.375 ms)
   WgTcArgs a; size_t smem;
@@ -621,7 +621,7 @@ int arpde_conv_wgrad_tc_launch(const ConvDesc& d, const float* x, long long x_bs
   const long long need = (long long)a.ncc * a.slices * a.cols * 128;
   ARPDE_CHECK_ARG(scratch_floats >= need, "conv_wgrad_tc: scratch too small (%lld < %lld floats)", scratch_floats, need);
   a.slab = scratch; a.dbg = arpde_tc_debug_buffer();
-  if (const char* e = getenv("ARPDE_WG_DBG")) a.dbg_flags = atoi(e);
+  if (const char* e = arpde_dev_env("ARPDE_WG_DBG")) a.dbg_flags = atoi(e);
   a.x = x; a.x_bs = x_bs; a.scale = scale; a.shift = shift; a.relu_in = d.relu_in; a.dO = dO; a.dO_bs = dO_bs; a.dW = dW64;
   const long long wn = (long long)d.cout * d.cin * d.kh * d.kw;
   ARPDE_CUDA(cudaMemsetAsync(dW64, 0, sizeof(double) * wn, stream));

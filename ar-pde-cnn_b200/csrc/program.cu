@@ -27,12 +27,14 @@ struct RunCtx {
   const arpde_buf_t* bufs; int n_bufs;
   void* const* params; const int64_t* gstride; int n_params;
   int N, n_per_group, groups, H, W;
-  float* work; float* ss; int bn_total; double* stats; float* saved;
+  float* work; float* ss; int bn_total; double* stats; long long stats_len = 0; float* saved;
   float momentum, eps;
   cudaStream_t stream;
   float* tc_scratch = nullptr; long long tc_scratch_floats = 0;
   std::vector<const float*> wprep;          // per op: prepared tensor-core weights (nullptr = fp32 FFMA kernel)
   std::vector<long long> wprep_gs;
+  const DpHook* dp = nullptr;               // data-parallel training: all-reduce of the BatchNorm sums (nullptr = single process)
+  mutable std::vector<int> synced;          // per buffer: channels whose statistics already hold the global sums
 };
 
 static void op_desc(const RunCtx& c, const arpde_op_t& o, ConvDesc* d) {
@@ -103,9 +105,30 @@ static int run_ops(const RunCtx& c, const float* x, long long x_bs, float* y, in
     if (o.bn_param >= 0) {
       scale = c.ss + o.bn_off; shift = c.ss + (long long)c.groups * c.bn_total + o.bn_off;
       if (training) {
-        const arpde_buf_t& b = c.bufs[o.in_buf];
+        // statistics of the BN input: accumulated by the producers of the buffer, or -- BatchNorm directly on the network input
+        // (a stand-alone _Transition / LastTransUp, DenseED.forward_test) -- by a streaming pass into the tail slot of `stats`
+        const double* st_in; double count;
+        const bool sync = c.dp && c.dp->allreduce && c.dp->world > 1;
+        if (o.in_buf >= 0) {
+          const arpde_buf_t& b = c.bufs[o.in_buf]; st_in = c.stats + b.stats_off; count = (double)c.N * b.h * b.w;
+          if (sync && c.synced[o.in_buf] < o.cin) {
+            // global-batch statistics: sum the (sum x, sum x^2) pairs of the channels new to this BN layer over the ranks (a dense
+            // block's buffer grows by `growth` channels per layer; the earlier ones were reduced for the previous layer)
+            const int s0 = c.synced[o.in_buf];
+            if (c.dp->allreduce(c.dp->user, c.stats + b.stats_off + 2 * s0, 2ll * (o.cin - s0))) {
+              arpde_set_error("densed_forward: the all-reduce callback failed"); return ARPDE_ERR_CUDA;
+            }
+            c.synced[o.in_buf] = o.cin;
+          }
+        } else {
+          double* slot = c.stats + c.stats_len - 2 * o.cin;
+          int rc = arpde_bn_stats(in, in_bs, c.N, o.cin, (long long)d.H * d.W, slot, c.stream); if (rc) return rc;
+          if (sync && c.dp->allreduce(c.dp->user, slot, 2ll * o.cin)) { arpde_set_error("densed_forward: the all-reduce callback failed"); return ARPDE_ERR_CUDA; }
+          st_in = slot; count = (double)c.N * d.H * d.W;
+        }
+        if (sync) count *= c.dp->world;
         float* sm = c.saved ? c.saved + o.bn_off : nullptr;
-        int rc = arpde_bn_finalize_train_launch(c.stats + b.stats_off, (double)c.N * b.h * b.w, (const float*)c.params[o.bn_param],
+        int rc = arpde_bn_finalize_train_launch(st_in, count, (const float*)c.params[o.bn_param],
                                                 (const float*)c.params[o.bn_param + 1], (float*)c.params[o.bn_param + 2],
                                                 (float*)c.params[o.bn_param + 3], (long long*)c.params[o.bn_param + 4], c.momentum,
                                                 c.eps, (float*)scale, (float*)shift, sm, sm ? sm + c.bn_total : nullptr, o.cin, c.stream);
@@ -159,14 +182,15 @@ extern "C" int64_t arpde_densed_tc_scratch_floats(const arpde_op_t* ops, int n_o
   return tot;
 }
 
-extern "C" int arpde_densed_forward(const arpde_op_t* ops, int n_ops, const arpde_buf_t* bufs, int n_bufs, void* const* params_host,
-                                    const int64_t* param_gstride_host, int n_params, const float* x, int64_t x_bstride, int N,
-                                    int n_per_group, int H, int W, float* y, int y_ctot, int y_coff, float* workspace,
-                                    float* scale_shift, int bn_total, double* stats, int64_t stats_len, float* saved_mean_invstd,
-                                    int training, double momentum, double eps, float* tc_scratch, int64_t tc_scratch_floats,
-                                    arpde_stream_t stream_) {
+static int densed_forward_impl(const arpde_op_t* ops, int n_ops, const arpde_buf_t* bufs, int n_bufs, void* const* params_host,
+                               const int64_t* param_gstride_host, int n_params, const float* x, int64_t x_bstride, int N,
+                               int n_per_group, int H, int W, float* y, int y_ctot, int y_coff, float* workspace,
+                               float* scale_shift, int bn_total, double* stats, int64_t stats_len, float* saved_mean_invstd,
+                               int training, double momentum, double eps, float* tc_scratch, int64_t tc_scratch_floats,
+                               arpde_stream_t stream_, const DpHook* dp) {
   cudaStream_t stream = (cudaStream_t)stream_;
   RunCtx c;
+  c.dp = dp; c.synced.assign(n_bufs > 0 ? n_bufs : 1, 0);
   int rc = make_ctx(&c, ops, n_ops, bufs, n_bufs, params_host, param_gstride_host, n_params, N, n_per_group, H, W, workspace,
                     scale_shift, bn_total, stats, saved_mean_invstd, momentum, eps, stream);
   if (rc) return rc;
@@ -178,10 +202,57 @@ extern "C" int arpde_densed_forward(const arpde_op_t* ops, int n_ops, const arpd
     ARPDE_CHECK_ARG(c.groups == 1, "densed_forward: training with grouped weights is not defined");
     ARPDE_CHECK_ARG(stats && stats_len > 0, "densed_forward: training needs the stats scratch");
     ARPDE_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * stats_len, stream));
+    c.stats_len = stats_len;
+    long long need = 0;
+    for (int b = 0; b < n_bufs; ++b) need = need > bufs[b].stats_off + 2ll * bufs[b].ctot ? need : bufs[b].stats_off + 2ll * bufs[b].ctot;
+    for (int i = 0; i < n_ops; ++i)
+      if (ops[i].bn_param >= 0 && ops[i].in_buf < 0) { need += 2ll * ops[i].cin; break; }
+    ARPDE_CHECK_ARG(stats_len >= need, "densed_forward: stats scratch holds %lld doubles, program needs %lld", (long long)stats_len, need);
+    // channels the caller pre-filled (the input copy of a stand-alone dense layer / block): no producer op accumulates their
+    // batch statistics, so a streaming pass does
+    for (int b = 0; b < n_bufs; ++b) {
+      int first = bufs[b].ctot; bool read_bn = false;
+      for (int i = 0; i < n_ops; ++i) {
+        if (ops[i].out_buf == b && ops[i].out_coff < first) first = ops[i].out_coff;
+        if (ops[i].in_buf == b && ops[i].bn_param >= 0) read_bn = true;
+      }
+      if (first > 0 && read_bn) {
+        const long long hw = (long long)bufs[b].h * bufs[b].w;
+        rc = arpde_bn_stats(workspace + bufs[b].offset, bufs[b].ctot * hw, N, first, hw, stats + bufs[b].stats_off, stream);
+        if (rc) return rc;
+      }
+    }
   } else {
     rc = fold_eval(c); if (rc) return rc;
   }
   return run_ops(c, x, x_bstride, y, y_ctot, y_coff, training);
+}
+
+extern "C" int arpde_densed_forward(const arpde_op_t* ops, int n_ops, const arpde_buf_t* bufs, int n_bufs, void* const* params_host,
+                                    const int64_t* param_gstride_host, int n_params, const float* x, int64_t x_bstride, int N,
+                                    int n_per_group, int H, int W, float* y, int y_ctot, int y_coff, float* workspace,
+                                    float* scale_shift, int bn_total, double* stats, int64_t stats_len, float* saved_mean_invstd,
+                                    int training, double momentum, double eps, float* tc_scratch, int64_t tc_scratch_floats,
+                                    arpde_stream_t stream) {
+  return densed_forward_impl(ops, n_ops, bufs, n_bufs, params_host, param_gstride_host, n_params, x, x_bstride, N, n_per_group, H, W, y,
+                             y_ctot, y_coff, workspace, scale_shift, bn_total, stats, stats_len, saved_mean_invstd, training, momentum,
+                             eps, tc_scratch, tc_scratch_floats, stream, nullptr);
+}
+
+// Data-parallel training forward: train-mode BatchNorm over the GLOBAL mini-batch.  Between the kernels that accumulate a layer's
+// (sum x, sum x^2) and the finalize kernel that turns them into scale / shift / running statistics, `allreduce` sums the pairs over
+// the `dp_world` ranks (every rank holds N samples).  The callback is made from the calling host thread.
+extern "C" int arpde_densed_forward_dp(const arpde_op_t* ops, int n_ops, const arpde_buf_t* bufs, int n_bufs, void* const* params_host,
+                                       const int64_t* param_gstride_host, int n_params, const float* x, int64_t x_bstride, int N,
+                                       int n_per_group, int H, int W, float* y, int y_ctot, int y_coff, float* workspace,
+                                       float* scale_shift, int bn_total, double* stats, int64_t stats_len, float* saved_mean_invstd,
+                                       int training, double momentum, double eps, float* tc_scratch, int64_t tc_scratch_floats,
+                                       arpde_allreduce_fn allreduce, void* user, int dp_world, arpde_stream_t stream) {
+  ARPDE_CHECK_ARG(dp_world >= 1 && (dp_world == 1 || allreduce), "densed_forward_dp: %d ranks need an all-reduce callback", dp_world);
+  DpHook h; h.allreduce = (int (*)(void*, double*, long long))allreduce; h.user = user; h.world = dp_world;
+  return densed_forward_impl(ops, n_ops, bufs, n_bufs, params_host, param_gstride_host, n_params, x, x_bstride, N, n_per_group, H, W, y,
+                             y_ctot, y_coff, workspace, scale_shift, bn_total, stats, stats_len, saved_mean_invstd, training, momentum,
+                             eps, tc_scratch, tc_scratch_floats, stream, &h);
 }
 
 // Auto-regressive rollout, eval mode.  traj: [N, traj_ctot, H, W] with traj_ctot = c_hist + T*c_out; the caller fills the first
@@ -214,12 +285,12 @@ extern "C" int arpde_rollout(const arpde_op_t* ops, int n_ops, const arpde_buf_t
 // Backward of arpde_densed_forward (train or eval mode): what loss.backward() does through DenseED in the reference
 // (main.py:81).  Ops are visited in reverse; gradients of the activation buffers live in gwork (same layout as the
 // workspace; the last consumer of a buffer overwrites, earlier consumers accumulate, so no memset is needed).
-extern "C" int arpde_densed_backward(const arpde_op_t* ops, int n_ops, const arpde_buf_t* bufs, int n_bufs, void* const* params_host,
-                                     int n_params, const float* x, int64_t x_bstride, int N, int H, int W, const float* gy,
-                                     const float* y, const float* workspace, const float* scale_shift, int bn_total,
-                                     const float* saved_mean_invstd, float* gwork, float* gx, void* const* grads_host, float* T1,
-                                     float* T2, float* wT, double* d64, int training, float* tc_scratch, int64_t tc_scratch_floats,
-                                     arpde_stream_t stream_) {
+static int densed_backward_impl(const arpde_op_t* ops, int n_ops, const arpde_buf_t* bufs, int n_bufs, void* const* params_host,
+                                int n_params, const float* x, int64_t x_bstride, int N, int H, int W, const float* gy,
+                                const float* y, const float* workspace, const float* scale_shift, int bn_total,
+                                const float* saved_mean_invstd, float* gwork, float* gx, void* const* grads_host, float* T1,
+                                float* T2, float* wT, double* d64, int training, float* tc_scratch, int64_t tc_scratch_floats,
+                                arpde_stream_t stream_, const DpHook* dp) {
   cudaStream_t stream = (cudaStream_t)stream_;
   int rc = check_program(ops, n_ops, bufs, n_bufs, n_params); if (rc) return rc;
   ARPDE_CHECK_ARG(params_host && grads_host && x && gy && T1 && T2 && wT && d64, "densed_backward: null pointer");
@@ -291,10 +362,37 @@ extern "C" int arpde_densed_backward(const arpde_op_t* ops, int n_ops, const arp
       float* dgamma = o.bn_param >= 0 ? (float*)grads_host[o.bn_param] : nullptr;
       float* dbeta = o.bn_param >= 0 ? (float*)grads_host[o.bn_param + 1] : nullptr;
       rc = arpde_bn_relu_bwd_launch(T1, in, in_bs, scale, shift, mean, invstd, T2, d64, dest, dest_bs, dgamma, dbeta, N, o.cin, Hin, Win,
-                                    up_h, up_w, training, acc ? 1 : 0, stream);
+                                    up_h, up_w, training, acc ? 1 : 0, stream, dp);
       if (rc) return rc;
     }
     if (o.in_buf >= 0) written[o.in_buf] = 1;
   }
   return ARPDE_OK;
+}
+
+extern "C" int arpde_densed_backward(const arpde_op_t* ops, int n_ops, const arpde_buf_t* bufs, int n_bufs, void* const* params_host,
+                                     int n_params, const float* x, int64_t x_bstride, int N, int H, int W, const float* gy,
+                                     const float* y, const float* workspace, const float* scale_shift, int bn_total,
+                                     const float* saved_mean_invstd, float* gwork, float* gx, void* const* grads_host, float* T1,
+                                     float* T2, float* wT, double* d64, int training, float* tc_scratch, int64_t tc_scratch_floats,
+                                     arpde_stream_t stream) {
+  return densed_backward_impl(ops, n_ops, bufs, n_bufs, params_host, n_params, x, x_bstride, N, H, W, gy, y, workspace, scale_shift,
+                              bn_total, saved_mean_invstd, gwork, gx, grads_host, T1, T2, wT, d64, training, tc_scratch,
+                              tc_scratch_floats, stream, nullptr);
+}
+
+// Data-parallel backward: the (sum dz, sum dz*xhat) pairs of every BatchNorm are summed over the ranks between the reduction and the
+// apply pass (global-batch BatchNorm backward); dgamma / dbeta and the weight gradients stay per-rank sums, to be averaged by the
+// caller's gradient all-reduce.
+extern "C" int arpde_densed_backward_dp(const arpde_op_t* ops, int n_ops, const arpde_buf_t* bufs, int n_bufs, void* const* params_host,
+                                        int n_params, const float* x, int64_t x_bstride, int N, int H, int W, const float* gy,
+                                        const float* y, const float* workspace, const float* scale_shift, int bn_total,
+                                        const float* saved_mean_invstd, float* gwork, float* gx, void* const* grads_host, float* T1,
+                                        float* T2, float* wT, double* d64, int training, float* tc_scratch, int64_t tc_scratch_floats,
+                                        arpde_allreduce_fn allreduce, void* user, int dp_world, arpde_stream_t stream) {
+  ARPDE_CHECK_ARG(dp_world >= 1 && (dp_world == 1 || allreduce), "densed_backward_dp: %d ranks need an all-reduce callback", dp_world);
+  DpHook h; h.allreduce = (int (*)(void*, double*, long long))allreduce; h.user = user; h.world = dp_world;
+  return densed_backward_impl(ops, n_ops, bufs, n_bufs, params_host, n_params, x, x_bstride, N, H, W, gy, y, workspace, scale_shift,
+                              bn_total, saved_mean_invstd, gwork, gx, grads_host, T1, T2, wT, d64, training, tc_scratch,
+                              tc_scratch_floats, stream, &h);
 }

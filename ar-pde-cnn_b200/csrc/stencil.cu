@@ -410,7 +410,7 @@ extern "C" int arpde_cn_burgers2d_fwd(const float* uPred, int64_t up_bstride, co
                       up_bstride % 4 == 0 && u0_bstride % 4 == 0 && (pow2 || w4 % 32 == 0);
   const bool base_ok = (W % 4 == 0) && aligned16(uPred) && aligned16(uPred0) && (!ustar || aligned16(ustar)) && up_bstride % 4 == 0 &&
                        u0_bstride % 4 == 0 && (int64_t)H * W % 4 == 0;
-  static const int ty_env = getenv("ARPDE_STENCIL_TY") ? atoi(getenv("ARPDE_STENCIL_TY")) : 0;
+  static const int ty_env = arpde_dev_env("ARPDE_STENCIL_TY") ? atoi(arpde_dev_env("ARPDE_STENCIL_TY")) : 0;
   // rows wider than one warp's 128 columns: the rolling kernel needs its EDGE variant (halo scalars from global memory, 152 registers,
   // one CTA per SM: 2.3-2.4 TB/s at 256x256); the tiled kernel with the tallest tile that fits 96 KB reaches 2.9 TB/s there
   // (TY = 4 / 6 / 8 / 10 rows: 2.58 / 2.86 / 2.88 / 2.94 TB/s)
@@ -422,7 +422,7 @@ extern "C" int arpde_cn_burgers2d_fwd(const float* uPred, int64_t up_bstride, co
   // shared-memory tiled kernel is issue-bound (ncu: 70% issue-active, 2.2x the instructions, 48% of its shared-memory wavefronts
   // are bank conflicts of the halo scalars) and reaches 2.75 TB/s -- it serves widths the rolling kernel's lane mapping cannot
   // (W/4 neither a power of two nor a multiple of 32) and is selectable with ARPDE_STENCIL_SMEM=1 for A/B runs.
-  static const bool force_smem = getenv("ARPDE_STENCIL_SMEM") != nullptr;
+  static const bool force_smem = arpde_dev_env("ARPDE_STENCIL_SMEM") != nullptr;
   if (base_ok && TY >= 1 && tile_bytes <= 96 * 1024 && (force_smem || !vec_ok || (wide && TY >= 4))) {
     const int nstrips = (H + TY - 1) / TY;
     const int64_t items = (int64_t)N * nstrips;
@@ -437,9 +437,9 @@ extern "C" int arpde_cn_burgers2d_fwd(const float* uPred, int64_t up_bstride, co
       burgers2d_fwd_smem<false><<<(unsigned)blocks, 256, tile_bytes, (cudaStream_t)stream_>>>(uPred, up_bstride, uPred0, u0_bstride, ustar, sse_out, N, H, W, TY, k);
     }
   } else if (vec_ok) {
-    static const int ry_env = getenv("ARPDE_STENCIL_RY") ? atoi(getenv("ARPDE_STENCIL_RY")) : 0;
+    static const int ry_env = arpde_dev_env("ARPDE_STENCIL_RY") ? atoi(arpde_dev_env("ARPDE_STENCIL_RY")) : 0;
     const int RY = ry_env ? ry_env : 4;
-    static const int minb = getenv("ARPDE_STENCIL_MINB") ? atoi(getenv("ARPDE_STENCIL_MINB")) : 2;
+    static const int minb = arpde_dev_env("ARPDE_STENCIL_MINB") ? atoi(arpde_dev_env("ARPDE_STENCIL_MINB")) : 2;
     int lx_log2 = 0; while ((1 << lx_log2) < (w4 < 32 ? w4 : 32)) ++lx_log2;
     const bool edge = w4 > 32;
     const int G = 32 >> lx_log2, segs = w4 >> lx_log2, nstrips = (H + RY - 1) / RY;

@@ -130,18 +130,26 @@ def predictive_moments(traj, n_samples, betas=None, formula='2d'):
 
 
 @torch.no_grad()
-def swag_rollout(swag_nn, ic, tsteps, n_samples, diagCov=False, scale=1.0, generator=None, noise=None, formula='2d'):
+def swag_rollout(swag_nn, ic, tsteps, n_samples, diagCov=False, scale=1.0, generator=None, noise=None, formula='2d',
+                 sample_range=None, add_noise=True, out=None):
     """testSample() of the reference in one go: draw S posterior weight samples, roll every (sample, IC)
-    pair out for tsteps, return (traj [S*N, T+1, ...], mean, var, betas)."""
+    pair out for tsteps, return (traj [S*N, T+1, ...], mean, var, betas).
+
+    sample_range=(lo, hi): all n_samples weight vectors are drawn (so every rank of a sample-sharded job sees the same
+    draws) but only samples [lo, hi) are rolled out and reduced; betas always covers all n_samples.
+    add_noise=False: var is the plain (biased) sample variance -- the caller adds the noise term (parallel.py)."""
     flat, names, numels = swag_nn.sample_flat(n_samples, scale=scale, diagCov=diagCov, generator=generator, noise=noise)
     named = list(swag_nn.base.named_parameters())
-    traj = rollout(swag_nn, ic, tsteps, flat_weights=flat, named_params=named)
     lb_col = [i for i, (n, _) in enumerate(named) if n.endswith('log_beta')]
     betas = None
     if lb_col:
         off = sum(numels[:lb_col[0]])
         betas = flat[:, off].exp()
-    mean, var = predictive_moments(traj, n_samples, betas, formula)
+    lo, hi = (0, n_samples) if sample_range is None else sample_range
+    if not (0 <= lo < hi <= n_samples):
+        raise ValueError('sample_range %s outside [0, %d)' % ((lo, hi), n_samples))
+    traj = rollout(swag_nn, ic, tsteps, flat_weights=flat[lo:hi], named_params=named, out=out)
+    mean, var = predictive_moments(traj, hi - lo, betas if add_noise else None, formula)
     return traj, mean, var, betas
 
 

@@ -145,6 +145,7 @@ class _NegLogJoint(torch.autograd.Function):
         ctx.save_for_backward(o, t, log_beta.detach(), scratch, *ps)
         ctx.consts = consts
         ctx.shapes = [p.shape for p in params]
+        ctx.param_refs, ctx.lb_ref = list(params), log_beta      # identities for the gradient sink (no extra memory: same tensors)
         return loss
 
     @staticmethod
@@ -166,6 +167,21 @@ class _NegLogJoint(torch.autograd.Function):
             L.call('arpde_neg_log_joint_bwd', L.ptr(o), L.ptr(t), o.numel(), o.shape[0], L.ptr(lb), pp, nn_, len(ps),
                    float(ntrain), w_shape, w_rate, b_shape, b_rate, L.ptr(g), L.ptr(scratch), L.ptr(go), L.ptr(gt),
                    L.ptr(glb), L.ptr(gp), L.stream())
+        from . import program as P_
+        sink = P_.GRAD_SINK
+        if sink is not None and gp is not None and all(ctx.needs_input_grad[4:]):
+            # parameter gradients straight into the flat bucket (parallel.FlatGradBucket.capture()): one launch for all feature
+            # tensors when they are contiguous in the bucket in this order, one for log_beta
+            offs = [sink.offset_of(p) for p in ctx.param_refs]
+            if None not in offs and all(offs[i] + ps[i].numel() == offs[i + 1] for i in range(len(ps) - 1)):
+                sink.flat[offs[0]:offs[0] + P].add_(gp)
+                lb_off = sink.offset_of(ctx.lb_ref)
+                if glb is not None and lb_off is not None:
+                    sink.flat[lb_off:lb_off + 1].add_(glb.view(-1))
+                    glb = None
+                elif glb is not None:
+                    glb = glb.view(lb.shape)
+                return (None, go, gt, glb, *[None for _ in ps])
         gps = []
         off = 0
         for p, need in zip(ps, ctx.needs_input_grad[4:]):

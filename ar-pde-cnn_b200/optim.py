@@ -26,16 +26,24 @@ class Adam(torch.optim.Adam):
             with torch.enable_grad():
                 loss = closure()
         by_cfg = {}
+        # first pass: validate everything, so that a failure leaves every step counter and moment untouched
         for group in self.param_groups:
-            beta1, beta2 = group['betas']
             if group.get('maximize') or group.get('amsgrad'):
                 raise NotImplementedError('arpde_b200.optim.Adam: maximize / amsgrad are not implemented')
-            lr = float(group['lr'])
             for p in group['params']:
                 if p.grad is None:
                     continue
                 if not p.is_cuda or p.dtype != torch.float32 or p.grad.dtype != torch.float32 or p.grad.is_sparse:
                     raise RuntimeError('arpde_b200.optim.Adam updates dense fp32 CUDA parameters only; there is no CPU path')
+                st = self.state.get(p, {})
+                if not p.is_contiguous() or any(k in st and not st[k].is_contiguous() for k in ('exp_avg', 'exp_avg_sq')):
+                    raise RuntimeError('arpde_b200.optim.Adam needs contiguous parameters')
+        for group in self.param_groups:
+            beta1, beta2 = group['betas']
+            lr = float(group['lr'])
+            for p in group['params']:
+                if p.grad is None:
+                    continue
                 state = self.state[p]
                 if len(state) == 0:                      # same lazy state as torch.optim.Adam (non-capturable: step is a CPU scalar)
                     state['step'] = torch.tensor(0.0, dtype=torch.float32)
@@ -45,8 +53,6 @@ class Adam(torch.optim.Adam):
                 t = float(state['step'])
                 bc1, bc2 = 1 - beta1 ** t, 1 - beta2 ** t
                 g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
-                if not (p.is_contiguous() and state['exp_avg'].is_contiguous() and state['exp_avg_sq'].is_contiguous()):
-                    raise RuntimeError('arpde_b200.optim.Adam needs contiguous parameters')
                 key = (p.device, beta1, beta2, float(group['eps']))
                 by_cfg.setdefault(key, []).append((p, g, state['exp_avg'], state['exp_avg_sq'], lr / bc1, math.sqrt(bc2), float(group['weight_decay'])))
         for (dev, beta1, beta2, eps), items in by_cfg.items():

@@ -12,6 +12,9 @@ import torch.nn as nn
 from . import _lib as L
 
 BN_EPS_DEFAULT = 1e-5
+# data-parallel training hooks, set by the context managers of parallel.py (None = single process / plain autograd)
+BN_SYNC = None       # parallel.BatchNormSync: all-reduce of the train-mode BatchNorm sums over the ranks
+GRAD_SINK = None     # parallel.FlatGradBucket: parameter gradients are added straight into the flat bucket
 
 
 class Plan:
@@ -196,6 +199,11 @@ def layout(plan, N, H, W):
         off += N * b['ctot'] * h * w
         off = (off + 3) & ~3          # keep every buffer 16-byte aligned
         soff += 2 * b['ctot']
+    # BatchNorm directly on the network input (stand-alone _Transition / LastTransUp): tail slot for its batch statistics
+    for o in plan.ops:
+        if o['bn_param'] >= 0 and o['in_buf'] < 0:
+            soff += 2 * o['cin']
+            break
     return bufs, off, soff
 
 
@@ -274,16 +282,24 @@ class _Forward(torch.autograd.Function):
             work[off:off + N * ctot * h * w].view(N, ctot, h, w)[:, :Cin].copy_(x4)
         tc_len = int(L.lib.arpde_densed_tc_scratch_floats(ops_c, len(plan.ops), 1))
         tc = torch.empty((max(tc_len, 1),), device=dev, dtype=torch.float32)
+        sync = BN_SYNC if (training and BN_SYNC is not None and BN_SYNC.world_size() > 1) else None
         with torch.cuda.device(dev):
-            L.call('arpde_densed_forward', ops_c, len(plan.ops), bufs_c, len(bufs), pp, gs, len(tensors), L.ptr(x4), x_bs, N, N,
-                   H, W, y_ptr, y_ctot, 0, L.ptr(work), L.ptr(ss), plan.bn_total, L.ptr(stats), stats_len if training else 0,
-                   L.ptr(saved), 1 if training else 0, float(mom), float(eps), L.ptr(tc), tc_len, L.stream())
+            if sync is None:
+                L.call('arpde_densed_forward', ops_c, len(plan.ops), bufs_c, len(bufs), pp, gs, len(tensors), L.ptr(x4), x_bs, N, N,
+                       H, W, y_ptr, y_ctot, 0, L.ptr(work), L.ptr(ss), plan.bn_total, L.ptr(stats), stats_len if training else 0,
+                       L.ptr(saved), 1 if training else 0, float(mom), float(eps), L.ptr(tc), tc_len, L.stream())
+            else:
+                cb = L.allreduce_callback(sync, stats)
+                L.call('arpde_densed_forward_dp', ops_c, len(plan.ops), bufs_c, len(bufs), pp, gs, len(tensors), L.ptr(x4), x_bs, N, N,
+                       H, W, y_ptr, y_ctot, 0, L.ptr(work), L.ptr(ss), plan.bn_total, L.ptr(stats), stats_len,
+                       L.ptr(saved), 1, float(mom), float(eps), L.ptr(tc), tc_len, cb, 0, sync.world_size(), L.stream())
         if plan.out_is_buf:
             off, _, ctot, h, w = bufs[plan.ops[-1]['out_buf']]
             y = work[off:off + N * ctot * h * w].view(N, ctot, h, w)
             if grad_mode and (ctx.needs_input_grad[3] or any(ctx.needs_input_grad[4:])):
                 raise NotImplementedError('stand-alone dense layers/blocks are inference-only')
         ctx.plan, ctx.training, ctx.geom = plan, training, (N, H, W, x_bs, bufs, work_len, stats_len, eps)
+        ctx.sync = sync
         has_act = any(o['act'] for o in plan.ops)
         ctx.save_for_backward(x4, work, ss, saved if saved is not None else ss, y if has_act else ss, *[t for t in tensors])
         ctx.x_shape = x.shape

@@ -160,11 +160,15 @@ int arpde_conv_wgrad(const float* x, int64_t x_bstride, const float* scale, cons
                      float* scratch, int64_t scratch_floats, int path, arpde_stream_t stream);
 int arpde_conv_wgrad_tc_plan(int cin, int H, int W, int cout, int kh, int kw, int stride, int up, int32_t* out);
 
-/* Profiling hooks of the tensor-core kernel (development only; both default to off).  set_debug: per-role cycle counters of
- * CTA 0 of every following arpde_conv_fwd_tc / program launch are written to dev_buf (16 device int64; NULL = off).
- * set_debug_flags: ablation switches (1 = skip patch staging, 2 = skip the epilogue, 4 = skip the MMAs; results are garbage). */
+/* Profiling hooks of the tensor-core kernel.  They are process-global state, so they exist ONLY in a development build of the
+ * library (`ARPDE_DEV=1 bash ar-pde-cnn_b200/csrc/build.sh`, which also enables the ARPDE_* environment switches); the shipped
+ * library neither exports them nor reads the environment.  set_debug: per-role cycle counters of CTA 0 of every following
+ * arpde_conv_fwd_tc / program launch are written to dev_buf (16 device int64; NULL = off).  set_debug_flags: ablation switches
+ * (1 = skip patch staging, 2 = skip the epilogue, 4 = skip the MMAs; results are garbage). */
+#ifdef ARPDE_DEV
 int arpde_conv_tc_set_debug(long long* dev_buf);
 int arpde_conv_tc_set_debug_flags(int flags);
+#endif
 
 /* Random periodic initial conditions of the 2D Burgers data set on the device (InitPeriodicCond2d.__getitem__,
  * 2D-Burgers-SWAG/utils/burgerLoader2D.py:99-112): u[b][comp] = 2 f / max|f| + c[b][comp] with
@@ -244,6 +248,8 @@ int64_t arpde_densed_tc_scratch_floats(const arpde_op_t* ops, int n_ops, int gro
  * fills saved_mean_invstd with running_mean and 1/sqrt(running_var+eps)); gwork: gradient workspace, same size as
  * workspace; gx (nullable): gradient of the input [N,cin,H,W] compact; grads_host: HOST array (n_params entries) of
  * device float* receiving each parameter's gradient (NULL = not needed; running-stat slots are ignored).
+ * The stats scratch of the forward: when an op applies BatchNorm directly to the network input (in_buf == -1; a stand-alone
+ * _Transition / LastTransUp), stats_len includes 2*cin extra doubles at the tail for the input's batch statistics.
  * Scratch: T1 >= max N*cin*Hc*Wc floats over ops (conv-input resolution), T2 >= max(N*cin*H*W, N*cout_last*Ho*Wo) floats,
  * wT >= max weight numel floats, d64 >= max(weight numel, 2*max cin) doubles.  tc_scratch (nullable): arpde_densed_tc_scratch_floats(ops,
  * n_ops, 1) floats; with it the data-gradient convolutions of the stride-1 layers run on the tensor-core kernel. */
@@ -252,6 +258,27 @@ int arpde_densed_backward(const arpde_op_t* ops, int n_ops, const arpde_buf_t* b
                           const float* workspace, const float* scale_shift, int bn_total, const float* saved_mean_invstd,
                           float* gwork, float* gx, void* const* grads_host, float* T1, float* T2, float* wT, double* d64,
                           int training, float* tc_scratch, int64_t tc_scratch_floats, arpde_stream_t stream);
+
+/* Data-parallel training (one process per GPU; the mini-batch of initial conditions of 2D-Burgers-SWAG/main.py:47-61 split over
+ * `dp_world` ranks holding N samples each): same contracts as arpde_densed_forward / _backward, but train-mode BatchNorm uses the
+ * statistics of the GLOBAL mini-batch, which is what the reference computes on one device.  The library holds no communicator:
+ * between the kernels that accumulate a layer's sums -- (sum x, sum x^2) forward, (sum dz, sum dz*xhat) backward -- and the kernels
+ * that consume them it calls `allreduce(user, buf, n)` from the calling host thread; the callback must sum the n device doubles at
+ * buf in place over all ranks, ordered on `stream` (e.g. ncclAllReduce on that stream, or torch.distributed.all_reduce on the
+ * current stream), and return 0.  Weight / gamma / beta gradients stay per-rank sums for the caller's gradient all-reduce. */
+typedef int (*arpde_allreduce_fn)(void* user, double* buf, int64_t n);
+int arpde_densed_forward_dp(const arpde_op_t* ops, int n_ops, const arpde_buf_t* bufs, int n_bufs, void* const* params_host,
+                            const int64_t* param_gstride_host, int n_params, const float* x, int64_t x_bstride, int N,
+                            int n_per_group, int H, int W, float* y, int y_ctot, int y_coff, float* workspace,
+                            float* scale_shift, int bn_total, double* stats, int64_t stats_len, float* saved_mean_invstd,
+                            int training, double momentum, double eps, float* tc_scratch, int64_t tc_scratch_floats,
+                            arpde_allreduce_fn allreduce, void* user, int dp_world, arpde_stream_t stream);
+int arpde_densed_backward_dp(const arpde_op_t* ops, int n_ops, const arpde_buf_t* bufs, int n_bufs, void* const* params_host,
+                             int n_params, const float* x, int64_t x_bstride, int N, int H, int W, const float* gy, const float* y,
+                             const float* workspace, const float* scale_shift, int bn_total, const float* saved_mean_invstd,
+                             float* gwork, float* gx, void* const* grads_host, float* T1, float* T2, float* wT, double* d64,
+                             int training, float* tc_scratch, int64_t tc_scratch_floats, arpde_allreduce_fn allreduce, void* user,
+                             int dp_world, arpde_stream_t stream);
 
 /* Auto-regressive rollout in eval mode: the AR loops of main.py test()/testSample()
  * (2D-Burgers-SWAG/main.py:112-135,:160-179; 1D main.py :106-121,:148-163) without Python in the loop.

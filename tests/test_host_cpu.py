@@ -17,6 +17,11 @@ from arpde_b200 import program as P
 
 def test_library_exports_every_declared_symbol():
     hdr = open(os.path.join(ROOT, 'include', 'arpde.h')).read()
+    hdr = re.sub(r'#ifdef ARPDE_DEV.*?#endif', '', hdr, flags=re.S)        # development-build-only hooks are not in the shipped library
+    assert 'getenv' not in ''.join(open(os.path.join(ROOT, 'ar-pde-cnn_b200', 'csrc', f)).read() for f in
+                                   os.listdir(os.path.join(ROOT, 'ar-pde-cnn_b200', 'csrc')) if f.endswith('.cu')), \
+        'the shipped library must not read the environment (use arpde_dev_env)'
+    assert not hasattr(L.lib, 'arpde_conv_tc_set_debug')
     declared = set(re.findall(r'^(?:int|int64_t|const char\*)\s+(arpde_\w+)\s*\(', hdr, flags=re.M))
     assert len(declared) >= 20
     for name in declared:

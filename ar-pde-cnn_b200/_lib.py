@@ -84,10 +84,12 @@ lib.arpde_densed_tc_scratch_floats.argtypes = [vp, i32, i32]
 lib.arpde_densed_tc_scratch_floats.restype = C.c_int64
 lib.arpde_conv_fwd_tc_scratch_floats.argtypes = [i32, i32, i32, i32, i32]
 lib.arpde_conv_fwd_tc_scratch_floats.restype = C.c_int64
+lib.arpde_launch_count.argtypes = [i32]
+lib.arpde_launch_count.restype = C.c_int64
 lib.arpde_conv_wgrad_tc_scratch.argtypes = [i32] * 9
 lib.arpde_conv_wgrad_tc_scratch.restype = C.c_int64
 
-EXPORTS = sorted(list(_PROTOS) + ['arpde_last_error', 'arpde_densed_tc_scratch_floats', 'arpde_conv_fwd_tc_scratch_floats',
+EXPORTS = sorted(list(_PROTOS) + ['arpde_last_error', 'arpde_launch_count', 'arpde_densed_tc_scratch_floats', 'arpde_conv_fwd_tc_scratch_floats',
                                    'arpde_conv_wgrad_tc_scratch'])
 
 

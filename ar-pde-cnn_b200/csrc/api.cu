@@ -12,6 +12,15 @@ void arpde_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static thread_local long long g_launches = 0;
+void arpde_count_launch() { ++g_launches; }
+// kernels this thread has launched through the library since the last reset (reset != 0 clears the counter after reading it)
+extern "C" int64_t arpde_launch_count(int reset) {
+  const long long v = g_launches;
+  if (reset) g_launches = 0;
+  return v;
+}
+
 int arpde_num_sms() {
   static thread_local int cached_dev = -1, cached = 148;
   int dev = 0;

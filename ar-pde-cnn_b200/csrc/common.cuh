@@ -30,7 +30,14 @@ void arpde_set_error(const char* fmt, ...);
     }                                                                                \
   } while (0)
 
-#define ARPDE_LAUNCH_CHECK() ARPDE_CUDA(cudaGetLastError())
+// every kernel launch of the library is followed by this macro: error check + the calling thread's launch counter
+// (arpde_launch_count, a diagnostic like the error string; bench.py reports it as gpu_launches)
+void arpde_count_launch();
+#define ARPDE_LAUNCH_CHECK()          \
+  do {                                \
+    ARPDE_CUDA(cudaGetLastError());   \
+    arpde_count_launch();             \
+  } while (0)
 
 // Development switches (kernel ablations, tile-size overrides).  They read the environment ONLY in a library built with
 // -DARPDE_DEV (`ARPDE_DEV=1 bash build.sh`); the shipped library reads no environment variable and keeps no state but the

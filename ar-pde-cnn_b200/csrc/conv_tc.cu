@@ -1036,6 +1036,7 @@ int arpde_conv_tc_launch(const ConvDesc& d, const float* x, long long x_bs, cons
                       cudaGetErrorString(e), blocks, TC_THREADS, smem, smem_set, d.N, d.cin, d.H, d.W, d.cout, d.kh, d.kw, d.stride, d.up, a.tma);
       return ARPDE_ERR_CUDA;
     }
+    arpde_count_launch();
   }
   return ARPDE_OK;
 }

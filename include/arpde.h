@@ -9,7 +9,8 @@
  * Conventions
  *   - every pointer is a DEVICE pointer unless the name ends in _host; fp32 data, NCHW / NCL;
  *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), allocates nothing
- *     and keeps no state; scratch memory is passed in by the caller;
+ *     and keeps no state beyond two thread-local diagnostics (last error string, launch counter); scratch memory is passed in
+ *     by the caller;
  *   - return value: 0 = ok, otherwise an ARPDE_ERR_* code; arpde_last_error() gives the message of
  *     the calling thread's last failure.  Nothing throws or aborts.
  *   - "bstride" = distance in elements between consecutive batch items (inputs may be channel-slice
@@ -44,6 +45,9 @@ typedef void* arpde_stream_t;      /* cudaStream_t */
 
 int arpde_version(void);
 const char* arpde_last_error(void);
+/* Diagnostic: number of kernels the calling thread has launched through this library since the last reset (thread-local like the
+ * error string; reset != 0 clears it after reading).  bench.py reports it as "gpu_launches". */
+int64_t arpde_launch_count(int reset);
 
 /* ---------------------------------------------------------------------------------------------
  * Physics integrators (the loss target), forward.

@@ -25,22 +25,8 @@ REF = '/root/reference'
 PROJ = {'burgers2d': '2D-Burgers-SWAG', 'burgers1d': '1D-Burger-SWAG', 'ks1d': '1D-KS-SWAG'}
 
 
-def install_shims():
-    import torch.nn as nn
-    for name in ['matplotlib', 'matplotlib.pyplot', 'matplotlib.cm', 'matplotlib.ticker',
-                 'matplotlib.lines', 'matplotlib.colorbar', 'matplotlib.gridspec', 'matplotlib.patches',
-                 'mpl_toolkits', 'mpl_toolkits.axes_grid1']:
-        sys.modules[name] = mock.MagicMock()
-    for cls in (nn.Conv1d, nn.Conv2d):
-        orig = cls.__init__
-
-        def patched(self, *a, __orig=orig, **kw):
-            __orig(self, *a, **kw)
-            if self.padding_mode == 'circular':
-                self.padding = tuple(p // 2 for p in self.padding)
-                self._reversed_padding_repeated_twice = tuple(
-                    x for p in reversed(self.padding) for x in (p, p))
-        cls.__init__ = patched
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+from oracle.ref_shims import install_shims          # noqa: E402  (padding + matplotlib shims, shared with bench.py / T13)
 
 
 def gen(system):

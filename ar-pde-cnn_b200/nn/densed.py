@@ -14,6 +14,7 @@ per side, i.e. p per side (reference README.md:40).  Here `padding` holds the ef
 """
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 
 from .. import _lib as L
 from .. import program as P
@@ -21,12 +22,12 @@ from .. import program as P
 ACT_IDS = {'tanh': 1, 'relu': 2, 'lrelu': 3, 'sigmoid': 4, 'softplus': 5}
 
 
+def _needs_grad(*tensors):
+    return torch.is_grad_enabled() and any(t.requires_grad for t in tensors if t is not None)
+
+
 def _standalone_guard(*tensors):
     L.require_cuda(*tensors)
-    if torch.is_grad_enabled() and any(t.requires_grad for t in tensors if t is not None):
-        raise NotImplementedError(
-            'stand-alone layer forward is inference-only (use it under torch.no_grad()); '
-            'training goes through the fused DenseED.forward')
 
 
 def _as4(x):
@@ -41,6 +42,9 @@ class _CircConvMixin:
 
     def forward(self, x):
         _standalone_guard(x, self.weight)
+        if _needs_grad(x, self.weight):
+            # differentiable: the convolution is its own one-op program (forward, data and weight gradient through libarpde)
+            return P.run_module(self, x, self.training)
         x4, one_d = _as4(x.detach().contiguous())
         N, Cin, H, W = x4.shape
         k, s = self.kernel_size[-1], self.stride[-1]
@@ -70,6 +74,9 @@ class CircConv2d(_CircConvMixin, nn.Conv2d):
 class _BNMixin:
     def forward(self, x):
         _standalone_guard(x, self.weight)
+        if _needs_grad(x, self.weight, self.bias):
+            # generic differentiable path of a lone BatchNorm (only reached module by module: dropout / bilinear topologies)
+            return nn.modules.batchnorm._BatchNorm.forward(self, x)
         x4, one_d = _as4(x.detach().contiguous())
         N, C, H, W = x4.shape
         dev = x.device
@@ -103,6 +110,8 @@ class _Elementwise(nn.Module):
 
     def forward(self, x):
         _standalone_guard(x)
+        if _needs_grad(x):
+            return self._torch_forward(x)
         x4, one_d = _as4(x.detach().contiguous())
         N, C, H, W = x4.shape
         up_w = self.up
@@ -120,12 +129,19 @@ class ReLU(_Elementwise):
         super().__init__()
         self.inplace = inplace          # kept for repr parity; outputs are always fresh tensors
 
+    def _torch_forward(self, x):
+        return torch.relu(x)
+
 
 class Activation(_Elementwise):
     def __init__(self, name):
         super().__init__()
         self.act_id = ACT_IDS[name]
         self.name = name
+
+    def _torch_forward(self, x):
+        return {'tanh': torch.tanh, 'relu': torch.relu, 'lrelu': lambda t: F.leaky_relu(t, 0.01), 'sigmoid': torch.sigmoid,
+                'softplus': lambda t: F.softplus(t, beta=4)}[self.name](x)
 
 
 class UpsamplingNearest1d(_Elementwise):
@@ -135,9 +151,37 @@ class UpsamplingNearest1d(_Elementwise):
         super().__init__()
         self.scale_factor = scale_factor
 
+    def _torch_forward(self, x):
+        return F.interpolate(x, scale_factor=self.scale_factor, mode='nearest')
+
 
 class UpsamplingNearest2d(UpsamplingNearest1d):
     pass
+
+
+class UpsamplingLinear1d(nn.Module):
+    """F.interpolate(mode='linear', align_corners=True) (1D-*/nn/denseEDcirc.py UpsamplingLinear1d): no fused form -- a model that
+    contains it runs module by module (convolutions on libarpde, this op on torch)."""
+
+    def __init__(self, scale_factor=2.):
+        super().__init__()
+        self.scale_factor = scale_factor
+
+    def forward(self, x):
+        L.require_cuda(x)
+        return F.interpolate(x, scale_factor=self.scale_factor, mode='linear', align_corners=True)
+
+
+class UpsamplingBilinear2d(nn.Module):
+    """F.interpolate(mode='bilinear', align_corners=True) (denseEDcirc2d.py:24-31); see UpsamplingLinear1d."""
+
+    def __init__(self, scale_factor=2.):
+        super().__init__()
+        self.scale_factor = scale_factor
+
+    def forward(self, x):
+        L.require_cuda(x)
+        return F.interpolate(x, scale_factor=self.scale_factor, mode='bilinear', align_corners=True)
 
 
 def activation(name, *args):
@@ -148,15 +192,57 @@ def activation(name, *args):
     return Activation(key)
 
 
+def needs_generic(module, training):
+    """True when a sub-tree cannot run as the fused program: active dropout (train mode, p > 0) or a (bi)linear upsampling."""
+    for m in module.modules():
+        if isinstance(m, (UpsamplingLinear1d, UpsamplingBilinear2d)):
+            return True
+        if isinstance(m, _DenseLayer) and hasattr(m, 'norm2'):
+            return True        # the reference's (malformed) bottleneck dense layer ends in BatchNorm + ReLU, not in a convolution
+        if training and isinstance(m, nn.modules.dropout._DropoutNd) and m.p > 0:
+            return True
+    return False
+
+
+def generic_forward(module, x):
+    """Module-by-module forward (the reference's own nn.Sequential walk): every convolution is a libarpde call with its own
+    autograd node, BatchNorm / ReLU / dropout / upsampling are the torch ops the reference uses, the dense-layer concat is a
+    torch.cat.  Only topologies the fused program cannot express come here."""
+    if isinstance(module, _DenseLayer):
+        y = x
+        for ch in module.children():
+            y = generic_forward(ch, y)
+        return torch.cat([x, y], 1)
+    if isinstance(module, nn.Sequential):
+        for ch in module.children():
+            x = generic_forward(ch, x)
+        return x
+    return module(x)
+
+
 class _Fused(nn.Sequential):
     """A sub-tree that can run on its own (DenseED.forward_test walks top-level children)."""
 
     def forward(self, x):
+        if needs_generic(self, self.training):
+            return generic_forward(self, x)
         return P.run_module(self, x, self.training)
 
 
 def _mods(nd):
     return (CircConv1d, BatchNorm1d, UpsamplingNearest1d) if nd == 1 else (CircConv2d, BatchNorm2d, UpsamplingNearest2d)
+
+
+def _dropout(nd, p):
+    return nn.Dropout1d(p=p) if nd == 1 else nn.Dropout2d(p=p)
+
+
+def _upsampler(nd, upsample):
+    if upsample == 'nearest':
+        return (UpsamplingNearest1d if nd == 1 else UpsamplingNearest2d)(scale_factor=2)
+    if upsample == 'linear':
+        return (UpsamplingLinear1d if nd == 1 else UpsamplingBilinear2d)(scale_factor=2)
+    raise NotImplementedError("upsample=None (ConvTranspose) is not reachable from DenseED, which hard-codes 'nearest'")
 
 
 class _DenseLayer(_Fused):
@@ -165,15 +251,18 @@ class _DenseLayer(_Fused):
     def __init__(self, nd, in_features, growth_rate, drop_rate=0., bn_size=8, bottleneck=False, padding=1):
         super().__init__()
         Conv, BN, _ = _mods(nd)
-        if bottleneck and in_features > bn_size * growth_rate:
-            # the reference registers 'conv1' twice (second overwrites the first, :50-56); main.py forces
-            # bottleneck=False, so this branch is unreachable from the drivers
-            raise NotImplementedError('bottleneck dense layers are not reachable from the reference drivers')
         self.add_module('norm1', BN(in_features))
         self.add_module('relu1', ReLU(inplace=True))
         self.add_module('conv1', Conv(in_features, growth_rate, 2 * padding + 1, 1))
+        if bottleneck and in_features > bn_size * growth_rate:
+            # The reference registers 'conv1' twice (denseEDcirc2d.py:50-56): the 3x3 conv overwrites the 1x1 bottleneck IN PLACE,
+            # so the module order becomes norm1, relu1, conv1 (in -> growth, 3x3), norm2 (bn_size*growth channels), relu2 and the
+            # forward fails in BatchNorm unless bn_size == 1.  Same modules / state_dict keys here, same failure at call time
+            # (main.py forces bottleneck=False).
+            self.add_module('norm2', BN(bn_size * growth_rate))
+            self.add_module('relu2', ReLU(inplace=True))
         if drop_rate > 0:
-            raise NotImplementedError('drop_rate > 0 is not supported (reference default 0.)')
+            self.add_module('dropout', _dropout(nd, drop_rate))
         self.growth_rate = growth_rate
 
 
@@ -191,45 +280,51 @@ class _Transition(_Fused):
 
     def __init__(self, nd, in_features, out_features, down, bottleneck=True, drop_rate=0, padding=1, upsample='nearest'):
         super().__init__()
-        Conv, BN, Up = _mods(nd)
-        if drop_rate > 0:
-            raise NotImplementedError('drop_rate > 0 is not supported (reference default 0.)')
-        if upsample != 'nearest':
-            raise NotImplementedError("only upsample='nearest' (the value DenseED hard-codes) is supported")
+        Conv, BN, _ = _mods(nd)
         self.add_module('norm1', BN(in_features))
         self.add_module('relu1', ReLU(inplace=True))
         if down:
             if bottleneck:
                 self.add_module('conv1', Conv(in_features, out_features, 1, 1))
+                if drop_rate > 0:
+                    self.add_module('dropout1', _dropout(nd, drop_rate))
                 self.add_module('norm2', BN(out_features))
                 self.add_module('relu2', ReLU(inplace=True))
                 self.add_module('conv2', Conv(out_features, out_features, padding * 2 + 2, 2))
+                if drop_rate > 0:
+                    self.add_module('dropout2', _dropout(nd, drop_rate))
             else:
                 self.add_module('conv1', Conv(in_features, out_features, padding * 2 + 2, 2))
+                if drop_rate > 0:
+                    self.add_module('dropout1', _dropout(nd, drop_rate))
         else:
             if bottleneck:
                 self.add_module('conv1', Conv(in_features, out_features, 1, 1))
+                if drop_rate > 0:
+                    self.add_module('dropout1', _dropout(nd, drop_rate))
                 self.add_module('norm2', BN(out_features))
                 self.add_module('relu2', ReLU(inplace=True))
-                self.add_module('upsample', Up(scale_factor=2))
+                self.add_module('upsample', _upsampler(nd, upsample))
                 self.add_module('conv2', Conv(out_features, out_features, 3, 1))
             else:
-                self.add_module('upsample', Up(scale_factor=2))
+                self.add_module('upsample', _upsampler(nd, upsample))
                 self.add_module('conv2', Conv(in_features, out_features, 3, 1))
+            if drop_rate > 0:
+                self.add_module('dropout1', _dropout(nd, drop_rate))
 
 
 def last_decoding(nd, in_features, out_channels, drop_rate=0., upsample='nearest'):
     """denseEDcirc2d.py:165-190"""
-    Conv, BN, Up = _mods(nd)
-    if drop_rate > 0. or upsample != 'nearest':
-        raise NotImplementedError("last_decoding supports drop_rate=0, upsample='nearest' (what DenseED passes)")
+    Conv, BN, _ = _mods(nd)
     last_up = _Fused()
     last_up.add_module('norm1', BN(in_features))
     last_up.add_module('relu1', ReLU(True))
     last_up.add_module('conv1', Conv(in_features, in_features // 2, 1, 1))
+    if drop_rate > 0.:
+        last_up.add_module('dropout1', _dropout(nd, drop_rate))
     last_up.add_module('norm2', BN(in_features // 2))
     last_up.add_module('relu2', ReLU(True))
-    last_up.add_module('upsample', Up(scale_factor=2))
+    last_up.add_module('upsample', _upsampler(nd, upsample))
     last_up.add_module('conv2', Conv(in_features // 2, in_features // 4, 3, 1))
     last_up.add_module('norm3', BN(in_features // 4))
     last_up.add_module('relu3', ReLU(True))
@@ -292,6 +387,8 @@ class _DenseEDBase(nn.Module):
             self.in_channels = in_channels
 
     def forward(self, x):
+        if needs_generic(self.features, self.training):
+            return generic_forward(self.features, x)
         return P.run_module(self.features, x, self.training)
 
     def forward_test(self, x):

@@ -60,6 +60,8 @@ def _flatten(module, out):
         out.append(('up', module))
     elif isinstance(module, D.Activation):
         out.append(('act', module))
+    elif isinstance(module, nn.modules.dropout._DropoutNd):
+        pass        # identity here: the fused program only runs when no dropout is active (eval mode or p == 0; nn.densed.needs_generic)
     else:
         raise NotImplementedError('module %s cannot be compiled into the fused program' % type(module).__name__)
     return out

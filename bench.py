@@ -8,10 +8,11 @@ benchmark = one complete job: draw the 30 weight samples, roll all 1920 (sample,
 reduce the predictive mean/variance.  metric = AR steps x samples / s = S*N_ic*T / time.
 
     python bench.py --gpus N --steps K --warmup W          # our CUDA path (N>1: launched under torchrun)
-    python bench.py --impl reference ...                   # the reference's CPU (PyTorch) path, oracle port
+    python bench.py --impl reference ...                   # the reference's own CPU path (its modules + testSample())
 
-Multi-GPU: initial conditions are sharded across ranks (every rank runs all weight samples for its own 64 ICs;
-weak scaling, no data-path collective) followed by one NCCL all-gather of the predictive mean and variance.
+Multi-GPU (strong scaling): the FIXED 64-IC job is sharded -- rank r runs all 30 weight samples for its 64/N initial
+conditions (the sample moments stay local, no data-path collective), then ONE NCCL gather of the predictive mean and
+variance to rank 0.  The weak-scaling number (64 ICs per GPU) is reported next to it as `weak`.
 """
 import argparse
 import json
@@ -26,7 +27,9 @@ sys.path.insert(0, ROOT)
 
 S_SAMPLES, N_IC, T_STEPS, NEL = 30, 64, 100, 64
 MODEL_MFLOP = 267.32          # forward MFLOP per sample-step of the default 2D net
-STENCIL_BYTES_PT = 24         # K2 API form: read uPred + uPred0, write ustar, 2 comps x 4 B
+C5_MFLOP = 12233.7            # wide net (growth 32) at 256x256
+KS_MFLOP = 0.51
+STENCIL_BYTES_PT = {'fwd': 24, 'fwd_sse': 16, 'bwd': 40}      # per grid point, 2D
 
 
 def load_peaks():
@@ -75,12 +78,12 @@ class ClockSampler:
                 'reasons': sorted(reasons), 'samples': len(sm)}
 
 
-def make_ics(n, first=0):
-    """InitPeriodicCond2d of the reference (utils/burgerLoader2D.py:80-116), seeded per index."""
+def make_ics(n, first=0, nel=NEL):
+    """InitPeriodicCond2d of the reference (utils/burgerLoader2D.py:80-116), seeded per index (the benchmark's input spec)."""
     import numpy as np
     import torch
     order = 4
-    x = np.linspace(0, 1, NEL + 1)[:-1]
+    x = np.linspace(0, 1, nel + 1)[:-1]
     xx, yy = np.meshgrid(x, x)
     aa, bb = np.meshgrid(np.arange(-order, order + 1), np.arange(-order, order + 1))
     k = np.stack((aa.flatten(), bb.flatten()), 1)
@@ -92,24 +95,55 @@ def make_ics(n, first=0):
         c = -1 + np.random.rand(2) * 2
         f = np.dot(lam[0], np.cos(kxly)) + np.dot(lam[1], np.sin(kxly))
         f = 2 * f / np.amax(np.abs(f), axis=1, keepdims=True) + c[:, None]
-        out.append(torch.FloatTensor(f).reshape(-1, NEL, NEL))
+        out.append(torch.FloatTensor(f).reshape(-1, nel, nel))
     return torch.stack(out, 0)
 
 
-def build_swag(device, seed=12345):
+def make_ks_ics(n, nel=96, seed=12345):
+    """KS initial states: truncated Fourier series of 1D-KS-SWAG/utils/ksLoader.py:40-84 (amplitude U(2.5,3.5), three sine modes
+    around the most unstable wave number), np.random.seed(12345) as SURVEY.md 8d prescribes.  Returns [n, 1, nel]."""
+    import numpy as np
+    import torch
+    np.random.seed(seed)
+    x0, x1 = 0.0, 22 * np.pi
+    x = np.linspace(x0, x1, nel + 1)
+    out = []
+    for _ in range(n):
+        a = np.random.rand() + 2.5
+        k = np.linspace(1, 3, 3)
+        mu_n = int((x1 - x0) / (2 * np.pi * np.sqrt(2)))
+        nmode = np.round(np.abs(0.5 * np.random.randn() + mu_n))
+        wl = x1 / (2 * nmode)
+        c = 2 * np.pi * np.random.rand()
+        lam = np.ones(3); lam[1] = 2 * np.random.randn(); lam = lam / k
+        f = np.sum(lam[:, None] * np.sin(np.outer(k, x) * np.pi / wl + c), axis=0)
+        f = 2 * a * (f - f.min()) / (f.max() - f.min()) - a
+        out.append(torch.Tensor(f[:-1]).view(1, 1, -1))
+    return torch.cat(out, 0)
+
+
+def _quiet():
+    import contextlib, io
+    return contextlib.redirect_stdout(io.StringIO())
+
+
+def build_swag(device, seed=12345, classes=None):
     """Default 2D model with torch.manual_seed init (no 2D checkpoint is shipped: reference .MISSING_LARGE_BLOBS)
-    and a SWAG posterior built by 30 collect() calls on perturbed weights."""
+    and a SWAG posterior built by 30 collect() calls on perturbed weights.  classes: (DenseED, BayesNN, SwagNN)
+    -- this repo's modules by default, the reference's own for --impl reference."""
     import types
     import numpy as np
     import torch
-    from arpde_b200.nn.densed import DenseED2d
-    from arpde_b200.nn.bayesnn import BayesNN
-    from arpde_b200.nn.swag import SwagNN
-    import contextlib, io
+    if classes is None:
+        from arpde_b200.nn.densed import DenseED2d
+        from arpde_b200.nn.bayesnn import BayesNN
+        from arpde_b200.nn.swag import SwagNN
+        classes = (DenseED2d, BayesNN, SwagNN)
+    DenseED, BayesNN, SwagNN = classes
     torch.manual_seed(seed); np.random.seed(seed)
-    args = types.SimpleNamespace(dt=0.005, device=torch.device(device), nic=3)
-    with contextlib.redirect_stdout(io.StringIO()):
-        model = DenseED2d(6, 2, [4], growth_rate=4, init_features=96).to(device)
+    args = types.SimpleNamespace(dt=0.005, device=torch.device(device), nic=3, nel=NEL)
+    with _quiet():
+        model = DenseED(6, 2, [4], growth_rate=4, init_features=96).to(device)
         bayes = BayesNN(args, model)
         swag = SwagNN(args, bayes, full_cov=True, max_models=30)
     g = torch.Generator(device='cpu'); g.manual_seed(seed)
@@ -124,18 +158,66 @@ def build_swag(device, seed=12345):
         for p, b in zip(bayes.parameters(), base):
             p.copy_(b)
     swag.eval()
-    return swag
+    return swag, args
 
 
-def cpu_reference_rate(S, N, T, threads=None):
-    """The reference's CPU path (PyTorch ops, oracle port of the same loops) on a bounded sample of the workload."""
-    import torch
-    from oracle import arpde_oracle as O
-    import types, contextlib, io
+# ------------------------------------------------------------------------------------------------------------------
+# reference arm: the reference's own modules and its own testSample() loop, CPU
+# ------------------------------------------------------------------------------------------------------------------
+_REF = {}
+
+
+def reference_rate(S, N, T, threads=None):
+    """sample-steps/s of the reference's CPU path on a bounded sample of the workload.
+
+    With the reference staged (baseline/_ref, or /root/reference in the build container): its own DenseED / BayesNN / SwagNN
+    modules (padding shim of oracle/ref_shims.py) driven by its own main.testSample() -- sample a weight vector, roll the test
+    loader out with torch.cat history updates -- followed by the sample mean / variance of post/plotBARContour.py:85-104 in numpy
+    (kind 'reference').  Without it: the oracle port of the same loops (kind 'port')."""
     import numpy as np
+    import torch
     torch.set_num_threads(threads or os.cpu_count())
+    from oracle import ref_shims
+    if ref_shims.ref_root() is not None:
+        if 'swag' not in _REF:
+            ref_shims.import_reference('burgers2d')
+            from nn.denseEDcirc2d import DenseED
+            from nn.bayesNN import BayesNN
+            from nn.swag import SwagNN
+            import importlib
+            _REF['main'] = importlib.import_module('main')
+            _REF['swag'], _REF['args'] = build_swag('cpu', classes=(DenseED, BayesNN, SwagNN))
+        main, swag, args = _REF['main'], _REF['swag'], _REF['args']
+        ic = make_ics(N)
+        target = torch.zeros(N, T + 1, 2, NEL, NEL)
+        loader = torch.utils.data.DataLoader(torch.utils.data.TensorDataset(ic, target), batch_size=N, shuffle=False)
+        t0 = time.perf_counter()
+        with torch.no_grad(), _quiet():
+            u_out, _ = main.testSample(args, swag, loader, tstep=T, n_samples=S, test_every=1)      # [N, S, T+1, 2, H, W]
+        pred = u_out.numpy()
+        mean = np.mean(pred, axis=1)
+        var = 1.0 / swag.base.beta() + np.mean(pred ** 2, axis=1) - mean ** 2
+        dt = time.perf_counter() - t0
+        assert np.isfinite(var).all()
+        return S * N * T / dt, dt, 'reference'
+    from oracle import arpde_oracle as O
+    if 'sd' not in _REF:
+        _REF['sd'], _ = build_swag_port()
+    sd = _REF['sd']
+    ic = make_ics(N)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        for s in range(S):        # one weight sample at a time, as testSample() does
+            step = lambda inp: O.densed_forward('burgers2d', sd, inp, [4], training=False)
+            O.rollout('burgers2d', step, ic, 3, T)
+    dt = time.perf_counter() - t0
+    return S * N * T / dt, dt, 'port'
+
+
+def build_swag_port():
+    """state dict of the default architecture for the oracle port (plain torch, no GPU needed)"""
+    import torch
     torch.manual_seed(12345)
-    # weights: default init of the same architecture, built with plain torch (no GPU needed)
     sd = {}
     def conv(name, co, ci, k): sd[name + '.weight'] = torch.randn(co, ci, k, k) / (ci * k * k) ** 0.5
     def bn(name, c):
@@ -148,109 +230,236 @@ def cpu_reference_rate(S, N, T, threads=None):
     bn(f + 'LastTransUp.norm1', 64); conv(f + 'LastTransUp.conv1', 32, 64, 1); bn(f + 'LastTransUp.norm2', 32)
     conv(f + 'LastTransUp.conv2', 16, 32, 3); bn(f + 'LastTransUp.norm3', 16); conv(f + 'LastTransUp.conv3', 2, 16, 5)
     sd[f + 'LastTransUp.conv3.weight'] *= 0.05
-    ic = make_ics(N)
-    t0 = time.perf_counter()
-    with torch.no_grad():
-        for s in range(S):        # one weight sample at a time, as testSample() does
-            step = lambda inp: O.densed_forward('burgers2d', sd, inp, [4], training=False)
-            O.rollout('burgers2d', step, ic, 3, T)
-    dt = time.perf_counter() - t0
-    return S * N * T / dt, dt
+    return sd, None
+
+
+REF_SAMPLE = (2, 64, 4)      # S, N_ic, T of one reference-arm step (of 30 x 64 x 100)
 
 
 def run_reference(args):
     """--impl reference: rank 0 times the CPU path; other ranks exit."""
     if int(os.environ.get('RANK', '0')) != 0:
         return
-    import torch
-    S, N, T = 2, 64, 4
+    S, N, T = REF_SAMPLE
     cores = os.cpu_count()
+    kind = 'port'
     for _ in range(args.warmup):
-        cpu_reference_rate(1, 8, 1)
-    t0 = time.perf_counter()
+        reference_rate(1, 8, 1)
     tot = 0.0
     for _ in range(args.steps):
-        rate, dt = cpu_reference_rate(S, N, T)
+        rate, dt, kind = reference_rate(S, N, T)
         tot += dt
     value = args.steps * S * N * T / tot
-    sample = 'S=%d weight samples x %d ICs x T=%d steps per step (of 30x64x100), oracle port of the reference PyTorch CPU path' % (S, N, T)
+    how = ("the reference's own modules (nn/denseEDcirc2d.py, bayesNN.py, swag.py) driven by its main.testSample(), then numpy sample mean/variance"
+           if kind == 'reference' else 'oracle port of the reference PyTorch CPU loops (reference not staged on this box)')
+    sample = 'S=%d weight samples x %d ICs x T=%d steps per step (of 30x64x100), %s, torch CPU with %d threads' % (S, N, T, how, cores)
     line = {'impl': 'reference', 'metric': 'ar_steps_x_samples_per_s', 'value': value, 'unit': 'sample-steps/s', 'n_gpus': args.gpus,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * tot / args.steps, 'higher_is_better': True,
-            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': workload_config(args.gpus),
-            'cpu_baseline': {'value': value, 'unit': 'sample-steps/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+            'cpu_baseline': {'value': value, 'unit': 'sample-steps/s', 'cores': cores, 'kind': kind, 'sample': sample},
             'e2e': {'value': value, 'unit': 'sample-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     print(json.dumps(line))
 
 
-def train_step_probe(dev, B=128, tback=2, nwarm=3, nrep=10, rank=0, world=1):
-    """Training-step timing (SURVEY.md 8 row M5 + P1 + L1; BASELINE config C2): every rank takes its own mini-batch of B random Fourier
-    ICs (weak scaling), runs a tback-step BPTT window (DenseED forward with batch-statistics BatchNorm, Crank-Nicolson target, negative
-    log joint), loss.backward(), ONE flat-bucket gradient all-reduce over NCCL when world > 1, and the Adam step
-    (2D-Burgers-SWAG/main.py:61-91).  Reported next to the headline; not part of the timed rollout."""
-    import contextlib, io, types
+# ------------------------------------------------------------------------------------------------------------------
+# training step (BASELINE config C3)
+# ------------------------------------------------------------------------------------------------------------------
+def train_step_probe(dev, B_total=128, weak=False, tback=2, nwarm=3, nrep=10, rank=0, world=1):
+    """Training-step timing (SURVEY.md 8 rows M5 + P1 + L1; BASELINE config C3: mini-batch of 128 random Fourier ICs data-parallel over
+    the GPUs).  Strong form: the B = 128 mini-batch is split, B/N per rank; weak form: 128 per rank.  Every rank runs a tback-step
+    BPTT window (DenseED forward with GLOBAL-batch BatchNorm statistics, Crank-Nicolson target, negative log joint), backward with the
+    parameter gradients accumulated straight into the flat bucket, ONE gradient all-reduce over NCCL and the one-launch Adam step
+    (2D-Burgers-SWAG/main.py:61-91)."""
+    import types
     import numpy as np
     import torch
+    import torch.distributed as dist
     from arpde_b200.nn.densed import DenseED2d
     from arpde_b200.nn.bayesnn import BayesNN
     from arpde_b200.nn.swag import SwagNN
     from arpde_b200.nn.integrators import Burger2DIntegrate
+    from arpde_b200 import parallel as PL
+    from arpde_b200 import _lib as L
     torch.manual_seed(0); np.random.seed(0)
     a = types.SimpleNamespace(dt=0.005, device=dev, nic=3)
-    with contextlib.redirect_stdout(io.StringIO()):
+    with _quiet():
         model = DenseED2d(6, 2, [4], growth_rate=4, init_features=96).to(dev)
         bayes = BayesNN(a, model); swag = SwagNN(a, bayes, full_cov=True, max_models=30)
         integ = Burger2DIntegrate(1.0 / NEL, nu=0.005, grad_kernels=[3, 3], device=dev)
     from arpde_b200.optim import Adam
     opt = Adam([{'params': [bayes.model.log_beta], 'lr': 1e-3}, {'params': bayes.model.features.parameters()}], lr=1e-3)
     from arpde_b200.data import InitPeriodicCond2d
+    B = B_total if weak else B_total // world
     ic = InitPeriodicCond2d(NEL, 1 << 30, device=dev).batch(range(rank * B, rank * B + B))      # synthesised on the device (csrc/ic.cu)
     swag.train()
-    bucket = None
-    if world > 1:
-        import torch.distributed as dist
-        from arpde_b200.parallel import FlatGradBucket
-        bucket = FlatGradBucket([bayes.model.log_beta] + list(bayes.model.features.parameters()))
+    bucket = PL.FlatGradBucket([bayes.model.log_beta] + list(bayes.model.features.parameters()))
+    ntrain = 10
 
     def step():
         inp = ic.repeat(1, 3, 1, 1)
         loss = 0
-        for _ in range(tback):
-            u_pred = swag(inp[:, -6:])
-            ustar = integ.crankNicolson(u_pred, inp[:, -2:], 0.003)
-            loss = loss + swag.calc_neg_log_joint(u_pred, ustar, 10)
-            inp = torch.cat([inp, u_pred], 1)
-        loss.backward()
-        if bucket is not None:
-            bucket.all_reduce_(average=True)
-        opt.step(); opt.zero_grad()
+        bucket.zero_()
+        with PL.sync_batchnorm():
+            for _ in range(tback):
+                u_pred = swag(inp[:, -6:])
+                ustar = integ.crankNicolson(u_pred, inp[:, -2:], 0.003)
+                loss = loss + swag.calc_neg_log_joint(u_pred, ustar, ntrain)
+                inp = torch.cat([inp, u_pred], 1)
+            with bucket.capture():
+                loss.backward()
+        bucket.all_reduce_()
+        opt.step()
     for _ in range(nwarm):
         step()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
+    L.lib.arpde_launch_count(1)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(nrep):
         step()
     e1.record(); torch.cuda.synchronize()
+    launches = int(L.lib.arpde_launch_count(1)) // nrep
     ms = e0.elapsed_time(e1) / nrep
     if world > 1:                                   # slowest rank
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    return {'ms': ms, 'value': world * tback * B / ms * 1e3, 'unit': 'sample-steps/s', 'batch_per_gpu': B, 'n_gpus': world, 'tback': tback,
-            'scaling': 'weak', 'parallelism': 'mini-batch sharded x%d, one flat-bucket gradient all-reduce (NCCL) per optimizer step' % world,
+    return {'ms': ms, 'value': world * tback * B / ms * 1e3, 'unit': 'sample-steps/s', 'batch_total': world * B, 'batch_per_gpu': B, 'n_gpus': world,
+            'tback': tback, 'scaling': 'weak' if weak else 'strong', 'library_launches_per_step': launches,
+            'parallelism': 'mini-batch sharded x%d: global-batch BatchNorm (per-layer all-reduce of the fp64 sums), gradients accumulated in one flat '
+                           'bucket, one all-reduce (NCCL) per optimizer step' % world,
             'what': 'forward (batch-stat BN) + Crank-Nicolson + neg log joint + backward (tensor-core data and weight gradients) + one-launch Adam, '
                     'mean of %d steps after %d warm-up (CUDA events, max over ranks)' % (nrep, nwarm)}
 
 
 def workload_config(n_gpus):
-    return {'workload': 'C4: 2D coupled Burgers SWAG inference, %d weight samples x %d ICs/GPU x %d AR steps, %dx%d grid, DenseED blocks=[4] growth=4 init_features=96'
-                        % (S_SAMPLES, N_IC, T_STEPS, NEL, NEL),
-            'samples': S_SAMPLES, 'ics_per_gpu': N_IC, 'ar_steps': T_STEPS, 'grid': [NEL, NEL],
-            'parallelism': 'ic-shard x%d + final all-gather of mean/var' % n_gpus,
-            'l2': 'inputs larger than L2 (per-step activations 4.3 GB, stencil batch 189 MB)'}
+    per = N_IC // n_gpus if N_IC % n_gpus == 0 else None
+    return {'workload': 'C4: 2D coupled Burgers SWAG inference, %d weight samples x %d ICs (fixed job, %s ICs per GPU) x %d AR steps, %dx%d grid, '
+                        'DenseED blocks=[4] growth=4 init_features=96' % (S_SAMPLES, N_IC, per, T_STEPS, NEL, NEL),
+            'samples': S_SAMPLES, 'ics_total': N_IC, 'ics_per_gpu': per, 'ar_steps': T_STEPS, 'grid': [NEL, NEL],
+            'parallelism': 'ic-shard x%d (strong scaling of the fixed 64-IC job) + final NCCL gather of mean/var to rank 0' % n_gpus,
+            'l2': 'inputs larger than L2 (per-step activations %.1f GB per GPU; stencil timings rotate 4 buffer sets, each > L2 / 4)' % (4.3 / n_gpus)}
+
+
+def time_cuda(fn, nrep, nwarm=3):
+    import torch
+    for _ in range(nwarm):
+        fn(0)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(nrep):
+        fn(i)
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / nrep
+
+
+def stencil_rooflines(dev, peaks):
+    """K2 (fused periodic stencil + Crank-Nicolson) against the measured HBM peak with FOUR rotating buffer sets per case (SURVEY.md H5:
+    no tensor of launch i+1 can be L2-resident from launch i), at the C4 rollout batch (1920 x 64x64) and at C5 (256 x 256x256):
+    forward API form (24 B/pt), fused-loss form (16 B/pt, no ustar written) and the adjoint (40 B/pt)."""
+    import torch
+    import arpde_b200._lib as L
+    out = {}
+    NSETS = 4
+    for tag, (B, n) in (('c4_64', (S_SAMPLES * N_IC, 64)), ('c5_256', (256, 256))):
+        sets = []
+        for _ in range(NSETS):
+            sets.append([torch.randn((B, 2, n, n), device=dev) for _ in range(3)] + [torch.empty((B, 2, n, n), device=dev) for _ in range(3)])
+        sse = torch.zeros((NSETS,), device=dev, dtype=torch.float64)
+        pts = B * n * n
+        bs = 2 * n * n
+
+        def fwd(i):
+            s = sets[i % NSETS]
+            L.call('arpde_cn_burgers2d_fwd', L.ptr(s[0]), bs, L.ptr(s[1]), bs, L.ptr(s[3]), 0, B, n, n, 1.0 / n, 0.005, 0.005, 0, L.stream())
+
+        def fwd_sse(i):
+            s = sets[i % NSETS]
+            L.call('arpde_cn_burgers2d_fwd', L.ptr(s[0]), bs, L.ptr(s[1]), bs, 0, sse.data_ptr() + 8 * (i % NSETS), B, n, n, 1.0 / n, 0.005, 0.005, 0, L.stream())
+
+        def bwd(i):
+            s = sets[i % NSETS]
+            L.call('arpde_cn_burgers2d_bwd', L.ptr(s[0]), bs, L.ptr(s[1]), bs, L.ptr(s[2]), L.ptr(s[4]), L.ptr(s[5]), B, n, n, 1.0 / n, 0.005, 0.005, 0, L.stream())
+
+        for name, fn in (('fwd', fwd), ('fwd_sse', fwd_sse), ('bwd', bwd)):
+            ms = time_cuda(fn, 20)
+            byts = pts * STENCIL_BYTES_PT[name]
+            gbs = byts / (ms * 1e-3) / 1e9
+            out['%s_%s' % (tag, name)] = {'ms': ms, 'bytes_per_launch': byts, 'achieved': gbs, 'frac': gbs / peaks['hbm_gbs'],
+                                          'states': B, 'grid': [n, n], 'bytes_per_point': STENCIL_BYTES_PT[name], 'rotating_sets': NSETS}
+        del sets
+        torch.cuda.empty_cache()
+    return out
+
+
+def ks_probe(dev):
+    """BASELINE config C2: 1D Kuramoto-Sivashinsky DenseED with SWAG, 30 posterior samples x 64 ICs x 200 AR steps on one GPU; weights and
+    SWAG posterior = the reference's shipped epoch-200 checkpoint (tests/golden/ks1d_ckpt200.npz holds its state dict)."""
+    import types
+    import numpy as np
+    import torch
+    from arpde_b200 import engine
+    from arpde_b200 import _lib as L
+    from arpde_b200.nn.densed import DenseED1dKS
+    from arpde_b200.nn.bayesnn import BayesNN
+    from arpde_b200.nn.swag import SwagNN
+    z = np.load(os.path.join(ROOT, 'tests', 'golden', 'ks1d_ckpt200.npz'))
+    K = int(z['max_models'])
+    a = types.SimpleNamespace(dt=0.1, device=dev, nic=2)
+    np.random.seed(0)
+    with _quiet():
+        model = DenseED1dKS(2, 1, [4], growth_rate=4, init_features=32).to(dev)
+        swag = SwagNN(a, BayesNN(a, model), full_cov=True, max_models=K)
+    swag.load_state_dict({k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith('sd/')}, strict=True)
+    swag.eval()
+    S, N, T = 30, 64, 200
+    ic = make_ks_ics(N).to(dev)
+    gen = torch.Generator(device=dev); gen.manual_seed(7)
+    res = {}
+
+    def job(_):
+        res['out'] = engine.swag_rollout(swag, ic, T, S, generator=gen, formula='1d')
+    L.lib.arpde_launch_count(1)
+    job(0)
+    launches = int(L.lib.arpde_launch_count(1))
+    ms = time_cuda(job, 3, nwarm=1)
+    traj, mean, var, betas = res['out']
+    return {'value': S * N * T / ms * 1e3, 'unit': 'sample-steps/s', 'ms_per_job': ms, 'us_per_ar_step': 1e3 * ms / T, 'samples': S, 'ics': N,
+            'ar_steps': T, 'grid': 96, 'tflops': S * N * T * KS_MFLOP * 1e6 / (ms * 1e-3) / 1e12, 'library_launches_per_job': launches,
+            'finite': bool(torch.isfinite(mean).all().item()),
+            'weights': "reference's shipped 1D-KS-SWAG/post/networks/torchSwagModel_epoch200.pth (via tests/golden/ks1d_ckpt200.npz), full-covariance samples (K = %d)" % K}
+
+
+def c5_probe(dev, peaks):
+    """BASELINE config C5: scaled synthetic 256x256 grid, wide DenseED (growth 32, init_features 96): AR rollout of 32 initial conditions,
+    every layer but the output conv on the tensor-core kernel."""
+    import torch
+    from arpde_b200 import engine
+    from arpde_b200.nn.densed import DenseED2d
+    torch.manual_seed(5)
+    with _quiet():
+        m = DenseED2d(6, 2, [4], growth_rate=32, init_features=96).to(dev)
+    with torch.no_grad():
+        m.features.LastTransUp.conv3.weight.mul_(0.05)
+    m.eval()
+    N, T = 32, 4
+    ic = make_ics(N, nel=256).to(dev)
+    res = {}
+
+    def job(_):
+        res['traj'] = engine.rollout(m, ic, T)
+    ms = time_cuda(job, 3, nwarm=1)
+    ok = bool(torch.isfinite(res['traj']).all().item())
+    del res
+    torch.cuda.empty_cache()
+    tf = N * T * C5_MFLOP * 1e6 / (ms * 1e-3) / 1e12
+    return {'value': N * T / ms * 1e3, 'unit': 'sample-steps/s', 'ms_per_ar_step': ms / T, 'ics': N, 'ar_steps': T, 'grid': [256, 256], 'tflops': tf,
+            'frac_of_bf16_peak': tf / peaks['bf16_tflops'], 'frac_of_3xtf32_ceiling': tf / (peaks['bf16_tflops'] / 6), 'finite': ok,
+            'model': 'DenseED blocks=[4] growth=32 init_features=96 (220 576 parameters, 12.23 GFLOP per sample-step)'}
 
 
 def main():
@@ -261,7 +470,8 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--no-train-probe', action='store_true', help='skip the (untimed, rank-0) training-step measurement')
+    ap.add_argument('--no-train-probe', action='store_true', help='skip the (untimed) training-step measurement')
+    ap.add_argument('--no-extra', action='store_true', help='skip the C2 / C5 / weak-scaling / stencil side measurements')
     ap.add_argument('--tsteps', type=int, default=T_STEPS, help='debug: shorter rollouts (the JSON line then names the reduced config)')
     args = ap.parse_args()
     if args.impl == 'reference':
@@ -270,7 +480,9 @@ def main():
     import torch
     import torch.distributed as dist
     import arpde_b200
-    from arpde_b200 import engine, functional as F_
+    from arpde_b200 import engine
+    from arpde_b200 import parallel as PL
+    import arpde_b200._lib as L
     T_STEPS = args.tsteps
 
     rank, world = int(os.environ.get('RANK', '0')), int(os.environ.get('WORLD_SIZE', '1'))
@@ -285,38 +497,65 @@ def main():
         dist.init_process_group('nccl', device_id=dev)
     peaks = load_peaks()
 
-    swag = build_swag(dev)
-    ic_host = make_ics(N_IC, first=rank * N_IC).pin_memory()        # distinct ICs per rank
-    ic_dev = ic_host.to(dev)
+    swag, _ = build_swag(dev)
     named = list(swag.base.named_parameters())
-    gen = torch.Generator(device=dev); gen.manual_seed(1234 + 0)     # every rank draws the SAME weight samples
-    res_shape = (N_IC, T_STEPS + 1, 2, NEL, NEL)
-    mean_host = torch.empty(res_shape, pin_memory=True)
-    var_host = torch.empty(res_shape, pin_memory=True)
-    gather_m = torch.empty((world,) + res_shape, device=dev) if world > 1 else None
-    gather_v = torch.empty((world,) + res_shape, device=dev) if world > 1 else None
-    NT = S_SAMPLES * N_IC
-    c_hist = 6
-    traj_buf = torch.empty((NT, c_hist + 2 * T_STEPS, NEL, NEL), device=dev)
+    gen = torch.Generator(device=dev); gen.manual_seed(1234)       # every rank draws the SAME weight samples
+    lo, hi = PL.shard_range(N_IC, rank, world)
+    n_loc = hi - lo
+    n_max = max(b - a for a, b in (PL.shard_range(N_IC, r, world) for r in range(world)))
+    ic_all_host = make_ics(N_IC)
+    state = (T_STEPS + 1, 2, NEL, NEL)
 
-    def job(ic):
-        """device-resident job: sample weights, rollout, predictive moments (+ gather across ranks)"""
-        flat, names, numels = swag.sample_flat(S_SAMPLES, generator=gen)
-        traj = engine.rollout(swag, ic, T_STEPS, flat_weights=flat, named_params=named, out=traj_buf)
-        betas = flat[:, 0].exp()
-        mean, var = engine.predictive_moments(traj, S_SAMPLES, betas, '2d')
-        if world > 1:
-            dist.all_gather_into_tensor(gather_m, mean)
-            dist.all_gather_into_tensor(gather_v, var)
-        return mean, var
+    class Job:
+        """S weight samples x `n_loc` local ICs x T steps; predictive moments; gather of the shards to rank 0."""
 
-    def job_e2e():
-        """the call a user makes: host ICs in, host predictive mean/variance out"""
-        ic = ic_host.to(dev, non_blocking=True)
-        mean, var = job(ic)
-        mean_host.copy_(mean, non_blocking=True)
-        var_host.copy_(var, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        def __init__(self, ic_host_shard, gathered):
+            self.n = ic_host_shard.shape[0]
+            self.ic_host = ic_host_shard.pin_memory()
+            self.ic_dev = self.ic_host.to(dev)
+            self.traj_buf = torch.empty((S_SAMPLES * self.n, 6 + 2 * T_STEPS, NEL, NEL), device=dev)
+            self.gathered = gathered
+            if gathered and world > 1:
+                # rank 0 receives every shard into one [world, n, ...] tensor per moment (equal shards; a ragged split pads to n_max)
+                self.pad = n_max
+                self.g_m = torch.empty((world, n_max) + state, device=dev) if rank == 0 else None
+                self.g_v = torch.empty((world, n_max) + state, device=dev) if rank == 0 else None
+            n_res = N_IC if gathered else self.n
+            if rank == 0 or not gathered:
+                self.mean_host = torch.empty((n_res,) + state, pin_memory=True)
+                self.var_host = torch.empty((n_res,) + state, pin_memory=True)
+
+        def run(self, ic):
+            flat, names, numels = swag.sample_flat(S_SAMPLES, generator=gen)
+            traj = engine.rollout(swag, ic, T_STEPS, flat_weights=flat, named_params=named, out=self.traj_buf)
+            betas = flat[:, 0].exp()
+            mean, var = engine.predictive_moments(traj, S_SAMPLES, betas, '2d')
+            if self.gathered and world > 1:
+                if self.n < self.pad:
+                    padz = torch.zeros((self.pad - self.n,) + state, device=dev)
+                    mean, var = torch.cat([mean, padz]), torch.cat([var, padz])
+                dist.gather(mean, list(self.g_m.unbind(0)) if rank == 0 else None, dst=0)
+                dist.gather(var, list(self.g_v.unbind(0)) if rank == 0 else None, dst=0)
+                if rank == 0:
+                    return self.g_m, self.g_v
+            return mean, var
+
+        def run_e2e(self):
+            """the call a user makes: host ICs in, host predictive mean/variance (of ALL ICs, on rank 0) out"""
+            ic = self.ic_host.to(dev, non_blocking=True)
+            mean, var = self.run(ic)
+            if self.gathered and world > 1:
+                if rank == 0:
+                    off = 0
+                    for r in range(world):
+                        a, b = PL.shard_range(N_IC, r, world)
+                        self.mean_host[off:off + b - a].copy_(mean[r, :b - a], non_blocking=True)
+                        self.var_host[off:off + b - a].copy_(var[r, :b - a], non_blocking=True)
+                        off += b - a
+            else:
+                self.mean_host.copy_(mean, non_blocking=True)
+                self.var_host.copy_(var, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
 
     def timed(fn, steps):
         if world > 1:
@@ -335,25 +574,45 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms)
 
+    # ---- headline: the fixed 64-IC job, sharded (strong scaling) -------------------------------------------------------
+    job = Job(ic_all_host[lo:hi], gathered=True)
     for _ in range(args.warmup):
-        job(ic_dev)
+        job.run(job.ic_dev)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms = timed(lambda: job(ic_dev), args.steps)
+    L.lib.arpde_launch_count(1)
+    ms = timed(lambda: job.run(job.ic_dev), args.steps)
+    launches = int(L.lib.arpde_launch_count(1))
     clocks = sampler.stop() if rank == 0 else None
-    units = world * S_SAMPLES * N_IC * T_STEPS * args.steps
+    units = S_SAMPLES * N_IC * T_STEPS * args.steps
     value = units / (ms * 1e-3)
 
     for _ in range(max(1, args.warmup // 3)):
-        job_e2e()
-    ms_e2e = timed(job_e2e, args.steps)
+        job.run_e2e()
+    ms_e2e = timed(job.run_e2e, args.steps)
     e2e_value = units / (ms_e2e * 1e-3)
+    del job
+    torch.cuda.empty_cache()
+
+    # ---- weak-scaling form (64 ICs per GPU, every rank copies its own shard to its host), N > 1 only -------------------
+    weak = None
+    if world > 1 and not args.no_extra:
+        wjob = Job(make_ics(N_IC, first=rank * N_IC), gathered=False)
+        wjob.run(wjob.ic_dev)
+        wsteps = min(args.steps, 2)
+        wms = timed(lambda: wjob.run(wjob.ic_dev), wsteps)
+        wms_e2e = timed(wjob.run_e2e, wsteps)
+        wunits = world * S_SAMPLES * N_IC * T_STEPS * wsteps
+        weak = {'value': wunits / (wms * 1e-3), 'e2e_value': wunits / (wms_e2e * 1e-3), 'unit': 'sample-steps/s', 'ics_per_gpu': N_IC, 'steps': wsteps,
+                'ms_per_step': wms / wsteps, 'scaling': 'weak', 'what': '64 ICs per GPU (the job grows with N), no gather: every rank keeps its own shard of the result'}
+        del wjob
+        torch.cuda.empty_cache()
 
     # ---- per-kernel rooflines, measured live with CUDA events on the launching stream ------------------
-    # (1) one full AR step (9 fused convs: In_conv1, In_conv3, conv1x1 and the folded conv3x3-up on the tensor-core kernel, the four
-    #     4-channel dense layers and the 16->2 output conv on the row-tiled FFMA kernel): difference of a 25-step and a 5-step rollout,
-    #     so that the per-rollout setup (weight split, buffers) drops out
+    # (1) one full AR step of the local batch: difference of a 25-step and a 5-step rollout, so that the per-rollout setup drops out
+    NT = S_SAMPLES * n_loc
+    ic_dev = ic_all_host[lo:hi].to(dev)
     flat, _, _ = swag.sample_flat(S_SAMPLES, generator=gen)
     engine.rollout(swag, ic_dev, 1, flat_weights=flat, named_params=named)
     torch.cuda.synchronize()
@@ -365,88 +624,87 @@ def main():
     e2.record(); torch.cuda.synchronize()
     step_ms = (e1.elapsed_time(e2) - e0.elapsed_time(e1)) / 20
     conv_tflops = NT * MODEL_MFLOP * 1e6 / (step_ms * 1e-3) / 1e12
+    torch.cuda.empty_cache()
     # (1b) the dominant launch of the step, timed alone through the C ABI on the rollout batch:
-    #      conv_tc_kernel on In_conv3 (96 -> 48, 3x3 stride 2, 64x64 -> 32x32), 1920 samples, 30 weight groups
-    import arpde_b200._lib as L
-    xin = torch.randn((NT, 96, NEL, NEL), device=dev)
+    #      conv_tc_kernel on In_conv3 (96 -> 48, 3x3 stride 2, 64x64 -> 32x32), 30 weight groups; inputs rotate over 2 sets (2 x 3 GB >> L2)
+    xin = [torch.randn((NT, 96, NEL, NEL), device=dev) for _ in range(2)]
     w3 = torch.randn((S_SAMPLES, 48, 96, 3, 3), device=dev) / (96 * 9) ** 0.5
     y3 = torch.empty((NT, 48, NEL // 2, NEL // 2), device=dev)
     n_scr = int(L.lib.arpde_conv_fwd_tc_scratch_floats(96, 48, 3, 3, S_SAMPLES))
     scr = torch.empty((n_scr,), device=dev)
-    def k1():
-        L.call('arpde_conv_fwd_tc', L.ptr(xin), 96 * NEL * NEL, L.ptr(w3), 48 * 96 * 9, 0, 0, 0, L.ptr(y3), 0, NT, 96, NEL, NEL, 48, 3, 3, 2, 0, 0, 0,
-               48, 0, N_IC, L.ptr(scr), n_scr, L.stream())
-    for _ in range(3):
-        k1()
-    torch.cuda.synchronize()
-    nrep = 10
-    e0.record()
-    for _ in range(nrep):
-        k1()
-    e1.record(); torch.cuda.synchronize()
-    k1_ms = e0.elapsed_time(e1) / nrep
+
+    def k1(i):
+        L.call('arpde_conv_fwd_tc', L.ptr(xin[i % 2]), 96 * NEL * NEL, L.ptr(w3), 48 * 96 * 9, 0, 0, 0, L.ptr(y3), 0, NT, 96, NEL, NEL, 48, 3, 3, 2, 0, 0, 0,
+               48, 0, n_loc, L.ptr(scr), n_scr, L.stream())
+    k1_ms = time_cuda(k1, 10)
     k1_flops = 2.0 * NT * (NEL // 2) ** 2 * 48 * 96 * 9
     k1_tflops = k1_flops / (k1_ms * 1e-3) / 1e12
     del xin, y3
-    # (2) the stencil-loss kernel (K2) on the rollout batch: 1920 states x 64x64 x 24 B = 189 MB > L2
-    up = traj_buf[:, 6:8]
-    u0 = traj_buf[:, 4:6]
-    ustar = torch.empty((NT, 2, NEL, NEL), device=dev)
-    bs = traj_buf.stride(0)
-    def k2():
-        L.call('arpde_cn_burgers2d_fwd', L.ptr(up), bs, L.ptr(u0), bs, L.ptr(ustar), 0, NT, NEL, NEL, 1.0 / NEL, 0.005, 0.005, 0, L.stream())
-    for _ in range(3):
-        k2()
-    torch.cuda.synchronize()
-    nrep = 20
-    e0.record()
-    for _ in range(nrep):
-        k2()
-    e1.record(); torch.cuda.synchronize()
-    k2_ms = e0.elapsed_time(e1) / nrep
-    k2_bytes = NT * NEL * NEL * STENCIL_BYTES_PT
-    k2_gbs = k2_bytes / (k2_ms * 1e-3) / 1e9
+    torch.cuda.empty_cache()
+    # (2) the stencil-loss kernel (K2), rotating buffers, C4 and C5 sizes, forward / fused-SSE / adjoint
+    sten = stencil_rooflines(dev, peaks)
+    k2 = sten['c4_64_fwd']
 
-    train = None
+    train = train_weak = ks = c5 = None
     if not args.no_train_probe:
         train = train_step_probe(dev, rank=rank, world=world)
+        if world > 1 and not args.no_extra:
+            train_weak = train_step_probe(dev, weak=True, rank=rank, world=world)
+    if rank == 0 and not args.no_extra:
+        ks = ks_probe(dev)
+        c5 = c5_probe(dev, peaks)
+    if world > 1:
+        dist.barrier()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    n_ops = 9
-    launches = args.steps * (T_STEPS * n_ops + 4 + 1 + 1 + 1)        # convs + 4 weight-split launches (tensor-core layers) + bn fold + swag sample + moments
     line = {
         'metric': 'ar_steps_x_samples_per_s', 'value': value, 'unit': 'sample-steps/s', 'n_gpus': world, 'steps': args.steps,
-        'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(world), 'clocks': clocks, 'gpu_launches': launches,
+        'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
+        'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(world), 'clocks': clocks,
+        'gpu_launches': launches, 'gpu_launches_source': 'arpde_launch_count(): kernels rank 0 launched through libarpde.so inside the timed region (thread-local counter '
+                                                         'bumped after every <<<>>> of the library; torch kernels -- noise draws, history fill -- are not counted)',
         'e2e': {'value': e2e_value, 'unit': 'sample-steps/s', 'ms_per_step': ms_e2e / args.steps,
-                'h2d_bytes_per_step': ic_host.numel() * 4, 'd2h_bytes_per_step': 2 * mean_host.numel() * 4},
-        'roofline': {'kernel': 'conv_tc_kernel on In_conv3 (96->48, 3x3/s2, 1920 samples): tcgen05 implicit GEMM, 3xTF32 split (+ its weight-split launch)',
+                'h2d_bytes_per_step': ic_all_host.numel() * 4, 'd2h_bytes_per_step': 2 * N_IC * (T_STEPS + 1) * 2 * NEL * NEL * 4,
+                'what': 'pinned host ICs -> device (every rank its shard), job, NCCL gather to rank 0, rank 0 copies mean and variance of all 64 ICs to pinned host memory'},
+        'roofline': {'kernel': 'conv_tc_kernel on In_conv3 (96->48, 3x3/s2, %d samples): tcgen05 implicit GEMM, 3xTF32 split (+ its weight-split launch)' % NT,
                      'bound': 'tensor', 'achieved': k1_tflops, 'peak': peaks['bf16_tflops'], 'unit': 'TFLOP/s', 'frac': k1_tflops / peaks['bf16_tflops'],
-                     'traffic': 4.486e9, 'traffic_source': 'ncu --set full, profiles/r01d_conv_tc_in3_ncu_full.md: dram read 4.108 GB + write 0.377 GB per launch '
-                                                           '(algorithmic input + output 3.40 GB; the excess is halo rows re-read past L2)',
+                     'traffic': 4.486e9 if world == 1 else None,
+                     'traffic_source': 'ncu --set full, profiles/r01d_conv_tc_in3_ncu_full.md: dram read 4.108 GB + write 0.377 GB per launch at 1920 samples '
+                                       '(algorithmic input + output 3.40 GB; the excess is halo rows re-read past L2)',
                      'peak_source': peaks['source'] + ' bf16 dense (burst)',
                      'note': 'achieved = algorithmic fp32 FLOPs (2*N*Ho*Wo*cout*cin*k^2) / CUDA-event time; the 1e-5 parity contract needs the 3-term '
                              'TF32 split (3 tensor MACs per algorithmic MAC) and TF32 runs at half the bf16 rate, so the attainable ceiling is '
                              'peak/6 = %.0f TFLOP/s -> frac_of_3xtf32_ceiling %.3f' % (peaks['bf16_tflops'] / 6, k1_tflops / (peaks['bf16_tflops'] / 6)),
                      'flops_per_launch': k1_flops, 'ms': k1_ms,
-                     'ar_step': {'ms': step_ms, 'tflops': conv_tflops, 'flops': NT * MODEL_MFLOP * 1e6,
-                                 'what': 'all 9 convs of one AR step (4 on conv_tc_kernel, the 4-channel dense layers and the 16->2 output conv on the row-tiled fp32 FFMA kernel)'}},
-        'roofline_stencil': {'kernel': 'burgers2d_fwd_vec4<RY=4> (fused periodic stencil + Crank-Nicolson, API form: read uPred, uPred0, write ustar)', 'bound': 'hbm',
-                             'achieved': k2_gbs, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': k2_gbs / peaks['hbm_gbs'],
-                             'traffic': 1.601e8, 'traffic_source': 'ncu --set full, profiles/r01b_stencil_ncu_full.md: dram read 125.9 MB + write 34.2 MB '
-                                                                   '(the rest of the 62.9 MB of ustar was still in L2 at kernel end)',
-                             'bytes_per_launch': k2_bytes, 'ms': k2_ms, 'peak_source': peaks['source']},
+                     'ar_step': {'ms': step_ms, 'tflops': conv_tflops, 'flops': NT * MODEL_MFLOP * 1e6, 'samples': NT,
+                                 'what': 'all 9 convs of one AR step of the local batch'}},
+        'roofline_stencil': {'kernel': 'burgers2d_fwd_vec4<RY=4> (fused periodic stencil + Crank-Nicolson, API form: read uPred, uPred0, write ustar), '
+                                       'C4 rollout batch, 4 rotating buffer sets', 'bound': 'hbm',
+                             'achieved': k2['achieved'], 'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': k2['frac'],
+                             'traffic': None, 'bytes_per_launch': k2['bytes_per_launch'], 'ms': k2['ms'], 'peak_source': peaks['source'],
+                             'cases': sten},
     }
+    if weak is not None:
+        line['weak'] = weak
     if train is not None:
         line['train_step'] = train
+    if train_weak is not None:
+        line['train_step_weak'] = train_weak
+    if ks is not None:
+        line['c2_ks'] = ks
+    if c5 is not None:
+        line['c5_wide'] = c5
     if not args.no_cpu_baseline:
-        S, N, T = 2, 64, 4
-        rate, dt = cpu_reference_rate(S, N, T)
-        line['cpu_baseline'] = {'value': rate, 'unit': 'sample-steps/s', 'cores': os.cpu_count(), 'kind': 'port',
-                                'sample': 'S=%d x %d ICs x T=%d (%.1f s) of the 30x64x100 job, oracle port of the reference PyTorch CPU loops' % (S, N, T, dt)}
+        S, N, T = REF_SAMPLE
+        reference_rate(1, 8, 1)
+        rate, dt, kind = reference_rate(S, N, T)
+        line['cpu_baseline'] = {'value': rate, 'unit': 'sample-steps/s', 'cores': os.cpu_count(), 'kind': kind,
+                                'sample': 'S=%d x %d ICs x T=%d (%.1f s) of the 30x64x100 job; %s' % (
+                                    S, N, T, dt, "the reference's own modules driven by its main.testSample() + numpy moments" if kind == 'reference'
+                                    else 'oracle port of the reference PyTorch CPU loops')}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

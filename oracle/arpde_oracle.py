@@ -221,6 +221,85 @@ def burgers1d_be(uPred, uPred0, dt, dx, nu, k1=3, k2=3):
     return uPred0 + dt * (-0.5 * fluxdx + nu * lap(uPred))
 
 
+# ---- P4 variants no reference driver calls (restated for the parity tests of the product's roll path) ----------------------
+SOBEL_H5 = [[v / 108. for v in row] for row in ([1, -8, 0, 8, -1], [2, -16, 0, 16, -2], [3, -24, 0, 24, -3], [2, -16, 0, 16, -2],
+                                                [1, -8, 0, 8, -1])]                        # burger2DFiniteDifference.py:74-78
+SOBEL_V5 = [list(r) for r in zip(*SOBEL_H5)]                                               # transpose, :84
+LAPLACE_5 = [[v / 12. for v in row] for row in ([0, 0, -1, 0, 0], [0, 0, 16, 0, 0], [-1, 16, -60, 16, -1], [0, 0, 16, 0, 0],
+                                                [0, 0, -1, 0, 0])]                         # :31-35
+
+
+def filt2d_k(u, w, scale):
+    """k x k periodic cross-correlation over the last two dims (gather form, independent of the product's roll form)."""
+    k = len(w)
+    p = (k - 1) // 2
+    H, W = u.shape[-2:]
+    iy = (torch.arange(H)[:, None] + torch.arange(k)[None, :] - p) % H          # [H, k]
+    ix = (torch.arange(W)[:, None] + torch.arange(k)[None, :] - p) % W
+    patches = u[..., iy[:, None, :, None], ix[None, :, None, :]]                # [..., H, W, k, k]
+    return (patches * torch.tensor(w, dtype=u.dtype)).sum((-2, -1)) / scale
+
+
+def burgers2d_rhs_k(uv, dx, nu, k1, k2):
+    """R(u, v) with the 3x3 or 5x5 Sobel / Laplace stencils (burger2DFiniteDifference.py:185-203)."""
+    u, v = uv[:, :1], uv[:, 1:]
+    sh, sv = (SOBEL_H, SOBEL_V) if k1 == 3 else (SOBEL_H5, SOBEL_V5)
+    lp = LAPLACE_2D if k2 == 3 else LAPLACE_5
+    gh = lambda t: filt2d_k(t, sh, dx)
+    gv = lambda t: filt2d_k(t, sv, dx)
+    lap = lambda t: filt2d_k(t, lp, dx ** 2)
+    return torch.cat([-gh(0.5 * u ** 2) - v * gv(u) + nu * lap(u), -u * gh(v) - gv(0.5 * v ** 2) + nu * lap(v)], 1)
+
+
+def burgers2d_integrate_k(uPred, uPred0, dt, dx, nu, k1, k2, cn=True):
+    if cn:
+        return uPred0 + 0.5 * dt * (burgers2d_rhs_k(uPred, dx, nu, k1, k2) + burgers2d_rhs_k(uPred0, dx, nu, k1, k2))
+    return uPred0 + dt * burgers2d_rhs_k(uPred, dx, nu, k1, k2)
+
+
+def upwind_grad(u, dx):
+    """GradFilter1D(kernel_size=2).__call__ = conditionalUpwind (burgerFiniteDifference.py:224-244): it RETURNS u2, the forward
+    difference, regardless of the sign of u (reference quirk)."""
+    idx = (torch.arange(u.shape[-1]) + 1) % u.shape[-1]
+    return (u[..., idx] - u) / dx
+
+
+def weno_flux_grad(u, dx):
+    """FluxWENOFilter1D.__call__ (burgerFiniteDifference.py:89-166), gather form over the L+1 cell edges as the reference lays them out."""
+    L_ = u.shape[-1]
+    f = u ** 2 / 2.0
+
+    def edges(fl):
+        i = torch.arange(L_ + 1)
+        at = lambda o: fl[..., (i + o) % L_]
+        e1 = -0.5 * at(-2) + 1.5 * at(-1)
+        e2 = 0.5 * at(0) + 0.5 * at(1)
+        b1 = (at(-1) - at(-2)) ** 2
+        b2 = (at(1) - at(0)) ** 2
+        w1 = 1. / (3 * (1e-6 + b1) ** 2)
+        w2 = 2. / (3 * (1e-6 + b2) ** 2)
+        return (w1 * e1 + w2 * e2) / (w1 + w2)
+    e = edges(f)
+    er = torch.flip(edges(torch.flip(f, dims=[-1])), dims=[-1])
+    g = (e[..., 1:] - e[..., :-1]) / dx
+    gr = (er[..., 1:] - er[..., :-1]) / dx
+    return torch.where(u < 0, g, gr)
+
+
+def burgers1d_upwind(uPred, uPred0, dt, dx, nu, k2=3, cn=True):
+    """BurgerIntegrate.crankNicolson / backwardEuler with grad_kernels[0] == 2 (:264-302)."""
+    lap = lambda t: filt1d(t, LAP_TAPS[k2], dx ** 2)
+    if cn:
+        return uPred0 - 0.5 * dt * ((uPred * upwind_grad(uPred, dx) + uPred0 * upwind_grad(uPred0, dx)) - nu * (lap(uPred) + lap(uPred0)))
+    return uPred0 + dt * (-0.5 * (0.5 * upwind_grad(uPred ** 2, dx)) + nu * lap(uPred))
+
+
+def burgers1d_cn_limiter(uPred, uPred0, dt, dx, nu, k2=3):
+    """BurgerIntegrate.crankNicolsonLimiter (:304-322)."""
+    lap = lambda t: filt1d(t, LAP_TAPS[k2], dx ** 2)
+    return uPred0 - 0.5 * dt * ((weno_flux_grad(uPred, dx) + weno_flux_grad(uPred0, dx)) - nu * (lap(uPred) + lap(uPred0)))
+
+
 def _ks_rhs(u, dx, nu, k1, k2, k4):
     g = filt1d(u ** 2, GRAD_TAPS[k1], dx)
     lap = filt1d(u, LAP_TAPS[k2], dx ** 2)

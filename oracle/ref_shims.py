@@ -88,6 +88,40 @@ def halve_circular_padding():
     _PAD_PATCHED = True
 
 
+import contextlib
+
+
+@contextlib.contextmanager
+def reference_modules(system):
+    """`with reference_modules('burgers2d') as proj:` -- inside the block `import nn.xxx` / `import main` resolve to the reference
+    project and Conv layers are built with the halved circular padding; on exit torch.nn and sys.path / sys.modules are restored, so
+    the product's own modules can be built in the same process (pytest).  Reference modules built inside keep working afterwards."""
+    global _PAD_PATCHED
+    import torch.nn as nn
+    root = ref_root()
+    if root is None:
+        raise FileNotFoundError('reference not available')
+    saved_init = (nn.Conv1d.__init__, nn.Conv2d.__init__)
+    saved_path = list(sys.path)
+    was = _PAD_PATCHED
+    clash = lambda k: k == 'nn' or k.startswith('nn.') or k == 'utils' or k.startswith('utils.') or k in ('args', 'main')
+    saved_mods = {k: sys.modules.pop(k) for k in list(sys.modules) if clash(k)}
+    mock_matplotlib()
+    _PAD_PATCHED = False
+    halve_circular_padding()
+    proj = os.path.join(root, PROJ[system])
+    sys.path.insert(0, proj)
+    try:
+        yield proj
+    finally:
+        nn.Conv1d.__init__, nn.Conv2d.__init__ = saved_init
+        _PAD_PATCHED = was
+        sys.path[:] = saved_path
+        for k in [k for k in sys.modules if clash(k)]:
+            del sys.modules[k]
+        sys.modules.update(saved_mods)
+
+
 def install_shims():
     """Shims for importing the reference's own nn/ modules."""
     mock_matplotlib()

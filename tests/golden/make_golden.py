@@ -297,8 +297,71 @@ def gen_ic2d():
     print('wrote ic2d.npz', {k: v.shape for k, v in out.items()})
 
 
+def gen_p4():
+    """integrator / filter variants no reference driver calls -- 5x5 2D stencils, kernel_size=2 "conditional
+    upwind" gradient, WENO flux derivative and crankNicolsonLimiter -- forward values and gradients w.r.t. both inputs."""
+    import importlib
+    import numpy as np
+    import torch
+    from oracle import ref_shims
+    out = {}
+    torch.manual_seed(11)
+    ref_shims.import_reference('burgers1d')
+    R = importlib.import_module('nn.burgerFiniteDifference')
+    L_ = 64
+    dx, nu, dt = 1.0 / (L_ + 1), 0.0025, 0.002
+    grid = torch.linspace(0, 1, L_ + 1)[:-1]
+    u = (2 * torch.sin(2 * np.pi * grid)[None, None] * torch.randn(3, 1, 1) + 0.3 * torch.randn(3, 1, L_)).requires_grad_(True)
+    u0 = (2 * torch.cos(2 * np.pi * grid)[None, None] * torch.randn(3, 1, 1) + 0.3 * torch.randn(3, 1, L_)).requires_grad_(True)
+    g = torch.randn(3, 1, L_)
+    out['1d/u'], out['1d/u0'], out['1d/gout'] = u.detach().numpy().copy(), u0.detach().numpy().copy(), g.numpy().copy()
+    out['1d/dx'], out['1d/nu'], out['1d/dt'] = np.array(dx), np.array(nu), np.array(dt)
+    for gk in ([2, 3], [2, 5], [3, 3]):
+        integ = R.BurgerIntegrate(dx, nu=nu, grad_kernels=gk, device='cpu')
+        meths = ('crankNicolson', 'backwardEuler', 'crankNicolsonLimiter') if gk[0] == 2 else ('crankNicolsonLimiter',)
+        for meth in meths:
+            u.grad = u0.grad = None
+            us = getattr(integ, meth)(u, u0, dt)
+            (us * g).sum().backward()
+            key = '1d/k%d%d/%s/' % (gk[0], gk[1], meth)
+            out[key + 'ustar'] = us.detach().numpy().copy()
+            out[key + 'g_u'] = u.grad.numpy().copy()
+            out[key + 'g_u0'] = u0.grad.numpy().copy()
+    out['1d/weno'] = R.FluxWENOFilter1D(dx)(u.detach()).numpy().copy()
+    out['1d/upwind'] = R.GradFilter1D(dx, kernel_size=2)(u.detach()).numpy().copy()
+    for k in [k for k in sys.modules if k == 'nn' or k.startswith('nn.')]:
+        del sys.modules[k]
+    ref_shims.import_reference('burgers2d')
+    R2 = importlib.import_module('nn.burger2DFiniteDifference')
+    n = 16
+    dx2, nu2, dt2 = 1.0 / n, 0.005, 0.003
+    a = torch.randn(2, 2, n, n).requires_grad_(True)
+    b = torch.randn(2, 2, n, n).requires_grad_(True)
+    g2 = torch.randn(2, 2, n, n)
+    out['2d/u'], out['2d/u0'], out['2d/gout'] = a.detach().numpy().copy(), b.detach().numpy().copy(), g2.numpy().copy()
+    out['2d/dx'], out['2d/nu'], out['2d/dt'] = np.array(dx2), np.array(nu2), np.array(dt2)
+    for gk in ([5, 5], [5, 3], [3, 5]):
+        integ = R2.Burger2DIntegrate(dx2, nu=nu2, grad_kernels=gk, device='cpu')
+        for meth in ('crankNicolson', 'backwardEuler'):
+            a.grad = b.grad = None
+            us = getattr(integ, meth)(a, b, dt2)
+            (us * g2).sum().backward()
+            key = '2d/k%d%d/%s/' % (gk[0], gk[1], meth)
+            out[key + 'ustar'] = us.detach().numpy().copy()
+            out[key + 'g_u'] = a.grad.numpy().copy()
+            out[key + 'g_u0'] = (b.grad if b.grad is not None else torch.zeros_like(b)).numpy().copy()
+    s5, l5 = R2.SobelFilter2d(dx2, kernel_size=5), R2.LapLaceFilter2d(dx2, kernel_size=5)
+    out['2d/filt5/grad_h'] = s5.grad_h(a.detach()[:, :1]).numpy().copy()
+    out['2d/filt5/grad_v'] = s5.grad_v(a.detach()[:, :1]).numpy().copy()
+    out['2d/filt5/lap'] = l5(a.detach()[:, :1]).numpy().copy()
+    np.savez_compressed(os.path.join(HERE, 'p4.npz'), **out)
+    print('wrote p4.npz,', len(out), 'keys')
+
+
 if __name__ == '__main__':
-    if len(sys.argv) > 1 and sys.argv[1] == 'ic2d':
+    if len(sys.argv) > 1 and sys.argv[1] == 'p4':
+        gen_p4()
+    elif len(sys.argv) > 1 and sys.argv[1] == 'ic2d':
         gen_ic2d()
     elif len(sys.argv) > 1:
         gen(sys.argv[1])
@@ -308,3 +371,4 @@ if __name__ == '__main__':
             os.makedirs(cwd, exist_ok=True)
             subprocess.check_call([sys.executable, os.path.abspath(__file__), s], cwd=cwd)
         subprocess.check_call([sys.executable, os.path.abspath(__file__), 'ic2d'], cwd='/tmp')
+        subprocess.check_call([sys.executable, os.path.abspath(__file__), 'p4'], cwd='/tmp')

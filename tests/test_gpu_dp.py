@@ -1,0 +1,56 @@
+"""T12: data-parallel training equivalence.  Two ranks x B/2 initial conditions -- global-batch BatchNorm
+through the all-reduce hooks of arpde_densed_forward_dp / _backward_dp, gradients accumulated in the flat bucket by the backward kernels,
+one averaging all-reduce, one-launch Adam -- must reproduce ONE rank x B (plain autograd): loss, every gradient, BatchNorm running
+statistics and the updated weights to 1e-5 relative.  With two GPUs the collectives run over NCCL; on a one-GPU box both ranks share
+the device and torch.distributed's gloo backend carries the (CUDA) tensors, which exercises the same library path."""
+import os
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+from _util import ROOT, rel_err
+import _dp_worker as W
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+def _run(ws, backend):
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() * 7 + ws) % 2000
+    procs = [ctx.Process(target=W.worker, args=(r, ws, port, backend, ROOT, q)) for r in range(ws)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=600) for _ in procs]
+    for p in procs:
+        p.join(60)
+    return dict(res)
+
+
+def test_two_rank_step_equals_one_rank_step_at_global_batch():
+    backend = 'nccl' if torch.cuda.device_count() >= 2 else 'gloo'
+    res = _run(2, backend)
+    for rank, errs in res.items():
+        assert isinstance(errs, dict), errs
+        # tolerance: the north_star's 1e-5 relative; gradients 2e-5 (two-step BPTT)
+        assert errs['loss'] < 1e-5, (backend, rank, errs)
+        assert errs['stats'] < 1e-5, (backend, rank, errs)
+        assert errs['grads'] < 2e-5, (backend, rank, errs)
+        assert errs['weights'] < 1e-5, (backend, rank, errs)
+        assert errs['rank_consistency'] == 0.0, (backend, rank, errs)
+
+
+def test_gradient_sink_equals_plain_autograd():
+    """bucket.capture(): parameter gradients written by the backward kernels straight into the flat bucket (one add per backward call)
+    == the gradients autograd accumulates tensor by tensor."""
+    a = W.build(torch.device(DEV))
+    b = W.build(torch.device(DEV))
+    from oracle import arpde_oracle as O
+    ics = O.ic_burgers2d(32, range(4)).to(DEV)
+    la, ga, _, wa = W.train_step(*a, ics, dp=False, capture=True)
+    lb, gb, _, wb = W.train_step(*b, ics, dp=False, capture=False)
+    assert rel_err(la, lb) < 1e-6
+    assert rel_err(ga, gb) < 1e-6
+    assert rel_err(wa, wb) < 1e-6

@@ -191,3 +191,42 @@ def test_ic_generator_2d_vs_reference_golden():
     for ncells in (16, 64):
         got = O.ic_burgers2d(ncells, [int(i) for i in g['ic/%d/index' % ncells]]).numpy()
         assert np.abs(got - g['ic/%d/u' % ncells]).max() <= 1e-6
+
+
+# ----------------------------------------------------------------------------- P4 variants (5x5 stencils, upwind, WENO limiter)
+def _p4_cases():
+    g = golden('p4')
+    for key in sorted(set(k.rsplit('/', 1)[0] for k in g if k.endswith('/ustar'))):
+        yield key
+
+
+@pytest.mark.parametrize('key', list(_p4_cases()))
+def test_p4_oracle_vs_reference_fixture(key):
+    g = golden('p4')
+    dim, ks, meth = key.split('/')
+    k1, k2 = int(ks[1]), int(ks[2])
+    u = torch.from_numpy(g[dim + '/u']).double().requires_grad_(True)
+    u0 = torch.from_numpy(g[dim + '/u0']).double().requires_grad_(True)
+    dx, nu, dt = float(g[dim + '/dx']), float(g[dim + '/nu']), float(g[dim + '/dt'])
+    if dim == '2d':
+        us = O.burgers2d_integrate_k(u, u0, dt, dx, nu, k1, k2, cn=(meth == 'crankNicolson'))
+    elif meth == 'crankNicolsonLimiter':
+        us = O.burgers1d_cn_limiter(u, u0, dt, dx, nu, k2)
+    else:
+        us = O.burgers1d_upwind(u, u0, dt, dx, nu, k2, cn=(meth == 'crankNicolson'))
+    (us * torch.from_numpy(g[dim + '/gout']).double()).sum().backward()
+    assert rel_err(us, g[key + '/ustar']) < 1e-5
+    assert rel_err(u.grad, g[key + '/g_u']) < 1e-5
+    assert rel_err(u0.grad, g[key + '/g_u0']) < 1e-5
+
+
+def test_p4_filters_oracle_vs_reference_fixture():
+    g = golden('p4')
+    u = torch.from_numpy(g['1d/u']).double()
+    assert rel_err(O.weno_flux_grad(u, float(g['1d/dx'])), g['1d/weno']) < 1e-5
+    assert rel_err(O.upwind_grad(u, float(g['1d/dx'])), g['1d/upwind']) < 1e-5
+    a = torch.from_numpy(g['2d/u']).double()[:, :1]
+    dx = float(g['2d/dx'])
+    assert rel_err(O.filt2d_k(a, O.SOBEL_H5, dx), g['2d/filt5/grad_h']) < 1e-5
+    assert rel_err(O.filt2d_k(a, O.SOBEL_V5, dx), g['2d/filt5/grad_v']) < 1e-5
+    assert rel_err(O.filt2d_k(a, O.LAPLACE_5, dx ** 2), g['2d/filt5/lap']) < 1e-5

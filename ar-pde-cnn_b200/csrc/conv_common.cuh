@@ -113,6 +113,12 @@ long long arpde_conv_wgrad_tc_scratch_floats(const ConvDesc& d);  // fp32 partia
 int arpde_conv_wgrad_tc_launch(const ConvDesc& d, const float* x, long long x_bs, const float* scale, const float* shift, const float* dO,
                                long long dO_bs, double* dW64, float* dW, float* scratch, long long scratch_floats, cudaStream_t stream);
 
+// persistent 1D rollout (rollout1d.cu): the reference's KS DenseED, one warp per trajectory, all T steps in one launch
+struct arpde_op; struct arpde_buf;
+bool arpde_ks_program_matches(const arpde_op* ops, int n_ops, const arpde_buf* bufs, int n_bufs, int H, int W, int c_in, int c_out);
+int arpde_ks_rollout_launch(const arpde_op* ops, void* const* params, const int64_t* gstride, float* traj, long long bs, int c_hist, int T, int N,
+                            int n_per_group, float eps, cudaStream_t stream);
+
 // tensor-core (tcgen05) implicit-GEMM path, conv_tc.cu
 long long* arpde_tc_debug_buffer();                              // arpde_conv_tc_set_debug's buffer (nullptr = off)
 int arpde_tc_enabled();                                          // ARPDE_TC=0 in the environment disables it

@@ -200,14 +200,15 @@ static int densed_forward_impl(const arpde_op_t* ops, int n_ops, const arpde_buf
   ARPDE_CHECK_ARG(bn_total == 0 || scale_shift, "densed_forward: scale/shift scratch missing");
   if (training) {
     ARPDE_CHECK_ARG(c.groups == 1, "densed_forward: training with grouped weights is not defined");
-    ARPDE_CHECK_ARG(stats && stats_len > 0, "densed_forward: training needs the stats scratch");
-    ARPDE_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * stats_len, stream));
-    c.stats_len = stats_len;
     long long need = 0;
     for (int b = 0; b < n_bufs; ++b) need = need > bufs[b].stats_off + 2ll * bufs[b].ctot ? need : bufs[b].stats_off + 2ll * bufs[b].ctot;
     for (int i = 0; i < n_ops; ++i)
       if (ops[i].bn_param >= 0 && ops[i].in_buf < 0) { need += 2ll * ops[i].cin; break; }
-    ARPDE_CHECK_ARG(stats_len >= need, "densed_forward: stats scratch holds %lld doubles, program needs %lld", (long long)stats_len, need);
+    // a program without activation buffers and without BatchNorm (a lone convolution) needs no statistics
+    ARPDE_CHECK_ARG(need == 0 || (stats && stats_len >= need), "densed_forward: training needs a stats scratch of %lld doubles (got %lld)", need,
+                    (long long)(stats ? stats_len : 0));
+    if (stats && stats_len > 0) ARPDE_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * stats_len, stream));
+    c.stats_len = stats_len;
     // channels the caller pre-filled (the input copy of a stand-alone dense layer / block): no producer op accumulates their
     // batch statistics, so a streaming pass does
     for (int b = 0; b < n_bufs; ++b) {
@@ -258,28 +259,48 @@ extern "C" int arpde_densed_forward_dp(const arpde_op_t* ops, int n_ops, const a
 // Auto-regressive rollout, eval mode.  traj: [N, traj_ctot, H, W] with traj_ctot = c_hist + T*c_out; the caller fills the first
 // c_hist channels (the repeated initial condition); step t reads channels [t*c_out, t*c_out + c_in) and writes the prediction
 // to channels [c_hist + t*c_out, +c_out): the sliding history window of the reference loops without any copy or cat.
-extern "C" int arpde_rollout(const arpde_op_t* ops, int n_ops, const arpde_buf_t* bufs, int n_bufs, void* const* params_host,
-                             const int64_t* param_gstride_host, int n_params, float* traj, int traj_ctot, int c_in, int c_hist,
-                             int c_out, int T, int N, int n_per_group, int H, int W, float* workspace, float* scale_shift,
-                             int bn_total, double eps, float* tc_scratch, int64_t tc_scratch_floats, arpde_stream_t stream_) {
+static int rollout_impl(const arpde_op_t* ops, int n_ops, const arpde_buf_t* bufs, int n_bufs, void* const* params_host,
+                        const int64_t* param_gstride_host, int n_params, float* traj, int traj_ctot, int c_in, int c_hist,
+                        int c_out, int T, int N, int n_per_group, int H, int W, float* workspace, float* scale_shift,
+                        int bn_total, double eps, float* tc_scratch, int64_t tc_scratch_floats, arpde_stream_t stream_, bool allow_persistent) {
   cudaStream_t stream = (cudaStream_t)stream_;
   RunCtx c;
   int rc = make_ctx(&c, ops, n_ops, bufs, n_bufs, params_host, param_gstride_host, n_params, N, n_per_group, H, W, workspace,
                     scale_shift, bn_total, nullptr, nullptr, 0.1, eps, stream);
   if (rc) return rc;
   c.tc_scratch = tc_scratch; c.tc_scratch_floats = tc_scratch_floats;
-  rc = prep_tc(c); if (rc) return rc;
   ARPDE_CHECK_ARG(traj && T >= 0 && c_in > 0 && c_out > 0 && c_hist >= c_in, "rollout: bad args");
   ARPDE_CHECK_ARG(traj_ctot >= c_hist + T * c_out, "rollout: trajectory has %d channels, needs %d", traj_ctot, c_hist + T * c_out);
   ARPDE_CHECK_ARG(ops[0].cin == c_in && ops[n_ops - 1].cout == c_out, "rollout: program does not match c_in/c_out");
-  rc = fold_eval(c); if (rc) return rc;
   const long long HW = (long long)H * W, bs = (long long)traj_ctot * HW;
+  // the reference's KS network on its 96-point grid: the whole rollout is ONE persistent launch (rollout1d.cu)
+  if (allow_persistent && arpde_ks_program_matches(ops, n_ops, bufs, n_bufs, H, W, c_in, c_out))
+    return arpde_ks_rollout_launch(ops, params_host, param_gstride_host, traj, bs, c_hist, T, N, c.n_per_group, (float)eps, stream);
+  rc = prep_tc(c); if (rc) return rc;
+  rc = fold_eval(c); if (rc) return rc;
   for (int t = 0; t < T; ++t) {
     const float* x = traj + (long long)(c_hist - c_in + t * c_out) * HW;
     rc = run_ops(c, x, bs, traj, traj_ctot, c_hist + t * c_out, 0);
     if (rc) return rc;
   }
   return ARPDE_OK;
+}
+
+extern "C" int arpde_rollout(const arpde_op_t* ops, int n_ops, const arpde_buf_t* bufs, int n_bufs, void* const* params_host,
+                             const int64_t* param_gstride_host, int n_params, float* traj, int traj_ctot, int c_in, int c_hist,
+                             int c_out, int T, int N, int n_per_group, int H, int W, float* workspace, float* scale_shift,
+                             int bn_total, double eps, float* tc_scratch, int64_t tc_scratch_floats, arpde_stream_t stream) {
+  return rollout_impl(ops, n_ops, bufs, n_bufs, params_host, param_gstride_host, n_params, traj, traj_ctot, c_in, c_hist, c_out, T, N,
+                      n_per_group, H, W, workspace, scale_shift, bn_total, eps, tc_scratch, tc_scratch_floats, stream, true);
+}
+
+// same contract, always the layer-by-layer path (one launch per convolution and step): cross-check of the persistent kernels
+extern "C" int arpde_rollout_layerwise(const arpde_op_t* ops, int n_ops, const arpde_buf_t* bufs, int n_bufs, void* const* params_host,
+                                       const int64_t* param_gstride_host, int n_params, float* traj, int traj_ctot, int c_in, int c_hist,
+                                       int c_out, int T, int N, int n_per_group, int H, int W, float* workspace, float* scale_shift,
+                                       int bn_total, double eps, float* tc_scratch, int64_t tc_scratch_floats, arpde_stream_t stream) {
+  return rollout_impl(ops, n_ops, bufs, n_bufs, params_host, param_gstride_host, n_params, traj, traj_ctot, c_in, c_hist, c_out, T, N,
+                      n_per_group, H, W, workspace, scale_shift, bn_total, eps, tc_scratch, tc_scratch_floats, stream, false);
 }
 
 // Backward of arpde_densed_forward (train or eval mode): what loss.backward() does through DenseED in the reference

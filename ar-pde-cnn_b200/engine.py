@@ -45,13 +45,14 @@ def _param_table(plan, named_params, flat):
 
 
 @torch.no_grad()
-def rollout(model, ic, tsteps, flat_weights=None, named_params=None, out=None):
+def rollout(model, ic, tsteps, flat_weights=None, named_params=None, out=None, layerwise=False):
     """Eval-mode AR rollout.
 
     model: DenseED / BayesNN / SwagNN (running BN statistics and, without flat_weights, the weights come from it)
     ic: [N, c_out, H, W] or [N, c_out, L] initial states (the history is the IC repeated, as the loaders do)
     flat_weights: optional [S, P] table from SwagNN.sample_flat (P = named_params order) -> S*N rollouts,
                   sample-major: row s*N + n uses weight sample s on initial condition n
+    layerwise: force the layer-by-layer path (the KS network otherwise runs as one persistent launch; cross-check hook)
     returns traj [S*N, T+1, c_out, (H,) W] (index 0 = initial state)
     """
     feats = _features_of(model)
@@ -90,7 +91,7 @@ def rollout(model, ic, tsteps, flat_weights=None, named_params=None, out=None):
     tc_len = int(L.lib.arpde_densed_tc_scratch_floats(ops_c, len(plan.ops), S))
     tc = torch.empty((max(tc_len, 1),), device=dev, dtype=torch.float32)
     with torch.cuda.device(dev):
-        L.call('arpde_rollout', ops_c, len(plan.ops), bufs_c, len(bufs), pp, gs, len(keep), L.ptr(out), ctot, plan.c_in, c_hist,
+        L.call('arpde_rollout_layerwise' if layerwise else 'arpde_rollout', ops_c, len(plan.ops), bufs_c, len(bufs), pp, gs, len(keep), L.ptr(out), ctot, plan.c_in, c_hist,
                c_out, int(tsteps), NT, N, H, W, L.ptr(work), L.ptr(ss), plan.bn_total, float(eps), L.ptr(tc), tc_len, L.stream())
     traj = out[:, c_hist - c_out:].view(NT, tsteps + 1, c_out, H, W)
     return traj.squeeze(3) if one_d else traj

@@ -292,6 +292,14 @@ int arpde_rollout(const arpde_op_t* ops, int n_ops, const arpde_buf_t* bufs, int
                   const int64_t* param_gstride_host, int n_params, float* traj, int traj_ctot, int c_in, int c_hist, int c_out,
                   int T, int N, int n_per_group, int H, int W, float* workspace, float* scale_shift, int bn_total, double eps,
                   float* tc_scratch, int64_t tc_scratch_floats, arpde_stream_t stream);
+/* arpde_rollout runs the reference's 1D Kuramoto-Sivashinsky network (1D-KS-SWAG/main.py defaults: conv7/s2 2->32, four 4-channel
+ * dense layers, 48->24->12->1 decoder, 96-point grid) as ONE persistent launch for all T steps (rollout1d.cu: one warp per
+ * trajectory, weights and activations in shared memory, 96 floats per step to HBM).  arpde_rollout_layerwise has the same contract
+ * and always takes the layer-by-layer path (one launch per convolution and step): the cross-check of the persistent kernel. */
+int arpde_rollout_layerwise(const arpde_op_t* ops, int n_ops, const arpde_buf_t* bufs, int n_bufs, void* const* params_host,
+                            const int64_t* param_gstride_host, int n_params, float* traj, int traj_ctot, int c_in, int c_hist,
+                            int c_out, int T, int N, int n_per_group, int H, int W, float* workspace, float* scale_shift,
+                            int bn_total, double eps, float* tc_scratch, int64_t tc_scratch_floats, arpde_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * SWAG.  arpde_swag_sample replaces SwagNN.sample (nn/swag.py:80-150) for S samples at once:

@@ -22,10 +22,17 @@ from oracle import ref_shims    # noqa: E402
 
 pytestmark = pytest.mark.gpu
 
-# Two epochs of Adam on an untrained net: fp32 reassociation differences (1e-6 per forward) grow through ~20 optimizer steps.
-# Measured growth stays below 1e-3 on the epoch losses; the reference prints 6 significant digits.
-LOSS_TOL = 2e-3
-PRED_TOL = 2e-2
+# Two epochs of Adam on an untrained net amplify fp32 reassociation differences (1e-6 per forward) through ~20-60 optimizer steps of
+# BPTT; how much is CALIBRATED, not guessed: the same command is also run on the reference's own modules ON THIS GPU (cuDNN, TF32 off),
+# and the spread between the reference's two backends (CUDA here vs the CPU fixture) is the yardstick -- the drop-in must stay within
+# SPREAD_FACTOR x that spread (or FLOOR, whichever is larger) of the reference-on-CUDA run.
+SPREAD_FACTOR = 5.0
+FLOOR = 2e-3
+
+
+def _close(ours, ref_cuda, ref_cpu, key):
+    spread = abs(ref_cuda - ref_cpu)
+    return abs(ours - ref_cuda) <= max(SPREAD_FACTOR * spread, FLOOR * abs(ref_cuda)), (key, ours, ref_cuda, ref_cpu)
 
 
 @pytest.mark.parametrize('system', ['burgers2d', 'burgers1d', 'ks1d'])
@@ -35,11 +42,17 @@ def test_reference_main_runs_on_dropin(system):
     gold = json.load(open(os.path.join(GOLDEN, 't13_main.json')))[system]
     assert gold['argv'] == T13.ARGS[system]
     got = T13.run(system, 'dropin')
-    assert [e['epoch'] for e in got['epochs']] == [e['epoch'] for e in gold['epochs']] == [1, 2]
-    for a, b in zip(got['epochs'], gold['epochs']):
+    ref = T13.run(system, 'ref')            # the reference's own nn/ modules on this GPU
+    print(system, 'dropin   :', got['epochs'], got['preds'][:2])
+    print(system, 'ref cuda :', ref['epochs'], ref['preds'][:2])
+    print(system, 'ref cpu  :', gold['epochs'], gold['preds'][:2])
+    assert [e['epoch'] for e in got['epochs']] == [e['epoch'] for e in ref['epochs']] == [e['epoch'] for e in gold['epochs']] == [1, 2]
+    for a, b, c in zip(got['epochs'], ref['epochs'], gold['epochs']):
         for k in ('loss', 'mse', 'noise'):
-            assert abs(a[k] - b[k]) <= LOSS_TOL * abs(b[k]), (system, k, a, b)
-    assert len(got['preds']) == len(gold['preds']) > 0
-    for a, b in zip(got['preds'], gold['preds']):
-        assert a['shape'] == b['shape']
-        assert abs(a['absmean_first4'] - b['absmean_first4']) <= PRED_TOL * abs(b['absmean_first4']), (system, a, b)
+            ok, info = _close(a[k], b[k], c[k], (system, a['epoch'], k))
+            assert ok, info
+    assert len(got['preds']) == len(ref['preds']) == len(gold['preds']) > 0
+    for a, b, c in zip(got['preds'], ref['preds'], gold['preds']):
+        assert a['shape'] == b['shape'] == c['shape']
+        ok, info = _close(a['absmean_first4'], b['absmean_first4'], c['absmean_first4'], (system, 'pred'))
+        assert ok, info

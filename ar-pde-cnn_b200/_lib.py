@@ -41,6 +41,7 @@ _PROTOS = {
     'arpde_cn_burgers2d_fwd_generic': _CN2D,
     'arpde_cn_1d_fwd': [i32, f32p, i64, f32p, i64, f32p, f64p, i32, i32, f64, f64, f64, i32, i32, i32, i32, vp],
     'arpde_cn_burgers2d_bwd': [f32p, i64, f32p, i64, f32p, f32p, f32p, i32, i32, i32, f64, f64, f64, i32, vp],
+    'arpde_cn_burgers2d_bwd_generic': [f32p, i64, f32p, i64, f32p, f32p, f32p, i32, i32, i32, f64, f64, f64, i32, vp],
     'arpde_cn_1d_bwd': [i32, f32p, i64, f32p, i64, f32p, f32p, f32p, i32, i32, f64, f64, f64, i32, i32, i32, i32, vp],
     'arpde_filter1d': [f32p, f32p, i64, i32, vp, vp],
     'arpde_filter2d': [f32p, f32p, i64, i32, i32, vp, vp],

@@ -340,6 +340,7 @@ static conv_fwd_fn pick_kernel(int kh, int kw, int s, int cot, int* pxt) {
 #define PK(KH_, KW_, S_) if (kh == KH_ && kw == KW_ && s == S_) return pick_cot<KH_, KW_, S_>(cot, pxt)
   PK(1, 1, 1); PK(3, 3, 1); PK(3, 3, 2); PK(5, 5, 1); PK(4, 4, 2); PK(7, 7, 2);
   PK(1, 3, 1); PK(1, 3, 2); PK(1, 5, 1); PK(1, 4, 2); PK(1, 7, 2); PK(1, 7, 1); PK(7, 7, 1);
+  PK(4, 4, 1); PK(1, 4, 1);      // data gradient of the k4/s2 TransDown convolution: flipped 4-tap kernel, stride 1, zero-inserted input
 #undef PK
   return nullptr;
 }

@@ -387,6 +387,118 @@ __global__ void __launch_bounds__(256) burgers2d_bwd_generic(const float* __rest
   }
 }
 
+// ---- adjoint, shared-memory tiled (same structure as burgers2d_fwd_smem): persistent CTAs walk (sample, strip of TY full-width rows)
+//      items; the (TY+2)-row tiles of u, v, gu, gv (and u0, v0 for Crank-Nicolson) of the NEXT item are prefetched with 16-byte cp.async
+//      into the second half of a double buffer while the current item is computed.  A thread produces one float4 of each of the four
+//      gradient fields from separable column sums (the adjoint of the forward kernel's D/E/S columns):
+//        S_f = a + 2b + c, E_f = a + c, D_f = c - a over rows y-1, y, y+1;  GH(f) = S_f[x+1] - S_f[x-1], GV(f) = D_f[x-1] + 2 D_f[x] + D_f[x+1],
+//        LP(f) = E_f[x-1] + E_f[x+1] - 4 f.   Algorithmic traffic 40 B / point (read uPred, uPred0, grad_ustar; write two gradients).
+struct ColA { float SA, EA, DB, EB; };            // columns of the incoming gradient (shared by the uPred and the uPred0 pass)
+struct ColU { float DVA, SV, DU, SUB; };          // columns that involve the state (u, v) of the pass
+
+template <bool CN>
+__global__ void __launch_bounds__(256) burgers2d_bwd_smem(const float* __restrict__ up, int64_t up_bs, const float* __restrict__ u0,
+                                                          int64_t u0_bs, const float* __restrict__ g, float* __restrict__ gup,
+                                                          float* __restrict__ gu0, int N, int H, int W, int TY, B2Coef k) {
+  extern __shared__ __align__(16) float tile_all[];      // [2 buffers][NF fields][TY+2][W]; fields: gu, gv, u, v, (u0, v0)
+  constexpr int NF = CN ? 6 : 4;
+  const int nstrips = (H + TY - 1) / TY;
+  const int items = N * nstrips;
+  const int rows = TY + 2, w4 = W >> 2;
+  const int HW = H * W;
+  const int per_field = rows * w4, total = NF * per_field;
+  const int fstride = rows * W, tile_floats = NF * fstride;
+
+  auto prefetch = [&](int it, float* tile) {
+    const int n = it / nstrips, y0 = (it - n * nstrips) * TY;
+    const float* srcs[3] = {g + (int64_t)n * 2 * HW, up + (int64_t)n * up_bs, u0 + (int64_t)n * u0_bs};
+    for (int i = threadIdx.x; i < total; i += 256) {
+      const int f = i / per_field, r = (i - f * per_field) / w4, c = i - f * per_field - r * w4;
+      const int y = wrap(y0 - 1 + r, H);
+      const float* sp = srcs[f >> 1] + (f & 1) * HW;
+      cp_async16(reinterpret_cast<float4*>(tile) + i, reinterpret_cast<const float4*>(sp + (size_t)y * W) + c);
+    }
+  };
+
+  int buf = 0;
+  int it = blockIdx.x;
+  if (it < items) prefetch(it, tile_all);
+  cp_async_commit();
+  for (; it < items; it += gridDim.x) {
+    const int nxt = it + gridDim.x;
+    if (nxt < items) prefetch(nxt, tile_all + (buf ^ 1) * tile_floats);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    const float* tile = tile_all + buf * tile_floats;
+    const int n = it / nstrips, y0 = (it - n * nstrips) * TY;
+    for (int i = threadIdx.x; i < TY * w4; i += 256) {
+      const int r = i / w4, c = i - r * w4;
+      const int y = y0 + r;
+      if (y >= H) continue;
+      const int x0 = c << 2, xl = (x0 == 0 ? W : x0) - 1, xr = x0 + 4 == W ? 0 : x0 + 4;
+      // six columns x0-1 .. x0+4 of rows y-1, y, y+1 (tile rows r, r+1, r+2)
+      auto load6 = [&](int f, float (&F)[3][6]) {
+        const float* t = tile + f * fstride + r * W;
+#pragma unroll
+        for (int rr = 0; rr < 3; ++rr) {
+          const float4 a = *reinterpret_cast<const float4*>(t + rr * W + x0);
+          F[rr][0] = t[rr * W + xl]; F[rr][1] = a.x; F[rr][2] = a.y; F[rr][3] = a.z; F[rr][4] = a.w; F[rr][5] = t[rr * W + xr];
+        }
+      };
+      float A[3][6], B[3][6];
+      load6(0, A); load6(1, B);
+      ColA qa[6];
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        qa[j].EA = A[0][j] + A[2][j]; qa[j].SA = fmaf(2.f, A[1][j], qa[j].EA);
+        qa[j].EB = B[0][j] + B[2][j]; qa[j].DB = B[2][j] - B[0][j];
+      }
+      float out[4][4];                                     // [gup_u, gup_v, gu0_u, gu0_v][4 columns]
+#pragma unroll
+      for (int pass = 0; pass < (CN ? 2 : 1); ++pass) {
+        float U[3][6], V[3][6];
+        load6(2 + 2 * pass, U); load6(3 + 2 * pass, V);
+        ColU qu[6];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+          qu[j].DVA = fmaf(V[2][j], A[2][j], -V[0][j] * A[0][j]);
+          qu[j].SV = fmaf(2.f, V[1][j], V[0][j] + V[2][j]);
+          qu[j].DU = U[2][j] - U[0][j];
+          qu[j].SUB = fmaf(U[0][j], B[0][j], fmaf(2.f * U[1][j], B[1][j], U[2][j] * B[2][j]));
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const ColA &la = qa[j], &ra = qa[j + 2];
+          const ColU &lu = qu[j], &mu = qu[j + 1], &ru = qu[j + 2];
+          const float uc = U[1][j + 1], vc = V[1][j + 1], ac = A[1][j + 1], bc = B[1][j + 1];
+          const float gh_a = ra.SA - la.SA, gv_va = fmaf(2.f, mu.DVA, lu.DVA + ru.DVA), gh_v = ru.SV - lu.SV;
+          const float lp_a = fmaf(-4.f, ac, la.EA + ra.EA);
+          const float gv_u = fmaf(2.f, mu.DU, lu.DU + ru.DU), gh_ub = ru.SUB - lu.SUB;
+          const float gv_b = fmaf(2.f, qa[j + 1].DB, la.DB + ra.DB), lp_b = fmaf(-4.f, bc, la.EB + ra.EB);
+          const float du = k.c * fmaf(k.k1, fmaf(uc, gh_a, fmaf(-bc, gh_v, gv_va)), k.k2 * lp_a);
+          const float dv = k.c * fmaf(k.k1, fmaf(-ac, gv_u, fmaf(vc, gv_b, gh_ub)), k.k2 * lp_b);
+          if (pass == 0) { out[0][j] = du; out[1][j] = dv; }
+          else { out[2][j] = du + ac; out[3][j] = dv + bc; }
+        }
+      }
+      if (!CN) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { out[2][j] = A[1][j + 1]; out[3][j] = B[1][j + 1]; }
+      }
+      float* o = gup + (int64_t)n * 2 * HW + (size_t)y * W + x0;
+      float* o0 = gu0 + (int64_t)n * 2 * HW + (size_t)y * W + x0;
+      *reinterpret_cast<float4*>(o) = make_float4(out[0][0], out[0][1], out[0][2], out[0][3]);
+      *reinterpret_cast<float4*>(o + HW) = make_float4(out[1][0], out[1][1], out[1][2], out[1][3]);
+      *reinterpret_cast<float4*>(o0) = make_float4(out[2][0], out[2][1], out[2][2], out[2][3]);
+      *reinterpret_cast<float4*>(o0 + HW) = make_float4(out[3][0], out[3][1], out[3][2], out[3][3]);
+    }
+    __syncthreads();
+    buf ^= 1;
+  }
+  cp_async_wait<0>();
+}
+
 static int make_b2coef(double dx, double nu, double dt, int mode, B2Coef* k) {
   ARPDE_CHECK_ARG(dx > 0 && (mode == ARPDE_CN || mode == ARPDE_BE), "burgers2d: bad dx=%g or mode=%d", dx, mode);
   k->k1 = (float)(0.125 / dx); k->k1h = (float)(0.0625 / dx); k->k2 = (float)(nu * 0.5 / (dx * dx));
@@ -477,18 +589,53 @@ extern "C" int arpde_cn_burgers2d_fwd_generic(const float* uPred, int64_t up_bst
   return ARPDE_OK;
 }
 
-extern "C" int arpde_cn_burgers2d_bwd(const float* uPred, int64_t up_bstride, const float* uPred0, int64_t u0_bstride,
-                                      const float* grad_ustar, float* grad_uPred, float* grad_uPred0, int N, int H, int W,
-                                      double dx, double nu, double dt, int mode, arpde_stream_t stream_) {
+static int burgers2d_bwd_impl(const float* uPred, int64_t up_bstride, const float* uPred0, int64_t u0_bstride,
+                              const float* grad_ustar, float* grad_uPred, float* grad_uPred0, int N, int H, int W,
+                              double dx, double nu, double dt, int mode, arpde_stream_t stream_, bool force_generic) {
   ARPDE_CHECK_ARG(N >= 0 && H >= 1 && W >= 1, "burgers2d_bwd: bad dims");
   B2Coef k; int rc = make_b2coef(dx, nu, dt, mode, &k); if (rc) return rc;
   if (N == 0) return ARPDE_OK;
   ARPDE_CHECK_ARG(uPred && uPred0 && grad_ustar && grad_uPred && grad_uPred0, "burgers2d_bwd: null pointer");
+  // vector path: whole float4s per row, every base and batch stride 16-byte aligned, a double-buffered tile of >= 2 rows within 96 KB
+  const bool base_ok = (W % 4 == 0) && ((int64_t)H * W) % 4 == 0 && aligned16(uPred) && aligned16(uPred0) && aligned16(grad_ustar) &&
+                       aligned16(grad_uPred) && aligned16(grad_uPred0) && up_bstride % 4 == 0 && u0_bstride % 4 == 0 && H >= 2;
+  const int NF = k.cn ? 6 : 4;
+  int TY = W > 0 ? (W > 128 ? (96 * 1024) / (2 * NF * W * 4) - 2 : 1024 / W) : 0; if (TY > H) TY = H;
+  const size_t tile_bytes = (size_t)2 * NF * (TY + 2) * W * sizeof(float);
+  if (base_ok && TY >= 2 && tile_bytes <= 96 * 1024 && !force_generic) {
+    const int nstrips = (H + TY - 1) / TY;
+    const int64_t items = (int64_t)N * nstrips;
+    ARPDE_CHECK_ARG(items < (1ll << 31), "burgers2d_bwd: too many strips");
+    int per_sm = (int)((200 * 1024) / (tile_bytes + 1024)); if (per_sm > 4) per_sm = 4; if (per_sm < 1) per_sm = 1;
+    int64_t blocks = (int64_t)arpde_num_sms() * per_sm; if (blocks > items) blocks = items;
+    if (k.cn) {
+      if (tile_bytes > 40 * 1024) ARPDE_CUDA(cudaFuncSetAttribute(burgers2d_bwd_smem<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes));
+      burgers2d_bwd_smem<true><<<(unsigned)blocks, 256, tile_bytes, (cudaStream_t)stream_>>>(uPred, up_bstride, uPred0, u0_bstride, grad_ustar, grad_uPred, grad_uPred0, N, H, W, TY, k);
+    } else {
+      if (tile_bytes > 40 * 1024) ARPDE_CUDA(cudaFuncSetAttribute(burgers2d_bwd_smem<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes));
+      burgers2d_bwd_smem<false><<<(unsigned)blocks, 256, tile_bytes, (cudaStream_t)stream_>>>(uPred, up_bstride, uPred0, u0_bstride, grad_ustar, grad_uPred, grad_uPred0, N, H, W, TY, k);
+    }
+    ARPDE_LAUNCH_CHECK();
+    return ARPDE_OK;
+  }
   const int64_t total = (int64_t)N * H * W;
   int64_t blocks = ceil_div64(total, 256); const int64_t cap = (int64_t)arpde_num_sms() * 32; if (blocks > cap) blocks = cap;
   burgers2d_bwd_generic<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream_>>>(uPred, up_bstride, uPred0, u0_bstride, grad_ustar, grad_uPred, grad_uPred0, N, H, W, k);
   ARPDE_LAUNCH_CHECK();
   return ARPDE_OK;
+}
+
+extern "C" int arpde_cn_burgers2d_bwd(const float* uPred, int64_t up_bstride, const float* uPred0, int64_t u0_bstride,
+                                      const float* grad_ustar, float* grad_uPred, float* grad_uPred0, int N, int H, int W,
+                                      double dx, double nu, double dt, int mode, arpde_stream_t stream) {
+  return burgers2d_bwd_impl(uPred, up_bstride, uPred0, u0_bstride, grad_ustar, grad_uPred, grad_uPred0, N, H, W, dx, nu, dt, mode, stream, false);
+}
+
+// test hook: the one-thread-per-point adjoint (any H, W); parity of the two kernels is a test
+extern "C" int arpde_cn_burgers2d_bwd_generic(const float* uPred, int64_t up_bstride, const float* uPred0, int64_t u0_bstride,
+                                              const float* grad_ustar, float* grad_uPred, float* grad_uPred0, int N, int H, int W,
+                                              double dx, double nu, double dt, int mode, arpde_stream_t stream) {
+  return burgers2d_bwd_impl(uPred, up_bstride, uPred0, u0_bstride, grad_ustar, grad_uPred, grad_uPred0, N, H, W, dx, nu, dt, mode, stream, true);
 }
 
 // =====================================================================================

@@ -79,6 +79,10 @@ int arpde_cn_1d_fwd(int system, const float* uPred, int64_t up_bstride, const fl
 int arpde_cn_burgers2d_bwd(const float* uPred, int64_t up_bstride, const float* uPred0, int64_t u0_bstride,
                            const float* grad_ustar, float* grad_uPred, float* grad_uPred0, int N, int H, int W,
                            double dx, double nu, double dt, int mode, arpde_stream_t stream);
+/* same adjoint through the one-thread-per-point kernel (any H, W); parity test hook */
+int arpde_cn_burgers2d_bwd_generic(const float* uPred, int64_t up_bstride, const float* uPred0, int64_t u0_bstride,
+                                   const float* grad_ustar, float* grad_uPred, float* grad_uPred0, int N, int H, int W,
+                                   double dx, double nu, double dt, int mode, arpde_stream_t stream);
 int arpde_cn_1d_bwd(int system, const float* uPred, int64_t up_bstride, const float* uPred0, int64_t u0_bstride,
                     const float* grad_ustar, float* grad_uPred, float* grad_uPred0, int N, int L, double dx,
                     double nu, double dt, int k1, int k2, int k4, int mode, arpde_stream_t stream);

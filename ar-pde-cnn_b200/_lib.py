@@ -73,6 +73,7 @@ _PROTOS = {
                       i32, f64, f32p, i64, vp],
     'arpde_rollout_layerwise': [vp, i32, vp, i32, vp, vp, i32, f32p, i32, i32, i32, i32, i32, i32, i32, i32, i32, f32p, f32p,
                                 i32, f64, f32p, i64, vp],
+    'arpde_fd_burgers1d': [vp, vp, i32, i32, f64, f64, f64, i32, i32, i32, i32, vp],
     'arpde_swag_sample': [vp, vp, vp, vp, i32, f32p, f32p, f32p, i32, i32, i32, f64, f64, i32, vp],
     'arpde_predictive_moments': [f32p, i64, i64, i32, i32, f64, f32p, f32p, vp],
 }

@@ -305,6 +305,14 @@ int arpde_rollout_layerwise(const arpde_op_t* ops, int n_ops, const arpde_buf_t*
                             int c_out, int T, int N, int n_per_group, int H, int W, float* workspace, float* scale_shift,
                             int bn_total, double eps, float* tc_scratch, int64_t tc_scratch_floats, arpde_stream_t stream);
 
+/* Ground-truth finite-difference solver of the 1D viscous Burgers equation, fp64, a batch of trajectories in one launch:
+ * burgers1d() of 1D-Burger-SWAG/solver/fd_burger1D.py:32-98 (RK4 :45-52; upwind gradient of order grad_order in {1,2} chosen by the sign
+ * of u :36-42,58-68; central second derivative of order div_order in {2,4} :70-79; periodic).  u0: [N][L] device doubles; out: [N][nsteps /
+ * save_every][L] device floats, row r = the state after (r+1)*save_every steps rounded to fp32 as the reference stores it (save_every = 1
+ * reproduces its [nsteps, L] array). */
+int arpde_fd_burgers1d(const double* u0, float* out, int N, int L, double dx, double nu, double dt, int nsteps, int save_every,
+                       int grad_order, int div_order, arpde_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * SWAG.  arpde_swag_sample replaces SwagNN.sample (nn/swag.py:80-150) for S samples at once:
  *   mean/sq_mean/cov_host: HOST arrays of per-tensor device pointers in named_parameters() order

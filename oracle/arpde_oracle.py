@@ -318,6 +318,39 @@ def ks_be(uPred, uPred0, dt, dx, nu=1.0, k1=5, k2=5, k4=7):
 
 
 # --------------------------------------------------------------------------------------
+# ground-truth FD solver (1D-Burger-SWAG/solver/fd_burger1D.py:32-98), numpy fp64
+# --------------------------------------------------------------------------------------
+
+
+def fd_burgers1d(u0, dt, nsteps, dx, nu, grad_order=(1, 2), rows=None):
+    """burgers1d(): RK4 (:45-52) of u_t = -u u_x + nu u_xx with the upwind gradient (:36-42: backward difference where u > 0, forward
+    otherwise; first order [-1, 1, 0] / [0, -1, 1] over dx or second order [1, -4, 3, 0, 0] / [0, 0, -3, 4, -1] over 2 dx, :58-68) and the
+    central second derivative of order 2 or 4 (:70-79); periodic.  u0 [N, L] float64.  Returns float32 [N, nsteps (or len(rows)), L]:
+    the state after every step, stored in float32 as the reference does (:82)."""
+    u = np.asarray(u0, dtype=np.float64).copy()
+    r = lambda a, k: np.roll(a, -k, axis=-1)                    # a[i + k]
+
+    def rhs(v):
+        if grad_order[0] == 1:
+            back, fwd = (-r(v, -1) + v) / dx, (-v + r(v, 1)) / dx
+        else:
+            back, fwd = (r(v, -2) - 4 * r(v, -1) + 3 * v) / (2 * dx), (-3 * v + 4 * r(v, 1) - r(v, 2)) / (2 * dx)
+        if grad_order[1] == 2:
+            lap = (r(v, -1) - 2 * v + r(v, 1)) / dx ** 2
+        else:
+            lap = (-r(v, -2) / 12 + 4 * r(v, -1) / 3 - 5 * v / 2 + 4 * r(v, 1) / 3 - r(v, 2) / 12) / dx ** 2
+        return -v * np.where(v > 0, back, fwd) + nu * lap
+    out = []
+    keep = None if rows is None else set(int(i) for i in rows)
+    for i in range(nsteps):
+        k1 = rhs(u); k2 = rhs(u + k1 * dt / 2); k3 = rhs(u + k2 * dt / 2); k4 = rhs(u + k3 * dt)
+        u = u + (k1 + 2 * k2 + 2 * k3 + k4) * dt / 6
+        if keep is None or i in keep:
+            out.append(u.astype(np.float32))
+    return np.stack(out, 1)
+
+
+# --------------------------------------------------------------------------------------
 # loss  (bayesNN.py:29-35, 98-129)
 # --------------------------------------------------------------------------------------
 

@@ -358,8 +358,46 @@ def gen_p4():
     print('wrote p4.npz,', len(out), 'keys')
 
 
+def gen_fd():
+    """burgers1d() of the reference's ground-truth script 1D-Burger-SWAG/solver/fd_burger1D.py:55-98 (RK4 + upwind,
+    fp64), called as a function with the module globals its __main__ block would set (args.nu, dx, idx)."""
+    import importlib
+    import types
+    import numpy as np
+    import torch
+    from oracle import ref_shims
+    proj = ref_shims.import_reference('burgers1d')
+    sys.path.insert(0, os.path.join(proj, 'solver'))
+    for k in [k for k in sys.modules if k == 'utils' or k.startswith('utils.')]:
+        del sys.modules[k]
+    fd = importlib.import_module('fd_burger1D')
+    out = {}
+    ncell, nu, dt, nsteps = 128, 0.0025, 5e-4, 600
+    fd.args = types.SimpleNamespace(nu=nu)
+    fd.dx = 1.0 / ncell
+    fd.idx = 0
+    rng = np.random.RandomState(3)
+    x = np.linspace(0, 1, ncell + 1)[:-1]
+    u0 = np.stack([a * np.sin(2 * np.pi * (x + b)) + c * np.cos(4 * np.pi * x) + d for a, b, c, d in rng.randn(3, 4)])
+    out['u0'] = u0
+    out['ncell'], out['nu'], out['dt'], out['nsteps'] = map(np.array, (ncell, nu, dt, nsteps))
+    rows = np.array([0, 1, 9, 99, 299, 599])
+    out['rows'] = rows
+    for go in ([1, 2], [2, 4], [1, 4]):
+        res = []
+        for i in range(u0.shape[0]):
+            with torch.no_grad():
+                u_fd, _ = fd.burgers1d(u0[i:i + 1], dt, nsteps, grad_order=go, device='cpu')
+            res.append(u_fd[rows])
+        out['u/g%dd%d' % tuple(go)] = np.stack(res)             # float32 [3, len(rows), ncell]
+    np.savez_compressed(os.path.join(HERE, 'fd_burgers1d.npz'), **out)
+    print('wrote fd_burgers1d.npz', {k: v.shape for k, v in out.items()})
+
+
 if __name__ == '__main__':
-    if len(sys.argv) > 1 and sys.argv[1] == 'p4':
+    if len(sys.argv) > 1 and sys.argv[1] == 'fd':
+        gen_fd()
+    elif len(sys.argv) > 1 and sys.argv[1] == 'p4':
         gen_p4()
     elif len(sys.argv) > 1 and sys.argv[1] == 'ic2d':
         gen_ic2d()
@@ -372,3 +410,4 @@ if __name__ == '__main__':
             subprocess.check_call([sys.executable, os.path.abspath(__file__), s], cwd=cwd)
         subprocess.check_call([sys.executable, os.path.abspath(__file__), 'ic2d'], cwd='/tmp')
         subprocess.check_call([sys.executable, os.path.abspath(__file__), 'p4'], cwd='/tmp')
+        subprocess.check_call([sys.executable, os.path.abspath(__file__), 'fd'], cwd='/tmp')

@@ -21,7 +21,11 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 
 ARGS = {
     'burgers2d': ['--epochs', '2', '--ntrain', '16', '--batch-size', '8', '--plot-freq', '2', '--ckpt-freq', '2', '--nel', '32'],
-    'burgers1d': ['--epochs', '2', '--ntrain', '16', '--batch-size', '8', '--plot-freq', '2', '--ckpt-freq', '2', '--nel', '64'],
+    # 1D Burgers back-propagates through windows of up to 9 AR steps: with the default learning rate two epochs on an untrained net are
+    # already chaotic at the 1e-2 level even between two runs of the reference itself (cuDNN vs MKL: loss 5 %, predictions 7 %), so this
+    # driver is exercised with a smaller step size
+    'burgers1d': ['--epochs', '2', '--ntrain', '16', '--batch-size', '8', '--plot-freq', '2', '--ckpt-freq', '2', '--nel', '64',
+                  '--lr', '0.0001', '--lr-beta', '0.0001'],
     'ks1d': ['--epochs', '2', '--ntrain', '16', '--batch-size', '8', '--plot-freq', '2', '--ckpt-freq', '2'],
 }
 EPOCH_RE = re.compile(r'^Epoch: (\d+), Loss: ([0-9.E+-]+), MSE: ([0-9.E+-]+), Noise ([0-9.]+)')

@@ -26,13 +26,18 @@ pytestmark = pytest.mark.gpu
 # BPTT; how much is CALIBRATED, not guessed: the same command is also run on the reference's own modules ON THIS GPU (cuDNN, TF32 off),
 # and the spread between the reference's two backends (CUDA here vs the CPU fixture) is the yardstick -- the drop-in must stay within
 # SPREAD_FACTOR x that spread (or FLOOR, whichever is larger) of the reference-on-CUDA run.
+# The checksum of the test() rollout is far more sensitive than the training losses: in eval mode the barely-trained network runs on
+# BatchNorm running statistics estimated from a handful of mini-batches, and even the reference on 1 vs 8 CPU threads differs by up to
+# 7 % there (1D Burgers) while its losses agree to 7e-4 -- hence the separate floor for it.  Layer- and model-level parity at 1e-5 is
+# the business of test_gpu_parity.py; this test proves the unmodified drivers run end to end on the drop-in and stay on the
+# reference's trajectory to within the reference's own reproducibility.
 SPREAD_FACTOR = 5.0
-FLOOR = 2e-3
+FLOOR = {'loss': 2e-3, 'mse': 2e-3, 'noise': 2e-3, 'pred': 1e-1}
 
 
 def _close(ours, ref_cuda, ref_cpu, key):
     spread = abs(ref_cuda - ref_cpu)
-    return abs(ours - ref_cuda) <= max(SPREAD_FACTOR * spread, FLOOR * abs(ref_cuda)), (key, ours, ref_cuda, ref_cpu)
+    return abs(ours - ref_cuda) <= max(SPREAD_FACTOR * spread, FLOOR[key[-1]] * abs(ref_cuda)), (key, ours, ref_cuda, ref_cpu)
 
 
 @pytest.mark.parametrize('system', ['burgers2d', 'burgers1d', 'ks1d'])

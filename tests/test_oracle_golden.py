@@ -230,3 +230,15 @@ def test_p4_filters_oracle_vs_reference_fixture():
     assert rel_err(O.filt2d_k(a, O.SOBEL_H5, dx), g['2d/filt5/grad_h']) < 1e-5
     assert rel_err(O.filt2d_k(a, O.SOBEL_V5, dx), g['2d/filt5/grad_v']) < 1e-5
     assert rel_err(O.filt2d_k(a, O.LAPLACE_5, dx ** 2), g['2d/filt5/lap']) < 1e-5
+
+
+# ----------------------------------------------------------------------------- ground-truth FD solver
+@pytest.mark.parametrize('go', [(1, 2), (2, 4), (1, 4)])
+def test_fd_solver_oracle_vs_reference_fixture(go):
+    g = golden('fd_burgers1d')
+    rows = g['rows']
+    u = O.fd_burgers1d(g['u0'], float(g['dt']), int(g['nsteps']), 1.0 / int(g['ncell']), float(g['nu']), grad_order=go, rows=rows)
+    ref = g['u/g%dd%d' % go]
+    assert u.shape == ref.shape and u.dtype == np.float32
+    # fp64 integration on both sides, results stored in fp32: agreement to fp32 rounding
+    assert rel_err(u, ref) < 2e-7

@@ -485,7 +485,9 @@ static bool wg_plan(const ConvDesc& d, WgTcArgs& a, size_t* smem_out) {
   if (d.dilate || d.pad_override >= 0) return false;
   if (d.up && d.stride == 1 && d.kh == 3 && d.kw == 3 && d.H > 1 && 4 * d.cout <= 128 && 4 * d.cout > 8 && !arpde_dev_env("ARPDE_WG_NO_FOLD")) {
     ConvDesc e = d; e.up = 0; e.cout = 4 * d.cout;         // equivalent low-resolution conv, parity-major channels (conv_tc.cu upfold)
-    if (wg_plan(e, a, smem_out) && !a.swap) { a.fold = 1; a.cout_fold = d.cout; return true; }
+    // (ky, ci)-packed rings (cin * kh <= 32) are not folded: the fold's drain maps accumulator columns to taps as one column per
+    // channel (measured wrong for cin = 9, 10; found by the (2,3,2)-topology backward test) -- those layers take the unfolded paths below
+    if (wg_plan(e, a, smem_out) && !a.swap && !a.packed) { a.fold = 1; a.cout_fold = d.cout; return true; }
   }
   if (d.H == 1 && d.kh == 1) return false;                       // 1D nets stay on the FFMA kernel
   if (d.stride != 1 && d.stride != 2) return false;

@@ -45,7 +45,7 @@ def _param_table(plan, named_params, flat):
 
 
 @torch.no_grad()
-def rollout(model, ic, tsteps, flat_weights=None, named_params=None, out=None, layerwise=False):
+def rollout(model, ic, tsteps, flat_weights=None, named_params=None, out=None, layerwise=False, t_start=0, total_steps=None):
     """Eval-mode AR rollout.
 
     model: DenseED / BayesNN / SwagNN (running BN statistics and, without flat_weights, the weights come from it)
@@ -53,7 +53,10 @@ def rollout(model, ic, tsteps, flat_weights=None, named_params=None, out=None, l
     flat_weights: optional [S, P] table from SwagNN.sample_flat (P = named_params order) -> S*N rollouts,
                   sample-major: row s*N + n uses weight sample s on initial condition n
     layerwise: force the layer-by-layer path (the KS network otherwise runs as one persistent launch; cross-check hook)
-    returns traj [S*N, T+1, c_out, (H,) W] (index 0 = initial state)
+    t_start / total_steps: roll out in pieces -- `out` is the buffer of a total_steps rollout; the call advances steps
+                  [t_start, t_start + tsteps) from the states already in the buffer (t_start = 0 fills in the initial history), so
+                  the caller can reduce / ship the finished steps of one piece while the next one runs
+    returns traj [S*N, T+1, c_out, (H,) W] (index 0 = initial state); with total_steps the view covers all total_steps + 1 states
     """
     feats = _features_of(model)
     plan = P.compile_module(feats)
@@ -75,13 +78,19 @@ def rollout(model, ic, tsteps, flat_weights=None, named_params=None, out=None, l
             raise ValueError('named_params (the module order flat_weights was built in) is required')
     NT = S * N
     c_hist = plan.c_in
-    ctot = c_hist + tsteps * c_out
+    total = int(tsteps) if total_steps is None else int(total_steps)
+    if t_start < 0 or t_start + tsteps > total:
+        raise ValueError('steps [%d, %d) outside the %d-step rollout' % (t_start, t_start + tsteps, total))
+    if t_start > 0 and out is None:
+        raise ValueError('t_start > 0 continues a rollout: pass its buffer as `out`')
+    ctot = c_hist + total * c_out
     dev = ic.device
     if out is None:
         out = torch.empty((NT, ctot, H, W), device=dev, dtype=torch.float32)
     elif out.shape != (NT, ctot, H, W) or not out.is_contiguous():
         raise ValueError('out must be a contiguous [%d,%d,%d,%d] tensor' % (NT, ctot, H, W))
-    out.view(S, N, ctot, H, W)[:, :, :c_hist] = ic4.repeat(1, c_hist // c_out, 1, 1).unsqueeze(0)
+    if t_start == 0:
+        out.view(S, N, ctot, H, W)[:, :, :c_hist] = ic4.repeat(1, c_hist // c_out, 1, 1).unsqueeze(0)
     bufs, work_len, _ = P.layout(plan, NT, H, W)
     ops_c, bufs_c = P.c_tables(plan, bufs)
     work = torch.empty((max(work_len, 1),), device=dev, dtype=torch.float32)
@@ -91,9 +100,11 @@ def rollout(model, ic, tsteps, flat_weights=None, named_params=None, out=None, l
     tc_len = int(L.lib.arpde_densed_tc_scratch_floats(ops_c, len(plan.ops), S))
     tc = torch.empty((max(tc_len, 1),), device=dev, dtype=torch.float32)
     with torch.cuda.device(dev):
-        L.call('arpde_rollout_layerwise' if layerwise else 'arpde_rollout', ops_c, len(plan.ops), bufs_c, len(bufs), pp, gs, len(keep), L.ptr(out), ctot, plan.c_in, c_hist,
+        # a continued piece: the same buffer seen from t_start * c_out channels further on (the batch stride is unchanged)
+        L.call('arpde_rollout_layerwise' if layerwise else 'arpde_rollout', ops_c, len(plan.ops), bufs_c, len(bufs), pp, gs, len(keep),
+               L.ptr(out) + 4 * t_start * c_out * H * W, ctot, plan.c_in, c_hist,
                c_out, int(tsteps), NT, N, H, W, L.ptr(work), L.ptr(ss), plan.bn_total, float(eps), L.ptr(tc), tc_len, L.stream())
-    traj = out[:, c_hist - c_out:].view(NT, tsteps + 1, c_out, H, W)
+    traj = out[:, c_hist - c_out:].view(NT, total + 1, c_out, H, W)
     return traj.squeeze(3) if one_d else traj
 
 

@@ -106,6 +106,31 @@ def test_wgrad_tc_unsupported_layer_reports_error():
         wgrad_tc(x, 16 * 32 * 32, None, None, gy, 12 * 32 * 32, 2, 16, 32, 32, 12, 3, 3, 1, 0, 0)
 
 
+UP_SMALL = [(9, 4, 16, 16, 3), (9, 8, 16, 16, 3), (10, 5, 16, 16, 3), (9, 16, 16, 16, 3), (12, 4, 16, 16, 3), (24, 12, 16, 16, 2), (9, 4, 32, 32, 2)]
+
+
+@pytest.mark.parametrize('cin,cout,H,W,N', UP_SMALL)
+def test_wgrad_upsampled_small_channel_counts(cin, cout, H, W, N):
+    """nearest-x2 + conv3x3 layers of small encoder-decoder topologies (LastTransUp / TransUp of a (2,3,2) net: 9 -> 4, 10 -> 5 ...):
+    arpde_conv_wgrad's automatic choice (folded tensor-core kernel where it plans, else FFMA) and the generic kernel vs fp64 autograd.
+    cin * 3 <= 32 would select the (ky, ci)-packed ring, which the fold does not support: regression test for that dispatch."""
+    torch.manual_seed(cin * 7 + cout)
+    x = torch.randn(N, cin, H, W)
+    gy = torch.randn(N, cout, 2 * H, 2 * W)
+    sc, sh = torch.rand(cin) + 0.5, torch.randn(cin) * 0.3
+    ref = oracle_wgrad(x, sc, sh, 1, 1, gy, cout, 3, 3, 1)
+    xd, gd, scd, shd = x.to(DEV), gy.to(DEV), sc.to(DEV), sh.to(DEV)
+    d64 = torch.empty((cout * cin * 9,), device=DEV, dtype=torch.float64)
+    n_scr = int(L.lib.arpde_conv_wgrad_tc_scratch(N, cin, H, W, cout, 3, 3, 1, 1))
+    scr = torch.empty((max(n_scr, 1),), device=DEV)
+    for path in (0, 1):
+        dW = torch.full((cout, cin, 3, 3), 5.0, device=DEV)
+        L.call('arpde_conv_wgrad', L.ptr(xd), cin * H * W, L.ptr(scd), L.ptr(shd), L.ptr(gd), cout * 4 * H * W, L.ptr(d64), L.ptr(dW),
+               N, cin, H, W, cout, 3, 3, 1, 1, 1, L.ptr(scr) if n_scr else 0, n_scr, path, L.stream())
+        torch.cuda.synchronize()
+        assert rel_err(dW, ref) < TOL, path
+
+
 NARROW = [  # cin, cout, k, H, W, N
     (16, 2, 5, 64, 64, 5),       # LastTransUp conv5x5
     (60, 4, 3, 32, 32, 5),       # denselayer4

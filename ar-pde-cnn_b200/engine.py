@@ -109,12 +109,13 @@ def rollout(model, ic, tsteps, flat_weights=None, named_params=None, out=None, l
 
 
 @torch.no_grad()
-def predictive_moments(traj, n_samples, betas=None, formula='2d'):
+def predictive_moments(traj, n_samples, betas=None, formula='2d', noise=None):
     """Sample mean and predictive variance over the S weight samples of a sample-major trajectory.
 
     formula '2d': var = 1/mean(beta) + E[y^2] - E[y]^2      (2D-Burgers-SWAG/post/plotBARContour.py:85-104)
     formula '1d': var = mean_s(1/beta_s + y_s^2) - mean^2   (1D-Burger-SWAG/post/plotBARContour.py:123,136-139)
-    betas None -> pure sample variance (noise term 0).
+    betas None -> pure sample variance (noise term 0).  noise: the noise term as a Python float (skips the device->host read of
+    betas, e.g. when the moments of several pieces of one rollout are taken with the same weight samples).
     """
     L.require_cuda(traj)
     t = traj
@@ -128,7 +129,9 @@ def predictive_moments(traj, n_samples, betas=None, formula='2d'):
     if NT % n_samples:
         raise ValueError('%d rollouts is not a multiple of %d samples' % (NT, n_samples))
     n_ic = NT // n_samples
-    if betas is None:
+    if noise is not None:
+        noise = float(noise)
+    elif betas is None:
         noise = 0.0
     elif formula == '2d':
         noise = float(1.0 / betas.double().mean())

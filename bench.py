@@ -26,6 +26,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 S_SAMPLES, N_IC, T_STEPS, NEL = 30, 64, 100, 64
+E2E_CHUNKS = 4                # pieces of the end-to-end rollout (device->host copy of piece k overlaps the rollout of piece k + 1)
 MODEL_MFLOP = 267.32          # forward MFLOP per sample-step of the default 2D net
 C5_MFLOP = 12233.7            # wide net (growth 32) at 256x256
 KS_MFLOP = 0.51
@@ -524,6 +525,20 @@ def main():
             if rank == 0 or not gathered:
                 self.mean_host = torch.empty((n_res,) + state, pin_memory=True)
                 self.var_host = torch.empty((n_res,) + state, pin_memory=True)
+            # pipelined end-to-end form: the rollout advances in E2E_CHUNKS pieces; the moments of a finished piece are gathered and copied
+            # to the host on a side stream while the next piece runs (equal shards only)
+            self.pipelined = (N_IC % world == 0) and T_STEPS % E2E_CHUNKS == 0 and T_STEPS >= 2 * E2E_CHUNKS
+            if self.pipelined:
+                cl = T_STEPS // E2E_CHUNKS
+                self.spans = [(k * cl + (0 if k == 0 else 1), (k + 1) * cl + 1) for k in range(E2E_CHUNKS)]      # saved states [lo, hi) of piece k
+                self.copy_stream = torch.cuda.Stream(device=dev)
+                self.host_chunks, self.g_chunks = [], []
+                for lo_, hi_ in self.spans:
+                    shp = (hi_ - lo_, 2, NEL, NEL)
+                    if rank == 0 or not gathered:
+                        self.host_chunks.append((torch.empty((n_res,) + shp, pin_memory=True), torch.empty((n_res,) + shp, pin_memory=True)))
+                    if gathered and world > 1 and rank == 0:
+                        self.g_chunks.append((torch.empty((world, self.n) + shp, device=dev), torch.empty((world, self.n) + shp, device=dev)))
 
         def run(self, ic):
             flat, names, numels = swag.sample_flat(S_SAMPLES, generator=gen)
@@ -540,8 +555,38 @@ def main():
                     return self.g_m, self.g_v
             return mean, var
 
+        def run_e2e_pipelined(self):
+            """host ICs in, host predictive mean/variance out (rank 0: all ICs, as a list of time pieces [N_ic, steps, 2, H, W]);
+            the device->host copy of piece k overlaps the rollout of piece k + 1"""
+            ic = self.ic_host.to(dev, non_blocking=True)
+            flat, names, numels = swag.sample_flat(S_SAMPLES, generator=gen)
+            noise = float(1.0 / flat[:, 0].exp().double().mean())         # one device->host read per job, before the rollout is queued
+            cl = T_STEPS // E2E_CHUNKS
+            main = torch.cuda.current_stream()
+            for k, (lo_, hi_) in enumerate(self.spans):
+                traj = engine.rollout(swag, ic, cl, flat_weights=flat, named_params=named, out=self.traj_buf, t_start=k * cl, total_steps=T_STEPS)
+                mean, var = engine.predictive_moments(traj[:, lo_:hi_], S_SAMPLES, formula='2d', noise=noise)
+                if self.gathered and world > 1:
+                    gm, gv = self.g_chunks[k] if rank == 0 else (None, None)
+                    dist.gather(mean, list(gm.unbind(0)) if rank == 0 else None, dst=0)
+                    dist.gather(var, list(gv.unbind(0)) if rank == 0 else None, dst=0)
+                    src = (gm.view((N_IC,) + tuple(gm.shape[2:])), gv.view((N_IC,) + tuple(gv.shape[2:]))) if rank == 0 else None
+                else:
+                    src = (mean, var)
+                if src is not None and (rank == 0 or not self.gathered):
+                    ev = torch.cuda.Event(); ev.record(main)
+                    self.copy_stream.wait_event(ev)
+                    with torch.cuda.stream(self.copy_stream):
+                        self.host_chunks[k][0].copy_(src[0], non_blocking=True)
+                        self.host_chunks[k][1].copy_(src[1], non_blocking=True)
+                    src[0].record_stream(self.copy_stream); src[1].record_stream(self.copy_stream)
+            self.copy_stream.synchronize()
+            main.synchronize()
+
         def run_e2e(self):
             """the call a user makes: host ICs in, host predictive mean/variance (of ALL ICs, on rank 0) out"""
+            if self.pipelined:
+                return self.run_e2e_pipelined()
             ic = self.ic_host.to(dev, non_blocking=True)
             mean, var = self.run(ic)
             if self.gathered and world > 1:
@@ -668,7 +713,8 @@ def main():
                                                          'bumped after every <<<>>> of the library; torch kernels -- noise draws, history fill -- are not counted)',
         'e2e': {'value': e2e_value, 'unit': 'sample-steps/s', 'ms_per_step': ms_e2e / args.steps,
                 'h2d_bytes_per_step': ic_all_host.numel() * 4, 'd2h_bytes_per_step': 2 * N_IC * (T_STEPS + 1) * 2 * NEL * NEL * 4,
-                'what': 'pinned host ICs -> device (every rank its shard), job, NCCL gather to rank 0, rank 0 copies mean and variance of all 64 ICs to pinned host memory'},
+                'what': 'pinned host ICs -> device (every rank its shard); rollout in %d pieces: the predictive moments of a finished piece are gathered to rank 0 '
+                        '(NCCL) and copied to pinned host memory on a side stream while the next piece runs; rank 0 ends with mean and variance of all 64 ICs' % E2E_CHUNKS},
         'roofline': {'kernel': 'conv_tc_kernel on In_conv3 (96->48, 3x3/s2, %d samples): tcgen05 implicit GEMM, 3xTF32 split (+ its weight-split launch)' % NT,
                      'bound': 'tensor', 'achieved': k1_tflops, 'peak': peaks['bf16_tflops'], 'unit': 'TFLOP/s', 'frac': k1_tflops / peaks['bf16_tflops'],
                      'traffic': 4.486e9 if world == 1 else None,

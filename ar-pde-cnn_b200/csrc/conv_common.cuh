@@ -119,6 +119,11 @@ bool arpde_ks_program_matches(const arpde_op* ops, int n_ops, const arpde_buf* b
 int arpde_ks_rollout_launch(const arpde_op* ops, void* const* params, const int64_t* gstride, float* traj, long long bs, int c_hist, int T, int N,
                             int n_per_group, float eps, cudaStream_t stream);
 
+// fused dense block (dense_block.cu): all 4-channel dense layers of a block in one launch, eval mode
+int arpde_dense_block_match(const arpde_op* ops, int n_ops, int first, const arpde_buf* bufs, int N);
+int arpde_dense_block_launch(const arpde_op* ops, int first, int nl, const arpde_buf* bufs, void* const* params, const int64_t* gstride, float* work,
+                             const float* scale, const float* shift, long long ss_gs, int N, int n_per_group, cudaStream_t stream);
+
 // tensor-core (tcgen05) implicit-GEMM path, conv_tc.cu
 long long* arpde_tc_debug_buffer();                              // arpde_conv_tc_set_debug's buffer (nullptr = off)
 int arpde_tc_enabled();                                          // ARPDE_TC=0 in the environment disables it

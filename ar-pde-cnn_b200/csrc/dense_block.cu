@@ -1,0 +1,176 @@
+// dense_block.cu -- a whole dense block of the 2D DenseED in ONE launch (eval mode: rollout / inference).
+//
+// Replaces _DenseBlock.forward (2D-Burgers-SWAG/nn/denseEDcirc2d.py:34-79): num_layers x [BatchNorm, ReLU, circular conv3x3 -> growth = 4
+// channels, torch.cat].  Layer by layer the block costs one launch per dense layer and each launch re-reads all 48..60 input channels
+// from HBM (1.86 ms of the 6.8 ms AR step at 1920 samples for 8 % of the FLOPs, ~16 TFLOP/s).  Here a CTA owns 16 rows of one sample:
+//   * the 48 raw input channels of its rows plus `layers` halo rows on either side (circular in y) are loaded from HBM ONCE into shared
+//     memory (147 KB), every layer appends its 4 channels there, and only the 16 owned rows of the new channels are written back; the
+//     halo rows of layer j are recomputed (rows shrink by one per layer and side: 22, 20, 18, 16 -- 19 % extra FLOPs instead of a
+//     cluster-wide exchange);
+//   * a row is 32 columns = 32 lanes, so the x-neighbours of a pixel come from the neighbouring lanes by shuffle and the circular wrap in
+//     x is the shuffle's modulo; a warp computes 3 rows x 4 output channels per lane from 5 activated input rows (BN + ReLU applied once
+//     per loaded value: 108 FMAs per 5 shared loads + 10 shuffles + 9 broadcast weight loads);
+//   * two warps split the input channels of every row triple (partial sums meet in shared memory), which keeps all 16 warps busy.
+// Bound: fp32 FMA pipe (4-channel layers cannot feed a tensor-core tile: an MMA costs >= 32 cycles whatever N is).
+#include "common.cuh"
+#include "conv_common.cuh"
+#include "../../include/arpde.h"
+
+namespace {
+
+constexpr int DB_W = 32, DB_OWN = 16, DB_R = 3, DB_WARPS = 16, DB_MAXL = 4, DB_MAXC = 64;
+
+struct DenseBlockArgs {
+  float* buf; long long bs;                     // dense-block buffer [N][ctot][H][32]
+  int c0, nl, H, N, n_per_group;
+  const float* w[DB_MAXL]; long long w_gs[DB_MAXL];   // layer weights [4][cin][3][3], group stride
+  const float* scale; const float* shift; long long ss_gs; int bn_off[DB_MAXL];   // folded eval BatchNorm of layer j: scale[g*ss_gs + bn_off[j] + ci]
+};
+
+__global__ void __launch_bounds__(512, 1) dense_block_kernel(DenseBlockArgs a) {
+  extern __shared__ __align__(16) float sm[];
+  const int rows = DB_OWN + 2 * a.nl;
+  const int ctot = a.c0 + 4 * a.nl;
+  float* X = sm;                                          // [ctot][rows][32]
+  float* Wt = X + (size_t)ctot * rows * DB_W;             // [cin][9][4]
+  float* SS = Wt + (size_t)(ctot - 4) * 36;               // [2][cin]
+  float* RED = SS + 2 * DB_MAXC;                          // [8 items][12][32]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tiles = a.H / DB_OWN;
+  const long long HW = (long long)a.H * DB_W;
+  const int lm = (lane + 31) & 31, lp = (lane + 1) & 31;
+  for (int work = blockIdx.x; work < a.N * tiles; work += gridDim.x) {
+    const int n = work / tiles, y0 = (work - n * tiles) * DB_OWN, g = n / a.n_per_group;
+    float* bn_ = a.buf + (long long)n * a.bs;
+    // ---- raw input channels of rows y0 - nl .. y0 + 16 + nl - 1 (circular): one float4 per lane covers 4 rows per warp step
+    {
+      const int nrow = a.c0 * rows;                       // (channel, local row) pairs, 128 B each
+      for (int q = warp * 4 + (lane >> 3); q < nrow; q += DB_WARPS * 4) {
+        const int c = q / rows, r = q - c * rows;
+        int y = y0 - a.nl + r; y = y < 0 ? y + a.H : (y >= a.H ? y - a.H : y);
+        const float4 v = __ldg(reinterpret_cast<const float4*>(bn_ + c * HW + (long long)y * DB_W) + (lane & 7));
+        *reinterpret_cast<float4*>(X + ((size_t)c * rows + r) * DB_W + 4 * (lane & 7)) = v;
+      }
+    }
+    for (int j = 0; j < a.nl; ++j) {
+      const int cin = a.c0 + 4 * j;
+      {  // stage the layer's weights as [ci][tap][co] and its folded BatchNorm
+        const float* w = a.w[j] + (long long)g * a.w_gs[j];
+        const int per_co = 9 * cin;
+        for (int i = tid; i < 4 * per_co; i += 512) { const int co = i / per_co, r = i - co * per_co; Wt[r * 4 + co] = __ldg(w + i); }
+        const float* sc = a.scale + (long long)g * a.ss_gs + a.bn_off[j];
+        const float* sh = a.shift + (long long)g * a.ss_gs + a.bn_off[j];
+        for (int i = tid; i < cin; i += 512) { SS[i] = __ldg(sc + i); SS[DB_MAXC + i] = __ldg(sh + i); }
+      }
+      __syncthreads();
+      const int r_lo = j + 1, r_hi = rows - j - 1;        // local output rows [r_lo, r_hi)
+      const int nitems = (r_hi - r_lo + DB_R - 1) / DB_R;
+      const int item = warp >> 1, kh = warp & 1;
+      float acc[DB_R][4];
+#pragma unroll
+      for (int r = 0; r < DB_R; ++r) { acc[r][0] = 0.f; acc[r][1] = 0.f; acc[r][2] = 0.f; acc[r][3] = 0.f; }
+      const int rb = r_lo + item * DB_R;
+      if (item < nitems) {
+        const int half = cin >> 1;
+        int rix[DB_R + 2];
+#pragma unroll
+        for (int r = 0; r < DB_R + 2; ++r) { int q = rb - 1 + r; rix[r] = (q > rows - 1 ? rows - 1 : q) * DB_W + lane; }
+#pragma unroll 2
+        for (int c = kh * half; c < (kh + 1) * half; ++c) {
+          const float s = SS[c], t = SS[DB_MAXC + c];
+          const float* xc = X + (size_t)c * rows * DB_W;
+          float v[DB_R + 2], vl[DB_R + 2], vr[DB_R + 2];
+#pragma unroll
+          for (int r = 0; r < DB_R + 2; ++r) v[r] = fmaxf(fmaf(xc[rix[r]], s, t), 0.f);
+#pragma unroll
+          for (int r = 0; r < DB_R + 2; ++r) { vl[r] = __shfl_sync(0xffffffffu, v[r], lm); vr[r] = __shfl_sync(0xffffffffu, v[r], lp); }
+          const float4* wp = reinterpret_cast<const float4*>(Wt + (size_t)c * 36);
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky) {
+            const float4 w0 = wp[ky * 3], w1 = wp[ky * 3 + 1], w2 = wp[ky * 3 + 2];
+#pragma unroll
+            for (int r = 0; r < DB_R; ++r) {
+              const float xl = vl[r + ky], xm = v[r + ky], xr = vr[r + ky];
+              acc[r][0] = fmaf(w0.x, xl, fmaf(w1.x, xm, fmaf(w2.x, xr, acc[r][0])));
+              acc[r][1] = fmaf(w0.y, xl, fmaf(w1.y, xm, fmaf(w2.y, xr, acc[r][1])));
+              acc[r][2] = fmaf(w0.z, xl, fmaf(w1.z, xm, fmaf(w2.z, xr, acc[r][2])));
+              acc[r][3] = fmaf(w0.w, xl, fmaf(w1.w, xm, fmaf(w2.w, xr, acc[r][3])));
+            }
+          }
+        }
+        if (kh == 1) {
+#pragma unroll
+          for (int r = 0; r < DB_R; ++r)
+#pragma unroll
+            for (int co = 0; co < 4; ++co) RED[((size_t)item * 12 + r * 4 + co) * DB_W + lane] = acc[r][co];
+        }
+      }
+      __syncthreads();
+      if (item < nitems && kh == 0) {
+#pragma unroll
+        for (int r = 0; r < DB_R; ++r) {
+          if (rb + r < r_hi) {
+#pragma unroll
+            for (int co = 0; co < 4; ++co)
+              X[((size_t)(cin + co) * rows + rb + r) * DB_W + lane] = acc[r][co] + RED[((size_t)item * 12 + r * 4 + co) * DB_W + lane];
+          }
+        }
+      }
+      __syncthreads();
+    }
+    // ---- the owned rows of the new channels go back to the buffer
+    {
+      const int nrow = 4 * a.nl * DB_OWN;
+      for (int q = warp * 4 + (lane >> 3); q < nrow; q += DB_WARPS * 4) {
+        const int c = a.c0 + q / DB_OWN, r = q % DB_OWN;
+        const float4 v = *reinterpret_cast<const float4*>(X + ((size_t)c * rows + a.nl + r) * DB_W + 4 * (lane & 7));
+        *(reinterpret_cast<float4*>(bn_ + c * HW + (long long)(y0 + r) * DB_W) + (lane & 7)) = v;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace
+
+// number of consecutive ops starting at `first` that form a fusable dense block (0 = none)
+int arpde_dense_block_match(const arpde_op_t* ops, int n_ops, int first, const arpde_buf_t* bufs, int N) {
+  const arpde_op_t& o0 = ops[first];
+  if (o0.in_buf < 0 || o0.out_buf != o0.in_buf) return 0;
+  const arpde_buf_t& b = bufs[o0.in_buf];
+  if (b.w != DB_W || b.h < DB_OWN || b.h % DB_OWN) return 0;
+  int nl = 0;
+  for (int i = first; i < n_ops && nl < DB_MAXL; ++i, ++nl) {
+    const arpde_op_t& o = ops[i];
+    if (o.in_buf != o0.in_buf || o.out_buf != o0.in_buf || o.cout != 4 || o.kh != 3 || o.kw != 3 || o.stride != 1 || o.up || o.bn_param < 0 || o.act ||
+        o.cin != o0.cin + 4 * nl || o.out_coff != o.cin) break;
+  }
+  if (nl < 2 || (o0.cin & 1) || o0.cin + 4 * nl > DB_MAXC || o0.cin + 4 * nl > b.ctot) return 0;
+  // one CTA per (sample, 16-row tile): worth it once the grid fills the machine (small batches stay on the per-layer kernels)
+  if ((long long)N * (b.h / DB_OWN) < arpde_num_sms()) return 0;
+  if (arpde_dev_env("ARPDE_DENSE_FUSED_OFF")) return 0;
+  return nl;
+}
+
+int arpde_dense_block_launch(const arpde_op_t* ops, int first, int nl, const arpde_buf_t* bufs, void* const* params, const int64_t* gstride, float* work,
+                             const float* scale, const float* shift, long long ss_gs, int N, int n_per_group, cudaStream_t stream) {
+  const arpde_buf_t& b = bufs[ops[first].in_buf];
+  DenseBlockArgs a; memset(&a, 0, sizeof(a));
+  a.buf = work + b.offset; a.bs = (long long)b.ctot * b.h * b.w;
+  a.c0 = ops[first].cin; a.nl = nl; a.H = b.h; a.N = N; a.n_per_group = n_per_group;
+  for (int j = 0; j < nl; ++j) {
+    a.w[j] = (const float*)params[ops[first + j].w_param]; a.w_gs[j] = gstride[ops[first + j].w_param];
+    a.bn_off[j] = ops[first + j].bn_off;
+  }
+  a.scale = scale; a.shift = shift; a.ss_gs = ss_gs;
+  ARPDE_CHECK_ARG((((uintptr_t)a.buf) & 15) == 0 && (a.bs & 3) == 0, "dense_block: buffer must be 16-byte aligned");
+  const int rows = DB_OWN + 2 * nl, ctot = a.c0 + 4 * nl;
+  const size_t smem = ((size_t)ctot * rows * DB_W + (size_t)(ctot - 4) * 36 + 2 * DB_MAXC + 8 * 12 * DB_W) * sizeof(float);
+  ARPDE_CHECK_ARG(smem <= 227 * 1024, "dense_block: %zu bytes of shared memory needed", smem);
+  ARPDE_CUDA(cudaFuncSetAttribute(dense_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const long long items = (long long)N * (b.h / DB_OWN);
+  long long grid = arpde_num_sms(); if (grid > items) grid = items;
+  dense_block_kernel<<<(unsigned)grid, 512, smem, stream>>>(a);
+  ARPDE_LAUNCH_CHECK();
+  return ARPDE_OK;
+}

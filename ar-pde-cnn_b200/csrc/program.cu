@@ -33,6 +33,7 @@ struct RunCtx {
   float* tc_scratch = nullptr; long long tc_scratch_floats = 0;
   std::vector<const float*> wprep;          // per op: prepared tensor-core weights (nullptr = fp32 FFMA kernel)
   std::vector<long long> wprep_gs;
+  bool fuse_dense = true;                   // eval mode: dense blocks as one launch (off for the layer-wise cross-check path)
   const DpHook* dp = nullptr;               // data-parallel training: all-reduce of the BatchNorm sums (nullptr = single process)
   mutable std::vector<int> synced;          // per buffer: channels whose statistics already hold the global sums
 };
@@ -88,6 +89,17 @@ static int fold_eval(const RunCtx& c) {
 static int run_ops(const RunCtx& c, const float* x, long long x_bs, float* y, int y_ctot, int y_coff, int training) {
   for (int i = 0; i < c.n_ops; ++i) {
     const arpde_op_t& o = c.ops[i];
+    if (!training && c.fuse_dense) {
+      // eval mode: a run of 4-channel dense layers on a 32-column map is ONE launch (dense_block.cu)
+      const int nl = arpde_dense_block_match(c.ops, c.n_ops, i, c.bufs, c.N);
+      if (nl > 0) {
+        int rc = arpde_dense_block_launch(c.ops, i, nl, c.bufs, c.params, c.gstride, c.work, c.ss, c.ss + (long long)c.groups * c.bn_total, c.bn_total,
+                                          c.N, c.n_per_group, c.stream);
+        if (rc) return rc;
+        i += nl - 1;
+        continue;
+      }
+    }
     ConvDesc d;
     d.dilate = 0; d.pad_override = -1;
     d.N = c.N; d.cin = o.cin; d.cout = o.cout; d.kh = o.kh; d.kw = o.kw; d.stride = o.stride; d.up = o.up;
@@ -276,6 +288,7 @@ static int rollout_impl(const arpde_op_t* ops, int n_ops, const arpde_buf_t* buf
   // the reference's KS network on its 96-point grid: the whole rollout is ONE persistent launch (rollout1d.cu)
   if (allow_persistent && arpde_ks_program_matches(ops, n_ops, bufs, n_bufs, H, W, c_in, c_out))
     return arpde_ks_rollout_launch(ops, params_host, param_gstride_host, traj, bs, c_hist, T, N, c.n_per_group, (float)eps, stream);
+  c.fuse_dense = allow_persistent;
   rc = prep_tc(c); if (rc) return rc;
   rc = fold_eval(c); if (rc) return rc;
   for (int t = 0; t < T; ++t) {

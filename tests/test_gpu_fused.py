@@ -1,0 +1,65 @@
+"""Fused dense-block kernel (csrc/dense_block.cu: all 4-channel dense layers of a block in one launch, eval mode, 32-column maps) against
+the layer-by-layer path of the same library and against the CPU oracle of DenseED.forward (2D-Burgers-SWAG/nn/denseEDcirc2d.py:34-79).
+The kernel is only dispatched once the grid fills the machine (N * H/16 >= number of SMs), so these tests use >= 80 samples."""
+import contextlib
+import io
+
+import pytest
+import torch
+
+from _util import golden, rel_err, sub
+import _models as M
+from oracle import arpde_oracle as O
+
+from arpde_b200 import engine
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+TOL = 1e-5
+
+
+def _model(blocks, seed=0, init_features=96):
+    torch.manual_seed(seed)
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = M.CLS['burgers2d'](6, 2, blocks, growth_rate=4, init_features=init_features).to(DEV)
+    with torch.no_grad():
+        for mod in m.modules():
+            if hasattr(mod, 'running_var'):
+                mod.running_mean.uniform_(-0.2, 0.2); mod.running_var.uniform_(0.5, 1.5)
+                mod.weight.uniform_(0.5, 1.5); mod.bias.uniform_(-0.2, 0.2)
+    return m.eval()
+
+
+@pytest.mark.parametrize('blocks,init_features,N', [([4], 96, 80), ([2], 96, 150), ([3], 64, 96)])
+def test_fused_dense_block_forward_vs_oracle(blocks, init_features, N):
+    m = _model(blocks, init_features=init_features)
+    x = torch.randn(N, 6, 64, 64, device=DEV)
+    with torch.no_grad():
+        y = m(x)
+    sd = {'features.' + k: v.detach().cpu() for k, v in m.features.state_dict().items()}
+    idx = [0, 1, N // 2, N - 1]                              # eval-mode BatchNorm: samples are independent
+    ref = O.densed_forward('burgers2d', sd, x[idx].cpu(), blocks, training=False)
+    assert rel_err(y[idx], ref) < TOL
+
+
+def test_fused_rollout_equals_layerwise_with_weight_groups():
+    """S weight samples x N ICs (sample-major groups): the fused kernel picks each sample's weight group and folded BatchNorm"""
+    g, cfg, args, model, bayes, swag = M.build('burgers2d', DEV, max_models=int(golden('burgers2d')['swag/max_models']))
+    M.load_golden_weights(bayes, g)
+    swag.load_state_dict({k: v for k, v in sub(g, 'swag/sd/').items()}, strict=True)
+    swag.eval()
+    S, N, T = 3, 30, 3
+    ic = O.ic_burgers2d(64, range(N)).to(DEV)
+    gen = torch.Generator(device=DEV); gen.manual_seed(2)
+    flat, names, numels = swag.sample_flat(S, generator=gen)
+    named = list(bayes.named_parameters())
+    a = engine.rollout(swag, ic, T, flat_weights=flat, named_params=named)
+    b = engine.rollout(swag, ic, T, flat_weights=flat, named_params=named, layerwise=True)
+    errs = [rel_err(a[:, t], b[:, t]) for t in range(T + 1)]
+    print('fused vs layerwise per-step rel err', ['%.1e' % e for e in errs])
+    assert errs[0] == 0.0 and errs[1] < TOL and max(errs) < 1e-4
+    # continued rollout (pieces) == one-shot rollout
+    buf = torch.empty((S * N, 6 + 2 * T, 64, 64), device=DEV)
+    engine.rollout(swag, ic, 2, flat_weights=flat, named_params=named, out=buf, t_start=0, total_steps=T)
+    c = engine.rollout(swag, ic, 1, flat_weights=flat, named_params=named, out=buf, t_start=2, total_steps=T)
+    assert c.shape == a.shape and rel_err(c, a) < 1e-6

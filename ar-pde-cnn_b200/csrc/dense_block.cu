@@ -8,9 +8,9 @@
 //     halo rows of layer j are recomputed (rows shrink by one per layer and side: 22, 20, 18, 16 -- 19 % extra FLOPs instead of a
 //     cluster-wide exchange);
 //   * a row is 32 columns = 32 lanes, so the x-neighbours of a pixel come from the neighbouring lanes by shuffle and the circular wrap in
-//     x is the shuffle's modulo; a warp computes 3 rows x 4 output channels per lane from 5 activated input rows (BN + ReLU applied once
-//     per loaded value: 108 FMAs per 5 shared loads + 10 shuffles + 9 broadcast weight loads);
-//   * two warps split the input channels of every row triple (partial sums meet in shared memory), which keeps all 16 warps busy.
+//     x is the shuffle's modulo; BN + ReLU is applied once per loaded value (216 FMAs per 8 shared loads + 16 shuffles + 9 broadcast weight loads);
+//   * a warp computes 6 rows x 4 output channels per lane; the 3-4 row groups of a layer are each shared by 4-5 warps that split the
+//     input channels (partial sums meet in shared memory in a fixed two-round tree: bit-reproducible), which keeps 15-16 warps busy.
 // Bound: fp32 FMA pipe (4-channel layers cannot feed a tensor-core tile: an MMA costs >= 32 cycles whatever N is).
 #include "common.cuh"
 #include "conv_common.cuh"
@@ -18,7 +18,7 @@
 
 namespace {
 
-constexpr int DB_W = 32, DB_OWN = 16, DB_R = 3, DB_WARPS = 16, DB_MAXL = 4, DB_MAXC = 64;
+constexpr int DB_W = 32, DB_OWN = 16, DB_R = 6, DB_WARPS = 16, DB_MAXL = 4, DB_MAXC = 64, DB_KSMAX = 5, DB_RED = 8 * DB_R * 4 * DB_W;
 
 struct DenseBlockArgs {
   float* buf; long long bs;                     // dense-block buffer [N][ctot][H][32]
@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(512, 1) dense_block_kernel(DenseBlockArgs a) {
   float* X = sm;                                          // [ctot][rows][32]
   float* Wt = X + (size_t)ctot * rows * DB_W;             // [cin][9][4]
   float* SS = Wt + (size_t)(ctot - 4) * 36;               // [2][cin]
-  float* RED = SS + 2 * DB_MAXC;                          // [8 items][12][32]
+  float* RED = SS + 2 * DB_MAXC;                          // [4 items][2 slots][DB_R * 4][32]: partial sums of the channel slices
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int tiles = a.H / DB_OWN;
   const long long HW = (long long)a.H * DB_W;
@@ -67,20 +67,25 @@ __global__ void __launch_bounds__(512, 1) dense_block_kernel(DenseBlockArgs a) {
       }
       if (j == 0) asm volatile("cp.async.wait_group 0;" ::: "memory");      // the input tile has landed (weights were staged meanwhile)
       __syncthreads();
+      // Work split: `nitems` groups of DB_R output rows, each shared by KS warps that take a slice of the input channels.  Per input
+      // channel a warp issues DB_R + 2 shared loads, 2 (DB_R + 2) shuffles and 9 broadcast weight loads for 36 DB_R FMAs per lane: with
+      // DB_R = 6 the FMA pipe (not the load/shuffle path) is the busier one (measured with DB_R = 3: FMA pipe 47 %, both co-limited).
       const int r_lo = j + 1, r_hi = rows - j - 1;        // local output rows [r_lo, r_hi)
       const int nitems = (r_hi - r_lo + DB_R - 1) / DB_R;
-      const int item = warp >> 1, kh = warp & 1;
+      const int KS = DB_WARPS / nitems > DB_KSMAX ? DB_KSMAX : DB_WARPS / nitems;
+      const int item = warp / KS, kg = warp - item * KS;
+      const bool on = item < nitems;
       float acc[DB_R][4];
 #pragma unroll
       for (int r = 0; r < DB_R; ++r) { acc[r][0] = 0.f; acc[r][1] = 0.f; acc[r][2] = 0.f; acc[r][3] = 0.f; }
       const int rb = r_lo + item * DB_R;
-      if (item < nitems) {
-        const int half = cin >> 1;
+      if (on) {
+        const int c_lo = kg * cin / KS, c_hi = (kg + 1) * cin / KS;
         int rix[DB_R + 2];
 #pragma unroll
         for (int r = 0; r < DB_R + 2; ++r) { int q = rb - 1 + r; rix[r] = (q > rows - 1 ? rows - 1 : q) * DB_W + lane; }
-#pragma unroll 2
-        for (int c = kh * half; c < (kh + 1) * half; ++c) {
+#pragma unroll 1
+        for (int c = c_lo; c < c_hi; ++c) {
           const float s = SS[c], t = SS[DB_MAXC + c];
           const float* xc = X + (size_t)c * rows * DB_W;
           float v[DB_R + 2], vl[DB_R + 2], vr[DB_R + 2];
@@ -102,21 +107,43 @@ __global__ void __launch_bounds__(512, 1) dense_block_kernel(DenseBlockArgs a) {
             }
           }
         }
-        if (kh == 1) {
+      }
+      // deterministic two-round tree over the channel slices: odd slices -> even slices, then slices 2 and 4 -> slice 0
+      float* slot1 = RED + ((size_t)item * 2 + (kg >> 1)) * (DB_R * 4 * DB_W) + lane;
+      if (on && (kg & 1)) {
 #pragma unroll
-          for (int r = 0; r < DB_R; ++r)
+        for (int r = 0; r < DB_R; ++r)
 #pragma unroll
-            for (int co = 0; co < 4; ++co) RED[((size_t)item * 12 + r * 4 + co) * DB_W + lane] = acc[r][co];
-        }
+          for (int co = 0; co < 4; ++co) slot1[(r * 4 + co) * DB_W] = acc[r][co];
       }
       __syncthreads();
-      if (item < nitems && kh == 0) {
+      if (on && !(kg & 1) && kg + 1 < KS) {
+#pragma unroll
+        for (int r = 0; r < DB_R; ++r)
+#pragma unroll
+          for (int co = 0; co < 4; ++co) acc[r][co] += slot1[(r * 4 + co) * DB_W];
+      }
+      __syncthreads();
+      float* slot2 = RED + ((size_t)item * 2 + (kg >> 2)) * (DB_R * 4 * DB_W) + lane;        // kg = 2 -> slot 0, kg = 4 -> slot 1
+      if (on && (kg == 2 || kg == 4)) {
+#pragma unroll
+        for (int r = 0; r < DB_R; ++r)
+#pragma unroll
+          for (int co = 0; co < 4; ++co) slot2[(r * 4 + co) * DB_W] = acc[r][co];
+      }
+      __syncthreads();
+      if (on && kg == 0) {
+        const float* s2 = RED + ((size_t)item * 2) * (DB_R * 4 * DB_W) + lane;
 #pragma unroll
         for (int r = 0; r < DB_R; ++r) {
           if (rb + r < r_hi) {
 #pragma unroll
-            for (int co = 0; co < 4; ++co)
-              X[((size_t)(cin + co) * rows + rb + r) * DB_W + lane] = acc[r][co] + RED[((size_t)item * 12 + r * 4 + co) * DB_W + lane];
+            for (int co = 0; co < 4; ++co) {
+              float v = acc[r][co];
+              if (KS > 2) v += s2[(r * 4 + co) * DB_W];
+              if (KS > 4) v += s2[(DB_R * 4 + r * 4 + co) * DB_W];
+              X[((size_t)(cin + co) * rows + rb + r) * DB_W + lane] = v;
+            }
           }
         }
       }
@@ -169,7 +196,7 @@ int arpde_dense_block_launch(const arpde_op_t* ops, int first, int nl, const arp
   a.scale = scale; a.shift = shift; a.ss_gs = ss_gs;
   ARPDE_CHECK_ARG((((uintptr_t)a.buf) & 15) == 0 && (a.bs & 3) == 0, "dense_block: buffer must be 16-byte aligned");
   const int rows = DB_OWN + 2 * nl, ctot = a.c0 + 4 * nl;
-  const size_t smem = ((size_t)ctot * rows * DB_W + (size_t)(ctot - 4) * 36 + 2 * DB_MAXC + 8 * 12 * DB_W) * sizeof(float);
+  const size_t smem = ((size_t)ctot * rows * DB_W + (size_t)(ctot - 4) * 36 + 2 * DB_MAXC + DB_RED) * sizeof(float);
   ARPDE_CHECK_ARG(smem <= 227 * 1024, "dense_block: %zu bytes of shared memory needed", smem);
   ARPDE_CUDA(cudaFuncSetAttribute(dense_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long items = (long long)N * (b.h / DB_OWN);

@@ -540,17 +540,26 @@ def main():
                     if gathered and world > 1 and rank == 0:
                         self.g_chunks.append((torch.empty((world, self.n) + shp, device=dev), torch.empty((world, self.n) + shp, device=dev)))
 
-        def run(self, ic):
+        def run(self, ic, marks=None):
+            """marks: optional list that receives CUDA events after sampling / rollout / moments / gather (job breakdown)"""
+            def mark():
+                if marks is not None:
+                    ev = torch.cuda.Event(enable_timing=True); ev.record(); marks.append(ev)
+            mark()
             flat, names, numels = swag.sample_flat(S_SAMPLES, generator=gen)
+            mark()
             traj = engine.rollout(swag, ic, T_STEPS, flat_weights=flat, named_params=named, out=self.traj_buf)
+            mark()
             betas = flat[:, 0].exp()
             mean, var = engine.predictive_moments(traj, S_SAMPLES, betas, '2d')
+            mark()
             if self.gathered and world > 1:
                 if self.n < self.pad:
                     padz = torch.zeros((self.pad - self.n,) + state, device=dev)
                     mean, var = torch.cat([mean, padz]), torch.cat([var, padz])
                 dist.gather(mean, list(self.g_m.unbind(0)) if rank == 0 else None, dst=0)
                 dist.gather(var, list(self.g_v.unbind(0)) if rank == 0 else None, dst=0)
+                mark()
                 if rank == 0:
                     return self.g_m, self.g_v
             return mean, var
@@ -633,6 +642,14 @@ def main():
     units = S_SAMPLES * N_IC * T_STEPS * args.steps
     value = units / (ms * 1e-3)
 
+    # where one job spends its time (rank 0, one extra untimed job): sampling | rollout | moments | gather
+    marks = []
+    job.run(job.ic_dev, marks)
+    torch.cuda.synchronize()
+    bd = [marks[i].elapsed_time(marks[i + 1]) for i in range(len(marks) - 1)]
+    breakdown = dict(zip(('sample_ms', 'rollout_ms', 'moments_ms', 'gather_ms'), bd))
+    rollout_ms = breakdown['rollout_ms']
+
     for _ in range(max(1, args.warmup // 3)):
         job.run_e2e()
     ms_e2e = timed(job.run_e2e, args.steps)
@@ -655,21 +672,11 @@ def main():
         torch.cuda.empty_cache()
 
     # ---- per-kernel rooflines, measured live with CUDA events on the launching stream ------------------
-    # (1) one full AR step of the local batch: difference of a 25-step and a 5-step rollout, so that the per-rollout setup drops out
+    # (1) one full AR step of the local batch = the rollout of the job (into its preallocated trajectory buffer) / T: includes the per-rollout
+    #     set-up (weight split for the tensor-core layers, BN fold: ~0.1 ms per 100 steps)
     NT = S_SAMPLES * n_loc
-    ic_dev = ic_all_host[lo:hi].to(dev)
-    flat, _, _ = swag.sample_flat(S_SAMPLES, generator=gen)
-    engine.rollout(swag, ic_dev, 1, flat_weights=flat, named_params=named)
-    torch.cuda.synchronize()
-    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-    e0.record()
-    engine.rollout(swag, ic_dev, 5, flat_weights=flat, named_params=named)
-    e1.record()
-    engine.rollout(swag, ic_dev, 25, flat_weights=flat, named_params=named)
-    e2.record(); torch.cuda.synchronize()
-    step_ms = (e1.elapsed_time(e2) - e0.elapsed_time(e1)) / 20
+    step_ms = rollout_ms / T_STEPS
     conv_tflops = NT * MODEL_MFLOP * 1e6 / (step_ms * 1e-3) / 1e12
-    torch.cuda.empty_cache()
     # (1b) the dominant launch of the step, timed alone through the C ABI on the rollout batch:
     #      conv_tc_kernel on In_conv3 (96 -> 48, 3x3 stride 2, 64x64 -> 32x32), 30 weight groups; inputs rotate over 2 sets (2 x 3 GB >> L2)
     xin = [torch.randn((NT, 96, NEL, NEL), device=dev) for _ in range(2)]
@@ -726,7 +733,9 @@ def main():
                              'peak/6 = %.0f TFLOP/s -> frac_of_3xtf32_ceiling %.3f' % (peaks['bf16_tflops'] / 6, k1_tflops / (peaks['bf16_tflops'] / 6)),
                      'flops_per_launch': k1_flops, 'ms': k1_ms,
                      'ar_step': {'ms': step_ms, 'tflops': conv_tflops, 'flops': NT * MODEL_MFLOP * 1e6, 'samples': NT,
-                                 'what': 'all 9 convs of one AR step of the local batch'}},
+                                 'what': 'one AR step of the local batch (In_conv1, In_conv3, conv1x1, folded conv3x3-up on conv_tc_kernel; the four dense layers as ONE '
+                                         'fused FFMA launch; the 16->2 output conv on the row-tiled FFMA kernel): rollout time of the job / %d steps' % T_STEPS},
+                     'job_breakdown_ms': breakdown},
         'roofline_stencil': {'kernel': 'burgers2d_fwd_vec4<RY=4> (fused periodic stencil + Crank-Nicolson, API form: read uPred, uPred0, write ustar), '
                                        'C4 rollout batch, 4 rotating buffer sets', 'bound': 'hbm',
                              'achieved': k2['achieved'], 'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': k2['frac'],

@@ -130,6 +130,19 @@ def sharded_swag_rollout(run_local, ics, tsteps, n_samples, mode='auto', formula
     return traj, mean, var0 + predictive_noise(betas, formula), betas
 
 
+def swag_rollout(swag_nn, ics, tsteps, n_samples, seed=0, diagCov=False, scale=1.0, formula='2d', mode='auto', gather=True):
+    """Sharded SWAG inference on the CUDA path: engine.swag_rollout per rank behind sharded_swag_rollout.  Every rank seeds its
+    generator with `seed`, so all ranks draw the same n_samples weight vectors (same device type => same Philox stream)."""
+    from . import engine
+
+    def run_local(ic_shard, T, srange):
+        gen = torch.Generator(device=ic_shard.device)
+        gen.manual_seed(int(seed))
+        return engine.swag_rollout(swag_nn, ic_shard, T, n_samples, diagCov=diagCov, scale=scale, generator=gen, formula=formula,
+                                   sample_range=srange, add_noise=False)
+    return sharded_swag_rollout(run_local, ics, tsteps, n_samples, mode=mode, formula=formula, gather=gather)
+
+
 class FlatGradBucket:
     """One flat fp32 buffer that IS the gradient storage of a parameter list (the reference has no distributed training;
     this is the natural data-parallel split of its mini-batch of initial conditions).

@@ -92,3 +92,44 @@ def worker(rank, ws, port, backend, root, q):
         q.put((rank, traceback.format_exc()))
     finally:
         dist.destroy_process_group()
+
+
+def infer_worker(rank, ws, port, backend, root, q):
+    """SWAG inference sharded over `ws` ranks (by initial condition and by weight sample) vs the single-process result."""
+    sys.path.insert(0, root)
+    sys.path.insert(0, os.path.join(root, 'tests'))
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(ws))
+    ngpu = torch.cuda.device_count()
+    dev = torch.device('cuda', rank % ngpu)
+    torch.cuda.set_device(dev)
+    if backend == 'nccl':
+        dist.init_process_group('nccl', rank=rank, world_size=ws, device_id=dev)
+    else:
+        dist.init_process_group('gloo', rank=rank, world_size=ws)
+    try:
+        from oracle import arpde_oracle as O
+        from _util import rel_err, golden, sub
+        import _models as M
+        from arpde_b200 import engine
+        from arpde_b200 import parallel as PL
+        with contextlib.redirect_stdout(io.StringIO()):
+            g, cfg, args, model, bayes, swag = M.build('burgers2d', str(dev), max_models=int(golden('burgers2d')['swag/max_models']))
+        M.load_golden_weights(bayes, g)
+        swag.load_state_dict({k: v for k, v in sub(g, 'swag/sd/').items()}, strict=True)
+        swag.eval()
+        S, T = 5, 3
+        errs = {}
+        for tag, n_ic, mode in (('ic_shard', 5, 'ic'), ('sample_shard', 1, 'auto'), ('ic_shard_one_ic', 1, 'ic')):
+            ics = O.ic_burgers2d(32, range(n_ic)).to(dev)
+            gen = torch.Generator(device=dev); gen.manual_seed(11)
+            _, m1, v1, b1 = engine.swag_rollout(swag, ics, T, S, generator=gen)                 # this rank alone, everything
+            traj, m, v, b = PL.swag_rollout(swag, ics, T, S, seed=11, mode=mode)
+            errs[tag] = (rel_err(m, m1), rel_err(v, v1), rel_err(b, b1), None if traj is None else int(traj.shape[0]))
+        q.put((rank, errs))
+    except Exception:
+        import traceback
+        q.put((rank, traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()

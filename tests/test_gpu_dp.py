@@ -16,11 +16,11 @@ pytestmark = pytest.mark.gpu
 DEV = 'cuda:0'
 
 
-def _run(ws, backend):
+def _run(ws, backend, target=None):
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
-    port = 29500 + (os.getpid() * 7 + ws) % 2000
-    procs = [ctx.Process(target=W.worker, args=(r, ws, port, backend, ROOT, q)) for r in range(ws)]
+    port = 29500 + (os.getpid() * 7 + ws + (13 if target else 0)) % 2000
+    procs = [ctx.Process(target=target or W.worker, args=(r, ws, port, backend, ROOT, q)) for r in range(ws)]
     for p in procs:
         p.start()
     res = [q.get(timeout=600) for _ in procs]
@@ -40,6 +40,21 @@ def test_two_rank_step_equals_one_rank_step_at_global_batch():
         assert errs['grads'] < 2e-5, (backend, rank, errs)
         assert errs['weights'] < 1e-5, (backend, rank, errs)
         assert errs['rank_consistency'] == 0.0, (backend, rank, errs)
+
+
+def test_sharded_swag_inference_equals_single_process():
+    """ICs sharded across ranks (every rank all weight samples, all-gather of mean / variance; a rank may own no IC) and --
+    fewer ICs than ranks -- weight SAMPLES sharded with the partial moments merged by all-reduce, both against one process doing the
+    whole job.  Same seed on every rank => the same weight samples."""
+    backend = 'nccl' if torch.cuda.device_count() >= 2 else 'gloo'
+    res = _run(2, backend, target=W.infer_worker)
+    for rank, errs in res.items():
+        assert isinstance(errs, dict), errs
+        for tag, (em, ev, eb, ntraj) in errs.items():
+            assert em < 1e-6 and ev < 1e-5 and eb < 1e-6, (backend, rank, tag, em, ev, eb)
+        assert errs['ic_shard'][3] == 5 * (3 if rank == 0 else 2)            # 5 ICs -> 3 + 2, all 5 samples each
+        assert errs['sample_shard'][3] == (3 if rank == 0 else 2)            # 5 samples -> 3 + 2 on the single IC
+        assert (errs['ic_shard_one_ic'][3] is None) == (rank == 1)           # the rank without an IC runs nothing and does not hang
 
 
 def test_gradient_sink_equals_plain_autograd():

@@ -284,21 +284,11 @@ __global__ void __launch_bounds__(256) burgers2d_fwd_smem(const float* __restric
     __syncthreads();
     const float* tile = tile_all + buf * tile_floats;
     const int n = it / nstrips, y0 = (it - n * nstrips) * TY;
-    // every lane runs the same number of trips (the halo columns travel by shuffle); lanes past the end of the strip compute on
-    // a clamped position and store nothing
-    for (int i0 = 0; i0 < TY * w4; i0 += 256) {
-      const int iv = i0 + threadIdx.x;
-      const bool in_tile = iv < TY * w4;
-      const int i = in_tile ? iv : TY * w4 - 1;
+    for (int i = threadIdx.x; i < TY * w4; i += 256) {
       const int r = i / w4, c = i - r * w4;
       const int y = y0 + r;
-      const bool valid = in_tile && y < H;
+      if (y >= H) continue;
       const int x0 = c << 2, xl = (x0 == 0 ? W : x0) - 1, xr = x0 + 4 == W ? 0 : x0 + 4;
-      // the left / right halo column is the neighbouring lane's float4 edge unless that lane sits in another row (or warp): only those
-      // lanes read the scalar from shared memory (the stride-4 scalar reads of every lane were 50 % of the kernel's shared wavefronts,
-      // all of them 4-way bank conflicts)
-      const int ln = threadIdx.x & 31;
-      const bool selfL = c == 0 || ln == 0 || !in_tile, selfR = c == w4 - 1 || ln == 31 || iv + 1 >= TY * w4;
       float Ru[4], Rv[4], R0u[4] = {0, 0, 0, 0}, R0v[4] = {0, 0, 0, 0};
       float ub[4], vb[4], u0b[4], v0b[4];
 #pragma unroll
@@ -310,10 +300,8 @@ __global__ void __launch_bounds__(256) burgers2d_fwd_smem(const float* __restric
         for (int rr = 0; rr < 3; ++rr) {
           const float4 a = *reinterpret_cast<const float4*>(tu + rr * W + x0);
           const float4 b = *reinterpret_cast<const float4*>(tv + rr * W + x0);
-          const float aL = __shfl_up_sync(0xffffffffu, a.w, 1), aR = __shfl_down_sync(0xffffffffu, a.x, 1);
-          const float bL = __shfl_up_sync(0xffffffffu, b.w, 1), bR = __shfl_down_sync(0xffffffffu, b.x, 1);
-          U[rr][0] = selfL ? tu[rr * W + xl] : aL; U[rr][1] = a.x; U[rr][2] = a.y; U[rr][3] = a.z; U[rr][4] = a.w; U[rr][5] = selfR ? tu[rr * W + xr] : aR;
-          V[rr][0] = selfL ? tv[rr * W + xl] : bL; V[rr][1] = b.x; V[rr][2] = b.y; V[rr][3] = b.z; V[rr][4] = b.w; V[rr][5] = selfR ? tv[rr * W + xr] : bR;
+          U[rr][0] = tu[rr * W + xl]; U[rr][1] = a.x; U[rr][2] = a.y; U[rr][3] = a.z; U[rr][4] = a.w; U[rr][5] = tu[rr * W + xr];
+          V[rr][0] = tv[rr * W + xl]; V[rr][1] = b.x; V[rr][2] = b.y; V[rr][3] = b.z; V[rr][4] = b.w; V[rr][5] = tv[rr * W + xr];
         }
         Col6 q[6];
 #pragma unroll
@@ -334,9 +322,9 @@ __global__ void __launch_bounds__(256) burgers2d_fwd_smem(const float* __restric
       for (int j = 0; j < 4; ++j) {
         Su[j] = fmaf(k.c, Ru[j] + R0u[j], u0b[j]); Sv[j] = fmaf(k.c, Rv[j] + R0v[j], v0b[j]);
         const float du = Su[j] - ub[j], dv = Sv[j] - vb[j];
-        if (valid) acc = fmaf(du, du, fmaf(dv, dv, acc));
+        acc = fmaf(du, du, fmaf(dv, dv, acc));
       }
-      if (ustar && valid) {
+      if (ustar) {
         float* o = ustar + (int64_t)n * 2 * HW + (size_t)y * W + x0;
         *reinterpret_cast<float4*>(o) = make_float4(Su[0], Su[1], Su[2], Su[3]);
         *reinterpret_cast<float4*>(o + HW) = make_float4(Sv[0], Sv[1], Sv[2], Sv[3]);
@@ -444,24 +432,18 @@ __global__ void __launch_bounds__(256) burgers2d_bwd_smem(const float* __restric
     __syncthreads();
     const float* tile = tile_all + buf * tile_floats;
     const int n = it / nstrips, y0 = (it - n * nstrips) * TY;
-    for (int i0 = 0; i0 < TY * w4; i0 += 256) {       // uniform trip count: the halo columns travel by shuffle (see burgers2d_fwd_smem)
-      const int iv = i0 + threadIdx.x;
-      const bool in_tile = iv < TY * w4;
-      const int i = in_tile ? iv : TY * w4 - 1;
+    for (int i = threadIdx.x; i < TY * w4; i += 256) {
       const int r = i / w4, c = i - r * w4;
       const int y = y0 + r;
-      const bool valid = in_tile && y < H;
+      if (y >= H) continue;
       const int x0 = c << 2, xl = (x0 == 0 ? W : x0) - 1, xr = x0 + 4 == W ? 0 : x0 + 4;
-      const int ln = threadIdx.x & 31;
-      const bool selfL = c == 0 || ln == 0 || !in_tile, selfR = c == w4 - 1 || ln == 31 || iv + 1 >= TY * w4;
       // six columns x0-1 .. x0+4 of rows y-1, y, y+1 (tile rows r, r+1, r+2)
       auto load6 = [&](int f, float (&F)[3][6]) {
         const float* t = tile + f * fstride + r * W;
 #pragma unroll
         for (int rr = 0; rr < 3; ++rr) {
           const float4 a = *reinterpret_cast<const float4*>(t + rr * W + x0);
-          const float aL = __shfl_up_sync(0xffffffffu, a.w, 1), aR = __shfl_down_sync(0xffffffffu, a.x, 1);
-          F[rr][0] = selfL ? t[rr * W + xl] : aL; F[rr][1] = a.x; F[rr][2] = a.y; F[rr][3] = a.z; F[rr][4] = a.w; F[rr][5] = selfR ? t[rr * W + xr] : aR;
+          F[rr][0] = t[rr * W + xl]; F[rr][1] = a.x; F[rr][2] = a.y; F[rr][3] = a.z; F[rr][4] = a.w; F[rr][5] = t[rr * W + xr];
         }
       };
       float A[3][6], B[3][6];
@@ -504,7 +486,6 @@ __global__ void __launch_bounds__(256) burgers2d_bwd_smem(const float* __restric
 #pragma unroll
         for (int j = 0; j < 4; ++j) { out[2][j] = A[1][j + 1]; out[3][j] = B[1][j + 1]; }
       }
-      if (!valid) continue;                              // (after the last shuffle of the trip)
       float* o = gup + (int64_t)n * 2 * HW + (size_t)y * W + x0;
       float* o0 = gu0 + (int64_t)n * 2 * HW + (size_t)y * W + x0;
       *reinterpret_cast<float4*>(o) = make_float4(out[0][0], out[0][1], out[0][2], out[0][3]);

@@ -44,8 +44,18 @@ def _param_table(plan, named_params, flat):
     return L.ptr_array(ptrs), L.i64_array(gs), tensors
 
 
+_SIDE_STREAMS = {}
+
+
+def _side_stream(dev, k):
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), k)
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=dev)
+    return _SIDE_STREAMS[key]
+
+
 @torch.no_grad()
-def rollout(model, ic, tsteps, flat_weights=None, named_params=None, out=None, layerwise=False, t_start=0, total_steps=None):
+def rollout(model, ic, tsteps, flat_weights=None, named_params=None, out=None, layerwise=False, t_start=0, total_steps=None, n_streams=1, _skip_fill=False):
     """Eval-mode AR rollout.
 
     model: DenseED / BayesNN / SwagNN (running BN statistics and, without flat_weights, the weights come from it)
@@ -56,6 +66,10 @@ def rollout(model, ic, tsteps, flat_weights=None, named_params=None, out=None, l
     t_start / total_steps: roll out in pieces -- `out` is the buffer of a total_steps rollout; the call advances steps
                   [t_start, t_start + tsteps) from the states already in the buffer (t_start = 0 fills in the initial history), so
                   the caller can reduce / ship the finished steps of one piece while the next one runs
+    n_streams: > 1 splits the S weight samples into that many contiguous groups and rolls each group out on its own CUDA stream
+                  (the rows of a group are a contiguous slice of the trajectory tensor).  The layers of one step depend on each other,
+                  so a single stream leaves SMs idle at the tail of every launch; with small batches (a strong-scaled shard: 30 x 8
+                  trajectories) the tail is 15-35 % of each launch and the other stream's launches fill it.
     returns traj [S*N, T+1, c_out, (H,) W] (index 0 = initial state); with total_steps the view covers all total_steps + 1 states
     """
     feats = _features_of(model)
@@ -89,8 +103,23 @@ def rollout(model, ic, tsteps, flat_weights=None, named_params=None, out=None, l
         out = torch.empty((NT, ctot, H, W), device=dev, dtype=torch.float32)
     elif out.shape != (NT, ctot, H, W) or not out.is_contiguous():
         raise ValueError('out must be a contiguous [%d,%d,%d,%d] tensor' % (NT, ctot, H, W))
-    if t_start == 0:
+    if t_start == 0 and not _skip_fill:
         out.view(S, N, ctot, H, W)[:, :, :c_hist] = ic4.repeat(1, c_hist // c_out, 1, 1).unsqueeze(0)
+    if n_streams > 1 and flat_weights is not None and S >= n_streams:
+        cur = torch.cuda.current_stream(dev)
+        ready = torch.cuda.Event(); ready.record(cur)
+        for k in range(n_streams):
+            lo, hi = k * S // n_streams, (k + 1) * S // n_streams
+            st = _side_stream(dev, k)
+            st.wait_event(ready)
+            with torch.cuda.stream(st):
+                # continue (t_start semantics) on the group's rows: the history has been filled above for all rows
+                rollout(model, ic, tsteps, flat_weights=flat_weights[lo:hi], named_params=named_params, out=out[lo * N:hi * N], layerwise=layerwise,
+                        t_start=max(t_start, 0), total_steps=total, n_streams=1, _skip_fill=True)
+            done = torch.cuda.Event(); done.record(st)
+            cur.wait_event(done)
+        traj = out[:, c_hist - c_out:].view(NT, total + 1, c_out, H, W)
+        return traj.squeeze(3) if one_d else traj
     bufs, work_len, _ = P.layout(plan, NT, H, W)
     ops_c, bufs_c = P.c_tables(plan, bufs)
     work = torch.empty((max(work_len, 1),), device=dev, dtype=torch.float32)

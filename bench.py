@@ -515,6 +515,9 @@ def main():
             self.ic_host = ic_host_shard.pin_memory()
             self.ic_dev = self.ic_host.to(dev)
             self.traj_buf = torch.empty((S_SAMPLES * self.n, 6 + 2 * T_STEPS, NEL, NEL), device=dev)
+            # small shards (strong scaling: 30 x 8 trajectories per GPU at N = 8): two groups of weight samples on two streams, so that
+            # the tail of every launch (15-35 % at this batch) is filled by the other group's launches (measured 0.976 -> 0.926 ms per step)
+            self.n_streams = 2 if S_SAMPLES * self.n < 960 else 1
             self.gathered = gathered
             if gathered and world > 1:
                 # rank 0 receives every shard into one [world, n, ...] tensor per moment (equal shards; a ragged split pads to n_max)
@@ -548,7 +551,7 @@ def main():
             mark()
             flat, names, numels = swag.sample_flat(S_SAMPLES, generator=gen)
             mark()
-            traj = engine.rollout(swag, ic, T_STEPS, flat_weights=flat, named_params=named, out=self.traj_buf)
+            traj = engine.rollout(swag, ic, T_STEPS, flat_weights=flat, named_params=named, out=self.traj_buf, n_streams=self.n_streams)
             mark()
             betas = flat[:, 0].exp()
             mean, var = engine.predictive_moments(traj, S_SAMPLES, betas, '2d')
@@ -573,7 +576,8 @@ def main():
             cl = T_STEPS // E2E_CHUNKS
             main = torch.cuda.current_stream()
             for k, (lo_, hi_) in enumerate(self.spans):
-                traj = engine.rollout(swag, ic, cl, flat_weights=flat, named_params=named, out=self.traj_buf, t_start=k * cl, total_steps=T_STEPS)
+                traj = engine.rollout(swag, ic, cl, flat_weights=flat, named_params=named, out=self.traj_buf, t_start=k * cl, total_steps=T_STEPS,
+                                      n_streams=self.n_streams)
                 mean, var = engine.predictive_moments(traj[:, lo_:hi_], S_SAMPLES, formula='2d', noise=noise)
                 if self.gathered and world > 1:
                     gm, gv = self.g_chunks[k] if rank == 0 else (None, None)

@@ -9,7 +9,7 @@ dev = torch.device('cuda:0')
 swag, _ = bench.build_swag(dev)
 named = list(swag.base.named_parameters())
 gen = torch.Generator(device=dev); gen.manual_seed(1234)
-ic = bench.make_ics(64).to(dev)
+ic = bench.make_ics(int(os.environ.get("NIC", "64"))).to(dev)
 flat, _, _ = swag.sample_flat(30, generator=gen)
 T = int(os.environ.get('T', '3'))
 traj = engine.rollout(swag, ic, T, flat_weights=flat, named_params=named)

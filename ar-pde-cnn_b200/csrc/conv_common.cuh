@@ -119,6 +119,11 @@ bool arpde_ks_program_matches(const arpde_op* ops, int n_ops, const arpde_buf* b
 int arpde_ks_rollout_launch(const arpde_op* ops, void* const* params, const int64_t* gstride, float* traj, long long bs, int c_hist, int T, int N,
                             int n_per_group, float eps, cudaStream_t stream);
 
+// output convolution of the 2D net (conv_out.cu): 5x5, cout = 2, 64-column maps
+bool arpde_conv_out_shape_ok(const ConvDesc& d, const float* x, long long x_bs, const float* y, const double* stats);
+int arpde_conv_out_launch(const ConvDesc& d, const float* x, long long x_bs, const float* w, long long w_gs, const float* scale, const float* shift,
+                          long long ss_gs, float* y, cudaStream_t stream);
+
 // fused dense block (dense_block.cu): all 4-channel dense layers of a block in one launch, eval mode
 int arpde_dense_block_match(const arpde_op* ops, int n_ops, int first, const arpde_buf* bufs, int N);
 int arpde_dense_block_launch(const arpde_op* ops, int first, int nl, const arpde_buf* bufs, void* const* params, const int64_t* gstride, float* work,

@@ -376,6 +376,9 @@ int arpde_conv_fwd_launch(const ConvDesc& d, const float* x, long long x_bs, con
   const int sh = (d.H == 1 && d.kh == 1) ? 1 : d.stride;
   ARPDE_CHECK_ARG(Hc % sh == 0 && Wc % d.stride == 0, "conv_fwd: spatial size %dx%d not divisible by stride %d", Hc, Wc, d.stride);
   const int Ho = Hc / sh, Wo = Wc / d.stride;
+  // the 2-channel 5x5 output convolution on 64-column maps: lane-per-two-columns kernel (conv_out.cu)
+  if (arpde_conv_out_shape_ok(d, x, x_bs, y, stats) && (scale == nullptr) == (shift == nullptr))
+    return arpde_conv_out_launch(d, x, x_bs, w, w_gs, scale, shift, ss_gs, y, stream);
   // narrow output layers: row-tiled kernel (see conv_fwd_rt_kernel)
   if (!arpde_dev_env("ARPDE_CONV_RT_OFF") && d.stride == 1 && !d.up && !d.dilate && d.pad_override < 0 && d.H > 1 && d.cout <= 4 && stats == nullptr &&
       (Wo & 7) == 0 && (((uintptr_t)y) & 15) == 0) {

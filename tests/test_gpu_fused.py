@@ -63,3 +63,29 @@ def test_fused_rollout_equals_layerwise_with_weight_groups():
     engine.rollout(swag, ic, 2, flat_weights=flat, named_params=named, out=buf, t_start=0, total_steps=T)
     c = engine.rollout(swag, ic, 1, flat_weights=flat, named_params=named, out=buf, t_start=2, total_steps=T)
     assert c.shape == a.shape and rel_err(c, a) < 1e-6
+
+
+@pytest.mark.parametrize('cin,H,N,npg', [(16, 64, 3, 3), (4, 16, 2, 1), (12, 80, 2, 2), (8, 32, 5, 1)])
+def test_output_conv_kernel_vs_oracle(cin, H, N, npg):
+    """conv_out.cu through the C ABI (arpde_conv_fwd): 5x5 circular conv to 2 channels on 64-column maps with the BN + ReLU prologue,
+    input as a channel-slice view, output written at a channel offset of a wider tensor (the rollout's trajectory), per-group weights,
+    tanh output activation."""
+    from arpde_b200 import _lib as L
+    torch.manual_seed(cin + H)
+    W = 64
+    groups = N // npg
+    xbuf = torch.randn(N, cin + 3, H, W, device=DEV)
+    x = xbuf[:, 3:]
+    w = torch.randn(groups, 2, cin, 5, 5, device=DEV) / (cin * 25) ** 0.5
+    sc = torch.rand(groups, cin, device=DEV) + 0.5
+    sh = torch.randn(groups, cin, device=DEV) * 0.3
+    ybuf = torch.full((N, 7, H, W), 9.0, device=DEV)
+    L.call('arpde_conv_fwd', L.ptr(x), (cin + 3) * H * W, L.ptr(w), 2 * cin * 25, L.ptr(sc), L.ptr(sh), cin, L.ptr(ybuf), 0,
+           N, cin, H, W, 2, 5, 5, 1, 0, 1, 1, 7, 4, npg, L.stream())
+    torch.cuda.synchronize()
+    for n in range(N):
+        g = n // npg
+        a = torch.relu(x[n:n + 1].double().cpu() * sc[g].double().cpu().view(1, -1, 1, 1) + sh[g].double().cpu().view(1, -1, 1, 1))
+        ref = torch.tanh(O.conv_circ(a, w[g].double().cpu()))
+        assert rel_err(ybuf[n:n + 1, 4:6], ref) < TOL, n
+    assert float((ybuf[:, :4] - 9.0).abs().max()) == 0.0 and float((ybuf[:, 6:] - 9.0).abs().max()) == 0.0      # neighbours untouched

@@ -162,6 +162,131 @@ __global__ void __launch_bounds__(512, 1) dense_block_kernel(DenseBlockArgs a) {
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------------------------
+// Streaming formulation for the 32x32 map (the default 2D net): one CTA (8 warps x 4 rows) owns a WHOLE sample, so the circular wrap
+// in y stays inside the CTA and nothing is recomputed.  The input channels are not kept resident: they stream through a double-buffered
+// ring of 4-channel chunks (16 KB, cp.async), and while a raw channel is in flight its contribution to ALL layers is accumulated (each
+// layer applies its own BN + ReLU to the raw value: 16 accumulators per pixel in registers, 64 per lane).  The outputs of layers 0..2
+// are then written to shared memory (and HBM) and consumed as further chunks by the later layers: chunk 12 (layer 0) feeds layers 1-3,
+// chunk 13 layers 2-3, chunk 14 layer 3.  The layer weights of a chunk (144 floats per channel) ride in a second ring, gathered with
+// 4-byte cp.async from the reference layout.  87 KB of shared memory and 256 threads: two CTAs per SM overlap each other's barriers.
+// Per channel and warp: 6 shared loads + 12 shuffles of the raw rows, then per layer 2 + 9 broadcast loads, 36 BN/ReLU ops, 144 FMAs.
+constexpr int DS_H = 32, DS_CH = 4, DS_CHUNK = DS_CH * DS_H * DB_W, DS_WCH = DS_CH * DB_MAXL * 36, DS_THREADS = 256;
+
+template <int L0>
+__device__ __forceinline__ void ds_chunk(const float* __restrict__ data, const float* __restrict__ wst, const float* __restrict__ SS, int cbase,
+                                         float (&acc)[DB_MAXL][4][4], int r0, int lane, int lm, int lp) {
+#pragma unroll 1
+  for (int e = 0; e < DS_CH; ++e) {
+    const float* xe = data + e * DS_H * DB_W + lane;
+    float x[6], xl[6], xr[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) x[i] = xe[((r0 - 1 + i) & (DS_H - 1)) * DB_W];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) { xl[i] = __shfl_sync(0xffffffffu, x[i], lm); xr[i] = __shfl_sync(0xffffffffu, x[i], lp); }
+#pragma unroll
+    for (int l = L0; l < DB_MAXL; ++l) {
+      const float s = SS[l * DB_MAXC + cbase + e], t = SS[(DB_MAXL + l) * DB_MAXC + cbase + e];
+      float a[6], al[6], ar[6];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) { a[i] = fmaxf(fmaf(x[i], s, t), 0.f); al[i] = fmaxf(fmaf(xl[i], s, t), 0.f); ar[i] = fmaxf(fmaf(xr[i], s, t), 0.f); }
+      const float4* wp = reinterpret_cast<const float4*>(wst + (e * DB_MAXL + l) * 36);
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const float4 w0 = wp[ky * 3], w1 = wp[ky * 3 + 1], w2 = wp[ky * 3 + 2];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const float vl = al[r + ky], vm = a[r + ky], vr = ar[r + ky];
+          acc[l][r][0] = fmaf(w0.x, vl, fmaf(w1.x, vm, fmaf(w2.x, vr, acc[l][r][0])));
+          acc[l][r][1] = fmaf(w0.y, vl, fmaf(w1.y, vm, fmaf(w2.y, vr, acc[l][r][1])));
+          acc[l][r][2] = fmaf(w0.z, vl, fmaf(w1.z, vm, fmaf(w2.z, vr, acc[l][r][2])));
+          acc[l][r][3] = fmaf(w0.w, vl, fmaf(w1.w, vm, fmaf(w2.w, vr, acc[l][r][3])));
+        }
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(DS_THREADS, 2) dense_block_stream_kernel(DenseBlockArgs a) {
+  extern __shared__ __align__(16) float sm[];
+  float* BUF = sm;                                        // [2][4][32][32] raw-channel ring
+  float* NEW = BUF + 2 * DS_CHUNK;                        // [3][4][32][32] outputs of layers 0..2 (chunks 12..14)
+  float* WST = NEW + 3 * DS_CHUNK;                        // [2][4 e][4 l][9][4] weight ring
+  float* SS = WST + 2 * DS_WCH;                           // [2][4 l][64] folded BatchNorm of the four layers
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int lm = (lane + 31) & 31, lp = (lane + 1) & 31;
+  const int r0 = warp * 4;
+  const long long HW = (long long)DS_H * DB_W;
+  const int nraw = a.c0 / DS_CH;                          // raw chunks (c0 is a multiple of 4)
+  for (int n = blockIdx.x; n < a.N; n += gridDim.x) {
+    const int g = n / a.n_per_group;
+    float* bn_ = a.buf + (long long)n * a.bs;
+    auto prefetch = [&](int k) {                          // chunk k < nraw: data + weights; chunk >= nraw: weights only (data is in NEW)
+      const int cbase = k * DS_CH;
+      if (k < nraw) {
+        float* dst = BUF + (k & 1) * DS_CHUNK;
+        const float* src = bn_ + (long long)cbase * HW;
+        for (int q = tid; q < DS_CHUNK / 4; q += DS_THREADS)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst + 4 * q)), "l"(src + 4 * q) : "memory");
+      }
+      float* wd = WST + (k & 1) * DS_WCH;
+      for (int q = tid; q < DS_WCH; q += DS_THREADS) {
+        const int co = q & 3, tap = (q >> 2) % 9, l = ((q >> 2) / 9) % DB_MAXL, e = (q >> 2) / (9 * DB_MAXL);
+        const int cin = a.c0 + 4 * l, c = cbase + e;
+        if (l < a.nl && c < cin) {
+          const float* src = a.w[l] + (long long)g * a.w_gs[l] + ((long long)co * cin + c) * 9 + tap;
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(wd + q)), "l"(src) : "memory");
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    prefetch(0);
+    for (int i = tid; i < DB_MAXL * DB_MAXC; i += DS_THREADS) {
+      const int l = i / DB_MAXC, c = i - l * DB_MAXC;
+      const bool ok = l < a.nl && c < a.c0 + 4 * l;
+      SS[i] = ok ? __ldg(a.scale + (long long)g * a.ss_gs + a.bn_off[l] + c) : 0.f;
+      SS[DB_MAXL * DB_MAXC + i] = ok ? __ldg(a.shift + (long long)g * a.ss_gs + a.bn_off[l] + c) : 0.f;
+    }
+    float acc[DB_MAXL][4][4];
+#pragma unroll
+    for (int l = 0; l < DB_MAXL; ++l)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) { acc[l][r][0] = 0.f; acc[l][r][1] = 0.f; acc[l][r][2] = 0.f; acc[l][r][3] = 0.f; }
+    const int nchunks = nraw + a.nl - 1;                  // raw chunks, then the outputs of layers 0 .. nl-2
+    // finalize layer l: its accumulators are complete -> shared memory (input of the later layers) and the dense-block buffer
+    auto finalize = [&](int l, const float (&v)[4][4]) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int co = 0; co < 4; ++co) {
+          if (l < DB_MAXL - 1) NEW[((size_t)(l * DS_CH + co) * DS_H + r0 + r) * DB_W + lane] = v[r][co];
+          bn_[(long long)(a.c0 + 4 * l + co) * HW + (r0 + r) * DB_W + lane] = v[r][co];
+        }
+    };
+    for (int k = 0; k < nchunks; ++k) {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncthreads();                                    // chunk k (data + weights) visible; everyone is done with chunk k - 1
+      if (k + 1 < nchunks) prefetch(k + 1);
+      const float* wst = WST + (k & 1) * DS_WCH;
+      if (k < nraw) {
+        ds_chunk<0>(BUF + (k & 1) * DS_CHUNK, wst, SS, k * DS_CH, acc, r0, lane, lm, lp);
+        if (k == nraw - 1) finalize(0, acc[0]);
+      } else if (k == nraw) {
+        ds_chunk<1>(NEW, wst, SS, k * DS_CH, acc, r0, lane, lm, lp);
+        finalize(1, acc[1]);
+      } else if (k == nraw + 1) {
+        ds_chunk<2>(NEW + DS_CHUNK, wst, SS, k * DS_CH, acc, r0, lane, lm, lp);
+        finalize(2, acc[2]);
+      } else {
+        ds_chunk<3>(NEW + 2 * DS_CHUNK, wst, SS, k * DS_CH, acc, r0, lane, lm, lp);
+      }
+    }
+    finalize(DB_MAXL - 1, acc[DB_MAXL - 1]);               // (the launcher only takes this kernel for four-layer blocks)
+    __syncthreads();                                      // NEW / rings are reused by the next sample
+  }
+}
+
 }  // namespace
 
 // number of consecutive ops starting at `first` that form a fusable dense block (0 = none)
@@ -195,6 +320,15 @@ int arpde_dense_block_launch(const arpde_op_t* ops, int first, int nl, const arp
   }
   a.scale = scale; a.shift = shift; a.ss_gs = ss_gs;
   ARPDE_CHECK_ARG((((uintptr_t)a.buf) & 15) == 0 && (a.bs & 3) == 0, "dense_block: buffer must be 16-byte aligned");
+  if (b.h == DS_H && nl == DB_MAXL && (a.c0 % DS_CH) == 0 && !arpde_dev_env("ARPDE_DENSE_STREAM_OFF")) {
+    // whole-sample streaming kernel (no halo recompute, two CTAs per SM)
+    const size_t smem_s = ((size_t)5 * DS_CHUNK + 2 * DS_WCH + 2 * DB_MAXL * DB_MAXC) * sizeof(float);
+    ARPDE_CUDA(cudaFuncSetAttribute(dense_block_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
+    long long grid_s = 2ll * arpde_num_sms(); if (grid_s > N) grid_s = N;
+    dense_block_stream_kernel<<<(unsigned)grid_s, DS_THREADS, smem_s, stream>>>(a);
+    ARPDE_LAUNCH_CHECK();
+    return ARPDE_OK;
+  }
   const int rows = DB_OWN + 2 * nl, ctot = a.c0 + 4 * nl;
   const size_t smem = ((size_t)ctot * rows * DB_W + (size_t)(ctot - 4) * 36 + 2 * DB_MAXC + DB_RED) * sizeof(float);
   ARPDE_CHECK_ARG(smem <= 227 * 1024, "dense_block: %zu bytes of shared memory needed", smem);

@@ -158,11 +158,14 @@ def _compare_with_reference_module(ours, ref, x, seed, check_grads=True, tol=TOL
         # Both sides are fp32 autograd chains with different summation orders, so a pre-activation within ~1e-6 of zero can flip its
         # ReLU mask on one side: one pixel of one gradient map then moves by its full value (measured on the default net: 3 seeds of 4
         # agree to 6e-6 in every tensor, the 4th shows 2e-3 in the tensors upstream of one flipped pixel).  A flip is local, an indexing
-        # or mask-stream error is not: the relative L2 error is held to GRAD_TOL of test_gpu_parity.py, the max-norm error to 2e-2.
+        # or mask-stream error is not.  The partner here is cuDNN in fp32, whose weight gradients are atomically accumulated: two runs of
+        # the REFERENCE differ by 4e-4 (relative L2) in In_conv1.weight of this net (a 5e-4-sized gradient left over from cancelling
+        # terms), while this library accumulates weight gradients in fp64 and reproduces bit for bit.  Bounds: relative L2 2e-3, max-norm
+        # 2e-2; the tight check of the same topology is test_m4_encoder_decoder_backward_vs_oracle (fp64 autograd, 2e-5).
         l2 = lambda a, b: float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30))
-        assert l2(ga, gb) < 2e-4 and rel_err(ga, gb) < 2e-2
+        assert l2(ga, gb) < 2e-3 and rel_err(ga, gb) < 2e-2
         for n in pa:
-            assert l2(pa[n], pb[n]) < 2e-4 and rel_err(pa[n], pb[n]) < 2e-2, n
+            assert l2(pa[n], pb[n]) < 2e-3 and rel_err(pa[n], pb[n]) < 2e-2, n
     for k in sa:
         assert rel_err(sa[k], sb[k]) < tol, k
 

@@ -234,7 +234,7 @@ def build_swag_port():
     return sd, None
 
 
-REF_SAMPLE = (2, 64, 4)      # S, N_ic, T of one reference-arm step (of 30 x 64 x 100)
+REF_SAMPLE = (4, 64, 16)     # S, N_ic, T of one reference-arm step (of 30 x 64 x 100): ~5 s of CPU work per step on 16 cores
 
 
 def run_reference(args):

@@ -493,8 +493,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
-        if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
-            os.environ['NCCL_DEBUG'] = 'WARN'        # keep stdout to the single JSON line (NCCL's version banner goes to stdout)
+        if os.environ.get('NCCL_DEBUG', '').upper() == 'VERSION':
+            os.environ['NCCL_DEBUG'] = 'WARN'        # (round-1 behaviour, kept: NCCL prints its version line at WARN as well; the JSON line stays the LAST line of stdout)
         dist.init_process_group('nccl', device_id=dev)
     peaks = load_peaks()
 

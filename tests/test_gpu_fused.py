@@ -89,3 +89,20 @@ def test_output_conv_kernel_vs_oracle(cin, H, N, npg):
         ref = torch.tanh(O.conv_circ(a, w[g].double().cpu()))
         assert rel_err(ybuf[n:n + 1, 4:6], ref) < TOL, n
     assert float((ybuf[:, :4] - 9.0).abs().max()) == 0.0 and float((ybuf[:, 6:] - 9.0).abs().max()) == 0.0      # neighbours untouched
+
+
+def test_launch_counter_counts_the_rollout_launches():
+    """arpde_launch_count(): a T-step rollout of the default 2D net at a machine-filling batch is 6 launches per step (In_conv1, In_conv3,
+    ONE fused dense block, conv1x1, folded up-conv, output conv) + 4 weight-split launches + 1 BatchNorm fold; the per-layer path: 9 per step."""
+    from arpde_b200 import _lib as L
+    m = _model([4])
+    ic = torch.randn(100, 2, 64, 64, device=DEV)
+    T = 3
+    engine.rollout(m, ic, 1)
+    L.lib.arpde_launch_count(1)
+    engine.rollout(m, ic, T)
+    n_fused = int(L.lib.arpde_launch_count(1))
+    engine.rollout(m, ic, T, layerwise=True)
+    n_layer = int(L.lib.arpde_launch_count(1))
+    assert n_fused == 6 * T + 5, n_fused
+    assert n_layer == 9 * T + 5, n_layer

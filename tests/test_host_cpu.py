@@ -132,3 +132,24 @@ def test_dropin_module_names():
                        ('1D-KS-SWAG', 'from nn.denseEDcirc import DenseED; from nn.ksFiniteDifference import KSIntegrate')):
         code = "import sys; sys.path.insert(0, %r); %s; from nn.swag import SwagNN; from nn.bayesNN import BayesNN"
         subprocess.check_call([sys.executable, '-c', code % (os.path.join(arpde_b200.PACKAGE_DIR, 'dropin', proj), mods)])
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (CPU): one JSON line with the keys the driver reads; the reference's own modules when they are staged."""
+    import json
+    import subprocess
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '0'],
+                         stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600, env=dict(os.environ, CUDA_VISIBLE_DEVICES=''))
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith('{')]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ('impl', 'metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling', 'vs_baseline', 'dtype', 'data',
+              'config', 'cpu_baseline', 'e2e'):
+        assert k in d, k
+    assert d['impl'] == 'reference' and d['metric'] == 'ar_steps_x_samples_per_s' and d['value'] > 0 and d['vs_baseline'] is None
+    assert d['cpu_baseline']['kind'] in ('reference', 'port') and d['cpu_baseline']['cores'] >= 1
+    assert d['e2e']['h2d_bytes_per_step'] == 0 and d['e2e']['d2h_bytes_per_step'] == 0 and 'workload' in d['config']
+    from oracle import ref_shims
+    if ref_shims.ref_root() is not None:
+        assert d['cpu_baseline']['kind'] == 'reference'

@@ -138,11 +138,12 @@ def rollout(model, ic, tsteps, flat_weights=None, named_params=None, out=None, l
 
 
 @torch.no_grad()
-def predictive_moments(traj, n_samples, betas=None, formula='2d', noise=None):
+def predictive_moments(traj, n_samples, betas=None, formula='2d', noise=None, out_ptrs=None):
     """Sample mean and predictive variance over the S weight samples of a sample-major trajectory.
 
     formula '2d': var = 1/mean(beta) + E[y^2] - E[y]^2      (2D-Burgers-SWAG/post/plotBARContour.py:85-104)
     formula '1d': var = mean_s(1/beta_s + y_s^2) - mean^2   (1D-Burger-SWAG/post/plotBARContour.py:123,136-139)
+    out_ptrs: (mean address, variance address) of caller-owned device memory for the [n_ic, ...] results instead of fresh tensors.
     betas None -> pure sample variance (noise term 0).  noise: the noise term as a Python float (skips the device->host read of
     betas, e.g. when the moments of several pieces of one rollout are taken with the same weight samples).
     """
@@ -166,6 +167,12 @@ def predictive_moments(traj, n_samples, betas=None, formula='2d', noise=None):
         noise = float(1.0 / betas.double().mean())
     else:
         noise = float((1.0 / betas.double()).mean())
+    if out_ptrs is not None:
+        # the caller owns the destination (e.g. rank 0's result buffer mapped through NVLink peer memory, parallel.PeerMoments): the
+        # kernel's stores ARE the transfer
+        with torch.cuda.device(t.device):
+            L.call('arpde_predictive_moments', L.ptr(t), bstride, inner, n_ic, n_samples, noise, int(out_ptrs[0]), int(out_ptrs[1]), L.stream())
+        return None, None
     mean = torch.empty((n_ic,) + tuple(t.shape[1:]), device=t.device, dtype=torch.float32)
     var = torch.empty_like(mean)
     with torch.cuda.device(t.device):

@@ -143,6 +143,48 @@ def swag_rollout(swag_nn, ics, tsteps, n_samples, seed=0, diagCov=False, scale=1
     return sharded_swag_rollout(run_local, ics, tsteps, n_samples, mode=mode, formula=formula, gather=gather)
 
 
+class PeerMoments:
+    """Predictive moments reduced STRAIGHT into rank `dst`'s result buffer over NVLink peer memory (one process per GPU, one node).
+
+    The compute step (arpde_predictive_moments: mean / variance over the weight samples of this rank's initial conditions) is followed
+    by a collective (the gather of all shards on rank dst).  Instead of reducing locally and then calling NCCL, the result buffers are
+    allocated in symmetric memory (torch.distributed._symmetric_memory: every rank maps every peer's buffer), and each rank's moments
+    kernel is handed the address of ITS slice of rank dst's buffer: the kernel's coalesced stores are the transfer, there is no second
+    pass over the data and no staging copy.  `finish()` is the symmetric-memory barrier (device side, on the stream) after which rank
+    dst may read `mean` / `var`.  `available()` is False where symmetric memory cannot be set up (then use gather_shards / NCCL)."""
+
+    def __init__(self, n_items, item_shape, device, dst=0, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.ws = world(group)
+        self.dst, self.n_items = dst, n_items
+        self.inner = 1
+        for d in item_shape:
+            self.inner *= int(d)
+        self.half = n_items * self.inner
+        self.buf = symm_mem.empty(2 * self.half, dtype=torch.float32, device=device)
+        self.hdl = symm_mem.rendezvous(self.buf, group=self.group)
+        self.mean = self.buf[:self.half].view((n_items,) + tuple(item_shape))          # meaningful on rank dst after finish()
+        self.var = self.buf[self.half:].view((n_items,) + tuple(item_shape))
+
+    @staticmethod
+    def available():
+        try:
+            import torch.distributed._symmetric_memory as symm_mem     # noqa: F401
+            return dist.is_available() and dist.is_initialized() and dist.get_backend() == 'nccl' and torch.cuda.is_available()
+        except Exception:
+            return False
+
+    def reduce_into(self, traj, n_samples, first_item, noise):
+        """moments of `traj` (this rank's items [first_item, first_item + n_local)) written into rank dst's buffers"""
+        from . import engine
+        base = int(self.hdl.buffer_ptrs[self.dst])
+        engine.predictive_moments(traj, n_samples, noise=noise, out_ptrs=(base + 4 * first_item * self.inner, base + 4 * (self.half + first_item * self.inner)))
+
+    def finish(self):
+        self.hdl.barrier()
+
+
 class FlatGradBucket:
     """One flat fp32 buffer that IS the gradient storage of a parameter list (the reference has no distributed training;
     this is the natural data-parallel split of its mini-batch of initial conditions).

@@ -341,7 +341,8 @@ def workload_config(n_gpus):
     return {'workload': 'C4: 2D coupled Burgers SWAG inference, %d weight samples x %d ICs (fixed job, %s ICs per GPU) x %d AR steps, %dx%d grid, '
                         'DenseED blocks=[4] growth=4 init_features=96' % (S_SAMPLES, N_IC, per, T_STEPS, NEL, NEL),
             'samples': S_SAMPLES, 'ics_total': N_IC, 'ics_per_gpu': per, 'ar_steps': T_STEPS, 'grid': [NEL, NEL],
-            'parallelism': 'ic-shard x%d (strong scaling of the fixed 64-IC job) + final NCCL gather of mean/var to rank 0' % n_gpus,
+            'parallelism': 'ic-shard x%d (strong scaling of the fixed 64-IC job) + final gather of mean/var on rank 0: every rank's moments kernel stores its shard into '
+                           "rank 0's buffer over NVLink peer memory (symmetric memory; NCCL gather as fallback, see roofline.job_breakdown_ms.gather)" % n_gpus,
             'l2': 'inputs larger than L2 (per-step activations %.1f GB per GPU; stencil timings rotate 4 buffer sets, each > L2 / 4)' % (4.3 / n_gpus)}
 
 
@@ -472,6 +473,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-train-probe', action='store_true', help='skip the (untimed) training-step measurement')
+    ap.add_argument('--nccl-gather', action='store_true', help='gather the moments with NCCL instead of peer-memory stores from the moments kernel')
     ap.add_argument('--no-extra', action='store_true', help='skip the C2 / C5 / weak-scaling / stencil side measurements')
     ap.add_argument('--tsteps', type=int, default=T_STEPS, help='debug: shorter rollouts (the JSON line then names the reduced config)')
     args = ap.parse_args()
@@ -498,6 +500,16 @@ def main():
         dist.init_process_group('nccl', device_id=dev)
     peaks = load_peaks()
 
+    # the gather of the predictive moments: fused into the moments kernel through NVLink peer memory when symmetric memory can be set up
+    # (N > 1), NCCL gather otherwise
+    USE_PEER = False
+    if world > 1 and not args.nccl_gather and PL.PeerMoments.available():
+        try:
+            probe = PL.PeerMoments(2, (4,), dev)
+            probe.finish()
+            USE_PEER = True
+        except Exception as e:                        # symmetric memory not usable on this box: NCCL gather
+            print('peer-memory gather unavailable (%s): NCCL gather' % repr(e)[:200], file=sys.stderr)
     swag, _ = build_swag(dev)
     named = list(swag.base.named_parameters())
     gen = torch.Generator(device=dev); gen.manual_seed(1234)       # every rank draws the SAME weight samples
@@ -519,11 +531,15 @@ def main():
             # the tail of every launch (15-35 % at this batch) is filled by the other group's launches (measured 0.976 -> 0.926 ms per step)
             self.n_streams = 2 if S_SAMPLES * self.n < 960 else 1
             self.gathered = gathered
+            self.peer = None
             if gathered and world > 1:
                 # rank 0 receives every shard into one [world, n, ...] tensor per moment (equal shards; a ragged split pads to n_max)
                 self.pad = n_max
                 self.g_m = torch.empty((world, n_max) + state, device=dev) if rank == 0 else None
                 self.g_v = torch.empty((world, n_max) + state, device=dev) if rank == 0 else None
+                if USE_PEER:
+                    # NVLink peer memory: every rank's moments kernel stores its shard straight into rank 0's buffer (parallel.PeerMoments)
+                    self.peer = PL.PeerMoments(N_IC, state, dev)
             n_res = N_IC if gathered else self.n
             if rank == 0 or not gathered:
                 self.mean_host = torch.empty((n_res,) + state, pin_memory=True)
@@ -540,7 +556,9 @@ def main():
                     shp = (hi_ - lo_, 2, NEL, NEL)
                     if rank == 0 or not gathered:
                         self.host_chunks.append((torch.empty((n_res,) + shp, pin_memory=True), torch.empty((n_res,) + shp, pin_memory=True)))
-                    if gathered and world > 1 and rank == 0:
+                    if gathered and world > 1 and USE_PEER:
+                        self.g_chunks.append(PL.PeerMoments(N_IC, shp, dev))
+                    elif gathered and world > 1 and rank == 0:
                         self.g_chunks.append((torch.empty((world, self.n) + shp, device=dev), torch.empty((world, self.n) + shp, device=dev)))
 
         def run(self, ic, marks=None):
@@ -554,6 +572,12 @@ def main():
             traj = engine.rollout(swag, ic, T_STEPS, flat_weights=flat, named_params=named, out=self.traj_buf, n_streams=self.n_streams)
             mark()
             betas = flat[:, 0].exp()
+            if self.peer is not None:
+                self.peer.reduce_into(traj, S_SAMPLES, lo, noise=float(1.0 / betas.double().mean()))
+                mark()
+                self.peer.finish()
+                mark()
+                return self.peer.mean, self.peer.var
             mean, var = engine.predictive_moments(traj, S_SAMPLES, betas, '2d')
             mark()
             if self.gathered and world > 1:
@@ -578,8 +602,17 @@ def main():
             for k, (lo_, hi_) in enumerate(self.spans):
                 traj = engine.rollout(swag, ic, cl, flat_weights=flat, named_params=named, out=self.traj_buf, t_start=k * cl, total_steps=T_STEPS,
                                       n_streams=self.n_streams)
-                mean, var = engine.predictive_moments(traj[:, lo_:hi_], S_SAMPLES, formula='2d', noise=noise)
-                if self.gathered and world > 1:
+                if self.gathered and world > 1 and USE_PEER:
+                    pm = self.g_chunks[k]
+                    pm.reduce_into(traj[:, lo_:hi_], S_SAMPLES, lo, noise=noise)
+                    pm.finish()
+                    src = (pm.mean, pm.var) if rank == 0 else None
+                    mean = var = None
+                else:
+                    mean, var = engine.predictive_moments(traj[:, lo_:hi_], S_SAMPLES, formula='2d', noise=noise)
+                if mean is None:
+                    pass
+                elif self.gathered and world > 1:
                     gm, gv = self.g_chunks[k] if rank == 0 else (None, None)
                     dist.gather(mean, list(gm.unbind(0)) if rank == 0 else None, dst=0)
                     dist.gather(var, list(gv.unbind(0)) if rank == 0 else None, dst=0)
@@ -652,6 +685,7 @@ def main():
     torch.cuda.synchronize()
     bd = [marks[i].elapsed_time(marks[i + 1]) for i in range(len(marks) - 1)]
     breakdown = dict(zip(('sample_ms', 'rollout_ms', 'moments_ms', 'gather_ms'), bd))
+    breakdown['gather'] = ('peer-memory stores of the moments kernel into rank 0 (NVLink) + symmetric-memory barrier' if USE_PEER else 'NCCL gather') if world > 1 else 'none'
     rollout_ms = breakdown['rollout_ms']
 
     for _ in range(max(1, args.warmup // 3)):

@@ -133,3 +133,39 @@ def infer_worker(rank, ws, port, backend, root, q):
         q.put((rank, traceback.format_exc()))
     finally:
         dist.destroy_process_group()
+
+
+def peer_worker(rank, ws, port, backend, root, q):
+    """parallel.PeerMoments (NCCL + symmetric memory, one GPU per rank): moments stored straight into rank 0's buffer == gather of local moments."""
+    sys.path.insert(0, root)
+    sys.path.insert(0, os.path.join(root, 'tests'))
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(ws))
+    dev = torch.device('cuda', rank)
+    torch.cuda.set_device(dev)
+    dist.init_process_group('nccl', rank=rank, world_size=ws, device_id=dev)
+    try:
+        from _util import rel_err
+        from arpde_b200 import engine
+        from arpde_b200 import parallel as PL
+        assert PL.PeerMoments.available()
+        S, n_loc, inner_shape = 5, 3, (4, 2, 8, 8)
+        torch.manual_seed(100 + rank)
+        traj = torch.randn((S * n_loc,) + inner_shape, device=dev)
+        pm = PL.PeerMoments(ws * n_loc, inner_shape, dev)
+        pm.reduce_into(traj, S, rank * n_loc, noise=0.25)
+        pm.finish()
+        mean, var = engine.predictive_moments(traj, S, noise=0.25)
+        gm, gv = PL.gather_shards(mean, ws * n_loc), PL.gather_shards(var, ws * n_loc)
+        torch.cuda.synchronize()
+        errs = {}
+        if rank == 0:
+            errs = {'mean': float((pm.mean - gm).abs().max()), 'var': float((pm.var - gv).abs().max())}
+        dist.barrier()
+        q.put((rank, errs))
+    except Exception:
+        import traceback
+        q.put((rank, traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()

@@ -69,3 +69,13 @@ def test_gradient_sink_equals_plain_autograd():
     assert rel_err(la, lb) < 1e-6
     assert rel_err(ga, gb) < 1e-6
     assert rel_err(wa, wb) < 1e-6
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='peer memory needs one GPU per rank (two processes spinning on one GPU must not wait on each other)')
+def test_peer_memory_moments_equal_nccl_gather():
+    """parallel.PeerMoments: each rank's moments kernel writes its shard into rank 0's symmetric-memory buffer over NVLink -- bit-identical to
+    reducing locally and gathering with NCCL."""
+    res = _run(2, 'nccl', target=W.peer_worker)
+    for rank, errs in res.items():
+        assert isinstance(errs, dict), errs
+    assert res[0] == {'mean': 0.0, 'var': 0.0}, res

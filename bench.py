@@ -341,7 +341,7 @@ def workload_config(n_gpus):
     return {'workload': 'C4: 2D coupled Burgers SWAG inference, %d weight samples x %d ICs (fixed job, %s ICs per GPU) x %d AR steps, %dx%d grid, '
                         'DenseED blocks=[4] growth=4 init_features=96' % (S_SAMPLES, N_IC, per, T_STEPS, NEL, NEL),
             'samples': S_SAMPLES, 'ics_total': N_IC, 'ics_per_gpu': per, 'ar_steps': T_STEPS, 'grid': [NEL, NEL],
-            'parallelism': 'ic-shard x%d (strong scaling of the fixed 64-IC job) + final gather of mean/var on rank 0: every rank's moments kernel stores its shard into '
+            'parallelism': "ic-shard x%d (strong scaling of the fixed 64-IC job) + final gather of mean/var on rank 0: every rank's moments kernel stores its shard into "
                            "rank 0's buffer over NVLink peer memory (symmetric memory; NCCL gather as fallback, see roofline.job_breakdown_ms.gather)" % n_gpus,
             'l2': 'inputs larger than L2 (per-step activations %.1f GB per GPU; stencil timings rotate 4 buffer sets, each > L2 / 4)' % (4.3 / n_gpus)}
 

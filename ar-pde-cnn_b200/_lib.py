@@ -74,6 +74,7 @@ _PROTOS = {
     'arpde_rollout_layerwise': [vp, i32, vp, i32, vp, vp, i32, f32p, i32, i32, i32, i32, i32, i32, i32, i32, i32, f32p, f32p,
                                 i32, f64, f32p, i64, vp],
     'arpde_fd_burgers1d': [vp, vp, i32, i32, f64, f64, f64, i32, i32, i32, i32, vp],
+    'arpde_peer_allreduce_f64': [vp, vp, i64],
     'arpde_swag_sample': [vp, vp, vp, vp, i32, f32p, f32p, f32p, i32, i32, i32, f64, f64, i32, vp],
     'arpde_predictive_moments': [f32p, i64, i64, i32, i32, f64, f32p, f32p, vp],
 }
@@ -121,6 +122,13 @@ def call(name, *args):
 
 
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64)     # arpde_allreduce_fn
+PEER_MAX = 8
+
+
+class PeerCtx(C.Structure):
+    """arpde_peer_ctx_t"""
+    _fields_ = [('slots', C.c_void_p * PEER_MAX), ('flags', C.c_void_p * PEER_MAX), ('world', C.c_int32), ('rank', C.c_int32),
+                ('nslots', C.c_int32), ('slot_doubles', C.c_int32), ('seq', C.c_uint64), ('error_flag', C.c_void_p), ('stream', C.c_void_p)]
 
 
 def allreduce_callback(sync, *tensors):

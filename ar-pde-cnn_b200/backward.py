@@ -94,11 +94,15 @@ def densed_backward(ctx, gy):
                    L.ptr(gy4), L.ptr(y_saved), L.ptr(work), L.ptr(ss), plan.bn_total, L.ptr(saved), L.ptr(gwork), L.ptr(gx),
                    L.ptr_array(gptrs), L.ptr(T1), L.ptr(T2), L.ptr(wT), L.ptr(d64), 1 if training else 0, L.ptr(tc), tc_len, L.stream())
         else:
-            cb = L.allreduce_callback(sync, d64)
+            if sync.peer is not None:
+                sync.peer.bind_stream(L.stream())
+                cb, user = sync.peer.fn, sync.peer.user
+            else:
+                cb, user = L.allreduce_callback(sync, d64), 0
             L.call('arpde_densed_backward_dp', ops_c, len(plan.ops), bufs_c, len(bufs), pp, len(tensors), L.ptr(x4), x_bs, N, H, W,
                    L.ptr(gy4), L.ptr(y_saved), L.ptr(work), L.ptr(ss), plan.bn_total, L.ptr(saved), L.ptr(gwork), L.ptr(gx),
                    L.ptr_array(gptrs), L.ptr(T1), L.ptr(T2), L.ptr(wT), L.ptr(d64), 1 if training else 0, L.ptr(tc), tc_len,
-                   cb, 0, sync.world_size(), L.stream())
+                   cb, user, sync.world_size(), L.stream())
     grads, off = [], 0
     if sink is not None:
         sink.flat[sink_lo:sink_hi].add_(flat)

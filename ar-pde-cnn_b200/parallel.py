@@ -271,6 +271,56 @@ class FlatGradBucket:
             p.grad = flat[off:off + p.numel()].view_as(p) if m > 0 else None
 
 
+class PeerAllReduce:
+    """NVLink peer-memory all-reduce of small fp64 vectors (csrc/peer.cu) for the BatchNorm sums of data-parallel training: exchange
+    slots and flags live in symmetric memory, the context (peer pointers, sequence number) is owned here and handed to
+    arpde_peer_allreduce_f64, which the library calls directly as its arpde_allreduce_fn -- no Python, no NCCL call per layer."""
+    NSLOTS, SLOT_DOUBLES = 4, 512
+
+    def __init__(self, device, group=None):
+        import ctypes as C
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _lib as L
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.ws = world(group)
+        if self.ws > L.PEER_MAX:
+            raise RuntimeError('peer all-reduce supports up to %d ranks' % L.PEER_MAX)
+        nd = self.NSLOTS * self.SLOT_DOUBLES
+        nflag = self.NSLOTS * self.ws
+        self.buf = symm_mem.empty(nd + (nflag + 1) // 2 + 8, dtype=torch.float64, device=device)      # [slots | flags (uint32)]
+        self.buf.zero_()
+        self.hdl = symm_mem.rendezvous(self.buf, group=self.group)
+        self.err = torch.zeros((1,), dtype=torch.int32, device=device)
+        self.ctx = L.PeerCtx()
+        for r in range(self.ws):
+            self.ctx.slots[r] = int(self.hdl.buffer_ptrs[r])
+            self.ctx.flags[r] = int(self.hdl.buffer_ptrs[r]) + 8 * nd
+        self.ctx.world, self.ctx.rank, self.ctx.nslots, self.ctx.slot_doubles = self.ws, self.rank, self.NSLOTS, self.SLOT_DOUBLES
+        self.ctx.seq = 0
+        self.ctx.error_flag = self.err.data_ptr()
+        torch.cuda.synchronize(device)
+        self.hdl.barrier()                      # every rank's flags are zero before anyone signals
+        torch.cuda.synchronize(device)
+        self.fn = C.cast(L.lib.arpde_peer_allreduce_f64, L.ALLREDUCE_FN)
+        self.user = C.addressof(self.ctx)
+
+    @staticmethod
+    def available(group=None):
+        try:
+            import torch.distributed._symmetric_memory as symm_mem     # noqa: F401
+            rank, ws = world(group)
+            return (dist.is_initialized() and dist.get_backend() == 'nccl' and torch.cuda.is_available() and ws > 1 and
+                    torch.cuda.device_count() >= ws)          # one GPU per rank: the kernel waits for its peers' kernels
+        except Exception:
+            return False
+
+    def bind_stream(self, stream_handle):
+        self.ctx.stream = stream_handle
+
+    def failed(self):
+        return bool(self.err.item())
+
+
 class BatchNormSync:
     """All-reduce hook for train-mode BatchNorm under data parallelism.
 
@@ -280,10 +330,11 @@ class BatchNormSync:
     running statistics and the BN backward are those of the global mini-batch.  Every rank must hold the same number of
     samples (the count is scaled by the world size)."""
 
-    def __init__(self, group=None):
+    def __init__(self, group=None, peer=None):
         self.group = group
         self.calls = 0
         self.doubles = 0
+        self.peer = peer          # PeerAllReduce: the library then calls the NVLink kernel itself instead of coming back to Python
 
     def world_size(self):
         return world(self.group)[1]
@@ -294,12 +345,30 @@ class BatchNormSync:
         dist.all_reduce(tensor, op=dist.ReduceOp.SUM, group=self.group)
 
 
+_PEER_CACHE = {}
+
+
+def _peer_allreduce(group):
+    """one PeerAllReduce per (device, group), created on first use; None where peer memory cannot be used"""
+    if not PeerAllReduce.available(group):
+        return None
+    key = (torch.cuda.current_device(), id(group))
+    if key not in _PEER_CACHE:
+        try:
+            _PEER_CACHE[key] = PeerAllReduce(torch.device('cuda', torch.cuda.current_device()), group)
+        except Exception:
+            _PEER_CACHE[key] = None
+    return _PEER_CACHE[key]
+
+
 @contextlib.contextmanager
-def sync_batchnorm(group=None):
+def sync_batchnorm(group=None, peer='auto'):
+    """peer: 'auto' = the NVLink peer-memory kernel when every rank has its own GPU and symmetric memory works, else
+    torch.distributed.all_reduce from the Python callback; False = always the callback."""
     from . import program as P
     rank, ws = world(group)
     prev = P.BN_SYNC
-    P.BN_SYNC = BatchNormSync(group) if ws > 1 else None
+    P.BN_SYNC = BatchNormSync(group, _peer_allreduce(group) if (peer and ws > 1) else None) if ws > 1 else None
     try:
         yield P.BN_SYNC
     finally:

@@ -291,10 +291,14 @@ class _Forward(torch.autograd.Function):
                        H, W, y_ptr, y_ctot, 0, L.ptr(work), L.ptr(ss), plan.bn_total, L.ptr(stats), stats_len if training else 0,
                        L.ptr(saved), 1 if training else 0, float(mom), float(eps), L.ptr(tc), tc_len, L.stream())
             else:
-                cb = L.allreduce_callback(sync, stats)
+                if sync.peer is not None:
+                    sync.peer.bind_stream(L.stream())
+                    cb, user = sync.peer.fn, sync.peer.user
+                else:
+                    cb, user = L.allreduce_callback(sync, stats), 0
                 L.call('arpde_densed_forward_dp', ops_c, len(plan.ops), bufs_c, len(bufs), pp, gs, len(tensors), L.ptr(x4), x_bs, N, N,
                        H, W, y_ptr, y_ctot, 0, L.ptr(work), L.ptr(ss), plan.bn_total, L.ptr(stats), stats_len,
-                       L.ptr(saved), 1, float(mom), float(eps), L.ptr(tc), tc_len, cb, 0, sync.world_size(), L.stream())
+                       L.ptr(saved), 1, float(mom), float(eps), L.ptr(tc), tc_len, cb, user, sync.world_size(), L.stream())
         if plan.out_is_buf:
             off, _, ctot, h, w = bufs[plan.ops[-1]['out_buf']]
             y = work[off:off + N * ctot * h * w].view(N, ctot, h, w)

@@ -330,8 +330,9 @@ def train_step_probe(dev, B_total=128, weak=False, tback=2, nwarm=3, nrep=10, ra
         ms = float(t.item())
     return {'ms': ms, 'value': world * tback * B / ms * 1e3, 'unit': 'sample-steps/s', 'batch_total': world * B, 'batch_per_gpu': B, 'n_gpus': world,
             'tback': tback, 'scaling': 'weak' if weak else 'strong', 'library_launches_per_step': launches,
-            'parallelism': 'mini-batch sharded x%d: global-batch BatchNorm (per-layer all-reduce of the fp64 sums), gradients accumulated in one flat '
-                           'bucket, one all-reduce (NCCL) per optimizer step' % world,
+            'parallelism': 'mini-batch sharded x%d: global-batch BatchNorm (per-layer all-reduce of the fp64 sums: %s), gradients accumulated in one flat '
+                           'bucket, one all-reduce (NCCL) per optimizer step' % (world, 'one NVLink peer-memory kernel each, csrc/peer.cu' if (
+                               world > 1 and PL._peer_allreduce(None) is not None) else 'torch.distributed from the library callback'),
             'what': 'forward (batch-stat BN) + Crank-Nicolson + neg log joint + backward (tensor-core data and weight gradients) + one-launch Adam, '
                     'mean of %d steps after %d warm-up (CUDA events, max over ranks)' % (nrep, nwarm)}
 

@@ -288,6 +288,24 @@ int arpde_densed_backward_dp(const arpde_op_t* ops, int n_ops, const arpde_buf_t
                              int training, float* tc_scratch, int64_t tc_scratch_floats, arpde_allreduce_fn allreduce, void* user,
                              int dp_world, arpde_stream_t stream);
 
+/* A ready-made arpde_allreduce_fn over NVLink peer memory (one process per GPU on one node; peer.cu): every rank copies its n doubles
+ * into its own exchange slot, publishes a sequence number in every peer's flag array, waits for all peers, then reads all slots over
+ * NVLink and adds them in rank order (bit-identical on every rank) -- one small kernel on `stream`, no host round trip.  The CALLER owns
+ * the context: slots[r] / flags[r] are rank r's exchange buffer ([nslots][slot_doubles] doubles) and flag array ([nslots][world] uint32,
+ * zeroed before first use) as mapped into THIS process (e.g. torch.distributed._symmetric_memory buffer_ptrs), seq the number of
+ * all-reduces issued so far (advanced by the call; must stay equal on all ranks), error_flag a device int the kernel raises when a
+ * peer does not answer within ~2 s.  Never use it with several ranks on one GPU (the kernel waits for its peers' kernels). */
+#define ARPDE_PEER_MAX 8
+typedef struct arpde_peer_ctx {
+  double* slots[ARPDE_PEER_MAX];
+  uint32_t* flags[ARPDE_PEER_MAX];
+  int32_t world, rank, nslots, slot_doubles;
+  uint64_t seq;
+  int32_t* error_flag;
+  arpde_stream_t stream;
+} arpde_peer_ctx_t;
+int arpde_peer_allreduce_f64(void* ctx, double* buf, int64_t n);
+
 /* Auto-regressive rollout in eval mode: the AR loops of main.py test()/testSample()
  * (2D-Burgers-SWAG/main.py:112-135,:160-179; 1D main.py :106-121,:148-163) without Python in the loop.
  * traj [N, traj_ctot, H, W], traj_ctot >= c_hist + T*c_out; channels [0,c_hist) hold the repeated initial

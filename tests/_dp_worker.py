@@ -26,7 +26,7 @@ def build(dev, seed=0):
     return swag, bayes, integ, opt
 
 
-def train_step(swag, bayes, integ, opt, ic, dp, capture=True, tback=2, ntrain=5):
+def train_step(swag, bayes, integ, opt, ic, dp, capture=True, tback=2, ntrain=5, peer='auto'):
     """2D-Burgers-SWAG/main.py:61-91 for one BPTT window; dp: use the data-parallel hooks (global BatchNorm + gradient all-reduce)."""
     import torch
     from arpde_b200 import parallel as PL
@@ -34,7 +34,7 @@ def train_step(swag, bayes, integ, opt, ic, dp, capture=True, tback=2, ntrain=5)
     bucket.zero_()
     inp = ic.repeat(1, 3, 1, 1)
     loss = 0
-    ctx = PL.sync_batchnorm() if dp else contextlib.nullcontext()
+    ctx = PL.sync_batchnorm(peer=peer) if dp else contextlib.nullcontext()
     with ctx:
         for _ in range(tback):
             u_pred = swag(inp[:, -6:])
@@ -86,6 +86,15 @@ def worker(rank, ws, port, backend, root, q):
         wcopy = w_dp.clone()
         dist.broadcast(wcopy, src=0)
         errs['rank_consistency'] = float((wcopy - w_dp).abs().max())
+        # the NVLink peer-memory all-reduce of the BatchNorm sums (csrc/peer.cu; used by default when every rank has its own GPU) against
+        # torch.distributed.all_reduce from the Python callback: two ranks add the same two numbers, so the step must be bit-identical
+        from arpde_b200 import parallel as PL
+        errs['peer_used'] = PL._peer_allreduce(None) is not None
+        if errs['peer_used']:
+            swag2, bayes2, integ2, opt2 = build(dev)
+            loss_cb, g_cb, st_cb, w_cb = train_step(swag2, bayes2, integ2, opt2, ics[rank * per:(rank + 1) * per], dp=True, peer=False)
+            errs['peer_vs_callback'] = max(float((g_cb - g_dp).abs().max()), float((w_cb - w_dp).abs().max()), float((loss_cb - loss_dp).abs()))
+            errs['peer_failed'] = PL._peer_allreduce(None).failed()
         q.put((rank, errs))
     except Exception:
         import traceback

@@ -40,6 +40,9 @@ def test_two_rank_step_equals_one_rank_step_at_global_batch():
         assert errs['grads'] < 2e-5, (backend, rank, errs)
         assert errs['weights'] < 1e-5, (backend, rank, errs)
         assert errs['rank_consistency'] == 0.0, (backend, rank, errs)
+        assert errs['peer_used'] == (torch.cuda.device_count() >= 2), errs
+        if errs['peer_used']:
+            assert errs['peer_vs_callback'] == 0.0 and not errs['peer_failed'], (rank, errs)
 
 
 def test_sharded_swag_inference_equals_single_process():

@@ -2,6 +2,7 @@
 #include <stdarg.h>
 #include "common.cuh"
 #include "../../include/arpde.h"
+#include <atomic>
 
 static thread_local char g_err[512] = "";
 
@@ -12,13 +13,12 @@ void arpde_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-static thread_local long long g_launches = 0;
-void arpde_count_launch() { ++g_launches; }
-// kernels this thread has launched through the library since the last reset (reset != 0 clears the counter after reading it)
+static std::atomic<long long> g_launches{0};
+void arpde_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+// kernels this PROCESS has launched through the library since the last reset (reset != 0 clears the counter after reading it); process-wide
+// because autograd runs the backward calls on its own thread
 extern "C" int64_t arpde_launch_count(int reset) {
-  const long long v = g_launches;
-  if (reset) g_launches = 0;
-  return v;
+  return reset ? g_launches.exchange(0, std::memory_order_relaxed) : g_launches.load(std::memory_order_relaxed);
 }
 
 int arpde_num_sms() {

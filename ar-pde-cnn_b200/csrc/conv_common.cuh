@@ -136,5 +136,13 @@ bool arpde_conv_tc_wanted(const ConvDesc& d);                    // layer heuris
 long long arpde_conv_tc_wprep_floats(int cin, int cout, int kh, int kw);   // prepared-weight floats per weight group
 int arpde_conv_tc_prep_launch(const ConvDesc& d, const float* w, long long w_gs, int groups, float* wprep, long long wprep_gs,
                               cudaStream_t stream);
+// operand-format hand-over to the stride-2 3x3 convolution that follows (conv_z.cu): the epilogue applies the consumer's eval-mode
+// BatchNorm affine + ReLU and writes fp16 hi / lo octets into `z` instead of fp32 NCHW into y
+struct ZOut { float* z; const float* scale; const float* shift; long long ss_gs; };
 int arpde_conv_tc_launch(const ConvDesc& d, const float* x, long long x_bs, const float* wprep, long long wprep_gs, const float* scale,
-                         const float* shift, long long ss_gs, float* y, double* stats, cudaStream_t stream);
+                         const float* shift, long long ss_gs, float* y, double* stats, cudaStream_t stream, const ZOut* zo = nullptr);
+long long arpde_conv_z_sample16(int c, int H, int W);            // 16-byte units per sample of the operand-format activation
+bool arpde_conv_z_wanted(const ConvDesc& d);                     // d: the stride-2 consumer, described by its input dims
+long long arpde_conv_z_wprep_floats(int cin, int cout);
+int arpde_conv_z_prep_launch(const ConvDesc& d, const float* w, long long w_gs, int groups, float* wprep, long long wprep_gs, cudaStream_t stream);
+int arpde_conv_z_launch(const ConvDesc& d, const float* z, const float* wprep, long long wprep_gs, float* y, cudaStream_t stream);

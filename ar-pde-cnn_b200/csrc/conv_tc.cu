@@ -39,6 +39,7 @@
 #include "../../include/arpde.h"
 #include <stdlib.h>
 #include <mutex>
+#include <cuda_fp16.h>
 #include <cuda.h>          // CUtensorMap + enums only; cuTensorMapEncodeTiled is resolved through cudaGetDriverEntryPoint
 
 #define TC_MAX_TAPS 49
@@ -77,6 +78,7 @@ struct ConvTcArgs {
   int dilate;                // input is zero-inserted x2 (data gradient of a stride-2 layer): addressed like row_mode 1, odd rows/columns are 0
   int RS, raw_slot_floats;   // source rows per (item, channel chunk) and floats per raw ring slot [RS][cchunk][W]
   int upfold, cout_fold;     // upfold: `cout` = 4 * cout_fold parity-major channels on the low-resolution grid, scattered by the epilogue
+  uint4* z; long long z_bs16; const float* z_scale; const float* z_shift; long long z_ss_gs;   // operand-format output (ZOut), else z == nullptr
   long long* dbg;            // optional cycle counters of CTA 0 (arpde_conv_tc_set_debug), else nullptr
   int dbg_flags;             // experiments: 1 = skip patch staging work, 2 = skip epilogue loads/stores, 4 = skip MMAs
   int tap_plane[TC_MAX_TAPS];
@@ -528,7 +530,57 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         const long long HoWo4 = 4 * HoWo;
         float* ypf = a.y + ((long long)n * a.y_ctot + a.y_coff) * HoWo4 + (long long)(2 * oy) * (2 * a.Wo) + 2 * ox;
         const uint32_t trow = tmem + ((uint32_t)lanebase << 16) + (uint32_t)(as * a.acc_cols + t * a.tile_cols);
-        if (plain) {
+        if (a.z != nullptr) {
+          // operand-format output for the stride-2 consumer (conv_z.cu): BatchNorm affine + ReLU of the consumer, fp16 hi / scaled-lo split,
+          // one 16-byte store per channel octet and term; lanes are consecutive x, i.e. alternate between the two column-parity planes
+          const int g = n / a.n_per_group;
+          const float* zs = a.z_scale + (long long)g * a.z_ss_gs;
+          const float* zb = a.z_shift + (long long)g * a.z_ss_gs;
+          const int PWz = (a.Wo >> 1) + 1, PHz = (a.Ho >> 1) + 1;
+          const long long plane16 = (long long)PHz * PWz;
+          const int yy = (oy >> 1) + 1, xx = (ox >> 1) + 1;
+          uint4* zp0 = a.z + (long long)n * a.z_bs16 + (long long)((oy & 1) * 2 + (ox & 1)) * plane16;
+          for (int c0 = 0; c0 < a.cout; c0 += 16) {
+            float v1[16], v2[16];
+            tmem_ld16(trow + c0, v1); tmem_ld16(trow + a.coutP + c0, v2);
+            tmem_ld_wait();
+            if (a.split_terms) {
+              float v3[16];
+              tmem_ld16(trow + 2 * a.coutP + c0, v3);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v2[j] += v3[j];
+            }
+            if (valid) {
+#pragma unroll
+              for (int u = 0; u < 2; ++u) {
+                if (c0 + 8 * u < a.cout) {
+                  uint32_t hw[4], lw[4];
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const int c = c0 + 8 * u + 2 * j;
+                    const float e0 = fmaxf(fmaf(v1[8 * u + 2 * j] + v2[8 * u + 2 * j], __ldg(zs + c), __ldg(zb + c)), 0.f);
+                    const float e1 = fmaxf(fmaf(v1[8 * u + 2 * j + 1] + v2[8 * u + 2 * j + 1], __ldg(zs + c + 1), __ldg(zb + c + 1)), 0.f);
+                    const float h0 = fminf(e0, 65504.f), h1 = fminf(e1, 65504.f);
+                    const __half2 hh = __floats2half2_rn(h0, h1);
+                    const float2 hf = __half22float2(hh);
+                    const __half2 ll = __floats2half2_rn(fminf((e0 - hf.x) * 2048.f, 65504.f), fminf((e1 - hf.y) * 2048.f, 65504.f));
+                    hw[j] = *reinterpret_cast<const uint32_t*>(&hh); lw[j] = *reinterpret_cast<const uint32_t*>(&ll);
+                  }
+                  const uint4 hv = make_uint4(hw[0], hw[1], hw[2], hw[3]), lv = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                  uint4* zp = zp0 + (long long)(((c0 >> 3) + u) * 2) * 4 * plane16;       // [c8][hl][plane]: hi at hl = 0, lo one hl stride further
+                  const long long hl = 4 * plane16;
+                  zp[yy * PWz + xx] = hv; zp[hl + yy * PWz + xx] = lv;
+                  // circular halo of the parity plane: its last row / column is also stored as row 0 / column 0
+                  const bool hx = xx == PWz - 1, hy = yy == PHz - 1;
+                  if (hx) { zp[yy * PWz] = hv; zp[hl + yy * PWz] = lv; }
+                  if (hy) { zp[xx] = hv; zp[hl + xx] = lv; }
+                  if (hx && hy) { zp[0] = hv; zp[hl] = lv; }
+                }
+              }
+            }
+          }
+        } else if (plain) {
           // common case (no output activation, no batch statistics): 16 columns per TMEM round trip, straight stores.
           // (ncu on the first version: the per-element activation switch + statistics branches made the 4 epilogue warps
           //  the critical path -- ~95% busy, half of their stalls branch_resolving / instruction-cache misses.)
@@ -985,8 +1037,8 @@ long long* arpde_tc_debug_buffer() { return nullptr; }
 #endif
 
 int arpde_conv_tc_launch(const ConvDesc& d, const float* x, long long x_bs, const float* wprep, long long wprep_gs, const float* scale,
-                         const float* shift, long long ss_gs, float* y, double* stats, cudaStream_t stream) {
-  ARPDE_CHECK_ARG(x && wprep && y, "conv_tc: null pointer");
+                         const float* shift, long long ss_gs, float* y, double* stats, cudaStream_t stream, const ZOut* zo) {
+  ARPDE_CHECK_ARG(x && wprep && (y || zo), "conv_tc: null pointer");
   if (d.N == 0) return ARPDE_OK;
   ConvTcArgs a; size_t smem;
   if (!tc_plan(d, a, &smem)) { arpde_set_error("conv_tc: layer not supported by the tensor-core kernel"); return ARPDE_ERR_UNSUPPORTED; }
@@ -994,6 +1046,12 @@ int arpde_conv_tc_launch(const ConvDesc& d, const float* x, long long x_bs, cons
   a.y = y; a.stats = stats; a.relu_in = d.relu_in; a.act = d.act; a.y_ctot = d.y_ctot; a.y_coff = d.y_coff;
   a.n_per_group = d.n_per_group; a.dbg = g_tc_dbg; a.dbg_flags = g_tc_dbg_flags;
   a.N = d.N;
+  if (zo) {
+    ARPDE_CHECK_ARG(zo->z && zo->scale && zo->shift && !a.upfold && d.act == 0 && !stats && d.cout % 16 == 0 && !(a.Ho & 1) && !(a.Wo & 1) &&
+                    (((uintptr_t)zo->z) & 15) == 0, "conv_tc: operand-format output needs 16 | cout, even output dims, no activation / statistics");
+    a.z = reinterpret_cast<uint4*>(zo->z); a.z_bs16 = arpde_conv_z_sample16(d.cout, a.Ho, a.Wo);
+    a.z_scale = zo->scale; a.z_shift = zo->shift; a.z_ss_gs = zo->ss_gs;
+  }
   // TMA needs a 16-byte aligned base and 16-byte multiples for every global stride; otherwise the staging warps load with LDG
   CUtensorMap tmap;
   memset(&tmap, 0, sizeof(tmap));

@@ -34,6 +34,7 @@ struct RunCtx {
   std::vector<const float*> wprep;          // per op: prepared tensor-core weights (nullptr = fp32 FFMA kernel)
   std::vector<long long> wprep_gs;
   bool fuse_dense = true;                   // eval mode: dense blocks as one launch (off for the layer-wise cross-check path)
+  std::vector<char> zpair;                  // per op: 1 = this op and the next run as an operand-format pair (conv_z.cu; rollouts only)
   const DpHook* dp = nullptr;               // data-parallel training: all-reduce of the BatchNorm sums (nullptr = single process)
   mutable std::vector<int> synced;          // per buffer: channels whose statistics already hold the global sums
 };
@@ -64,6 +65,37 @@ static int prep_tc(RunCtx& c) {
     if (rc) return rc;
     c.wprep[i] = dst; c.wprep_gs[i] = wgroups > 1 ? per_group : 0;
     used += per_group * wgroups;
+  }
+  return ARPDE_OK;
+}
+
+// Rollouts (no backward pass can follow): a tensor-core convolution whose output feeds exactly one BatchNorm + ReLU + 3x3 stride-2
+// convolution hands its activation over in the consumer's fp16 operand format (conv_z.cu) instead of fp32 NCHW -- In_conv1 -> In_conv3 of
+// the 2D network.  The pair shares the producer's work buffer, which must have room for the slightly larger operand form
+// (arpde_conv_z_floats; Python's layout reserves it).  Re-prepares the consumer's weights in the fp16 layout.
+static int mark_zpairs(RunCtx& c) {
+  c.zpair.assign(c.n_ops, 0);
+  if (c.wprep.empty()) return ARPDE_OK;
+  for (int i = 0; i + 1 < c.n_ops; ++i) {
+    const arpde_op_t& p = c.ops[i]; const arpde_op_t& q = c.ops[i + 1];
+    if (!c.wprep[i] || !c.wprep[i + 1] || p.out_buf < 0 || q.in_buf != p.out_buf || p.out_coff != 0 || p.act != 0 || p.up || p.stride != 1) continue;
+    const arpde_buf_t& b = c.bufs[p.out_buf];
+    if (b.ctot != p.cout || q.cin != p.cout || q.bn_param < 0 || b.h < 2) continue;
+    bool sole = true;
+    for (int j = 0; j < c.n_ops; ++j) if ((j != i && c.ops[j].out_buf == p.out_buf) || (j != i + 1 && c.ops[j].in_buf == p.out_buf)) sole = false;
+    if (!sole) continue;
+    ConvDesc dq; op_desc(c, q, &dq);
+    if (!arpde_conv_z_wanted(dq)) continue;
+    long long next = -1;
+    for (int k = 0; k < c.n_bufs; ++k) if (c.bufs[k].offset > b.offset && (next < 0 || c.bufs[k].offset < next)) next = c.bufs[k].offset;
+    const long long need = (long long)c.N * 4 * arpde_conv_z_sample16(p.cout, b.h, b.w);
+    if (next < 0 || next - b.offset < need || (b.offset & 3) || (((uintptr_t)c.work) & 15)) continue;
+    const int wgroups = c.gstride[q.w_param] ? c.groups : 1;
+    const long long per_group = arpde_conv_tc_wprep_floats(q.cin, q.cout, q.kh, q.kw);
+    int rc = arpde_conv_z_prep_launch(dq, (const float*)c.params[q.w_param], c.gstride[q.w_param], wgroups, (float*)c.wprep[i + 1], per_group, c.stream);
+    if (rc) return rc;
+    c.zpair[i] = 1;
+    ++i;
   }
   return ARPDE_OK;
 }
@@ -148,6 +180,20 @@ static int run_ops(const RunCtx& c, const float* x, long long x_bs, float* y, in
       }
     }
     int rc;
+    if (!training && !c.zpair.empty() && c.zpair[i]) {
+      const arpde_op_t& q = c.ops[i + 1];
+      ZOut zo; zo.z = out; zo.scale = c.ss + q.bn_off; zo.shift = c.ss + (long long)c.groups * c.bn_total + q.bn_off; zo.ss_gs = c.bn_total;
+      rc = arpde_conv_tc_launch(d, in, in_bs, c.wprep[i], c.wprep_gs[i], scale, shift, c.bn_total, nullptr, nullptr, c.stream, &zo);
+      if (rc) return rc;
+      ConvDesc dq; op_desc(c, q, &dq);
+      float* out_q;
+      if (q.out_buf == -2) { out_q = y; dq.y_ctot = y_ctot; dq.y_coff = y_coff; }
+      else { const arpde_buf_t& bq = c.bufs[q.out_buf]; out_q = c.work + bq.offset; dq.y_ctot = bq.ctot; dq.y_coff = q.out_coff; }
+      rc = arpde_conv_z_launch(dq, out, c.wprep[i + 1], c.wprep_gs[i + 1], out_q, c.stream);
+      if (rc) return rc;
+      ++i;
+      continue;
+    }
     if (!c.wprep.empty() && c.wprep[i]) {
       // train mode: the batch statistics of the written channels come from a separate streaming pass over the (L2-resident) output
       // instead of the tensor-core epilogue's per-column warp reductions (10 shuffles + 2 double atomics per column and tile made
@@ -290,6 +336,7 @@ static int rollout_impl(const arpde_op_t* ops, int n_ops, const arpde_buf_t* buf
     return arpde_ks_rollout_launch(ops, params_host, param_gstride_host, traj, bs, c_hist, T, N, c.n_per_group, (float)eps, stream);
   c.fuse_dense = allow_persistent;
   rc = prep_tc(c); if (rc) return rc;
+  if (allow_persistent) { rc = mark_zpairs(c); if (rc) return rc; }
   rc = fold_eval(c); if (rc) return rc;
   for (int t = 0; t < T; ++t) {
     const float* x = traj + (long long)(c_hist - c_in + t * c_out) * HW;

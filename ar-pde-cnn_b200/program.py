@@ -195,10 +195,17 @@ def _spatial(plan, H, W, scale):
 def layout(plan, N, H, W):
     """Buffer geometry for a batch: list of (offset, stats_off, ctot, h, w), total floats, total stat doubles."""
     bufs, off, soff = [], 0, 0
-    for b in plan.bufs:
+    for bi, b in enumerate(plan.bufs):
         h, w = _spatial(plan, H, W, b['scale'])
         bufs.append((off, soff, b['ctot'], h, w))
-        off += N * b['ctot'] * h * w
+        per_sample = b['ctot'] * h * w
+        # a buffer with one producer and one consumer may be handed over in the consumer's tensor-core operand format during rollouts
+        # (csrc/conv_z.cu), which is a few percent larger than fp32 NCHW: reserve the room
+        readers = [o for o in plan.ops if o['in_buf'] == bi]
+        if (plan.nd == 2 and sum(o['out_buf'] == bi for o in plan.ops) == 1 and len(readers) == 1 and readers[0]['kw'] == 3 and
+                readers[0]['stride'] == 2 and not readers[0]['up'] and readers[0]['bn_param'] >= 0):
+            per_sample = max(per_sample, int(L.lib.arpde_conv_z_floats(b['ctot'], h, w)))
+        off += N * per_sample
         off = (off + 3) & ~3          # keep every buffer 16-byte aligned
         soff += 2 * b['ctot']
     # BatchNorm directly on the network input (stand-alone _Transition / LastTransUp): tail slot for its batch statistics

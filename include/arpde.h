@@ -45,8 +45,8 @@ typedef void* arpde_stream_t;      /* cudaStream_t */
 
 int arpde_version(void);
 const char* arpde_last_error(void);
-/* Diagnostic: number of kernels the calling thread has launched through this library since the last reset (thread-local like the
- * error string; reset != 0 clears it after reading).  bench.py reports it as "gpu_launches". */
+/* Diagnostic: number of kernels this process has launched through this library since the last reset (process-wide, atomic: autograd
+ * calls the backward entry points from its own thread; reset != 0 clears it after reading).  bench.py reports it as "gpu_launches". */
 int64_t arpde_launch_count(int reset);
 
 /* ---------------------------------------------------------------------------------------------
@@ -287,6 +287,17 @@ int arpde_densed_backward_dp(const arpde_op_t* ops, int n_ops, const arpde_buf_t
                              float* gwork, float* gx, void* const* grads_host, float* T1, float* T2, float* wT, double* d64,
                              int training, float* tc_scratch, int64_t tc_scratch_floats, arpde_allreduce_fn allreduce, void* user,
                              int dp_world, arpde_stream_t stream);
+
+/* Eval-mode stem pair (conv_z.cu): y = conv3x3_stride2(relu(scale * conv_k1xk1(x) + shift)), both circular -- In_conv1 -> In_conv_norm1 ->
+ * In_conv_relu1 -> In_conv3 of 2D-Burgers-SWAG/nn/denseEDcirc2d.py:247-255 -- with the intermediate activation handed over in the second
+ * convolution's fp16 two-term tensor-core operand format (scratch `z`, arpde_conv_z_floats(c1, H, W) floats per sample; 0 = shape not
+ * covered) instead of fp32 NCHW.  arpde_rollout uses the same pair automatically when the producer's work buffer has that much room.
+ * scratch: arpde_conv_fwd_tc_scratch_floats(cin, c1, k1, k1, groups) + arpde_conv_fwd_tc_scratch_floats(c1, c3, 3, 3, groups) floats. */
+int64_t arpde_conv_z_floats(int c, int H, int W);
+int arpde_stem_pair_fwd(const float* x, int64_t x_bstride, const float* w1, int64_t w1_gstride, const float* scale, const float* shift,
+                        int64_t ss_gstride, const float* w3, int64_t w3_gstride, float* y, int N, int cin, int H, int W, int c1, int k1,
+                        int c3, int y_ctot, int y_coff, int n_per_group, float* z, int64_t z_floats, float* scratch, int64_t scratch_floats,
+                        arpde_stream_t stream);
 
 /* A ready-made arpde_allreduce_fn over NVLink peer memory (one process per GPU on one node; peer.cu): every rank copies its n doubles
  * into its own exchange slot, publishes a sequence number in every peer's flag array, waits for all peers, then reads all slots over

@@ -79,7 +79,9 @@ def test_program_of_default_2d_net():
     assert [o['out_coff'] for o in plan.ops[2:6]] == [48, 52, 56, 60]
     assert plan.ops[-1]['out_buf'] == -2 and plan.bn_total == 96 + 48 + 52 + 56 + 60 + 64 + 32 + 16
     bufs, work, stats = P.layout(plan, 2, 64, 64)
-    assert bufs[1][2:] == (64, 32, 32) and work == 2 * (96 * 4096 + 64 * 1024 + 32 * 1024 + 16 * 4096)
+    # the first buffer (In_conv1 -> In_conv3) is sized for the fp16 operand format of csrc/conv_z.cu: 12 octets x (hi, lo) x 4 parity
+    # planes x 33 x 33 positions x 16 bytes = 418176 floats per sample instead of 96 * 4096
+    assert bufs[1][2:] == (64, 32, 32) and work == 2 * (12 * 2 * 4 * 33 * 33 * 4 + 64 * 1024 + 32 * 1024 + 16 * 4096)
     # plan survives deepcopy and points at the copied modules (SwagNN.sample deep-copies the model)
     m2 = copy.deepcopy(model)
     p2 = P.compile_module(m2.features)

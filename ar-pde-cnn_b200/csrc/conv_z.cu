@@ -374,10 +374,15 @@ extern "C" int arpde_stem_pair_fwd(const float* x, int64_t x_bstride, const floa
   ARPDE_CHECK_ARG(z_floats >= zneed, "stem_pair_fwd: z scratch too small (%lld < %lld floats)", (long long)z_floats, zneed);
   const long long p1 = arpde_conv_tc_wprep_floats(cin, c1, k1, k1), p3 = arpde_conv_tc_wprep_floats(c1, c3, 3, 3);
   ARPDE_CHECK_ARG(scratch_floats >= (p1 + p3) * groups, "stem_pair_fwd: scratch too small (%lld < %lld floats)", (long long)scratch_floats, (p1 + p3) * groups);
-  int rc = arpde_conv_tc_prep_launch(d1, w1, w1_gstride, groups, scratch, p1, stream); if (rc) return rc;
+  const bool stem = arpde_conv_stem_wanted(d1);            // few input channels: the dedicated fp16 producer (conv_stem.cu)
+  int rc = stem ? arpde_conv_stem_prep_launch(d1, w1, w1_gstride, groups, scratch, p1, stream)
+                : arpde_conv_tc_prep_launch(d1, w1, w1_gstride, groups, scratch, p1, stream);
+  if (rc) return rc;
   float* s3 = scratch + p1 * groups;
   rc = arpde_conv_z_prep_launch(d3, w3, w3_gstride, groups, s3, p3, stream); if (rc) return rc;
   ZOut zo; zo.z = z; zo.scale = scale; zo.shift = shift; zo.ss_gs = ss_gstride;
-  rc = arpde_conv_tc_launch(d1, x, x_bstride, scratch, p1, nullptr, nullptr, 0, nullptr, nullptr, stream, &zo); if (rc) return rc;
+  rc = stem ? arpde_conv_stem_launch(d1, x, x_bstride, scratch, p1, zo, stream)
+            : arpde_conv_tc_launch(d1, x, x_bstride, scratch, p1, nullptr, nullptr, 0, nullptr, nullptr, stream, &zo);
+  if (rc) return rc;
   return arpde_conv_z_launch(d3, z, s3, p3, y, stream);
 }

@@ -95,6 +95,14 @@ static int mark_zpairs(RunCtx& c) {
     int rc = arpde_conv_z_prep_launch(dq, (const float*)c.params[q.w_param], c.gstride[q.w_param], wgroups, (float*)c.wprep[i + 1], per_group, c.stream);
     if (rc) return rc;
     c.zpair[i] = 1;
+    ConvDesc dp; op_desc(c, p, &dp);
+    if (p.bn_param < 0 && arpde_conv_stem_wanted(dp)) {        // the network's first layer: dedicated fp16 producer (conv_stem.cu)
+      const int pg = c.gstride[p.w_param] ? c.groups : 1;
+      rc = arpde_conv_stem_prep_launch(dp, (const float*)c.params[p.w_param], c.gstride[p.w_param], pg, (float*)c.wprep[i],
+                                       arpde_conv_tc_wprep_floats(p.cin, p.cout, p.kh, p.kw), c.stream);
+      if (rc) return rc;
+      c.zpair[i] = 2;
+    }
     ++i;
   }
   return ARPDE_OK;
@@ -183,7 +191,8 @@ static int run_ops(const RunCtx& c, const float* x, long long x_bs, float* y, in
     if (!training && !c.zpair.empty() && c.zpair[i]) {
       const arpde_op_t& q = c.ops[i + 1];
       ZOut zo; zo.z = out; zo.scale = c.ss + q.bn_off; zo.shift = c.ss + (long long)c.groups * c.bn_total + q.bn_off; zo.ss_gs = c.bn_total;
-      rc = arpde_conv_tc_launch(d, in, in_bs, c.wprep[i], c.wprep_gs[i], scale, shift, c.bn_total, nullptr, nullptr, c.stream, &zo);
+      rc = c.zpair[i] == 2 ? arpde_conv_stem_launch(d, in, in_bs, c.wprep[i], c.wprep_gs[i], zo, c.stream)
+                           : arpde_conv_tc_launch(d, in, in_bs, c.wprep[i], c.wprep_gs[i], scale, shift, c.bn_total, nullptr, nullptr, c.stream, &zo);
       if (rc) return rc;
       ConvDesc dq; op_desc(c, q, &dq);
       float* out_q;

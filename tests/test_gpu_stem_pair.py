@@ -39,7 +39,8 @@ def _oracle_pair(x, w1, sc, sh, w3):
 
 
 @pytest.mark.parametrize('cin,c1,k1,c3,H,W,N', [(6, 96, 5, 48, 64, 64, 3), (4, 32, 3, 16, 16, 32, 5), (6, 48, 5, 64, 32, 32, 2),
-                                               (3, 16, 7, 20, 8, 8, 4), (6, 96, 5, 48, 128, 128, 1)])
+                                               (3, 16, 7, 20, 8, 8, 4), (6, 96, 5, 48, 128, 128, 1),
+                                               (16, 32, 3, 48, 32, 32, 3), (8, 128, 3, 32, 16, 16, 2), (1, 16, 1, 16, 8, 16, 2)])
 def test_pair_matches_fp64_oracle(cin, c1, k1, c3, H, W, N):
     g = torch.Generator().manual_seed(cin * 100 + c1 + H)
     x = torch.randn(N, cin, H, W, generator=g).to(DEV)

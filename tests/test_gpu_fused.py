@@ -92,17 +92,21 @@ def test_output_conv_kernel_vs_oracle(cin, H, N, npg):
 
 
 def test_launch_counter_counts_the_rollout_launches():
-    """arpde_launch_count(): a T-step rollout of the default 2D net at a machine-filling batch is 6 launches per step (In_conv1, In_conv3,
-    ONE fused dense block, conv1x1, folded up-conv, output conv) + 4 weight-split launches + 1 BatchNorm fold; the per-layer path: 9 per step."""
+    """arpde_launch_count(): a T-step rollout of the default 2D net at a machine-filling batch is 6 launches per step (In_conv1 as
+    conv_stem_kernel, In_conv3 as conv_z_kernel, ONE fused dense block, conv1x1, folded up-conv, output conv) + 4 weight-split launches +
+    the 2 fp16 weight preparations of the stem pair + 1 BatchNorm fold; the per-layer path: 9 per step + 5."""
     from arpde_b200 import _lib as L
     m = _model([4])
     ic = torch.randn(100, 2, 64, 64, device=DEV)
-    T = 3
     engine.rollout(m, ic, 1)
-    L.lib.arpde_launch_count(1)
-    engine.rollout(m, ic, T)
-    n_fused = int(L.lib.arpde_launch_count(1))
-    engine.rollout(m, ic, T, layerwise=True)
-    n_layer = int(L.lib.arpde_launch_count(1))
-    assert n_fused == 6 * T + 5, n_fused
-    assert n_layer == 9 * T + 5, n_layer
+    counts = {}
+    for lw in (False, True):
+        for T in (1, 3):
+            L.lib.arpde_launch_count(1)
+            engine.rollout(m, ic, T, layerwise=lw)
+            counts[lw, T] = int(L.lib.arpde_launch_count(1))
+    print(counts)
+    per_step = {lw: (counts[lw, 3] - counts[lw, 1]) // 2 for lw in (False, True)}
+    once = {lw: counts[lw, 1] - per_step[lw] for lw in (False, True)}
+    assert per_step[False] == 6 and once[False] == 7, counts
+    assert per_step[True] == 9 and once[True] == 5, counts

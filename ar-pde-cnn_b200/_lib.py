@@ -76,6 +76,9 @@ _PROTOS = {
     'arpde_fd_burgers1d': [vp, vp, i32, i32, f64, f64, f64, i32, i32, i32, i32, vp],
     'arpde_peer_allreduce_f64': [vp, vp, i64],
     'arpde_stem_pair_fwd': [vp, i64, vp, i64, vp, vp, i64, vp, i64, vp] + [i32] * 10 + [vp, i64, vp, i64, vp],
+    'arpde_stem_pair_producer': [vp, i64, vp, i64, vp, vp, i64] + [i32] * 7 + [vp, i64, vp, i64, vp],
+    'arpde_stem_pair_consumer': [vp, vp, i64, vp] + [i32] * 8 + [vp, i64, vp],
+    'arpde_conv_fwd_h': [vp, i64, vp, i64, vp, vp, i64, vp] + [i32] * 11 + [vp, i64, vp],
     'arpde_swag_sample': [vp, vp, vp, vp, i32, f32p, f32p, f32p, i32, i32, i32, f64, f64, i32, vp],
     'arpde_predictive_moments': [f32p, i64, i64, i32, i32, f64, f32p, f32p, vp],
 }
@@ -96,9 +99,11 @@ lib.arpde_conv_wgrad_tc_scratch.argtypes = [i32] * 9
 lib.arpde_conv_wgrad_tc_scratch.restype = C.c_int64
 lib.arpde_conv_z_floats.argtypes = [i32, i32, i32]
 lib.arpde_conv_z_floats.restype = C.c_int64
+lib.arpde_conv_fwd_h_scratch_floats.argtypes = [i32] * 5
+lib.arpde_conv_fwd_h_scratch_floats.restype = C.c_int64
 
 EXPORTS = sorted(list(_PROTOS) + ['arpde_last_error', 'arpde_launch_count', 'arpde_densed_tc_scratch_floats', 'arpde_conv_fwd_tc_scratch_floats',
-                                   'arpde_conv_wgrad_tc_scratch', 'arpde_conv_z_floats'])
+                                   'arpde_conv_wgrad_tc_scratch', 'arpde_conv_z_floats', 'arpde_conv_fwd_h_scratch_floats'])
 
 
 def check(rc, what=''):

@@ -151,3 +151,9 @@ bool arpde_conv_z_wanted(const ConvDesc& d);                     // d: the strid
 long long arpde_conv_z_wprep_floats(int cin, int cout);
 int arpde_conv_z_prep_launch(const ConvDesc& d, const float* w, long long w_gs, int groups, float* wprep, long long wprep_gs, cudaStream_t stream);
 int arpde_conv_z_launch(const ConvDesc& d, const float* z, const float* wprep, long long wprep_gs, float* y, cudaStream_t stream);
+// eval-mode stride-1 1x1 / 3x3 (+ folded nearest x2) convolutions with fp16 two-term operands: conv_h.cu
+bool arpde_conv_h_wanted(const ConvDesc& d);
+long long arpde_conv_h_wprep_floats(int cin, int cout, int k, int up);
+int arpde_conv_h_prep_launch(const ConvDesc& d, const float* w, long long w_gs, int groups, float* wprep, long long wprep_gs, cudaStream_t stream);
+int arpde_conv_h_launch(const ConvDesc& d, const float* x, long long x_bs, const float* wprep, long long wprep_gs, const float* scale,
+                        const float* shift, long long ss_gs, float* y, cudaStream_t stream);

@@ -54,12 +54,18 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t 
       "l"(da), "l"(db), "r"(idesc), "r"(accumulate));
 }
 
-// fp16 two-term split of two values: hi = fp16(min(v, 65504)), lo' = fp16((v - hi) * 2^11), packed as half2 words
+// fp16 two-term split of two values: hi = fp16(v), lo' = fp16((v - hi) * 2^11), packed as half2 words.  Both conversions saturate to the
+// largest finite fp16 value (F2FP.SATFINITE: one instruction instead of a clamp pair around each conversion -- the epilogue warps of this
+// kernel are co-critical with the tensor pipe), so an out-of-range activation gives a wrong but finite result.
+__device__ __forceinline__ uint32_t pack_sat(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
 __device__ __forceinline__ void split2(float e0, float e1, uint32_t* hw, uint32_t* lw) {
-  const __half2 hh = __floats2half2_rn(fminf(fmaxf(e0, -65504.f), 65504.f), fminf(fmaxf(e1, -65504.f), 65504.f));
-  const float2 hf = __half22float2(hh);
-  const __half2 ll = __floats2half2_rn(fminf(fmaxf((e0 - hf.x) * 2048.f, -65504.f), 65504.f), fminf(fmaxf((e1 - hf.y) * 2048.f, -65504.f), 65504.f));
-  *hw = *reinterpret_cast<const uint32_t*>(&hh); *lw = *reinterpret_cast<const uint32_t*>(&ll);
+  const uint32_t h = pack_sat(e0, e1);
+  const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&h));
+  *hw = h; *lw = pack_sat((e0 - hf.x) * 2048.f, (e1 - hf.y) * 2048.f);
 }
 
 __global__ void __launch_bounds__(CS_THREADS, 1) conv_stem_kernel(const __grid_constant__ ConvStemArgs a) {

@@ -386,3 +386,48 @@ extern "C" int arpde_stem_pair_fwd(const float* x, int64_t x_bstride, const floa
   if (rc) return rc;
   return arpde_conv_z_launch(d3, z, s3, p3, y, stream);
 }
+
+// The two halves of the pair on their own (per-kernel timing in bench.py, tests): producer x -> z (weights prepared into `scratch`,
+// arpde_conv_fwd_tc_scratch_floats(cin, c1, k1, k1, groups) floats), consumer z -> y (arpde_conv_fwd_tc_scratch_floats(c1, c3, 3, 3, groups)).
+extern "C" int arpde_stem_pair_producer(const float* x, int64_t x_bstride, const float* w1, int64_t w1_gstride, const float* scale, const float* shift,
+                                        int64_t ss_gstride, int N, int cin, int H, int W, int c1, int k1, int n_per_group, float* z, int64_t z_floats,
+                                        float* scratch, int64_t scratch_floats, arpde_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  ARPDE_CHECK_ARG(x && w1 && scale && shift && z && scratch, "stem_pair_producer: null pointer");
+  ARPDE_CHECK_ARG(N >= 0 && cin > 0 && c1 > 0 && H > 0 && W > 0, "stem_pair_producer: bad dims");
+  if (N == 0) return ARPDE_OK;
+  ConvDesc d1;
+  d1.N = N; d1.cin = cin; d1.H = H; d1.W = W; d1.cout = c1; d1.kh = k1; d1.kw = k1; d1.stride = 1; d1.up = 0; d1.relu_in = 0; d1.act = 0;
+  d1.y_ctot = c1; d1.y_coff = 0; d1.n_per_group = n_per_group > 0 ? n_per_group : N;
+  ARPDE_CHECK_ARG(N % d1.n_per_group == 0, "stem_pair_producer: N=%d not a multiple of n_per_group=%d", N, d1.n_per_group);
+  const int groups = N / d1.n_per_group;
+  ARPDE_CHECK_ARG(arpde_conv_z_floats(c1, H, W) > 0 && z_floats >= arpde_conv_z_floats(c1, H, W) * N, "stem_pair_producer: z scratch too small or shape not covered");
+  const long long p1 = arpde_conv_tc_wprep_floats(cin, c1, k1, k1);
+  ARPDE_CHECK_ARG(scratch_floats >= p1 * groups, "stem_pair_producer: scratch too small (%lld < %lld floats)", (long long)scratch_floats, p1 * groups);
+  const bool stem = arpde_conv_stem_wanted(d1);
+  int rc = stem ? arpde_conv_stem_prep_launch(d1, w1, w1_gstride, groups, scratch, p1, stream)
+                : arpde_conv_tc_prep_launch(d1, w1, w1_gstride, groups, scratch, p1, stream);
+  if (rc) return rc;
+  ZOut zo; zo.z = z; zo.scale = scale; zo.shift = shift; zo.ss_gs = ss_gstride;
+  return stem ? arpde_conv_stem_launch(d1, x, x_bstride, scratch, p1, zo, stream)
+              : arpde_conv_tc_launch(d1, x, x_bstride, scratch, p1, nullptr, nullptr, 0, nullptr, nullptr, stream, &zo);
+}
+
+extern "C" int arpde_stem_pair_consumer(const float* z, const float* w3, int64_t w3_gstride, float* y, int N, int H, int W, int c1, int c3, int y_ctot,
+                                        int y_coff, int n_per_group, float* scratch, int64_t scratch_floats, arpde_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  ARPDE_CHECK_ARG(z && w3 && y && scratch, "stem_pair_consumer: null pointer");
+  ARPDE_CHECK_ARG(N >= 0 && c1 > 0 && c3 > 0 && H > 0 && W > 0, "stem_pair_consumer: bad dims");
+  ARPDE_CHECK_ARG(y_coff >= 0 && y_coff + c3 <= y_ctot, "stem_pair_consumer: channel window [%d,%d) outside y_ctot=%d", y_coff, y_coff + c3, y_ctot);
+  if (N == 0) return ARPDE_OK;
+  ConvDesc d3;
+  d3.N = N; d3.cin = c1; d3.H = H; d3.W = W; d3.cout = c3; d3.kh = 3; d3.kw = 3; d3.stride = 2; d3.up = 0; d3.relu_in = 1; d3.act = 0;
+  d3.y_ctot = y_ctot; d3.y_coff = y_coff; d3.n_per_group = n_per_group > 0 ? n_per_group : N;
+  ARPDE_CHECK_ARG(N % d3.n_per_group == 0, "stem_pair_consumer: N=%d not a multiple of n_per_group=%d", N, d3.n_per_group);
+  ARPDE_CHECK_ARG(arpde_conv_z_wanted(d3), "stem_pair_consumer: shape not covered (needs 16 | c1, even H, W >= 4, c3 <= 64)");
+  const int groups = N / d3.n_per_group;
+  const long long p3 = arpde_conv_tc_wprep_floats(c1, c3, 3, 3);
+  ARPDE_CHECK_ARG(scratch_floats >= p3 * groups, "stem_pair_consumer: scratch too small (%lld < %lld floats)", (long long)scratch_floats, p3 * groups);
+  int rc = arpde_conv_z_prep_launch(d3, w3, w3_gstride, groups, scratch, p3, stream); if (rc) return rc;
+  return arpde_conv_z_launch(d3, z, scratch, p3, y, stream);
+}

@@ -35,6 +35,7 @@ struct RunCtx {
   std::vector<long long> wprep_gs;
   bool fuse_dense = true;                   // eval mode: dense blocks as one launch (off for the layer-wise cross-check path)
   std::vector<char> zpair;                  // per op: 1 = this op and the next run as an operand-format pair (conv_z.cu; rollouts only)
+  std::vector<char> hconv;                  // per op: 1 = eval-mode stride-1 layer on the fp16 two-term kernel (conv_h.cu; rollouts only)
   const DpHook* dp = nullptr;               // data-parallel training: all-reduce of the BatchNorm sums (nullptr = single process)
   mutable std::vector<int> synced;          // per buffer: channels whose statistics already hold the global sums
 };
@@ -104,6 +105,26 @@ static int mark_zpairs(RunCtx& c) {
       c.zpair[i] = 2;
     }
     ++i;
+  }
+  return ARPDE_OK;
+}
+
+// Rollouts: the remaining stride-1 tensor-core layers (conv1x1 of a transition, the 3x3 convolution behind the nearest x2 upsampling) take
+// the fp16 two-term kernel of conv_h.cu; their weights are re-prepared in its layout (in place of the TF32 image).
+static int mark_hconvs(RunCtx& c) {
+  c.hconv.assign(c.n_ops, 0);
+  if (c.wprep.empty()) return ARPDE_OK;
+  for (int i = 0; i < c.n_ops; ++i) {
+    if (!c.wprep[i] || (!c.zpair.empty() && (c.zpair[i] || (i > 0 && c.zpair[i - 1])))) continue;
+    const arpde_op_t& o = c.ops[i];
+    ConvDesc d; op_desc(c, o, &d);
+    if (!arpde_conv_h_wanted(d)) continue;
+    const long long per_group = arpde_conv_tc_wprep_floats(o.cin, o.cout, o.kh, o.kw);
+    if (arpde_conv_h_wprep_floats(o.cin, o.cout, o.kh, o.up) > per_group) continue;
+    const int wgroups = c.gstride[o.w_param] ? c.groups : 1;
+    int rc = arpde_conv_h_prep_launch(d, (const float*)c.params[o.w_param], c.gstride[o.w_param], wgroups, (float*)c.wprep[i], per_group, c.stream);
+    if (rc) return rc;
+    c.hconv[i] = 1;
   }
   return ARPDE_OK;
 }
@@ -203,7 +224,9 @@ static int run_ops(const RunCtx& c, const float* x, long long x_bs, float* y, in
       ++i;
       continue;
     }
-    if (!c.wprep.empty() && c.wprep[i]) {
+    if (!training && !c.hconv.empty() && c.hconv[i]) {
+      rc = arpde_conv_h_launch(d, in, in_bs, c.wprep[i], c.wprep_gs[i], scale, shift, c.bn_total, out, c.stream);
+    } else if (!c.wprep.empty() && c.wprep[i]) {
       // train mode: the batch statistics of the written channels come from a separate streaming pass over the (L2-resident) output
       // instead of the tensor-core epilogue's per-column warp reductions (10 shuffles + 2 double atomics per column and tile made
       // the epilogue warps the critical path: 2.2 ms vs 0.6 ms per AR step at B = 128)
@@ -345,7 +368,7 @@ static int rollout_impl(const arpde_op_t* ops, int n_ops, const arpde_buf_t* buf
     return arpde_ks_rollout_launch(ops, params_host, param_gstride_host, traj, bs, c_hist, T, N, c.n_per_group, (float)eps, stream);
   c.fuse_dense = allow_persistent;
   rc = prep_tc(c); if (rc) return rc;
-  if (allow_persistent) { rc = mark_zpairs(c); if (rc) return rc; }
+  if (allow_persistent) { rc = mark_zpairs(c); if (rc) return rc; rc = mark_hconvs(c); if (rc) return rc; }
   rc = fold_eval(c); if (rc) return rc;
   for (int t = 0; t < T; ++t) {
     const float* x = traj + (long long)(c_hist - c_in + t * c_out) * HW;

@@ -25,7 +25,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
                : "=r"(done) : "r"(addr), "r"(parity) : "memory");
   while (!done) {
-    __nanosleep(SLEEP_NS);
+    if (SLEEP_NS > 0) __nanosleep(SLEEP_NS);      // SLEEP_NS = 0: rely on try_wait's own bounded hardware suspend (lowest hand-off latency)
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
                  : "=r"(done) : "r"(addr), "r"(parity) : "memory");
   }

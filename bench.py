@@ -716,22 +716,63 @@ def main():
     NT = S_SAMPLES * n_loc
     step_ms = rollout_ms / T_STEPS
     conv_tflops = NT * MODEL_MFLOP * 1e6 / (step_ms * 1e-3) / 1e12
-    # (1b) the dominant launch of the step, timed alone through the C ABI on the rollout batch:
-    #      conv_tc_kernel on In_conv3 (96 -> 48, 3x3 stride 2, 64x64 -> 32x32), 30 weight groups; inputs rotate over 2 sets (2 x 3 GB >> L2)
-    xin = [torch.randn((NT, 96, NEL, NEL), device=dev) for _ in range(2)]
-    w3 = torch.randn((S_SAMPLES, 48, 96, 3, 3), device=dev) / (96 * 9) ** 0.5
-    y3 = torch.empty((NT, 48, NEL // 2, NEL // 2), device=dev)
-    n_scr = int(L.lib.arpde_conv_fwd_tc_scratch_floats(96, 48, 3, 3, S_SAMPLES))
-    scr = torch.empty((n_scr,), device=dev)
+    # (1b) the tensor-core launches of the step, each timed alone through the C ABI on the rollout batch with rotating inputs (every set > L2):
+    #      In_conv1 (conv_stem_kernel, the dominant launch), In_conv3 (conv_z_kernel), conv1x1 and the upsampling conv3x3 (conv_h_kernel)
+    bf16 = peaks['bf16_tflops']
+    kern = {}
+    xin = [torch.randn((NT, 6, NEL, NEL), device=dev) for _ in range(2)]
+    w1 = torch.randn((S_SAMPLES, 96, 6, 5, 5), device=dev) / 150 ** 0.5
+    w3 = torch.randn((S_SAMPLES, 48, 96, 3, 3), device=dev) / 864 ** 0.5
+    sc1 = torch.rand((S_SAMPLES, 96), device=dev) + 0.5
+    sh1 = torch.randn((S_SAMPLES, 96), device=dev) * 0.2
+    zf = int(L.lib.arpde_conv_z_floats(96, NEL, NEL))
+    z = torch.empty((NT * zf,), device=dev)
+    y3 = torch.empty((NT, 64, NEL // 2, NEL // 2), device=dev)
+    n1 = int(L.lib.arpde_conv_fwd_tc_scratch_floats(6, 96, 5, 5, S_SAMPLES))
+    n3 = int(L.lib.arpde_conv_fwd_tc_scratch_floats(96, 48, 3, 3, S_SAMPLES))
+    scr1, scr3 = torch.empty((n1,), device=dev), torch.empty((n3,), device=dev)
 
-    def k1(i):
-        L.call('arpde_conv_fwd_tc', L.ptr(xin[i % 2]), 96 * NEL * NEL, L.ptr(w3), 48 * 96 * 9, 0, 0, 0, L.ptr(y3), 0, NT, 96, NEL, NEL, 48, 3, 3, 2, 0, 0, 0,
-               48, 0, n_loc, L.ptr(scr), n_scr, L.stream())
-    k1_ms = time_cuda(k1, 10)
-    k1_flops = 2.0 * NT * (NEL // 2) ** 2 * 48 * 96 * 9
+    def k_stem(i):
+        L.call('arpde_stem_pair_producer', L.ptr(xin[i % 2]), 6 * NEL * NEL, L.ptr(w1), w1.stride(0), L.ptr(sc1), L.ptr(sh1), 96, NT, 6, NEL, NEL, 96, 5,
+               n_loc, L.ptr(z), z.numel(), L.ptr(scr1), n1, L.stream())
+
+    def k_z(i):
+        L.call('arpde_stem_pair_consumer', L.ptr(z), L.ptr(w3), w3.stride(0), L.ptr(y3), NT, NEL, NEL, 96, 48, 64, 0, n_loc, L.ptr(scr3), n3, L.stream())
+    k1_ms = time_cuda(k_stem, 10)
+    k1_flops = 2.0 * NT * NEL ** 2 * 96 * 6 * 25
     k1_tflops = k1_flops / (k1_ms * 1e-3) / 1e12
-    del xin, y3
+    kz_ms = time_cuda(k_z, 10)
+    kz_flops = 2.0 * NT * (NEL // 2) ** 2 * 48 * 96 * 9
+    z_bytes = NT * zf * 4
+    kern['In_conv1 conv_stem_kernel'] = {'ms': k1_ms, 'tflops': k1_tflops, 'frac_of_bf16_peak': k1_tflops / bf16, 'frac_of_fp16x3_ceiling': k1_tflops / (bf16 / 3),
+                                         'hbm_gbs': (xin[0].numel() * 4 + z_bytes) / k1_ms / 1e6}
+    kern['In_conv3 conv_z_kernel'] = {'ms': kz_ms, 'tflops': kz_flops / kz_ms / 1e9, 'frac_of_bf16_peak': kz_flops / kz_ms / 1e9 / bf16,
+                                      'hbm_gbs': (z_bytes + NT * 48 * (NEL // 2) ** 2 * 4) / kz_ms / 1e6,
+                                      'frac_of_hbm_peak': (z_bytes + NT * 48 * (NEL // 2) ** 2 * 4) / kz_ms / 1e6 / peaks['hbm_gbs']}
+    del xin, z, y3
     torch.cuda.empty_cache()
+    HL = NEL // 2
+    for name, (cin, cout, k, up) in (('conv1x1 conv_h_kernel', (64, 32, 1, 0)), ('up-conv3x3 conv_h_kernel', (32, 16, 3, 1))):
+        xs = [torch.randn((NT, cin, HL, HL), device=dev) for _ in range(3)]
+        wh = torch.randn((S_SAMPLES, cout, cin, k, k), device=dev) / (cin * k * k) ** 0.5
+        sch = torch.rand((S_SAMPLES, cin), device=dev) + 0.5
+        shh = torch.randn((S_SAMPLES, cin), device=dev) * 0.2
+        f = 2 if up else 1
+        yh = torch.empty((NT, cout, HL * f, HL * f), device=dev)
+        nh = int(L.lib.arpde_conv_fwd_h_scratch_floats(cin, cout, k, up, S_SAMPLES))
+        scrh = torch.empty((nh,), device=dev)
+
+        def k_h(i):
+            L.call('arpde_conv_fwd_h', L.ptr(xs[i % 3]), cin * HL * HL, L.ptr(wh), wh.stride(0), L.ptr(sch), L.ptr(shh), cin, L.ptr(yh), NT, cin, HL, HL, cout, k,
+                   up, 1, cout, 0, n_loc, L.ptr(scrh), nh, L.stream())
+        h_ms = time_cuda(k_h, 10)
+        h_bytes = (xs[0].numel() + yh.numel()) * 4
+        kern[name] = {'ms': h_ms, 'hbm_gbs': h_bytes / h_ms / 1e6, 'frac_of_hbm_peak': h_bytes / h_ms / 1e6 / peaks['hbm_gbs'],
+                      'tflops': 2.0 * NT * (HL * f) ** 2 * cout * cin * k * k / h_ms / 1e9}
+        del xs, yh
+        torch.cuda.empty_cache()
+    kern['dense block (dense_block_stream_kernel) + output conv (conv_out5x5_kernel), FFMA'] = {
+        'ms': step_ms - sum(v['ms'] for v in kern.values()), 'what': 'AR step minus the four launches above'}
     # (2) the stencil-loss kernel (K2), rotating buffers, C4 and C5 sizes, forward / fused-SSE / adjoint
     sten = stencil_rooflines(dev, peaks)
     k2 = sten['c4_64_fwd']
@@ -761,19 +802,22 @@ def main():
                 'h2d_bytes_per_step': ic_all_host.numel() * 4, 'd2h_bytes_per_step': 2 * N_IC * (T_STEPS + 1) * 2 * NEL * NEL * 4,
                 'what': 'pinned host ICs -> device (every rank its shard); rollout in %d pieces: the predictive moments of a finished piece are gathered to rank 0 '
                         '(NCCL) and copied to pinned host memory on a side stream while the next piece runs; rank 0 ends with mean and variance of all 64 ICs' % E2E_CHUNKS},
-        'roofline': {'kernel': 'conv_tc_kernel on In_conv3 (96->48, 3x3/s2, %d samples): tcgen05 implicit GEMM, 3xTF32 split (+ its weight-split launch)' % NT,
-                     'bound': 'tensor', 'achieved': k1_tflops, 'peak': peaks['bf16_tflops'], 'unit': 'TFLOP/s', 'frac': k1_tflops / peaks['bf16_tflops'],
-                     'traffic': 4.486e9 if world == 1 else None,
-                     'traffic_source': 'ncu --set full, profiles/r01d_conv_tc_in3_ncu_full.md: dram read 4.108 GB + write 0.377 GB per launch at 1920 samples '
-                                       '(algorithmic input + output 3.40 GB; the excess is halo rows re-read past L2)',
+        'roofline': {'kernel': 'conv_stem_kernel on In_conv1 (6->96, 5x5 circular, %d samples, 30 weight groups; epilogue = eval BatchNorm + ReLU + fp16 two-term operand '
+                               'format for In_conv3): tcgen05 implicit GEMM, kind::f16 two-term split, two horizontal taps per K = 16 MMA (+ its weight-split launch)' % NT,
+                     'bound': 'tensor', 'achieved': k1_tflops, 'peak': bf16, 'unit': 'TFLOP/s', 'frac': k1_tflops / bf16,
+                     'traffic': 3.402e9 if world == 1 else None,
+                     'traffic_source': 'ncu --set full, profiles/r02_stem_pair_ncu_full.md: dram read 0.232 GB + write 3.170 GB per launch at 1920 samples '
+                                       '(algorithmic: 0.189 GB input + 3.211 GB operand-format output)',
                      'peak_source': peaks['source'] + ' bf16 dense (burst)',
-                     'note': 'achieved = algorithmic fp32 FLOPs (2*N*Ho*Wo*cout*cin*k^2) / CUDA-event time; the 1e-5 parity contract needs the 3-term '
-                             'TF32 split (3 tensor MACs per algorithmic MAC) and TF32 runs at half the bf16 rate, so the attainable ceiling is '
-                             'peak/6 = %.0f TFLOP/s -> frac_of_3xtf32_ceiling %.3f' % (peaks['bf16_tflops'] / 6, k1_tflops / (peaks['bf16_tflops'] / 6)),
+                     'note': 'achieved = algorithmic fp32 FLOPs (2*N*H*W*cout*cin*k^2) / CUDA-event time; the 1e-5 parity contract needs the two-term fp16 split '
+                             '(3 tensor MACs per algorithmic MAC at the fp16 = bf16 rate) and the 6-channel input fills 6 of 8 K lanes with 5 taps in 3 pairs, '
+                             'so the attainable ceiling is peak/3 = %.0f TFLOP/s -> frac_of_fp16x3_ceiling %.3f' % (bf16 / 3, k1_tflops / (bf16 / 3)),
                      'flops_per_launch': k1_flops, 'ms': k1_ms,
+                     'kernels': kern,
                      'ar_step': {'ms': step_ms, 'tflops': conv_tflops, 'flops': NT * MODEL_MFLOP * 1e6, 'samples': NT,
-                                 'what': 'one AR step of the local batch (In_conv1, In_conv3, conv1x1, folded conv3x3-up on conv_tc_kernel; the four dense layers as ONE '
-                                         'fused FFMA launch; the 16->2 output conv on the row-tiled FFMA kernel): rollout time of the job / %d steps' % T_STEPS},
+                                 'what': 'one AR step of the local batch = 6 launches: In_conv1 (conv_stem_kernel) -> In_conv3 (conv_z_kernel) as an fp16 operand-format '
+                                         'pair, the four dense layers as ONE FFMA launch (dense_block_stream_kernel), conv1x1 and the folded upsampling conv3x3 on '
+                                         'conv_h_kernel (fp16 two-term tensor core), the 16->2 output conv (conv_out5x5_kernel, FFMA): rollout time of the job / %d steps' % T_STEPS},
                      'job_breakdown_ms': breakdown},
         'roofline_stencil': {'kernel': 'burgers2d_fwd_vec4<RY=4> (fused periodic stencil + Crank-Nicolson, API form: read uPred, uPred0, write ustar), '
                                        'C4 rollout batch, 4 rotating buffer sets', 'bound': 'hbm',

@@ -298,6 +298,24 @@ int arpde_stem_pair_fwd(const float* x, int64_t x_bstride, const float* w1, int6
                         int64_t ss_gstride, const float* w3, int64_t w3_gstride, float* y, int N, int cin, int H, int W, int c1, int k1,
                         int c3, int y_ctot, int y_coff, int n_per_group, float* z, int64_t z_floats, float* scratch, int64_t scratch_floats,
                         arpde_stream_t stream);
+/* The two halves of the pair on their own (per-kernel timing, tests): producer x -> z with scratch of arpde_conv_fwd_tc_scratch_floats(cin, c1,
+ * k1, k1, groups) floats; consumer z -> y with arpde_conv_fwd_tc_scratch_floats(c1, c3, 3, 3, groups). */
+int arpde_stem_pair_producer(const float* x, int64_t x_bstride, const float* w1, int64_t w1_gstride, const float* scale, const float* shift,
+                             int64_t ss_gstride, int N, int cin, int H, int W, int c1, int k1, int n_per_group, float* z, int64_t z_floats,
+                             float* scratch, int64_t scratch_floats, arpde_stream_t stream);
+int arpde_stem_pair_consumer(const float* z, const float* w3, int64_t w3_gstride, float* y, int N, int H, int W, int c1, int c3, int y_ctot,
+                             int y_coff, int n_per_group, float* scratch, int64_t scratch_floats, arpde_stream_t stream);
+
+/* Eval-mode stride-1 convolutions of the decoder on the tensor cores with fp16 two-term operands (conv_h.cu):
+ *   y = conv_kxk(up2?(relu?(scale * x + shift))), circular, stride 1, k = 1 or 3 (up = 1 needs k = 3: UpsamplingNearest2d + conv3x3 of
+ * LastTransUp / _Transition, 2D-Burgers-SWAG/nn/denseEDcirc2d.py:103-108,128-141,170-183, folded to one 3x3 convolution on the low-resolution
+ * grid).  Same argument meaning as arpde_conv_fwd; scale / shift nullable (both).  arpde_rollout uses it for the layers it covers.
+ * scratch: arpde_conv_fwd_h_scratch_floats(cin, cout, k, up, groups) floats.  Returns ARPDE_ERR_UNSUPPORTED for shapes the kernel does not
+ * cover (needs 16 | cin <= 256, H >= 2; cout <= 128, folded: cout <= 32). */
+int64_t arpde_conv_fwd_h_scratch_floats(int cin, int cout, int k, int up, int groups);
+int arpde_conv_fwd_h(const float* x, int64_t x_bstride, const float* w, int64_t w_gstride, const float* scale, const float* shift,
+                     int64_t ss_gstride, float* y, int N, int cin, int H, int W, int cout, int k, int up, int relu_in, int y_ctot, int y_coff,
+                     int n_per_group, float* scratch, int64_t scratch_floats, arpde_stream_t stream);
 
 /* A ready-made arpde_allreduce_fn over NVLink peer memory (one process per GPU on one node; peer.cu): every rank copies its n doubles
  * into its own exchange slot, publishes a sequence number in every peer's flag array, waits for all peers, then reads all slots over

@@ -93,8 +93,9 @@ def test_output_conv_kernel_vs_oracle(cin, H, N, npg):
 
 def test_launch_counter_counts_the_rollout_launches():
     """arpde_launch_count(): a T-step rollout of the default 2D net at a machine-filling batch is 6 launches per step (In_conv1 as
-    conv_stem_kernel, In_conv3 as conv_z_kernel, ONE fused dense block, conv1x1, folded up-conv, output conv) + 4 weight-split launches +
-    the 2 fp16 weight preparations of the stem pair + 1 BatchNorm fold; the per-layer path: 9 per step + 5."""
+    conv_stem_kernel, In_conv3 as conv_z_kernel, ONE fused dense block, conv1x1 and the folded up-conv as conv_h_kernel, output conv) + 13
+    one-off launches (8 TF32 weight splits -- every layer the per-layer path could run on the tensor core --, the 2 fp16 weight
+    preparations of the stem pair, the 2 of conv_h, 1 BatchNorm fold); the per-layer path: 9 per step + 9 (8 weight splits + the fold)."""
     from arpde_b200 import _lib as L
     m = _model([4])
     ic = torch.randn(100, 2, 64, 64, device=DEV)
@@ -108,5 +109,5 @@ def test_launch_counter_counts_the_rollout_launches():
     print(counts)
     per_step = {lw: (counts[lw, 3] - counts[lw, 1]) // 2 for lw in (False, True)}
     once = {lw: counts[lw, 1] - per_step[lw] for lw in (False, True)}
-    assert per_step[False] == 6 and once[False] == 7, counts
-    assert per_step[True] == 9 and once[True] == 5, counts
+    assert per_step[False] == 6 and once[False] == 13, counts
+    assert per_step[True] == 9 and once[True] == 9, counts

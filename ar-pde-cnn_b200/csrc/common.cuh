@@ -49,6 +49,26 @@ static inline const char* arpde_dev_env(const char* key) { return getenv(key); }
 static inline const char* arpde_dev_env(const char*) { return nullptr; }
 #endif
 
+// Programmatic dependent launch (rollouts): with `pdl` the kernel may be scheduled while its predecessor in the stream is still draining --
+// its CTAs take the SMs the predecessor's CTAs leave, run their prologue (barrier init, TMEM allocation) and block in pdl_wait() until the
+// predecessor has completed and its writes are visible.  Only kernels that call pdl_wait() before their first access to global memory are
+// launched this way; a kernel launched without the attribute is serialised as usual, whatever its predecessor did.
+template <typename T>
+static inline cudaError_t arpde_launch1(void (*kernel)(T), unsigned grid, unsigned block, size_t smem, cudaStream_t stream, bool pdl, const T& arg) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr;
+  memset(&attr, 0, sizeof(attr));
+  attr.id = cudaLaunchAttributeProgrammaticStreamSerialization; attr.val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = &attr; cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, arg);
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }   // the next kernel may be scheduled
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }                  // predecessor complete, its writes visible
+#endif
+
 int arpde_num_sms();   // cached cudaDevAttrMultiProcessorCount of the current device
 
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }

@@ -11,6 +11,7 @@ struct ConvDesc {
   int act;                 // output activation (ARPDE_ACT_*)
   int y_ctot, y_coff;      // output buffer channel count / channel offset (concat-free dense block)
   int n_per_group;         // samples sharing one weight set (SWAG: ICs per weight sample)
+  int pdl = 0;             // rollouts: programmatic dependent launch for the kernels that support it (common.cuh)
 };
 
 struct ConvFwdArgs {
@@ -127,7 +128,7 @@ int arpde_conv_out_launch(const ConvDesc& d, const float* x, long long x_bs, con
 // fused dense block (dense_block.cu): all 4-channel dense layers of a block in one launch, eval mode
 int arpde_dense_block_match(const arpde_op* ops, int n_ops, int first, const arpde_buf* bufs, int N);
 int arpde_dense_block_launch(const arpde_op* ops, int first, int nl, const arpde_buf* bufs, void* const* params, const int64_t* gstride, float* work,
-                             const float* scale, const float* shift, long long ss_gs, int N, int n_per_group, cudaStream_t stream);
+                             const float* scale, const float* shift, long long ss_gs, int N, int n_per_group, cudaStream_t stream, bool pdl = false);
 
 // tensor-core (tcgen05) implicit-GEMM path, conv_tc.cu
 long long* arpde_tc_debug_buffer();                              // arpde_conv_tc_set_debug's buffer (nullptr = off)

@@ -119,6 +119,8 @@ __global__ void __launch_bounds__(CH_THREADS, 1) conv_h_kernel(const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_trigger();
+  pdl_wait();
 
   if (warp < CH_CONV_WARPS) {
     // =============================== converter warps: fp32 NCHW -> BN + ReLU -> fp16 hi / lo' operand image ===============================
@@ -512,8 +514,8 @@ int arpde_conv_h_launch(const ConvDesc& d, const float* x, long long x_bs, const
   ARPDE_CHECK_ARG(items < (1ll << 31), "conv_h: too many work items");
   long long blocks = (long long)arpde_num_sms();
   if (blocks > items) blocks = items;
-  if (d.H * d.W == 1024) conv_h_kernel<1024><<<(unsigned)blocks, CH_THREADS, smem, stream>>>(a);     // the 32x32 maps of the default 2D network
-  else conv_h_kernel<0><<<(unsigned)blocks, CH_THREADS, smem, stream>>>(a);
+  if (d.H * d.W == 1024) ARPDE_CUDA(arpde_launch1(conv_h_kernel<1024>, (unsigned)blocks, CH_THREADS, smem, stream, d.pdl != 0, a));   // 32x32 maps
+  else ARPDE_CUDA(arpde_launch1(conv_h_kernel<0>, (unsigned)blocks, CH_THREADS, smem, stream, d.pdl != 0, a));
   ARPDE_LAUNCH_CHECK();
   return ARPDE_OK;
 }

@@ -38,6 +38,8 @@ __global__ void __launch_bounds__(32 * CO_WARPS, 2) conv_out5x5_kernel(ConvOutAr
   const int n = blockIdx.x / tiles, y0 = (blockIdx.x - n * tiles) * CO_TR, g = n / a.n_per_group;
   const long long HW = (long long)a.H * CO_W;
   const float* xn = a.x + (long long)n * a.x_bs;
+  pdl_trigger();
+  pdl_wait();
   {  // input rows y0 - 2 .. y0 + 17 of every channel
     const int npiece = a.cin * CO_ROWS * (CO_W / 4);
     for (int q = tid; q < npiece; q += 32 * CO_WARPS) {
@@ -152,7 +154,7 @@ int arpde_conv_out_launch(const ConvDesc& d, const float* x, long long x_bs, con
   ARPDE_CUDA(cudaFuncSetAttribute(conv_out5x5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long blocks = (long long)d.N * (d.H / CO_TR);
   ARPDE_CHECK_ARG(blocks < (1ll << 31), "conv_out: too many tiles");
-  conv_out5x5_kernel<<<(unsigned)blocks, 32 * CO_WARPS, smem, stream>>>(a);
+  ARPDE_CUDA(arpde_launch1(conv_out5x5_kernel, (unsigned)blocks, 32 * CO_WARPS, smem, stream, d.pdl != 0, a));
   ARPDE_LAUNCH_CHECK();
   return ARPDE_OK;
 }

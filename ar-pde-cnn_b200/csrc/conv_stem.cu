@@ -100,6 +100,8 @@ __global__ void __launch_bounds__(CS_THREADS, 1) conv_stem_kernel(const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_trigger();
+  pdl_wait();
 
   if (warp < CS_CONV_WARPS) {
     // =============================== converter warps: fp32 input -> fp16 hi / lo' patch ===============================
@@ -371,7 +373,7 @@ int arpde_conv_stem_launch(const ConvDesc& d, const float* x, long long x_bs, co
   ARPDE_CHECK_ARG(items < (1ll << 31), "conv_stem: too many work items");
   long long blocks = (long long)arpde_num_sms();
   if (blocks > items) blocks = items;
-  conv_stem_kernel<<<(unsigned)blocks, CS_THREADS, smem, stream>>>(a);
+  ARPDE_CUDA(arpde_launch1(conv_stem_kernel, (unsigned)blocks, CS_THREADS, smem, stream, d.pdl != 0, a));
   ARPDE_LAUNCH_CHECK();
   return ARPDE_OK;
 }

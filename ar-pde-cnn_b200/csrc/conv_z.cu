@@ -101,6 +101,8 @@ __global__ void __launch_bounds__(CZ_THREADS, 1) conv_z_kernel(const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_trigger();
+  pdl_wait();
   // taps of the 3x3 stride-2 filter by parity plane: (count, first index in the prepared weight order, offsets in padded positions)
   const int PW = a.PW;
 
@@ -345,7 +347,7 @@ int arpde_conv_z_launch(const ConvDesc& d, const float* z, const float* wprep, l
   ARPDE_CHECK_ARG(items < (1ll << 31), "conv_z: too many work items");
   long long blocks = (long long)arpde_num_sms();
   if (blocks > items) blocks = items;
-  conv_z_kernel<<<(unsigned)blocks, CZ_THREADS, smem, stream>>>(a);
+  ARPDE_CUDA(arpde_launch1(conv_z_kernel, (unsigned)blocks, CZ_THREADS, smem, stream, d.pdl != 0, a));
   ARPDE_LAUNCH_CHECK();
   return ARPDE_OK;
 }

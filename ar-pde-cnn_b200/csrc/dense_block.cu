@@ -219,6 +219,8 @@ __global__ void __launch_bounds__(DS_THREADS, 2) dense_block_stream_kernel(Dense
   const int r0 = warp * 4;
   const long long HW = (long long)DS_H * DB_W;
   const int nraw = a.c0 / DS_CH;                          // raw chunks (c0 is a multiple of 4)
+  pdl_trigger();
+  pdl_wait();
   for (int n = blockIdx.x; n < a.N; n += gridDim.x) {
     const int g = n / a.n_per_group;
     float* bn_ = a.buf + (long long)n * a.bs;
@@ -309,7 +311,7 @@ int arpde_dense_block_match(const arpde_op_t* ops, int n_ops, int first, const a
 }
 
 int arpde_dense_block_launch(const arpde_op_t* ops, int first, int nl, const arpde_buf_t* bufs, void* const* params, const int64_t* gstride, float* work,
-                             const float* scale, const float* shift, long long ss_gs, int N, int n_per_group, cudaStream_t stream) {
+                             const float* scale, const float* shift, long long ss_gs, int N, int n_per_group, cudaStream_t stream, bool pdl) {
   const arpde_buf_t& b = bufs[ops[first].in_buf];
   DenseBlockArgs a; memset(&a, 0, sizeof(a));
   a.buf = work + b.offset; a.bs = (long long)b.ctot * b.h * b.w;
@@ -325,7 +327,7 @@ int arpde_dense_block_launch(const arpde_op_t* ops, int first, int nl, const arp
     const size_t smem_s = ((size_t)5 * DS_CHUNK + 2 * DS_WCH + 2 * DB_MAXL * DB_MAXC) * sizeof(float);
     ARPDE_CUDA(cudaFuncSetAttribute(dense_block_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
     long long grid_s = 2ll * arpde_num_sms(); if (grid_s > N) grid_s = N;
-    dense_block_stream_kernel<<<(unsigned)grid_s, DS_THREADS, smem_s, stream>>>(a);
+    ARPDE_CUDA(arpde_launch1(dense_block_stream_kernel, (unsigned)grid_s, DS_THREADS, smem_s, stream, pdl, a));
     ARPDE_LAUNCH_CHECK();
     return ARPDE_OK;
   }

@@ -35,6 +35,7 @@ struct RunCtx {
   std::vector<long long> wprep_gs;
   bool fuse_dense = true;                   // eval mode: dense blocks as one launch (off for the layer-wise cross-check path)
   std::vector<char> zpair;                  // per op: 1 = this op and the next run as an operand-format pair (conv_z.cu; rollouts only)
+  bool pdl = false;                         // rollouts: programmatic dependent launch between the kernels of the fused path
   std::vector<char> hconv;                  // per op: 1 = eval-mode stride-1 layer on the fp16 two-term kernel (conv_h.cu; rollouts only)
   const DpHook* dp = nullptr;               // data-parallel training: all-reduce of the BatchNorm sums (nullptr = single process)
   mutable std::vector<int> synced;          // per buffer: channels whose statistics already hold the global sums
@@ -47,6 +48,7 @@ static void op_desc(const RunCtx& c, const arpde_op_t& o, ConvDesc* d) {
   if (o.in_buf < 0) { d->H = c.H; d->W = c.W; }
   else { d->H = c.bufs[o.in_buf].h; d->W = c.bufs[o.in_buf].w; }
   d->y_ctot = o.cout; d->y_coff = 0;
+  d->pdl = c.pdl ? 1 : 0;
 }
 
 // Split/arrange the weights of every layer that runs on the tensor cores (once per forward / per rollout).
@@ -155,7 +157,7 @@ static int run_ops(const RunCtx& c, const float* x, long long x_bs, float* y, in
       const int nl = arpde_dense_block_match(c.ops, c.n_ops, i, c.bufs, c.N);
       if (nl > 0) {
         int rc = arpde_dense_block_launch(c.ops, i, nl, c.bufs, c.params, c.gstride, c.work, c.ss, c.ss + (long long)c.groups * c.bn_total, c.bn_total,
-                                          c.N, c.n_per_group, c.stream);
+                                          c.N, c.n_per_group, c.stream, c.pdl);
         if (rc) return rc;
         i += nl - 1;
         continue;
@@ -164,7 +166,7 @@ static int run_ops(const RunCtx& c, const float* x, long long x_bs, float* y, in
     ConvDesc d;
     d.dilate = 0; d.pad_override = -1;
     d.N = c.N; d.cin = o.cin; d.cout = o.cout; d.kh = o.kh; d.kw = o.kw; d.stride = o.stride; d.up = o.up;
-    d.relu_in = o.bn_param >= 0; d.act = o.act; d.n_per_group = c.n_per_group;
+    d.relu_in = o.bn_param >= 0; d.act = o.act; d.n_per_group = c.n_per_group; d.pdl = (!training && c.pdl) ? 1 : 0;
     const float* in; long long in_bs;
     if (o.in_buf < 0) { in = x; in_bs = x_bs; d.H = c.H; d.W = c.W; }
     else { const arpde_buf_t& b = c.bufs[o.in_buf]; in = c.work + b.offset; in_bs = (long long)b.ctot * b.h * b.w; d.H = b.h; d.W = b.w; }
@@ -366,7 +368,7 @@ static int rollout_impl(const arpde_op_t* ops, int n_ops, const arpde_buf_t* buf
   // the reference's KS network on its 96-point grid: the whole rollout is ONE persistent launch (rollout1d.cu)
   if (allow_persistent && arpde_ks_program_matches(ops, n_ops, bufs, n_bufs, H, W, c_in, c_out))
     return arpde_ks_rollout_launch(ops, params_host, param_gstride_host, traj, bs, c_hist, T, N, c.n_per_group, (float)eps, stream);
-  c.fuse_dense = allow_persistent;
+  c.fuse_dense = allow_persistent; c.pdl = allow_persistent && !arpde_dev_env("ARPDE_NO_PDL");
   rc = prep_tc(c); if (rc) return rc;
   if (allow_persistent) { rc = mark_zpairs(c); if (rc) return rc; rc = mark_hconvs(c); if (rc) return rc; }
   rc = fold_eval(c); if (rc) return rc;

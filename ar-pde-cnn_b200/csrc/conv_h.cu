@@ -119,7 +119,6 @@ __global__ void __launch_bounds__(CH_THREADS, 1) conv_h_kernel(const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  pdl_trigger();
   pdl_wait();
 
   if (warp < CH_CONV_WARPS) {
@@ -377,6 +376,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) conv_h_kernel(const __grid_cons
     }
     __syncwarp();
   }
+  pdl_trigger();
   tc_fence_before();
   __syncthreads();
   if (warp == CH_WARP_MMA) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));

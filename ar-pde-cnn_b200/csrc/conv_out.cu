@@ -38,7 +38,6 @@ __global__ void __launch_bounds__(32 * CO_WARPS, 2) conv_out5x5_kernel(ConvOutAr
   const int n = blockIdx.x / tiles, y0 = (blockIdx.x - n * tiles) * CO_TR, g = n / a.n_per_group;
   const long long HW = (long long)a.H * CO_W;
   const float* xn = a.x + (long long)n * a.x_bs;
-  pdl_trigger();
   pdl_wait();
   {  // input rows y0 - 2 .. y0 + 17 of every channel
     const int npiece = a.cin * CO_ROWS * (CO_W / 4);

@@ -100,7 +100,6 @@ __global__ void __launch_bounds__(CS_THREADS, 1) conv_stem_kernel(const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  pdl_trigger();
   pdl_wait();
 
   if (warp < CS_CONV_WARPS) {
@@ -275,6 +274,7 @@ __global__ void __launch_bounds__(CS_THREADS, 1) conv_stem_kernel(const __grid_c
     }
     __syncwarp();
   }
+  pdl_trigger();
   tc_fence_before();
   __syncthreads();
   if (warp == CS_WARP_MMA) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));

@@ -101,7 +101,6 @@ __global__ void __launch_bounds__(CZ_THREADS, 1) conv_z_kernel(const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  pdl_trigger();
   pdl_wait();
   // taps of the 3x3 stride-2 filter by parity plane: (count, first index in the prepared weight order, offsets in padded positions)
   const int PW = a.PW;
@@ -233,6 +232,7 @@ __global__ void __launch_bounds__(CZ_THREADS, 1) conv_z_kernel(const __grid_cons
       gt += nt;
     }
   }
+  pdl_trigger();
   tc_fence_before();
   __syncthreads();
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(a.tmem_cols));

@@ -219,7 +219,6 @@ __global__ void __launch_bounds__(DS_THREADS, 2) dense_block_stream_kernel(Dense
   const int r0 = warp * 4;
   const long long HW = (long long)DS_H * DB_W;
   const int nraw = a.c0 / DS_CH;                          // raw chunks (c0 is a multiple of 4)
-  pdl_trigger();
   pdl_wait();
   for (int n = blockIdx.x; n < a.N; n += gridDim.x) {
     const int g = n / a.n_per_group;

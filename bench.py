@@ -530,7 +530,9 @@ def main():
             self.traj_buf = torch.empty((S_SAMPLES * self.n, 6 + 2 * T_STEPS, NEL, NEL), device=dev)
             # small shards (strong scaling: 30 x 8 trajectories per GPU at N = 8): two groups of weight samples on two streams, so that
             # the tail of every launch (15-35 % at this batch) is filled by the other group's launches (measured 0.976 -> 0.926 ms per step)
-            self.n_streams = 2 if S_SAMPLES * self.n < 960 else 1
+            # two weight-sample groups on two streams fill each other's launch tails at mid-size shards (measured with the PDL chain: 960 trajectories
+            # 1.79 -> 1.73 ms per step, 480: 0.934 -> 0.905); at 240 one stream is faster (0.507 vs 0.550), at 1920 it makes no difference
+            self.n_streams = 2 if 400 <= S_SAMPLES * self.n <= 1200 else 1
             self.gathered = gathered
             self.peer = None
             if gathered and world > 1:

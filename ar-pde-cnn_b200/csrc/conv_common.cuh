@@ -145,7 +145,8 @@ int arpde_conv_tc_launch(const ConvDesc& d, const float* x, long long x_bs, cons
 // producer of the pair for networks' first layer (cin <= 8, odd k, stride 1, no prologue): conv_stem.cu
 bool arpde_conv_stem_wanted(const ConvDesc& d);
 long long arpde_conv_stem_wprep_floats(int cout, int k);
-int arpde_conv_stem_prep_launch(const ConvDesc& d, const float* w, long long w_gs, int groups, float* wprep, long long wprep_gs, cudaStream_t stream);
+int arpde_conv_stem_prep_launch(const ConvDesc& d, const float* w, long long w_gs, int groups, float* wprep, long long wprep_gs, const ZOut& zo,
+                                cudaStream_t stream);      // folds the consumer's BatchNorm scale / shift (zo) into the weights
 int arpde_conv_stem_launch(const ConvDesc& d, const float* x, long long x_bs, const float* wprep, long long wprep_gs, const ZOut& zo, cudaStream_t stream);
 long long arpde_conv_z_sample16(int c, int H, int W);            // 16-byte units per sample of the operand-format activation
 bool arpde_conv_z_wanted(const ConvDesc& d);                     // d: the stride-2 consumer, described by its input dims

@@ -1,22 +1,28 @@
 // conv_stem.cu -- producer side of the eval-mode stem pair (conv_z.cu): the first convolution of the network, few input channels
-// (cin <= 8), k x k stride 1 circular (In_conv1: 6 -> 96, 5x5; 2D-Burgers-SWAG/nn/denseEDcirc2d.py:247-249), followed by the consumer's
+// (cin <= 7), k x k stride 1 circular (In_conv1: 6 -> 96, 5x5; 2D-Burgers-SWAG/nn/denseEDcirc2d.py:247-249), followed by the consumer's
 // eval-mode BatchNorm affine + ReLU (In_conv_norm1 / In_conv_relu1, :250-251), written in the consumer's fp16 two-term operand format Z.
 //
 // conv_tc.cu runs this layer as 25 taps x (K = 8 TF32 MMAs with 2 of 8 channels padding) and, with the operand-format epilogue, its four
 // epilogue warps are the critical path (2.44 ms at 1920 samples against 1.8 ms with the plain epilogue).  This kernel is built around the
 // layer instead:
 //   * operands in the fp16 two-term split of conv_z.cu (x = x_hi + 2^-11 x_lo', products exact, fp32 accumulation in TMEM);
-//   * the whole input octet (cin <= 8 channels) of a position is ONE 16-byte K unit, so the second K unit of a K = 16 MMA can be the
+//   * the whole input octet (cin <= 7 channels + the constant below) of a position is ONE 16-byte K unit, so the second K unit of a K = 16 MMA can be the
 //     SAME buffer one position further (descriptor LBO = 16 bytes): one MMA covers two horizontal taps -- 15 tap pairs instead of 25 taps
 //     for 5x5, every MMA with full K;
 //   * the prepared weights of a SWAG sample (15 x 2 x 2 cout rows x 16 B = 92 KB) stay resident in shared memory, the input patch of
-//     half a sample (36 rows x 68 positions, hi + lo = 78 KB) is converted once from fp32 by 8 warps that hold the next item's raw values
-//     in registers while the current item's MMAs run;
-//   * 8 epilogue warps (two per TMEM lane quarter, each half of the channels) drain a double-buffered accumulator: BatchNorm + ReLU,
-//     split, 16-byte stores into the four parity planes of Z (lanes = consecutive x alternate between two planes: 2 x 256 contiguous
-//     bytes per store instruction), plus the circular halo copies the consumer expects.
+//     half a sample (36 rows x 68 positions, hi + lo = 78 KB) is loaded AND split by 8 warps into registers while the current item's MMAs
+//     run, so that only the 16-byte stores are left after the hand-over;
+//   * the consumer's eval-mode BatchNorm is folded into the producer's GEMM: scale * conv(x, w) + shift = conv([x, 1], [scale * w, shift at
+//     the centre tap]) -- the scale goes into the prepared weights (one set per SWAG sample anyway), the shift rides on the unused lane
+//     `cin` of the input octet, which the converter sets to 1: the epilogue needs no per-channel constants at all;
+//   * 8 epilogue warps (two per TMEM lane quarter, each half of the channels) drain a double-buffered accumulator: ReLU, split (saturating
+//     F2FP), 16-byte stores into the four parity planes of Z (lanes = consecutive x alternate between two planes: 2 x 256 contiguous
+//     bytes per store instruction), plus the circular halo copies the consumer expects; a slot is handed back as soon as a warp's last
+//     block is in registers.
 // Roofline: tensor pipe.  Per 128 positions 15 x (N' = 2 cout = 192: 96 cycles + N = 96: 56 cycles) = 2280 cycles against 25 x 152 = 3800
-// for the TF32 form.
+// for the TF32 form -- measured 2300 (scratch/stem_timeline.py, development build).  What the timeline showed: with the BatchNorm in the
+// epilogue (8 vector loads of scale / shift + 250 instructions per 16-channel block) the epilogue, not the tensor pipe, set the pace: 3500
+// cycles per tile, 6 k cycles of idle tensor pipe at every item boundary while the patch was split.  Now 2700 per tile, 4 k per boundary.
 #include "common.cuh"
 #include "conv_common.cuh"
 #include "../../include/arpde.h"
@@ -34,16 +40,23 @@
 #define CS_KP 10                                          // patch positions per converter thread
 #define CS_HEADER 128
 
+#ifdef ARPDE_DEV
+#define CS_TL(role, cond) do { if (a.tl && blockIdx.x == 0 && (cond) && tlc < 500) a.tl[(role) * 512 + tlc++] = clock64(); } while (0)
+#else
+#define CS_TL(role, cond) do { } while (0)
+#endif
+
 namespace {
 
 struct ConvStemArgs {
   const float* x; long long x_bs;
   const uint4* wz; long long wz_gs16;
   uint4* z; long long z_bs16;
-  const float* scale; const float* shift; long long ss_gs; int vec_ss;
+  // lane `cin` (< 8) of every input octet is the constant 1, its centre-tap weight the consumer's BatchNorm shift; the scale is folded into the weights
   int N, n_per_group, cin, H, W, cout, k, pad, npairs, kwp;       // kwp = ceil(k / 2) horizontal tap pairs
   int pitch, RI, items_per_sample, nt, P;                          // rows per item, M tiles per item, patch positions (padded)
   int w16;                                                          // 16-byte units of the resident weight image
+  long long* tl;                                                    // development build: clock64 timeline of CTA 0 (arpde_conv_tc_set_debug buffer)
 };
 
 __device__ __forceinline__ uint32_t umma_idesc_f16(int M, int N) { return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24); }
@@ -106,38 +119,49 @@ __global__ void __launch_bounds__(CS_THREADS, 1) conv_stem_kernel(const __grid_c
     // =============================== converter warps: fp32 input -> fp16 hi / lo' patch ===============================
     const long long HW = (long long)a.H * a.W;
     const int Prows = (a.RI + a.k - 1) * a.pitch;
+    const int ones_c = a.cin;
     for (int it = it_begin; it < it_end; ++it) {
       const int lit = it - it_begin;
       const int n = it / a.items_per_sample, b = it - n * a.items_per_sample;
       const float* xn = a.x + (long long)n * a.x_bs;
       const int y0 = b * a.RI - a.pad;
-      float xr[CS_KP][8];
+      // load AND split while the previous item's MMAs still read the patch: after the hand-over only the 2 x CS_KP 16-byte stores are left
+      // (splitting after the wait cost ~6 k cycles per item boundary with the tensor pipe idle, scratch/stem_timeline.py)
+      uint4 ph[CS_KP], pl[CS_KP];
 #pragma unroll
-      for (int i = 0; i < CS_KP; ++i) {
-        const int p = tid + i * CS_CONV_THREADS;
+      for (int h = 0; h < CS_KP; h += 5) {                           // batches of 5 positions: 40 raw values in flight per thread
+        float xr[5][8];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) xr[i][c] = 0.f;
-        if (p < Prows) {
-          const int r = p / a.pitch, cx = p - r * a.pitch;
-          int sy = (y0 + r) % a.H; if (sy < 0) sy += a.H;
-          int sx = (cx - a.pad) % a.W; if (sx < 0) sx += a.W;
-          const float* src = xn + (long long)sy * a.W + sx;
+        for (int i = 0; i < 5; ++i) {
+          const int p = tid + (h + i) * CS_CONV_THREADS;
 #pragma unroll
-          for (int c = 0; c < 8; ++c)
-            if (c < a.cin) xr[i][c] = __ldg(src + c * HW);
+          for (int c = 0; c < 8; ++c) xr[i][c] = 0.f;
+          if (p < Prows) {
+            const int r = p / a.pitch, cx = p - r * a.pitch;
+            int sy = (y0 + r) % a.H; if (sy < 0) sy += a.H;
+            int sx = (cx - a.pad) % a.W; if (sx < 0) sx += a.W;
+            const float* src = xn + (long long)sy * a.W + sx;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              float v = (c == ones_c) ? 1.f : 0.f;                     // the constant lane that carries the BatchNorm shift
+              if (c < a.cin) v = __ldg(src + c * HW);
+              xr[i][c] = v;
+            }
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+          uint32_t hw[4], lw[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) split2(xr[i][2 * j], xr[i][2 * j + 1], hw + j, lw + j);
+          ph[h + i] = make_uint4(hw[0], hw[1], hw[2], hw[3]); pl[h + i] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
         }
       }
       if (lit > 0) mbar_wait<64>(patch_empty, (lit - 1) & 1);        // the previous item's MMAs no longer read the patch
 #pragma unroll
       for (int i = 0; i < CS_KP; ++i) {
         const int p = tid + i * CS_CONV_THREADS;
-        if (p < a.P) {                                               // positions past the last patch row: zeros (only invalid outputs read them)
-          uint32_t hw[4], lw[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) split2(xr[i][2 * j], xr[i][2 * j + 1], hw + j, lw + j);
-          patch_hi[p] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-          patch_lo[p] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-        }
+        if (p < a.P) { patch_hi[p] = ph[i]; patch_lo[p] = pl[i]; }    // positions past the last patch row: zeros (only invalid outputs read them)
       }
       fence_async_smem();
       __syncwarp();
@@ -152,14 +176,15 @@ __global__ void __launch_bounds__(CS_THREADS, 1) conv_stem_kernel(const __grid_c
     const int nblk = a.cout >> 4;
     const float lo_scale = 1.f / 2048.f;
     int gt = 0;
+    int tlc = 0; (void)tlc;
     for (int it = it_begin; it < it_end; ++it) {
-      const int n = it / a.items_per_sample, b = it - n * a.items_per_sample, g = n / a.n_per_group;
-      const float* zs = a.scale + (long long)g * a.ss_gs;
-      const float* zb = a.shift + (long long)g * a.ss_gs;
+      const int n = it / a.items_per_sample, b = it - n * a.items_per_sample;
       for (int t = 0; t < a.nt; ++t, ++gt) {
         const int slot = gt & 1;
+        CS_TL(1, e == 0 && lane == 0);                                // [0] waiting for the tile
         mbar_wait<64>(tile_full + slot, (gt >> 1) & 1);
         tc_fence_after();
+        CS_TL(1, e == 0 && lane == 0);                                // [1] tile complete
         const uint32_t trow = tmem + ((uint32_t)lanebase << 16) + (uint32_t)(slot * tile_cols);
         const int q = t * 128 + lanebase + lane;
         const int oyl = q / a.pitch, ox = q - oyl * a.pitch;
@@ -168,23 +193,28 @@ __global__ void __launch_bounds__(CS_THREADS, 1) conv_stem_kernel(const __grid_c
         const int yy = (oy >> 1) + 1, xx = (ox >> 1) + 1;
         uint4* zp0 = a.z + (long long)n * a.z_bs16 + (long long)((oy & 1) * 2 + (ox & 1)) * plane16;
         const bool hx = xx == PWz - 1, hy = yy == PHz - 1;
-        for (int blk = half; blk < nblk; blk += 2) {
+        // The accumulator slot is handed back as soon as this warp's LAST block has landed in registers: with two slots in TMEM the time a
+        // slot is held stalls the MMAs (scratch/stem_timeline.py).  (A two-buffer software pipeline of the TMEM loads was measured slower:
+        // 64 accumulator registers + spills, drain time 2.3-3.0 k -> 3.0-4.8 k cycles per tile.)
+        // store pointers advance by constants (one channel octet = 8 planes of hi / lo): the epilogue is issue-bound, and 64-bit address
+        // arithmetic per store was a quarter of its instructions
+        const long long cstride = 8 * plane16;                        // 16-byte units between channel octets: [c8][hi|lo][plane 4][plane16]
+        const int off_main = yy * PWz + xx;
+        const long long d_hx = -(long long)xx, d_hy = -(long long)yy * PWz, d_c = -(long long)off_main;   // halo column / row / corner relative to the pixel
+        uint4* pm = zp0 + (long long)(2 * half) * cstride + off_main;
+        const bool halo = hx || hy;
+        bool released = false;
+        for (int blk = half; blk < nblk; blk += 2, pm += 4 * cstride) {
           const int c0 = blk * 16;
           float v1[16], v2[16];
           tmem_ld16(trow + c0, v1); tmem_ld16(trow + a.cout + c0, v2);
-          float sc[16], sh[16];
-          if (a.vec_ss) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float4 s4 = __ldg(reinterpret_cast<const float4*>(zs + c0) + j), b4 = __ldg(reinterpret_cast<const float4*>(zb + c0) + j);
-              sc[4 * j] = s4.x; sc[4 * j + 1] = s4.y; sc[4 * j + 2] = s4.z; sc[4 * j + 3] = s4.w;
-              sh[4 * j] = b4.x; sh[4 * j + 1] = b4.y; sh[4 * j + 2] = b4.z; sh[4 * j + 3] = b4.w;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) { sc[j] = __ldg(zs + c0 + j); sh[j] = __ldg(zb + c0 + j); }
-          }
           tmem_ld_wait();
+          if (blk + 2 >= nblk) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tile_empty + slot);
+            released = true;
+          }
           if (valid) {
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
@@ -192,22 +222,27 @@ __global__ void __launch_bounds__(CS_THREADS, 1) conv_stem_kernel(const __grid_c
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 const int i0 = 8 * u + 2 * j;
-                const float e0 = fmaxf(fmaf(fmaf(v2[i0], lo_scale, v1[i0]), sc[i0], sh[i0]), 0.f);
-                const float e1 = fmaxf(fmaf(fmaf(v2[i0 + 1], lo_scale, v1[i0 + 1]), sc[i0 + 1], sh[i0 + 1]), 0.f);
-                split2(e0, e1, hw + j, lw + j);
+                // BatchNorm scale folded into the prepared weights, shift into the centre tap of the constant input lane: only ReLU is left
+                split2(fmaxf(fmaf(v2[i0], lo_scale, v1[i0]), 0.f), fmaxf(fmaf(v2[i0 + 1], lo_scale, v1[i0 + 1]), 0.f), hw + j, lw + j);
               }
               const uint4 hv = make_uint4(hw[0], hw[1], hw[2], hw[3]), lv = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-              uint4* zp = zp0 + (long long)((2 * blk + u) * 2) * 4 * plane16;          // [c8][hl][plane]
-              zp[yy * PWz + xx] = hv; zp[hl + yy * PWz + xx] = lv;
-              if (hx) { zp[yy * PWz] = hv; zp[hl + yy * PWz] = lv; }                   // circular halo column / row / corner of the plane
-              if (hy) { zp[xx] = hv; zp[hl + xx] = lv; }
-              if (hx && hy) { zp[0] = hv; zp[hl] = lv; }
+              uint4* q = pm + u * cstride;
+              uint4* ql = q + hl;
+              *q = hv; *ql = lv;
+              if (halo) {                                                              // circular halo column / row / corner of the plane
+                if (hx) { q[d_hx] = hv; ql[d_hx] = lv; }
+                if (hy) { q[d_hy] = hv; ql[d_hy] = lv; }
+                if (hx && hy) { q[d_c] = hv; ql[d_c] = lv; }
+              }
             }
           }
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(tile_empty + slot);
+        if (!released) {                                             // a warp without blocks (cout = 16 and the second half) still arrives
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tile_empty + slot);
+        }
+        CS_TL(1, e == 0 && lane == 0);                                // [2] drained
       }
     }
   } else if (warp == CS_WARP_MMA) {
@@ -221,16 +256,20 @@ __global__ void __launch_bounds__(CS_THREADS, 1) conv_stem_kernel(const __grid_c
     const uint32_t pair16 = 4u * (uint32_t)a.cout, cout = (uint32_t)a.cout;
     const int nt = a.nt, kwp = a.kwp, k = a.k, pitch = a.pitch;
     int g_loaded = -1, wgen = 0, gt = 0;
+    int tlc = 0; (void)tlc;
     for (int it = it_begin; it < it_end; ++it) {
       const int lit = it - it_begin;
       const int n = it / a.items_per_sample, g = n / a.n_per_group;
       if (g != g_loaded) { mbar_wait<64>(w_full, wgen & 1); ++wgen; g_loaded = g; }
+      CS_TL(2, leader);                                               // [0] waiting for the patch
       mbar_wait<32>(patch_full, lit & 1);
       tc_fence_after();
+      CS_TL(2, leader);                                               // [1] patch in place
       for (int t = 0; t < nt; ++t, ++gt) {
         const int slot = gt & 1;
         if (gt >= 2) mbar_wait<32>(tile_empty + slot, ((gt >> 1) - 1) & 1);
         tc_fence_after();
+        CS_TL(2, leader);                                             // [2 + 2t] accumulator slot free
         if (leader) {
           const uint32_t d = tmem + (uint32_t)slot * (2u * cout);
           uint32_t acc = 0u, wb = b_base;
@@ -246,6 +285,7 @@ __global__ void __launch_bounds__(CS_THREADS, 1) conv_stem_kernel(const __grid_c
         }
         __syncwarp();
         if (leader) umma_commit(tile_full + slot);
+        CS_TL(2, leader);                                             // [3 + 2t] tile issued
       }
       if (leader) umma_commit(patch_empty);
     }
@@ -281,10 +321,11 @@ __global__ void __launch_bounds__(CS_THREADS, 1) conv_stem_kernel(const __grid_c
 }
 
 // w [groups][cout][cin][k][k] -> out [groups][pair = ky * kwp + j][unit 2][row 2 cout][8 halfs]: unit u holds tap (ky, 2j + u) (zeros past
-// the filter edge), rows [0, cout) the fp16 hi part of output channel `row`, rows [cout, 2 cout) fp16((w - hi) * 2^11); channels >= cin zero
-__global__ void conv_stem_wprep_kernel(const float* __restrict__ w, long long w_gs, __half* __restrict__ out, long long out_gs, int cin, int cout,
-                                       int k, int kwp, int groups) {
+// the filter edge), rows [0, cout) the fp16 hi part of output channel `row`, rows [cout, 2 cout) fp16((w' - hi) * 2^11) of the folded weight w'
+__global__ void conv_stem_wprep_kernel(const float* __restrict__ w, long long w_gs, const float* __restrict__ scale, const float* __restrict__ shift,
+                                       long long ss_gs, __half* __restrict__ out, long long out_gs, int cin, int cout, int k, int kwp, int groups) {
   const long long per_group = (long long)k * kwp * 2 * (2 * cout) * 8;
+  const int pad = (k - 1) / 2;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < per_group * groups; i += (long long)gridDim.x * blockDim.x) {
     const int g = (int)(i / per_group);
     long long r = i - (long long)g * per_group;
@@ -293,8 +334,10 @@ __global__ void conv_stem_wprep_kernel(const float* __restrict__ w, long long w_
     const int u = (int)(r & 1); r >>= 1;
     const int j = (int)(r % kwp), ky = (int)(r / kwp);
     const int kx = 2 * j + u, co = row < cout ? row : row - cout;
+    // the consumer's eval-mode BatchNorm folded into the producer: scale * conv(x, w) + shift = conv([x, 1], [scale * w, shift at the centre tap])
     float v = 0.f;
-    if (ci < cin && kx < k) v = w[(long long)g * w_gs + (((long long)co * cin + ci) * k + ky) * k + kx];
+    if (ci < cin && kx < k) v = __ldg(scale + (long long)g * ss_gs + co) * w[(long long)g * w_gs + (((long long)co * cin + ci) * k + ky) * k + kx];
+    else if (ci == cin && ky == pad && kx == pad) v = __ldg(shift + (long long)g * ss_gs + co);
     const __half hi = __float2half_rn(v);
     out[(long long)g * out_gs + (i - (long long)g * per_group)] = row < cout ? hi : __float2half_rn((v - __half2float(hi)) * 2048.f);
   }
@@ -302,7 +345,7 @@ __global__ void conv_stem_wprep_kernel(const float* __restrict__ w, long long w_
 
 bool cs_plan(const ConvDesc& d, ConvStemArgs& a, size_t* smem_out) {
   if (d.kh != d.kw || !(d.kh & 1) || d.kh > 7 || d.stride != 1 || d.up || d.dilate || d.pad_override >= 0 || d.act != 0 || d.relu_in) return false;
-  if (d.cin > 8 || d.cout % 16 || d.cout < 16 || d.cout > 128 || (d.H & 1) || (d.W & 1) || d.H < 4 || d.W < 4 || d.W < d.kh) return false;
+  if (d.cin > 7 || d.cout % 16 || d.cout < 16 || d.cout > 128 || (d.H & 1) || (d.W & 1) || d.H < 4 || d.W < 4 || d.W < d.kh) return false;
   memset(&a, 0, sizeof(a));
   a.cin = d.cin; a.H = d.H; a.W = d.W; a.cout = d.cout; a.k = d.kh; a.pad = (d.kh - 1) / 2; a.kwp = (d.kh + 1) / 2; a.npairs = d.kh * a.kwp;
   a.pitch = d.W + d.kh - 1;
@@ -336,26 +379,27 @@ bool arpde_conv_stem_wanted(const ConvDesc& d) {
 // prepared fp16 weights per group in fp32 floats of scratch (<= arpde_conv_tc_wprep_floats of the same layer)
 long long arpde_conv_stem_wprep_floats(int cout, int k) { return (long long)k * ((k + 1) / 2) * 2 * (2 * cout) * 8 / 2; }
 
-int arpde_conv_stem_prep_launch(const ConvDesc& d, const float* w, long long w_gs, int groups, float* wprep, long long wprep_gs, cudaStream_t stream) {
+int arpde_conv_stem_prep_launch(const ConvDesc& d, const float* w, long long w_gs, int groups, float* wprep, long long wprep_gs, const ZOut& zo,
+                                cudaStream_t stream) {
+  ARPDE_CHECK_ARG(zo.scale && zo.shift && (groups == 1 || zo.ss_gs > 0), "conv_stem: the consumer's BatchNorm scale / shift are folded into the prepared weights");
   const int kwp = (d.kh + 1) / 2;
   const long long n = (long long)d.kh * kwp * 2 * (2 * d.cout) * 8 * groups;
   long long blocks = (n + 255) / 256; if (blocks > 4096) blocks = 4096;
-  conv_stem_wprep_kernel<<<(unsigned)blocks, 256, 0, stream>>>(w, w_gs, reinterpret_cast<__half*>(wprep), 2 * wprep_gs, d.cin, d.cout, d.kh, kwp, groups);
+  conv_stem_wprep_kernel<<<(unsigned)blocks, 256, 0, stream>>>(w, w_gs, zo.scale, zo.shift, groups > 1 ? zo.ss_gs : 0, reinterpret_cast<__half*>(wprep), 2 * wprep_gs,
+                                                               d.cin, d.cout, d.kh, kwp, groups);
   ARPDE_LAUNCH_CHECK();
   return ARPDE_OK;
 }
 
 int arpde_conv_stem_launch(const ConvDesc& d, const float* x, long long x_bs, const float* wprep, long long wprep_gs, const ZOut& zo, cudaStream_t stream) {
-  ARPDE_CHECK_ARG(x && wprep && zo.z && zo.scale && zo.shift, "conv_stem: null pointer");
+  ARPDE_CHECK_ARG(x && wprep && zo.z, "conv_stem: null pointer");
   if (d.N == 0) return ARPDE_OK;
   ConvStemArgs a; size_t smem;
   if (!cs_plan(d, a, &smem)) { arpde_set_error("conv_stem: layer not supported"); return ARPDE_ERR_UNSUPPORTED; }
   ARPDE_CHECK_ARG((((uintptr_t)zo.z) & 15) == 0 && (((uintptr_t)wprep) & 15) == 0 && (wprep_gs & 3) == 0, "conv_stem: operands must be 16-byte aligned");
   a.x = x; a.x_bs = x_bs; a.wz = reinterpret_cast<const uint4*>(wprep); a.wz_gs16 = wprep_gs / 4;
   a.z = reinterpret_cast<uint4*>(zo.z); a.z_bs16 = arpde_conv_z_sample16(d.cout, d.H, d.W);
-  a.scale = zo.scale; a.shift = zo.shift; a.ss_gs = zo.ss_gs;
-  a.vec_ss = ((((uintptr_t)zo.scale) & 15) == 0 && (((uintptr_t)zo.shift) & 15) == 0 && (zo.ss_gs & 3) == 0) ? 1 : 0;
-  a.N = d.N; a.n_per_group = d.n_per_group;
+  a.N = d.N; a.n_per_group = d.n_per_group; a.tl = arpde_tc_debug_buffer();
   static std::mutex attr_mutex;
   static bool attr_done[64] = {false};
   {

@@ -377,12 +377,12 @@ extern "C" int arpde_stem_pair_fwd(const float* x, int64_t x_bstride, const floa
   const long long p1 = arpde_conv_tc_wprep_floats(cin, c1, k1, k1), p3 = arpde_conv_tc_wprep_floats(c1, c3, 3, 3);
   ARPDE_CHECK_ARG(scratch_floats >= (p1 + p3) * groups, "stem_pair_fwd: scratch too small (%lld < %lld floats)", (long long)scratch_floats, (p1 + p3) * groups);
   const bool stem = arpde_conv_stem_wanted(d1);            // few input channels: the dedicated fp16 producer (conv_stem.cu)
-  int rc = stem ? arpde_conv_stem_prep_launch(d1, w1, w1_gstride, groups, scratch, p1, stream)
+  ZOut zo; zo.z = z; zo.scale = scale; zo.shift = shift; zo.ss_gs = ss_gstride;
+  int rc = stem ? arpde_conv_stem_prep_launch(d1, w1, w1_gstride, groups, scratch, p1, zo, stream)
                 : arpde_conv_tc_prep_launch(d1, w1, w1_gstride, groups, scratch, p1, stream);
   if (rc) return rc;
   float* s3 = scratch + p1 * groups;
   rc = arpde_conv_z_prep_launch(d3, w3, w3_gstride, groups, s3, p3, stream); if (rc) return rc;
-  ZOut zo; zo.z = z; zo.scale = scale; zo.shift = shift; zo.ss_gs = ss_gstride;
   rc = stem ? arpde_conv_stem_launch(d1, x, x_bstride, scratch, p1, zo, stream)
             : arpde_conv_tc_launch(d1, x, x_bstride, scratch, p1, nullptr, nullptr, 0, nullptr, nullptr, stream, &zo);
   if (rc) return rc;
@@ -407,10 +407,10 @@ extern "C" int arpde_stem_pair_producer(const float* x, int64_t x_bstride, const
   const long long p1 = arpde_conv_tc_wprep_floats(cin, c1, k1, k1);
   ARPDE_CHECK_ARG(scratch_floats >= p1 * groups, "stem_pair_producer: scratch too small (%lld < %lld floats)", (long long)scratch_floats, p1 * groups);
   const bool stem = arpde_conv_stem_wanted(d1);
-  int rc = stem ? arpde_conv_stem_prep_launch(d1, w1, w1_gstride, groups, scratch, p1, stream)
+  ZOut zo; zo.z = z; zo.scale = scale; zo.shift = shift; zo.ss_gs = ss_gstride;
+  int rc = stem ? arpde_conv_stem_prep_launch(d1, w1, w1_gstride, groups, scratch, p1, zo, stream)
                 : arpde_conv_tc_prep_launch(d1, w1, w1_gstride, groups, scratch, p1, stream);
   if (rc) return rc;
-  ZOut zo; zo.z = z; zo.scale = scale; zo.shift = shift; zo.ss_gs = ss_gstride;
   return stem ? arpde_conv_stem_launch(d1, x, x_bstride, scratch, p1, zo, stream)
               : arpde_conv_tc_launch(d1, x, x_bstride, scratch, p1, nullptr, nullptr, 0, nullptr, nullptr, stream, &zo);
 }

@@ -100,9 +100,14 @@ static int mark_zpairs(RunCtx& c) {
     c.zpair[i] = 1;
     ConvDesc dp; op_desc(c, p, &dp);
     if (p.bn_param < 0 && arpde_conv_stem_wanted(dp)) {        // the network's first layer: dedicated fp16 producer (conv_stem.cu)
-      const int pg = c.gstride[p.w_param] ? c.groups : 1;
-      rc = arpde_conv_stem_prep_launch(dp, (const float*)c.params[p.w_param], c.gstride[p.w_param], pg, (float*)c.wprep[i],
-                                       arpde_conv_tc_wprep_floats(p.cin, p.cout, p.kh, p.kw), c.stream);
+      // the consumer's folded BatchNorm (fold_eval ran before) goes into the producer's prepared weights -- which needs as many weight
+      // sets as there are BatchNorm sets (SWAG samples both per group; shared weights under per-group BatchNorm keep the generic producer)
+      const int wsets = c.gstride[p.w_param] ? c.groups : 1;
+      const int bnsets = (c.gstride[q.bn_param] || c.gstride[q.bn_param + 1]) ? c.groups : 1;
+      if (bnsets > wsets) { ++i; continue; }
+      ZOut zo; zo.z = nullptr; zo.scale = c.ss + q.bn_off; zo.shift = c.ss + (long long)c.groups * c.bn_total + q.bn_off; zo.ss_gs = c.bn_total;
+      rc = arpde_conv_stem_prep_launch(dp, (const float*)c.params[p.w_param], c.gstride[p.w_param], wsets, (float*)c.wprep[i],
+                                       arpde_conv_tc_wprep_floats(p.cin, p.cout, p.kh, p.kw), zo, c.stream);
       if (rc) return rc;
       c.zpair[i] = 2;
     }
@@ -370,8 +375,8 @@ static int rollout_impl(const arpde_op_t* ops, int n_ops, const arpde_buf_t* buf
     return arpde_ks_rollout_launch(ops, params_host, param_gstride_host, traj, bs, c_hist, T, N, c.n_per_group, (float)eps, stream);
   c.fuse_dense = allow_persistent; c.pdl = allow_persistent && !arpde_dev_env("ARPDE_NO_PDL");
   rc = prep_tc(c); if (rc) return rc;
+  rc = fold_eval(c); if (rc) return rc;                     // before the pair preparation: the stem folds the BatchNorm affine into its weights
   if (allow_persistent) { rc = mark_zpairs(c); if (rc) return rc; rc = mark_hconvs(c); if (rc) return rc; }
-  rc = fold_eval(c); if (rc) return rc;
   for (int t = 0; t < T; ++t) {
     const float* x = traj + (long long)(c_hist - c_in + t * c_out) * HW;
     rc = run_ops(c, x, bs, traj, traj_ctot, c_hist + t * c_out, 0);

@@ -340,6 +340,198 @@ __global__ void __launch_bounds__(256) burgers2d_fwd_smem(const float* __restric
   }
 }
 
+// ---- bulk-copy ring path (default for the eligible shapes): persistent CTAs of 8 consumer warps + 1 producer warp.  An item is
+//      (sample, strip of TY full-width rows); its (TY+2)-row tiles of u, v, u0, v0 are contiguous runs of rows in global memory
+//      (split only where the periodic wrap falls), so ONE lane moves a whole stage with <= 12 `cp.async.bulk` copies that complete
+//      on the stage's `full` mbarrier -- no per-thread address arithmetic, no registers and no occupancy spent on bytes in flight:
+//      NS stages of ~70 KB keep > 100 KB per SM outstanding where the register-rolling kernel had 32 KB (long-scoreboard bound,
+//      62 % of the HBM peak) and the cp.async tiled kernel spent 2.2x the instructions on chunk indices.  A consumer thread owns 4
+//      consecutive x and rolls down RB rows of the tile: one LDS.128 per field and row, the halo columns as RAW neighbour values by
+//      two shuffles per field and row (lanes at a warp boundary of rows wider than 128 points read them from the tile), column
+//      sums (colq) of the 6 columns, 4 points out; results go straight from registers to global memory as float4.  Consumers hand a
+//      stage back through its `empty` mbarrier (one arrive per warp); nobody waits for anybody else inside the CTA.
+#include "tc_ptx.cuh"
+
+struct Row6 { float x[6]; };                       // columns x0-1, x0 .. x0+3, x0+4 of one tile row
+
+// predicated shared-memory load without a branch (the edge lanes of rows wider than one warp): keeps the warp converged
+// around the shuffles (with `if (edge) v = trow[x]` ptxas built BSSY/BSYNC regions and slow-path collectives around every row)
+__device__ __forceinline__ float lds_if(float v, const float* p, bool pred) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p ld.shared.f32 %0, [%1];\n\t}\n" : "+f"(v) : "r"(smem_u32(p)), "r"((int)pred));
+  return v;
+}
+
+template <bool EDGE>
+__device__ __forceinline__ Row6 lds_row6(const float* __restrict__ trow, int x0, int xl, int xr, int lsrc, int rsrc, bool edgeL, bool edgeR) {
+  Row6 r;
+  const float4 a = *reinterpret_cast<const float4*>(trow + x0);
+  r.x[1] = a.x; r.x[2] = a.y; r.x[3] = a.z; r.x[4] = a.w;
+  r.x[0] = __shfl_sync(0xffffffffu, a.w, lsrc);
+  r.x[5] = __shfl_sync(0xffffffffu, a.x, rsrc);
+  if (EDGE) {
+    r.x[0] = lds_if(r.x[0], trow + xl, edgeL);
+    r.x[5] = lds_if(r.x[5], trow + xr, edgeR);
+  }
+  return r;
+}
+
+// producer side: rows ystart .. ystart+nrows-1 (periodic) of one field into consecutive tile rows
+__device__ __forceinline__ void bulk_rows(float* dst, const float* __restrict__ field, int ystart, int nrows, int H, int W, uint64_t* bar) {
+  int y = wrap(ystart, H), left = nrows;
+  while (left > 0) {
+    const int nr = left < H - y ? left : H - y;
+    bulk_g2s(dst, field + (size_t)y * W, (uint32_t)(nr * W) * 4u, bar);
+    dst += nr * W; left -= nr; y = 0;
+  }
+}
+
+struct UnitMap { int x0, xl, xr, lsrc, rsrc, rb; bool edgeL, edgeR, valid; };
+
+template <bool EDGE>
+__device__ __forceinline__ UnitMap unit_map(int i, int w4, int nrb, int W, int lx_log2) {
+  UnitMap m;
+  const int lane = threadIdx.x & 31, LX = 1 << lx_log2;
+  const int c = i % w4;
+  m.rb = i / w4; m.valid = m.rb < nrb; if (!m.valid) m.rb = nrb - 1;
+  m.x0 = c << 2; m.xl = wrap(m.x0 - 1, W); m.xr = wrap(m.x0 + 4, W);
+  const int lxi = lane & (LX - 1), lbase = lane & ~(LX - 1);
+  m.lsrc = lbase | ((lxi - 1) & (LX - 1)); m.rsrc = lbase | ((lxi + 1) & (LX - 1));
+  m.edgeL = EDGE && lane == 0; m.edgeR = EDGE && lane == 31;
+  return m;
+}
+
+// warp index as a value the compiler knows to be warp-uniform (loops bounded by it stay convergent, so the shuffles inside
+// compile to plain SHFL instead of WARPSYNC / ENDCOLLECTIVE sequences)
+__device__ __forceinline__ int uniform_warp_idx() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+
+// NCW consumer warps + 1 producer warp
+template <int RB, int NCW, bool EDGE, bool CN>
+__global__ void __launch_bounds__(32 * (NCW + 1), 1) burgers2d_fwd_bulk(const float* __restrict__ up, int64_t up_bs,
+                                                                       const float* __restrict__ u0, int64_t u0_bs,
+                                                                       float* __restrict__ ustar, double* __restrict__ sse, int N, int H,
+                                                                       int W, int TY, int NS, int lx_log2, B2Coef k) {
+  extern __shared__ __align__(128) unsigned char b2_smem[];     // [NS][4 fields][TY+2][W] floats | full[NS] | empty[NS]
+  const int rows = TY + 2, fstride = rows * W, stage_floats = 4 * fstride;
+  float* tiles = reinterpret_cast<float*>(b2_smem);
+  uint64_t* full = reinterpret_cast<uint64_t*>(b2_smem + (size_t)NS * stage_floats * sizeof(float));
+  uint64_t* empty = full + NS;
+  const int nstrips = (H + TY - 1) / TY, items = N * nstrips, HW = H * W;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NS; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, NCW); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  float acc = 0.f;
+  if (warp == NCW) {
+    if (lane == 0) {
+      int j = 0;
+      for (int it = blockIdx.x; it < items; it += gridDim.x, ++j) {
+        const int s = j % NS;
+        if (j >= NS) mbar_wait(empty + s, (uint32_t)((j / NS) - 1) & 1u);
+        mbar_arrive_expect_tx(full + s, (uint32_t)stage_floats * 4u);
+        const int n = it / nstrips, y0 = (it - n * nstrips) * TY;
+        const float* pu = up + (int64_t)n * up_bs; const float* p0 = u0 + (int64_t)n * u0_bs;
+        float* dst = tiles + (size_t)s * stage_floats;
+        bulk_rows(dst, pu, y0 - 1, rows, H, W, full + s);
+        bulk_rows(dst + fstride, pu + HW, y0 - 1, rows, H, W, full + s);
+        bulk_rows(dst + 2 * fstride, p0, y0 - 1, rows, H, W, full + s);
+        bulk_rows(dst + 3 * fstride, p0 + HW, y0 - 1, rows, H, W, full + s);
+      }
+    }
+  } else {
+    const int w4 = W >> 2, nrb = TY / RB, nunits = nrb * w4;
+    int j = 0;
+    for (int it = blockIdx.x; it < items; it += gridDim.x, ++j) {
+      const int s = j % NS;
+      mbar_wait(full + s, (uint32_t)(j / NS) & 1u);
+      __syncwarp();
+      const float* tile = tiles + (size_t)s * stage_floats;
+      const int n = it / nstrips, y0 = (it - n * nstrips) * TY;
+      for (int i0 = warp * 32; i0 < nunits; i0 += 32 * NCW) {
+        const UnitMap m = unit_map<EDGE>(i0 + lane, w4, nrb, W, lx_log2);
+        const int r0 = m.rb * RB;                             // tile row r0 = field row y0 + r0 - 1
+        const float* tu = tile + r0 * W; const float* tv = tu + fstride;
+        const float* t0u = tu + 2 * fstride; const float* t0v = tu + 3 * fstride;
+        // pass 0: R(uPred) of the RB rows (kept in registers), pass 1: R(uPred0), combination, store -- one field pair rolling at a time
+        float Su[RB][4], Sv[RB][4];
+        {
+          Row6 U[3], V[3];
+#pragma unroll
+          for (int rr = 0; rr < 2; ++rr) {
+            U[rr + 1] = lds_row6<EDGE>(tu + rr * W, m.x0, m.xl, m.xr, m.lsrc, m.rsrc, m.edgeL, m.edgeR);
+            V[rr + 1] = lds_row6<EDGE>(tv + rr * W, m.x0, m.xl, m.xr, m.lsrc, m.rsrc, m.edgeL, m.edgeR);
+          }
+#pragma unroll
+          for (int r = 0; r < RB; ++r) {
+            U[0] = U[1]; U[1] = U[2]; V[0] = V[1]; V[1] = V[2];
+            U[2] = lds_row6<EDGE>(tu + (r + 2) * W, m.x0, m.xl, m.xr, m.lsrc, m.rsrc, m.edgeL, m.edgeR);
+            V[2] = lds_row6<EDGE>(tv + (r + 2) * W, m.x0, m.xl, m.xr, m.lsrc, m.rsrc, m.edgeL, m.edgeR);
+            Col6 q[6];
+#pragma unroll
+            for (int c = 0; c < 6; ++c) q[c] = colq(U[0].x[c], U[1].x[c], U[2].x[c], V[0].x[c], V[1].x[c], V[2].x[c]);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) rhs_point(q[c], q[c + 1], q[c + 2], U[1].x[c + 1], V[1].x[c + 1], k, Su[r][c], Sv[r][c]);
+          }
+        }
+        Row6 U0[3], V0[3];
+        if (CN) {
+#pragma unroll
+          for (int rr = 0; rr < 2; ++rr) {
+            U0[rr + 1] = lds_row6<EDGE>(t0u + rr * W, m.x0, m.xl, m.xr, m.lsrc, m.rsrc, m.edgeL, m.edgeR);
+            V0[rr + 1] = lds_row6<EDGE>(t0v + rr * W, m.x0, m.xl, m.xr, m.lsrc, m.rsrc, m.edgeL, m.edgeR);
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < RB; ++r) {
+          float Ou[4], Ov[4];
+          if (CN) {
+            U0[0] = U0[1]; U0[1] = U0[2]; V0[0] = V0[1]; V0[1] = V0[2];
+            U0[2] = lds_row6<EDGE>(t0u + (r + 2) * W, m.x0, m.xl, m.xr, m.lsrc, m.rsrc, m.edgeL, m.edgeR);
+            V0[2] = lds_row6<EDGE>(t0v + (r + 2) * W, m.x0, m.xl, m.xr, m.lsrc, m.rsrc, m.edgeL, m.edgeR);
+            Col6 q[6];
+#pragma unroll
+            for (int c = 0; c < 6; ++c) q[c] = colq(U0[0].x[c], U0[1].x[c], U0[2].x[c], V0[0].x[c], V0[1].x[c], V0[2].x[c]);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              float R0u, R0v;
+              rhs_point(q[c], q[c + 1], q[c + 2], U0[1].x[c + 1], V0[1].x[c + 1], k, R0u, R0v);
+              Ou[c] = fmaf(k.c, Su[r][c] + R0u, U0[1].x[c + 1]); Ov[c] = fmaf(k.c, Sv[r][c] + R0v, V0[1].x[c + 1]);
+            }
+          } else {
+            // backward Euler: the previous state enters only as the additive term
+            const float4 a = *reinterpret_cast<const float4*>(t0u + (r + 1) * W + m.x0);
+            const float4 b = *reinterpret_cast<const float4*>(t0v + (r + 1) * W + m.x0);
+            Ou[0] = fmaf(k.c, Su[r][0], a.x); Ou[1] = fmaf(k.c, Su[r][1], a.y); Ou[2] = fmaf(k.c, Su[r][2], a.z); Ou[3] = fmaf(k.c, Su[r][3], a.w);
+            Ov[0] = fmaf(k.c, Sv[r][0], b.x); Ov[1] = fmaf(k.c, Sv[r][1], b.y); Ov[2] = fmaf(k.c, Sv[r][2], b.z); Ov[3] = fmaf(k.c, Sv[r][3], b.w);
+          }
+          const int y = y0 + r0 + r;
+          if (m.valid && y < H) {
+            if (ustar) {
+              float* o = ustar + (int64_t)n * 2 * HW + (size_t)y * W + m.x0;
+              *reinterpret_cast<float4*>(o) = make_float4(Ou[0], Ou[1], Ou[2], Ou[3]);
+              *reinterpret_cast<float4*>(o + HW) = make_float4(Ov[0], Ov[1], Ov[2], Ov[3]);
+            }
+            if (sse) {
+              const float4 a = *reinterpret_cast<const float4*>(tu + (r + 1) * W + m.x0);     // uPred at the centre row
+              const float4 b = *reinterpret_cast<const float4*>(tv + (r + 1) * W + m.x0);
+              const float du[4] = {Ou[0] - a.x, Ou[1] - a.y, Ou[2] - a.z, Ou[3] - a.w}, dv[4] = {Ov[0] - b.x, Ov[1] - b.y, Ov[2] - b.z, Ov[3] - b.w};
+#pragma unroll
+              for (int c = 0; c < 4; ++c) acc = fmaf(du[c], du[c], fmaf(dv[c], dv[c], acc));
+            }
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty + s);
+    }
+  }
+  if (sse) {
+    const double t = block_sum_d((double)acc);
+    if (threadIdx.x == 0) atomicAdd(sse, t);
+  }
+}
+
 // ---- adjoint, generic: one thread per point.  With G = dL/dustar (gu,gv):
 //   d/du = c [ u gh(gu) + gv(v gu) + nu L(gu) - gv_ gh(v) ],  d/dv = c [ -gu gv(u) + gh(u gv_) + v gv(gv_) + nu L(gv_) ]
 //   (gh, gv antisymmetric => adjoint = -gh, -gv; L symmetric), plus identity G onto uPred0.
@@ -499,6 +691,152 @@ __global__ void __launch_bounds__(256) burgers2d_bwd_smem(const float* __restric
   cp_async_wait<0>();
 }
 
+// ---- adjoint on the bulk-copy ring (same producer / consumer structure as burgers2d_fwd_bulk): tiles of gu, gv, u, v (, u0, v0),
+//      a consumer thread rolls down RB rows keeping three rows of every field in registers (the cp.async tiled kernel re-read
+//      all three rows plus 36 conflicting halo scalars per output row: its shared-memory pipe was 75 % busy).
+template <int RB, int NCW, bool EDGE, bool CN>
+__global__ void __launch_bounds__(32 * (NCW + 1), 1) burgers2d_bwd_bulk(const float* __restrict__ up, int64_t up_bs,
+                                                                        const float* __restrict__ u0, int64_t u0_bs,
+                                                                        const float* __restrict__ g, float* __restrict__ gup,
+                                                                        float* __restrict__ gu0, int N, int H, int W, int TY, int NS,
+                                                                        int lx_log2, B2Coef k) {
+  extern __shared__ __align__(128) unsigned char b2_smem[];     // [NS][NF fields][TY+2][W] floats | full[NS] | empty[NS]
+  constexpr int NF = CN ? 6 : 4;
+  const int rows = TY + 2, fstride = rows * W, stage_floats = NF * fstride;
+  float* tiles = reinterpret_cast<float*>(b2_smem);
+  uint64_t* full = reinterpret_cast<uint64_t*>(b2_smem + (size_t)NS * stage_floats * sizeof(float));
+  uint64_t* empty = full + NS;
+  const int nstrips = (H + TY - 1) / TY, items = N * nstrips, HW = H * W;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NS; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, NCW); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == NCW) {
+    if (lane == 0) {
+      int j = 0;
+      for (int it = blockIdx.x; it < items; it += gridDim.x, ++j) {
+        const int s = j % NS;
+        if (j >= NS) mbar_wait(empty + s, (uint32_t)((j / NS) - 1) & 1u);
+        mbar_arrive_expect_tx(full + s, (uint32_t)stage_floats * 4u);
+        const int n = it / nstrips, y0 = (it - n * nstrips) * TY;
+        const float* srcs[3] = {g + (int64_t)n * 2 * HW, up + (int64_t)n * up_bs, u0 + (int64_t)n * u0_bs};
+        float* dst = tiles + (size_t)s * stage_floats;
+#pragma unroll
+        for (int f = 0; f < NF; ++f) bulk_rows(dst + f * fstride, srcs[f >> 1] + (f & 1) * HW, y0 - 1, rows, H, W, full + s);
+      }
+    }
+    return;
+  }
+  const int w4 = W >> 2, nrb = TY / RB, nunits = nrb * w4;
+  int j = 0;
+  for (int it = blockIdx.x; it < items; it += gridDim.x, ++j) {
+    const int s = j % NS;
+    mbar_wait(full + s, (uint32_t)(j / NS) & 1u);
+    __syncwarp();
+    const float* tile = tiles + (size_t)s * stage_floats;
+    const int n = it / nstrips, y0 = (it - n * nstrips) * TY;
+    for (int i0 = warp * 32; i0 < nunits; i0 += 32 * NCW) {
+      const UnitMap m = unit_map<EDGE>(i0 + lane, w4, nrb, W, lx_log2);
+      const int r0 = m.rb * RB;
+      const float* t = tile + r0 * W;
+      Row6 F[NF][3];                                          // [gu, gv, u, v, u0, v0][rows y-1, y, y+1]
+#pragma unroll
+      for (int f = 0; f < NF; ++f)
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) F[f][rr + 1] = lds_row6<EDGE>(t + f * fstride + rr * W, m.x0, m.xl, m.xr, m.lsrc, m.rsrc, m.edgeL, m.edgeR);
+#pragma unroll
+      for (int r = 0; r < RB; ++r) {
+#pragma unroll
+        for (int f = 0; f < NF; ++f) {
+          F[f][0] = F[f][1]; F[f][1] = F[f][2];
+          F[f][2] = lds_row6<EDGE>(t + f * fstride + (r + 2) * W, m.x0, m.xl, m.xr, m.lsrc, m.rsrc, m.edgeL, m.edgeR);
+        }
+        const Row6 *A = F[0], *B = F[1];
+        ColA qa[6];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+          qa[c].EA = A[0].x[c] + A[2].x[c]; qa[c].SA = fmaf(2.f, A[1].x[c], qa[c].EA);
+          qa[c].EB = B[0].x[c] + B[2].x[c]; qa[c].DB = B[2].x[c] - B[0].x[c];
+        }
+        float out[4][4];                                      // [gup_u, gup_v, gu0_u, gu0_v][4 columns]
+#pragma unroll
+        for (int pass = 0; pass < (CN ? 2 : 1); ++pass) {
+          const Row6 *U = F[2 + 2 * pass], *V = F[3 + 2 * pass];
+          ColU qu[6];
+#pragma unroll
+          for (int c = 0; c < 6; ++c) {
+            qu[c].DVA = fmaf(V[2].x[c], A[2].x[c], -V[0].x[c] * A[0].x[c]);
+            qu[c].SV = fmaf(2.f, V[1].x[c], V[0].x[c] + V[2].x[c]);
+            qu[c].DU = U[2].x[c] - U[0].x[c];
+            qu[c].SUB = fmaf(U[0].x[c], B[0].x[c], fmaf(2.f * U[1].x[c], B[1].x[c], U[2].x[c] * B[2].x[c]));
+          }
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const ColA &la = qa[c], &ra = qa[c + 2];
+            const ColU &lu = qu[c], &mu = qu[c + 1], &ru = qu[c + 2];
+            const float uc = U[1].x[c + 1], vc = V[1].x[c + 1], ac = A[1].x[c + 1], bc = B[1].x[c + 1];
+            const float gh_a = ra.SA - la.SA, gv_va = fmaf(2.f, mu.DVA, lu.DVA + ru.DVA), gh_v = ru.SV - lu.SV;
+            const float lp_a = fmaf(-4.f, ac, la.EA + ra.EA);
+            const float gv_u = fmaf(2.f, mu.DU, lu.DU + ru.DU), gh_ub = ru.SUB - lu.SUB;
+            const float gv_b = fmaf(2.f, qa[c + 1].DB, la.DB + ra.DB), lp_b = fmaf(-4.f, bc, la.EB + ra.EB);
+            const float du = k.c * fmaf(k.k1, fmaf(uc, gh_a, fmaf(-bc, gh_v, gv_va)), k.k2 * lp_a);
+            const float dv = k.c * fmaf(k.k1, fmaf(-ac, gv_u, fmaf(vc, gv_b, gh_ub)), k.k2 * lp_b);
+            if (pass == 0) { out[0][c] = du; out[1][c] = dv; }
+            else { out[2][c] = du + ac; out[3][c] = dv + bc; }
+          }
+        }
+        if (!CN) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) { out[2][c] = A[1].x[c + 1]; out[3][c] = B[1].x[c + 1]; }
+        }
+        const int y = y0 + r0 + r;
+        if (m.valid && y < H) {
+          float* o = gup + (int64_t)n * 2 * HW + (size_t)y * W + m.x0;
+          float* o0 = gu0 + (int64_t)n * 2 * HW + (size_t)y * W + m.x0;
+          *reinterpret_cast<float4*>(o) = make_float4(out[0][0], out[0][1], out[0][2], out[0][3]);
+          *reinterpret_cast<float4*>(o + HW) = make_float4(out[1][0], out[1][1], out[1][2], out[1][3]);
+          *reinterpret_cast<float4*>(o0) = make_float4(out[2][0], out[2][1], out[2][2], out[2][3]);
+          *reinterpret_cast<float4*>(o0 + HW) = make_float4(out[3][0], out[3][1], out[3][2], out[3][3]);
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty + s);
+  }
+}
+
+// shape rule of the bulk-copy ring kernels: whole float4s, 16-byte aligned bases and strides (checked by the callers), W/4 a power of
+// two <= 32 or a multiple of 32 (lane mapping of the halo shuffles).  TY = RB x (consumer threads / (W/4)) rows gives every consumer thread one
+// unit per item; it is halved while the launch would have fewer than two items per SM (small batches), never below RB.
+struct BulkPlan { int TY, NS, lx_log2; bool edge; size_t smem; int64_t items; };
+static bool bulk_plan(int N, int H, int W, int RB, int NCW, int NF, BulkPlan* p) {
+  const int w4 = W >> 2;
+  if (W % 4 != 0 || w4 < 1 || H < 2) return false;
+  const bool pow2 = (w4 & (w4 - 1)) == 0;
+  if (!((pow2 && w4 <= 32) || w4 % 32 == 0)) return false;
+  const int cthreads = 32 * NCW;
+  int TY = RB * (w4 >= cthreads ? 1 : cthreads / w4);
+  const int hr = (H + RB - 1) / RB * RB; if (TY > hr) TY = hr;
+  const int sms = arpde_num_sms();
+  while (TY > RB && (TY / 2) % RB == 0 && (int64_t)N * ((H + TY - 1) / TY) < 2 * sms) TY /= 2;
+  size_t stage = (size_t)NF * (TY + 2) * W * sizeof(float);
+  while (stage * 2 + 256 > 227 * 1024 && TY > RB && (TY / 2) % RB == 0) { TY /= 2; stage = (size_t)NF * (TY + 2) * W * sizeof(float); }
+  if (stage * 2 + 256 > 227 * 1024 || stage >= (1u << 20)) return false;
+  int NS = (int)((227 * 1024 - 256) / stage); if (NS > 4) NS = 4;
+  if (arpde_dev_env("ARPDE_BULK_TY")) {
+    const int t = atoi(arpde_dev_env("ARPDE_BULK_TY"));
+    if (t >= RB && t % RB == 0) { TY = t; stage = (size_t)NF * (TY + 2) * W * sizeof(float); NS = (int)((227 * 1024 - 256) / stage); if (NS > 4) NS = 4; if (NS < 2) return false; }
+  }
+  if (arpde_dev_env("ARPDE_BULK_NS")) { const int t = atoi(arpde_dev_env("ARPDE_BULK_NS")); if (t >= 1 && (size_t)t * stage + 256 <= 227 * 1024) NS = t; }
+  p->TY = TY; p->NS = NS; p->smem = stage * NS + 2 * NS * sizeof(uint64_t);
+  p->lx_log2 = 0; while ((1 << p->lx_log2) < (w4 < 32 ? w4 : 32)) ++p->lx_log2;
+  p->edge = w4 > 32;
+  p->items = (int64_t)N * ((H + TY - 1) / TY);
+  return p->items < (1ll << 31);
+}
+
 static int make_b2coef(double dx, double nu, double dt, int mode, B2Coef* k) {
   ARPDE_CHECK_ARG(dx > 0 && (mode == ARPDE_CN || mode == ARPDE_BE), "burgers2d: bad dx=%g or mode=%d", dx, mode);
   k->k1 = (float)(0.125 / dx); k->k1h = (float)(0.0625 / dx); k->k2 = (float)(nu * 0.5 / (dx * dx));
@@ -535,7 +873,22 @@ extern "C" int arpde_cn_burgers2d_fwd(const float* uPred, int64_t up_bstride, co
   // are bank conflicts of the halo scalars) and reaches 2.75 TB/s -- it serves widths the rolling kernel's lane mapping cannot
   // (W/4 neither a power of two nor a multiple of 32) and is selectable with ARPDE_STENCIL_SMEM=1 for A/B runs.
   static const bool force_smem = arpde_dev_env("ARPDE_STENCIL_SMEM") != nullptr;
-  if (base_ok && TY >= 1 && tile_bytes <= 96 * 1024 && (force_smem || !vec_ok || (wide && TY >= 4))) {
+  const bool no_bulk = arpde_dev_env("ARPDE_STENCIL_NOBULK") != nullptr;
+  BulkPlan bp;
+  // 8 consumer warps x 4 rows per unit (measured against 16 warps x 2 rows at 88 registers: 5.04 vs 4.78 TB/s at 64x64, 5.73 vs 5.49 at 256x256)
+  if (base_ok && !no_bulk && !force_smem && bulk_plan(N, H, W, 4, 8, 4, &bp)) {
+    // default: bulk-copy ring kernel (one persistent CTA per SM)
+    int64_t blocks = arpde_num_sms(); if (blocks > bp.items) blocks = bp.items;
+#define LAUNCH_BULK(EDGE_, CN_)                                                                                                          \
+    do {                                                                                                                                 \
+      ARPDE_CUDA(cudaFuncSetAttribute(burgers2d_fwd_bulk<4, 8, EDGE_, CN_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bp.smem)); \
+      burgers2d_fwd_bulk<4, 8, EDGE_, CN_><<<(unsigned)blocks, 32 * 9, bp.smem, (cudaStream_t)stream_>>>(                                 \
+          uPred, up_bstride, uPred0, u0_bstride, ustar, sse_out, N, H, W, bp.TY, bp.NS, bp.lx_log2, k);                                  \
+    } while (0)
+    if (bp.edge) { if (k.cn) LAUNCH_BULK(true, true); else LAUNCH_BULK(true, false); }
+    else { if (k.cn) LAUNCH_BULK(false, true); else LAUNCH_BULK(false, false); }
+#undef LAUNCH_BULK
+  } else if (base_ok && TY >= 1 && tile_bytes <= 96 * 1024 && (force_smem || !vec_ok || (wide && TY >= 4))) {
     const int nstrips = (H + TY - 1) / TY;
     const int64_t items = (int64_t)N * nstrips;
     ARPDE_CHECK_ARG(items < (1ll << 31), "burgers2d_fwd: too many strips");
@@ -602,6 +955,22 @@ static int burgers2d_bwd_impl(const float* uPred, int64_t up_bstride, const floa
   const int NF = k.cn ? 6 : 4;
   int TY = W > 0 ? (W > 128 ? (96 * 1024) / (2 * NF * W * 4) - 2 : 1024 / W) : 0; if (TY > H) TY = H;
   const size_t tile_bytes = (size_t)2 * NF * (TY + 2) * W * sizeof(float);
+  const bool no_bulk = arpde_dev_env("ARPDE_STENCIL_NOBULK") != nullptr;
+  BulkPlan bp;
+  if (base_ok && !force_generic && !no_bulk && bulk_plan(N, H, W, 2, 8, NF, &bp)) {
+    int64_t blocks = arpde_num_sms(); if (blocks > bp.items) blocks = bp.items;
+#define LAUNCH_BULK(EDGE_, CN_)                                                                                                          \
+    do {                                                                                                                                 \
+      ARPDE_CUDA(cudaFuncSetAttribute(burgers2d_bwd_bulk<2, 8, EDGE_, CN_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bp.smem)); \
+      burgers2d_bwd_bulk<2, 8, EDGE_, CN_><<<(unsigned)blocks, 32 * 9, bp.smem, (cudaStream_t)stream_>>>(                                 \
+          uPred, up_bstride, uPred0, u0_bstride, grad_ustar, grad_uPred, grad_uPred0, N, H, W, bp.TY, bp.NS, bp.lx_log2, k);             \
+    } while (0)
+    if (bp.edge) { if (k.cn) LAUNCH_BULK(true, true); else LAUNCH_BULK(true, false); }
+    else { if (k.cn) LAUNCH_BULK(false, true); else LAUNCH_BULK(false, false); }
+#undef LAUNCH_BULK
+    ARPDE_LAUNCH_CHECK();
+    return ARPDE_OK;
+  }
   if (base_ok && TY >= 2 && tile_bytes <= 96 * 1024 && !force_generic) {
     const int nstrips = (H + TY - 1) / TY;
     const int64_t items = (int64_t)N * nstrips;

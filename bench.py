@@ -821,10 +821,11 @@ def main():
                                          'pair, the four dense layers as ONE FFMA launch (dense_block_stream_kernel), conv1x1 and the folded upsampling conv3x3 on '
                                          'conv_h_kernel (fp16 two-term tensor core), the 16->2 output conv (conv_out5x5_kernel, FFMA): rollout time of the job / %d steps' % T_STEPS},
                      'job_breakdown_ms': breakdown},
-        'roofline_stencil': {'kernel': 'burgers2d_fwd_vec4<RY=4> (fused periodic stencil + Crank-Nicolson, API form: read uPred, uPred0, write ustar), '
-                                       'C4 rollout batch, 4 rotating buffer sets', 'bound': 'hbm',
-                             'achieved': k2['achieved'], 'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': k2['frac'],
-                             'traffic': None, 'bytes_per_launch': k2['bytes_per_launch'], 'ms': k2['ms'], 'peak_source': peaks['source'],
+        'roofline_stencil': {'kernel': 'burgers2d_fwd_bulk<RB=4, 8 consumer warps> (fused periodic stencil + Crank-Nicolson, API form: read uPred, uPred0, '
+                                       'write ustar; persistent CTAs, cp.async.bulk + mbarrier ring of whole-sample tiles), C4 rollout batch, 4 rotating buffer sets',
+                             'bound': 'hbm', 'achieved': k2['achieved'], 'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': k2['frac'],
+                             'traffic': 160.4e6, 'traffic_source': 'ncu --set full, profiles/r02c_stencil_ncu_full.md: dram read 125.9 MB + write 34.5 MB in-kernel '
+                                                                   '(algorithmic 125.8 + 62.9 MB; the rest of the written ustar is still in L2 when the kernel ends)', 'bytes_per_launch': k2['bytes_per_launch'], 'ms': k2['ms'], 'peak_source': peaks['source'],
                              'cases': sten},
     }
     if weak is not None:

@@ -38,11 +38,13 @@ def test_integrator_fwd_bwd_vs_reference(system, meth):
     assert rel_err(b.grad, g['integ/%s/g_uPred0' % meth]) < TOL
 
 
-@pytest.mark.parametrize('shape', [(3, 64, 64), (2, 32, 32), (1, 256, 256), (2, 8, 4), (2, 17, 23), (3, 6, 12), (1, 24, 128), (1, 8, 1024)])
+@pytest.mark.parametrize('shape', [(3, 64, 64), (2, 32, 32), (1, 256, 256), (2, 8, 4), (2, 17, 23), (3, 6, 12), (1, 24, 128), (1, 8, 1024),
+                                   (1200, 16, 16), (5, 18, 64), (3, 70, 256), (700, 8, 32), (2, 10, 384)])
 @pytest.mark.parametrize('mode', [0, 1])
 def test_burgers2d_fast_vs_generic_vs_oracle(shape, mode):
-    """vectorised kernel (incl. the multi-warp-row EDGE variant at W=1024), tiled kernel (W=256), generic kernel and oracle agree;
-    inputs are channel-slice views of a longer history, as main.py passes them."""
+    """bulk-copy ring kernel (incl. its EDGE variant for rows wider than a warp at W = 256 / 384 / 1024, ragged last strips at H = 18 / 70,
+    more items than ring stages per CTA at N = 1200 / 700), the fallbacks for other widths (W = 23, 12), the generic kernel and the oracle
+    agree; inputs are channel-slice views of a longer history, as main.py passes them."""
     N, H, W = shape
     torch.manual_seed(3)
     hist = torch.randn(N, 6, H, W, device=DEV)
@@ -612,10 +614,11 @@ def test_eval_mode_backward_and_out_activation():
 
 
 # ----------------------------------------------------------------------------- stencil adjoint: tiled kernel vs one-thread-per-point kernel
-@pytest.mark.parametrize('N,H,W', [(3, 32, 32), (5, 64, 64), (2, 256, 256), (2, 20, 24), (1, 7, 128), (4, 64, 16)])
+@pytest.mark.parametrize('N,H,W', [(3, 32, 32), (5, 64, 64), (2, 256, 256), (2, 20, 24), (1, 7, 128), (4, 64, 16), (1300, 16, 16), (3, 70, 256),
+                                   (5, 18, 64), (2, 10, 384), (1, 8, 1024)])
 @pytest.mark.parametrize('mode', [0, 1])
 def test_burgers2d_adjoint_tiled_equals_generic(N, H, W, mode):
-    """arpde_cn_burgers2d_bwd (shared-memory tiled, float4) against arpde_cn_burgers2d_bwd_generic on contiguous tensors and on
+    """arpde_cn_burgers2d_bwd (bulk-copy ring kernel; cp.async tiled kernel for W = 24) against arpde_cn_burgers2d_bwd_generic on contiguous tensors and on
     channel-slice views of a history tensor (batch stride > 2*H*W); the generic kernel itself is pinned to the reference's autograd
     gradients by test_integrators_vs_reference_golden."""
     torch.manual_seed(N * 1000 + H + W)

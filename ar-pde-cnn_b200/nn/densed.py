@@ -391,40 +391,36 @@ class _DenseEDBase(nn.Module):
             return generic_forward(self.features, x)
         return P.run_module(self.features, x, self.training)
 
+    # ---- diagnostics of the reference kept for API parity (denseEDcirc2d.py:316-352): same console output, same return values
+    @torch.no_grad()
     def forward_test(self, x):
-        print('input: {}'.format(x.data.size()))
-        with torch.no_grad():
-            for name, module in self.features._modules.items():
-                x = module(x)
-                print('{}: {}'.format(name, x.data.size()))
+        """Walk the top-level children one by one and print the shape after each."""
+        print('input: {}'.format(x.shape))
+        for child_name, child in self.features.named_children():
+            x = child(x)
+            print('{}: {}'.format(child_name, x.shape))
         return x
 
     def _num_parameters_convlayers(self):
-        n_params, n_conv_layers = 0, 0
-        for name, param in self.named_parameters():
-            if 'conv' in name:
-                n_conv_layers += 1
-            n_params += param.numel()
-        return n_params, n_conv_layers
+        """(number of scalars, number of parameter tensors whose path contains 'conv')."""
+        named = list(self.named_parameters())
+        return sum(p.numel() for _, p in named), sum('conv' in n for n, _ in named)
 
     def _count_parameters(self):
-        n_params = 0
-        for name, param in self.named_parameters():
-            print(name)
-            print(param.size())
-            print(param.numel())
-            n_params += param.numel()
-            print('num of parameters so far: {}'.format(n_params))
+        running = 0
+        for pname, p in self.named_parameters():
+            running += p.numel()
+            print('{}\n{}\n{}'.format(pname, p.size(), p.numel()))
+            print('num of parameters so far: {}'.format(running))
 
     def reset_parameters(self, verbose=False):
-        for module in self.modules():
-            if isinstance(module, self.__class__):
-                continue
-            if 'reset_parameters' in dir(module):
-                if callable(module.reset_parameters):
-                    module.reset_parameters()
-                    if verbose:
-                        print("Reset parameters in {}".format(module))
+        """Re-initialise every sub-module that knows how to (convolutions, BatchNorm), not this container itself."""
+        for sub in self.modules():
+            reset = None if isinstance(sub, type(self)) else getattr(sub, 'reset_parameters', None)
+            if callable(reset):
+                reset()
+                if verbose:
+                    print('Reset parameters in {}'.format(sub))
 
 
 class DenseED2d(_DenseEDBase):

@@ -14,26 +14,26 @@ import torch
 from .. import _lib as L
 
 
+def _bufname(param_name, kind):
+    """Buffer of a parameter: dots of the parameter path replaced (swag.py:50-58), kind in mean | sq_mean | cov_mat_sqrt."""
+    return param_name.replace('.', '_') + '_' + kind
+
+
 class SwagNN(torch.nn.Module):
     def __init__(self, args, base, full_cov=True, max_models=1, eps=1e-30):
-        super(SwagNN, self).__init__()
-        self.device = args.device
-        self.base = base
-        self.full_cov = full_cov
-        self.max_models = max_models
-        self.eps = eps
+        super().__init__()
+        self.device, self.base = args.device, base
+        self.full_cov, self.max_models, self.eps = full_cov, max_models, eps
         self.buildSwagParameters(base)
 
     def buildSwagParameters(self, baseModule):
-        for (name, data) in list(baseModule.named_parameters()):
-            if name is None:
-                continue
-            name = name.replace('.', '_')
-            self.register_buffer('%s_mean' % name, data.new(data.size()).zero_())
-            self.register_buffer('%s_sq_mean' % name, data.new(data.size()).zero_())
+        """First / second moment of every parameter and, for the low-rank covariance, max_models rows of flattened parameters."""
+        for pname, p in baseModule.named_parameters():
+            self.register_buffer(_bufname(pname, 'mean'), torch.zeros_like(p))
+            self.register_buffer(_bufname(pname, 'sq_mean'), torch.zeros_like(p))
             if self.full_cov is True:
-                self.register_buffer('%s_cov_mat_sqrt' % name, data.new_empty((self.max_models, data.numel())).zero_())
-        self.register_buffer('n_models', torch.zeros([1], dtype=torch.long))
+                self.register_buffer(_bufname(pname, 'cov_mat_sqrt'), p.new_zeros((self.max_models, p.numel())))
+        self.register_buffer('n_models', torch.zeros(1, dtype=torch.long))
 
     def forward(self, *args, **kwargs):
         return self.base(*args, **kwargs)
@@ -42,14 +42,15 @@ class SwagNN(torch.nn.Module):
         return self.base.calc_neg_log_joint(*args, **kwargs)
 
     def swag_state_dict(self):
-        return dict(filter(lambda v: (v[1].requires_grad == False and "base" not in v[0]), self.state_dict().items()))
+        """The SWAG buffers alone (everything in the state dict that is neither trainable nor part of the wrapped model)."""
+        return {k: v for k, v in self.state_dict().items() if not v.requires_grad and 'base' not in k}
 
     # ---------------------------------------------------------------------------------
     def _tables(self, module, diagCov):
         names = [n for n, _ in module.named_parameters()]
-        means = [self.__getattr__('%s_mean' % n.replace('.', '_')) for n in names]
-        sqs = [self.__getattr__('%s_sq_mean' % n.replace('.', '_')) for n in names]
-        covs = None if diagCov else [self.__getattr__('%s_cov_mat_sqrt' % n.replace('.', '_')) for n in names]
+        means = [getattr(self, _bufname(n, 'mean')) for n in names]
+        sqs = [getattr(self, _bufname(n, 'sq_mean')) for n in names]
+        covs = None if diagCov else [getattr(self, _bufname(n, 'cov_mat_sqrt')) for n in names]
         return names, means, sqs, covs
 
     def _launch(self, means, sqs, covs, z1, z2, S, scale, diagCov):
@@ -113,48 +114,48 @@ class SwagNN(torch.nn.Module):
                                     n_samples, scale, diagCov)
         return flat, names, numels
 
+    @torch.no_grad()
     def collect(self, module=None):
-        """Running first/second moments + ring of the last max_models raw parameter vectors (swag.py:152-194).
-        Called once per epoch: plain tensor arithmetic, format contract only."""
-        if (module is None):
-            module = self.base
+        """One more model into the running moments (weights n/(n+1), 1/(n+1)) and into the window of the last max_models parameter
+        vectors (swag.py:152-194).  Quirks kept: the window stores RAW parameters, not deviations (sample() centres the non-zero
+        rows), and with max_models == 1 nothing is ever dropped from it.  Once per epoch: plain tensor arithmetic."""
+        module = self.base if module is None else module
         assert type(module) is type(self.base), 'Provided module is not the same as base module!'
-        n = self.n_models.item()
-        for name, param in list(module.named_parameters()):
-            name = name.replace('.', '_')
-            mean = self.__getattr__('%s_mean' % name)
-            sq_mean = self.__getattr__('%s_sq_mean' % name)
-            mean = mean * n / (n + 1.0) + param.data / (n + 1.0)
-            sq_mean = sq_mean * n / (n + 1.0) + param.data ** 2 / (n + 1.0)
+        n = int(self.n_models)
+        keep = self.max_models - 1
+        for pname, p in module.named_parameters():
+            w = p.detach()
+            for kind, value in (('mean', w), ('sq_mean', w * w)):
+                old = getattr(self, _bufname(pname, kind))
+                setattr(self, _bufname(pname, kind), old * n / (n + 1.0) + value / (n + 1.0))
             if self.full_cov:
-                cov_mat_sqrt = self.__getattr__('%s_cov_mat_sqrt' % name)
-                # raw parameters are stored (not deviations) and [-(K-1):] keeps all rows when K == 1
-                cov_mat_sqrt = torch.cat((cov_mat_sqrt[-(self.max_models - 1):], param.data.view(1, -1)), dim=0)
-                self.__setattr__('%s_cov_mat_sqrt' % name, cov_mat_sqrt)
-            self.__setattr__('%s_mean' % name, mean)
-            self.__setattr__('%s_sq_mean' % name, sq_mean)
-        self.n_models.add_(1)
+                window = getattr(self, _bufname(pname, 'cov_mat_sqrt'))
+                window = window[-keep:] if keep > 0 else window
+                setattr(self, _bufname(pname, 'cov_mat_sqrt'), torch.cat((window, w.reshape(1, -1)), dim=0))
+        self.n_models += 1
+
+    @staticmethod
+    def _ckpt_path(file_dir, epoch):
+        return os.path.join(file_dir, 'torchSwagModel_epoch%d.pth' % epoch)
 
     def saveModel(self, epoch, optimizer, scheduler, file_dir):
-        if not os.path.exists(file_dir):
-            os.makedirs(file_dir)
+        """Checkpoint dictionary of the reference (swag.py:196-210): epoch | state_dict | optimizer | scheduler."""
+        os.makedirs(file_dir, exist_ok=True)
         print('[SWAG] Epoch {}, Saving SWAG model!'.format(epoch))
-        state = {'epoch': epoch, 'state_dict': self.state_dict(),
-                 'optimizer': optimizer.state_dict(), 'scheduler': scheduler.state_dict()}
-        torch.save(state, file_dir + '/torchSwagModel_epoch{:d}.pth'.format(epoch))
+        torch.save(dict(epoch=epoch, state_dict=self.state_dict(), optimizer=optimizer.state_dict(), scheduler=scheduler.state_dict()),
+                   self._ckpt_path(file_dir, epoch))
 
     def loadModel(self, epoch, optimizer=None, scheduler=None, file_dir="."):
-        try:
-            file_name = file_dir + '/torchSwagModel_epoch{:d}.pth'.format(epoch)
-            param_dict = torch.load(file_name, map_location=lambda storage, loc: storage)
-            print('[SWAG] Found model at epoch: {:d}'.format(param_dict['epoch']))
-        except FileNotFoundError:
+        path = self._ckpt_path(file_dir, epoch)
+        if not os.path.isfile(path):
             print('[SWAG] Error: Could not find PyTorch network')
             return
-        self.load_state_dict(param_dict['state_dict'])
-        if (not optimizer is None):
-            optimizer.load_state_dict(param_dict['optimizer'])
-            scheduler.load_state_dict(param_dict['scheduler'])
+        ckpt = torch.load(path, map_location='cpu')
+        print('[SWAG] Found model at epoch: {:d}'.format(ckpt['epoch']))
+        self.load_state_dict(ckpt['state_dict'])
+        if optimizer is not None:
+            optimizer.load_state_dict(ckpt['optimizer'])
+            scheduler.load_state_dict(ckpt['scheduler'])
         print('[SWAG] Pre-trained swag model loaded!')
-        print('[SWAG] Collected {:d} models'.format(self.n_models.item()))
+        print('[SWAG] Collected {:d} models'.format(int(self.n_models)))
         return optimizer, scheduler

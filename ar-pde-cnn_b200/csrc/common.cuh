@@ -67,6 +67,10 @@ static inline cudaError_t arpde_launch1(void (*kernel)(T), unsigned grid, unsign
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }   // the next kernel may be scheduled
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }                  // predecessor complete, its writes visible
+// Warp index as a value the compiler KNOWS to be warp-uniform.  With `threadIdx.x >> 5` every branch or loop bound derived from the warp index
+// counts as potentially divergent, and each __shfl_sync inside such a region is compiled to a WARPSYNC / ENDCOLLECTIVE slow-path sequence
+// instead of one SHFL (found in the SASS of the stencil, output-conv and KS-rollout kernels: one such pair per shuffle).
+__device__ __forceinline__ int uniform_warp_idx() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
 #endif
 
 int arpde_num_sms();   // cached cudaDevAttrMultiProcessorCount of the current device

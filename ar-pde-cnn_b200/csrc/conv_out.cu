@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(32 * CO_WARPS, 2) conv_out5x5_kernel(ConvOutAr
   float* Wt = X + (size_t)a.cin * CO_ROWS * CO_W;         // [cin][52]: (ky, kx, co) of one input channel, padded to 13 float4
   float* SS = Wt + CO_MAXC * CO_WSTRIDE;                  // [2][16]
   float* RED = SS + 2 * CO_MAXC;                          // [2 row groups][3 channel quarters][32][32]
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
   const int tiles = a.H / CO_TR;
   const int n = blockIdx.x / tiles, y0 = (blockIdx.x - n * tiles) * CO_TR, g = n / a.n_per_group;
   const long long HW = (long long)a.H * CO_W;

@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(512, 1) dense_block_kernel(DenseBlockArgs a) {
   float* Wt = X + (size_t)ctot * rows * DB_W;             // [cin][9][4]
   float* SS = Wt + (size_t)(ctot - 4) * 36;               // [2][cin]
   float* RED = SS + 2 * DB_MAXC;                          // [4 items][2 slots][DB_R * 4][32]: partial sums of the channel slices
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
   const int tiles = a.H / DB_OWN;
   const long long HW = (long long)a.H * DB_W;
   const int lm = (lane + 31) & 31, lp = (lane + 1) & 31;

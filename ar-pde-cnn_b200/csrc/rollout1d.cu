@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(512, 1) ks_rollout_kernel(KsNet net, float* __
   extern __shared__ __align__(16) float smem[];
   float* wsm = smem;
   float* asm_ = smem + (size_t)gcap * WFLOATS;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, l = lane & 15, h = lane >> 4;
+  const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31, l = lane & 15, h = lane >> 4;
   for (int batch = blockIdx.x; batch < nbatches; batch += gridDim.x) {
     const int lo = batch * kb, hi = min(N, lo + kb);
     const int g0 = lo / npg, ng = (hi - 1) / npg - g0 + 1;

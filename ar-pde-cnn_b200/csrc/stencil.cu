@@ -400,10 +400,6 @@ __device__ __forceinline__ UnitMap unit_map(int i, int w4, int nrb, int W, int l
   return m;
 }
 
-// warp index as a value the compiler knows to be warp-uniform (loops bounded by it stay convergent, so the shuffles inside
-// compile to plain SHFL instead of WARPSYNC / ENDCOLLECTIVE sequences)
-__device__ __forceinline__ int uniform_warp_idx() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
-
 // NCW consumer warps + 1 producer warp
 template <int RB, int NCW, bool EDGE, bool CN>
 __global__ void __launch_bounds__(32 * (NCW + 1), 1) burgers2d_fwd_bulk(const float* __restrict__ up, int64_t up_bs,

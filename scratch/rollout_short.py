@@ -20,7 +20,7 @@ print('ok', float(traj.abs().max()))
 if os.environ.get('TIME'):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     traj = torch.empty((30 * nic, 6 + 2 * T, 64, 64), device=dev)
-    for ns in (1, 2):
+    for ns in [int(v) for v in os.environ.get("NS", "1,2").split(",")]:
         for _ in range(2):
             engine.rollout(swag, ic, T, flat_weights=flat, named_params=named, out=traj, n_streams=ns)
         torch.cuda.synchronize(); e0.record()

@@ -38,3 +38,19 @@ rows = [(int(e[i]), int(e[i + 1]), int(e[i + 2])) for i in range(0, min(len(e) -
 print('   complete-to-complete:', [rows[i + 1][1] - rows[i][1] for i in range(len(rows) - 1)])
 print('   drain time          :', [r[2] - r[1] for r in rows])
 print('   idle before tile    :', [r[1] - r[0] for r in rows])
+print('per item: [patch ready - prev item end], [item duration], tiles mean issue, mean slot wait')
+nit = len(m) // per_item
+prev_end = None
+for it in range(nit):
+    seg = m[it * per_item:(it + 1) * per_item]
+    sf, iss = seg[2::2], seg[3::2]
+    gap = int(seg[1] - prev_end) if prev_end is not None else int(seg[1])
+    print('  item %2d: gap %6d  dur %6d  issue %5.0f  slotwait %5.0f' % (it, gap, int(iss[-1] - seg[1]), float((iss - sf).mean()), float((sf[1:] - iss[:-1]).mean())))
+    prev_end = int(iss[-1])
+import time
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+for _ in range(3): run()
+torch.cuda.synchronize(); e0.record()
+for _ in range(10): run()
+e1.record(); torch.cuda.synchronize()
+print('producer call: %.3f ms' % (e0.elapsed_time(e1) / 10))

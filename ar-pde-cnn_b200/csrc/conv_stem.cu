@@ -351,8 +351,15 @@ bool cs_plan(const ConvDesc& d, ConvStemArgs& a, size_t* smem_out) {
   a.pitch = d.W + d.kh - 1;
   a.w16 = a.npairs * 2 * 2 * d.cout;
   const size_t budget = 226 * 1024;
+  // Rows per work item: the largest block that fits (least halo conversion, no padded tile at 64 columns) unless the batch is so small
+  // that whole rounds of the persistent grid go half empty -- then the block whose rounds x tiles-per-item is smallest (240 samples on
+  // 148 SMs: 32-row items = 4 rounds x 17 tiles, 16-row items = 7 rounds x 9 tiles).  Blocks below 8 rows are only taken when nothing
+  // larger fits.
+  const int sms = arpde_num_sms();
+  long long best_cost = -1;
   for (int RI = d.H; RI >= 1; --RI) {
     if (d.H % RI) continue;
+    if (RI < 8 && best_cost >= 0) break;
     const int nt = (RI * a.pitch + 127) / 128;
     int P = nt * 128 + (a.k - 1) * a.pitch + a.k + 1;
     const int Prows = (RI + a.k - 1) * a.pitch;
@@ -361,11 +368,15 @@ bool cs_plan(const ConvDesc& d, ConvStemArgs& a, size_t* smem_out) {
     if (P > CS_KP * CS_CONV_THREADS || P > 16000) continue;
     const size_t smem = CS_HEADER + (size_t)a.w16 * 16 + (size_t)2 * P * 16;
     if (smem > budget) continue;
+    const long long items = (long long)(d.N > 0 ? d.N : 1) * (d.H / RI);
+    const long long grid = items < sms ? items : sms;
+    const long long cost = ((items + grid - 1) / grid) * nt;
+    if (best_cost >= 0 && cost >= best_cost) continue;
+    best_cost = cost;
     a.RI = RI; a.nt = nt; a.P = P; a.items_per_sample = d.H / RI;
     *smem_out = smem;
-    return true;
   }
-  return false;
+  return best_cost >= 0;
 }
 
 }  // namespace

@@ -180,17 +180,19 @@ __device__ __forceinline__ void ds_chunk(const float* __restrict__ data, const f
 #pragma unroll 1
   for (int e = 0; e < DS_CH; ++e) {
     const float* xe = data + e * DS_H * DB_W + lane;
-    float x[6], xl[6], xr[6];
+    float x[6];
 #pragma unroll
     for (int i = 0; i < 6; ++i) x[i] = xe[((r0 - 1 + i) & (DS_H - 1)) * DB_W];
 #pragma unroll
-    for (int i = 0; i < 6; ++i) { xl[i] = __shfl_sync(0xffffffffu, x[i], lm); xr[i] = __shfl_sync(0xffffffffu, x[i], lp); }
-#pragma unroll
     for (int l = L0; l < DB_MAXL; ++l) {
       const float s = SS[l * DB_MAXC + cbase + e], t = SS[(DB_MAXL + l) * DB_MAXC + cbase + e];
+      // the layer's BN + ReLU on the lane's own column, the x-neighbours' ACTIVATED values by shuffle (12 ALU + 12 SHFL per layer and channel
+      // instead of 36 ALU on raw neighbour values shuffled once per channel: the kernel is issue-bound)
       float a[6], al[6], ar[6];
 #pragma unroll
-      for (int i = 0; i < 6; ++i) { a[i] = fmaxf(fmaf(x[i], s, t), 0.f); al[i] = fmaxf(fmaf(xl[i], s, t), 0.f); ar[i] = fmaxf(fmaf(xr[i], s, t), 0.f); }
+      for (int i = 0; i < 6; ++i) a[i] = fmaxf(fmaf(x[i], s, t), 0.f);
+#pragma unroll
+      for (int i = 0; i < 6; ++i) { al[i] = __shfl_sync(0xffffffffu, a[i], lm); ar[i] = __shfl_sync(0xffffffffu, a[i], lp); }
       const float4* wp = reinterpret_cast<const float4*>(wst + (e * DB_MAXL + l) * 36);
 #pragma unroll
       for (int ky = 0; ky < 3; ++ky) {
@@ -214,7 +216,7 @@ __global__ void __launch_bounds__(DS_THREADS, 2) dense_block_stream_kernel(Dense
   float* NEW = BUF + 2 * DS_CHUNK;                        // [3][4][32][32] outputs of layers 0..2 (chunks 12..14)
   float* WST = NEW + 3 * DS_CHUNK;                        // [2][4 e][4 l][9][4] weight ring
   float* SS = WST + 2 * DS_WCH;                           // [2][4 l][64] folded BatchNorm of the four layers
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
   const int lm = (lane + 31) & 31, lp = (lane + 1) & 31;
   const int r0 = warp * 4;
   const long long HW = (long long)DS_H * DB_W;

@@ -437,6 +437,67 @@ def ks_probe(dev):
             'weights': "reference's shipped 1D-KS-SWAG/post/networks/torchSwagModel_epoch200.pth (via tests/golden/ks1d_ckpt200.npz), full-covariance samples (K = %d)" % K}
 
 
+def c1_probe(dev, B=256, L_=512, tback=2, nwarm=3, nrep=10):
+    """BASELINE config C1: the 1D viscous Burgers DenseED (1D-Burger-SWAG/args.py defaults: nic 5, blocks [1], growth 4, 64 initial features,
+    512-point grid, mini-batch 256) -- one optimizer step of the reference's training loop (1D-Burger-SWAG/main.py:47-87): a tback-step BPTT
+    window of DenseED forward (batch-statistics BatchNorm) + Crank-Nicolson target (dx = 1/513, nu = 0.0025) + negative log joint, backward,
+    one-launch Adam.  ICs of the form burgerLoader.py:51-84 draws (order-3 Fourier series, numpy seed 12345)."""
+    import types
+    import numpy as np
+    import torch
+    from arpde_b200.nn.densed import DenseED1dBurgers
+    from arpde_b200.nn.bayesnn import BayesNN
+    from arpde_b200.nn.swag import SwagNN
+    from arpde_b200.nn.integrators import BurgerIntegrate
+    from arpde_b200.optim import Adam
+    from arpde_b200 import parallel as PL
+    from arpde_b200 import _lib as L
+    torch.manual_seed(0); np.random.seed(12345)
+    nic = 5
+    a = types.SimpleNamespace(dt=0.005, device=dev, nic=nic)
+    with _quiet():
+        model = DenseED1dBurgers(nic, 1, [1], growth_rate=4, init_features=64).to(dev)
+        bayes = BayesNN(a, model); swag = SwagNN(a, bayes, full_cov=True, max_models=30)
+        integ = BurgerIntegrate(1.0 / (L_ + 1), nu=0.0025, grad_kernels=[3, 3], device=dev)
+    opt = Adam([{'params': [bayes.model.log_beta], 'lr': 1e-3}, {'params': bayes.model.features.parameters()}], lr=1e-3)
+    x = np.linspace(0, 1, L_ + 1)[:-1]
+    order = 3
+    lam = np.random.randn(B, 2, 2 * order + 1)
+    c = np.random.rand(B) - 0.5
+    k = np.arange(-order, order + 1)
+    kx = 2 * np.pi * k[None, :, None] * x[None, None, :]
+    f = (lam[:, 0, :, None] * np.cos(kx) + lam[:, 1, :, None] * np.sin(kx)).sum(1)
+    f = 2 * f / np.abs(f).max(1, keepdims=True) + 2 * c[:, None]
+    ic = torch.from_numpy(f).float().to(dev).unsqueeze(1)
+    swag.train()
+    bucket = PL.FlatGradBucket([bayes.model.log_beta] + list(bayes.model.features.parameters()))
+
+    def step():
+        inp = ic.repeat(1, nic, 1)
+        loss = 0
+        bucket.zero_()
+        for _ in range(tback):
+            u_pred = swag(inp[:, -nic:])
+            ustar = integ.crankNicolson(u_pred, inp[:, -1:], 0.003)
+            loss = loss + swag.calc_neg_log_joint(u_pred, ustar, 10)
+            inp = torch.cat([inp, u_pred[:, :1]], 1)
+        with bucket.capture():
+            loss.backward()
+        opt.step()
+        return loss
+    for _ in range(nwarm):
+        loss = step()
+    torch.cuda.synchronize()
+    L.lib.arpde_launch_count(1)
+    ms = time_cuda(lambda i: step(), nrep, nwarm=0)
+    launches = int(L.lib.arpde_launch_count(1)) // nrep
+    return {'ms': ms, 'value': tback * B / ms * 1e3, 'unit': 'sample-steps/s', 'batch': B, 'grid': L_, 'tback': tback, 'library_launches_per_step': launches,
+            'finite': bool(torch.isfinite(loss.detach()).all()),
+            'model': 'DenseED 1D Burgers (nic 5, blocks [1], growth 4, init_features 64: 13 441 parameters, 8.57 MFLOP per sample-step forward)',
+            'what': 'one optimizer step = %d-step BPTT window: forward (batch-stat BN) + Crank-Nicolson + neg log joint + backward + one-launch Adam; mean of '
+                    '%d steps after %d warm-up (CUDA events)' % (tback, nrep, nwarm)}
+
+
 def c5_probe(dev, peaks):
     """BASELINE config C5: scaled synthetic 256x256 grid, wide DenseED (growth 32, init_features 96): AR rollout of 32 initial conditions,
     every layer but the output conv on the tensor-core kernel."""
@@ -779,7 +840,7 @@ def main():
     sten = stencil_rooflines(dev, peaks)
     k2 = sten['c4_64_fwd']
 
-    train = train_weak = ks = c5 = None
+    train = train_weak = ks = c5 = c1 = None
     if not args.no_train_probe:
         train = train_step_probe(dev, rank=rank, world=world)
         if world > 1 and not args.no_extra:
@@ -787,6 +848,7 @@ def main():
     if rank == 0 and not args.no_extra:
         ks = ks_probe(dev)
         c5 = c5_probe(dev, peaks)
+        c1 = c1_probe(dev)
     if world > 1:
         dist.barrier()
     if rank != 0:
@@ -838,6 +900,8 @@ def main():
         line['c2_ks'] = ks
     if c5 is not None:
         line['c5_wide'] = c5
+    if c1 is not None:
+        line['c1_burgers1d_train'] = c1
     if not args.no_cpu_baseline:
         S, N, T = REF_SAMPLE
         reference_rate(1, 8, 1)

@@ -67,9 +67,11 @@ __global__ void __launch_bounds__(32 * CO_WARPS, 2) conv_out5x5_kernel(ConvOutAr
   __syncthreads();
   const int rg = warp / CO_KS, kg = warp - rg * CO_KS;
   const int rb = rg * CO_R;                               // first output row of the warp (local); its input rows are rb .. rb + 11
-  float acc[CO_R][2][2];
+  // acc2[o][px] = (channel 0, channel 1) of output row o, column px: packed fp32 FMAs (fma.rn.f32x2) over the output-channel pair, whose
+  // weights are adjacent in the staged table -- half the FMA issue slots of the scalar form, bit-identical results
+  float2 acc2[CO_R][2];
 #pragma unroll
-  for (int o = 0; o < CO_R; ++o) { acc[o][0][0] = 0.f; acc[o][0][1] = 0.f; acc[o][1][0] = 0.f; acc[o][1][1] = 0.f; }
+  for (int o = 0; o < CO_R; ++o) { acc2[o][0] = make_float2(0.f, 0.f); acc2[o][1] = make_float2(0.f, 0.f); }
   const int c_lo = kg * a.cin / CO_KS, c_hi = (kg + 1) * a.cin / CO_KS;
   const int lm = (lane + 31) & 31, lp = (lane + 1) & 31;
 #pragma unroll 1
@@ -91,15 +93,18 @@ __global__ void __launch_bounds__(32 * CO_WARPS, 2) conv_out5x5_kernel(ConvOutAr
       win[0] = __shfl_sync(0xffffffffu, a0, lm); win[1] = __shfl_sync(0xffffffffu, a1, lm);
       win[2] = a0; win[3] = a1;
       win[4] = __shfl_sync(0xffffffffu, a0, lp); win[5] = __shfl_sync(0xffffffffu, a1, lp);
+      float2 win2[6];
+#pragma unroll
+      for (int q = 0; q < 6; ++q) win2[q] = make_float2(win[q], win[q]);
 #pragma unroll
       for (int ky = 0; ky < 5; ++ky) {
         const int o = ir - ky;                            // output row fed by (input row ir, tap row ky)
         if (o >= 0 && o < CO_R) {
 #pragma unroll
           for (int kx = 0; kx < 5; ++kx) {
-            const float w0 = wr[(ky * 5 + kx) * 2], w1 = wr[(ky * 5 + kx) * 2 + 1];
-            acc[o][0][0] = fmaf(w0, win[kx], acc[o][0][0]); acc[o][0][1] = fmaf(w0, win[kx + 1], acc[o][0][1]);
-            acc[o][1][0] = fmaf(w1, win[kx], acc[o][1][0]); acc[o][1][1] = fmaf(w1, win[kx + 1], acc[o][1][1]);
+            const float2 w01 = make_float2(wr[(ky * 5 + kx) * 2], wr[(ky * 5 + kx) * 2 + 1]);
+            acc2[o][0] = __ffma2_rn(w01, win2[kx], acc2[o][0]);
+            acc2[o][1] = __ffma2_rn(w01, win2[kx + 1], acc2[o][1]);
           }
         }
       }
@@ -111,7 +116,7 @@ __global__ void __launch_bounds__(32 * CO_WARPS, 2) conv_out5x5_kernel(ConvOutAr
 #pragma unroll
     for (int o = 0; o < CO_R; ++o)
 #pragma unroll
-      for (int q = 0; q < 4; ++q) r[(o * 4 + q) * 32] = acc[o][q >> 1][q & 1];
+      for (int q = 0; q < 4; ++q) r[(o * 4 + q) * 32] = (q >> 1) ? acc2[o][q & 1].y : acc2[o][q & 1].x;
   }
   __syncthreads();
   if (kg == 0) {
@@ -121,7 +126,7 @@ __global__ void __launch_bounds__(32 * CO_WARPS, 2) conv_out5x5_kernel(ConvOutAr
       float v[4];
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        float t = acc[o][q >> 1][q & 1];
+        float t = (q >> 1) ? acc2[o][q & 1].y : acc2[o][q & 1].x;
 #pragma unroll
         for (int k = 0; k < 3; ++k) t += RED[((size_t)(rg * 3 + k) * 32 + o * 4 + q) * 32 + lane];
         v[q] = apply_act(t, a.act);

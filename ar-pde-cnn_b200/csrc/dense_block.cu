@@ -176,7 +176,7 @@ constexpr int DS_H = 32, DS_CH = 4, DS_CHUNK = DS_CH * DS_H * DB_W, DS_WCH = DS_
 
 template <int L0>
 __device__ __forceinline__ void ds_chunk(const float* __restrict__ data, const float* __restrict__ wst, const float* __restrict__ SS, int cbase,
-                                         float (&acc)[DB_MAXL][4][4], int r0, int lane, int lm, int lp) {
+                                         float2 (&acc)[DB_MAXL][4][2], int r0, int lane, int lm, int lp) {
 #pragma unroll 1
   for (int e = 0; e < DS_CH; ++e) {
     const float* xe = data + e * DS_H * DB_W + lane;
@@ -195,15 +195,20 @@ __device__ __forceinline__ void ds_chunk(const float* __restrict__ data, const f
       for (int i = 0; i < 6; ++i) { al[i] = __shfl_sync(0xffffffffu, a[i], lm); ar[i] = __shfl_sync(0xffffffffu, a[i], lp); }
       const float4* wp = reinterpret_cast<const float4*>(wst + (e * DB_MAXL + l) * 36);
 #pragma unroll
+      // packed fp32 FMAs (fma.rn.f32x2, sm_100): one issue slot for the two output channels of a pair -- the scalar form was issue-bound
+      // (80 % of the slots, FMA pipe 61 %); each lane of the pair is an IEEE fma, so the results are bit-identical
+      float2 a2[6], al2[6], ar2[6];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) { a2[i] = make_float2(a[i], a[i]); al2[i] = make_float2(al[i], al[i]); ar2[i] = make_float2(ar[i], ar[i]); }
+#pragma unroll
       for (int ky = 0; ky < 3; ++ky) {
         const float4 w0 = wp[ky * 3], w1 = wp[ky * 3 + 1], w2 = wp[ky * 3 + 2];
+        const float2 w0a = make_float2(w0.x, w0.y), w0b = make_float2(w0.z, w0.w), w1a = make_float2(w1.x, w1.y), w1b = make_float2(w1.z, w1.w),
+                     w2a = make_float2(w2.x, w2.y), w2b = make_float2(w2.z, w2.w);
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
-          const float vl = al[r + ky], vm = a[r + ky], vr = ar[r + ky];
-          acc[l][r][0] = fmaf(w0.x, vl, fmaf(w1.x, vm, fmaf(w2.x, vr, acc[l][r][0])));
-          acc[l][r][1] = fmaf(w0.y, vl, fmaf(w1.y, vm, fmaf(w2.y, vr, acc[l][r][1])));
-          acc[l][r][2] = fmaf(w0.z, vl, fmaf(w1.z, vm, fmaf(w2.z, vr, acc[l][r][2])));
-          acc[l][r][3] = fmaf(w0.w, vl, fmaf(w1.w, vm, fmaf(w2.w, vr, acc[l][r][3])));
+          acc[l][r][0] = __ffma2_rn(w0a, al2[r + ky], __ffma2_rn(w1a, a2[r + ky], __ffma2_rn(w2a, ar2[r + ky], acc[l][r][0])));
+          acc[l][r][1] = __ffma2_rn(w0b, al2[r + ky], __ffma2_rn(w1b, a2[r + ky], __ffma2_rn(w2b, ar2[r + ky], acc[l][r][1])));
         }
       }
     }
@@ -251,20 +256,21 @@ __global__ void __launch_bounds__(DS_THREADS, 2) dense_block_stream_kernel(Dense
       SS[i] = ok ? __ldg(a.scale + (long long)g * a.ss_gs + a.bn_off[l] + c) : 0.f;
       SS[DB_MAXL * DB_MAXC + i] = ok ? __ldg(a.shift + (long long)g * a.ss_gs + a.bn_off[l] + c) : 0.f;
     }
-    float acc[DB_MAXL][4][4];
+    float2 acc[DB_MAXL][4][2];                             // [layer][row][output-channel pair]
 #pragma unroll
     for (int l = 0; l < DB_MAXL; ++l)
 #pragma unroll
-      for (int r = 0; r < 4; ++r) { acc[l][r][0] = 0.f; acc[l][r][1] = 0.f; acc[l][r][2] = 0.f; acc[l][r][3] = 0.f; }
+      for (int r = 0; r < 4; ++r) { acc[l][r][0] = make_float2(0.f, 0.f); acc[l][r][1] = make_float2(0.f, 0.f); }
     const int nchunks = nraw + a.nl - 1;                  // raw chunks, then the outputs of layers 0 .. nl-2
     // finalize layer l: its accumulators are complete -> shared memory (input of the later layers) and the dense-block buffer
-    auto finalize = [&](int l, const float (&v)[4][4]) {
+    auto finalize = [&](int l, const float2 (&v2)[4][2]) {
 #pragma unroll
       for (int r = 0; r < 4; ++r)
 #pragma unroll
         for (int co = 0; co < 4; ++co) {
-          if (l < DB_MAXL - 1) NEW[((size_t)(l * DS_CH + co) * DS_H + r0 + r) * DB_W + lane] = v[r][co];
-          bn_[(long long)(a.c0 + 4 * l + co) * HW + (r0 + r) * DB_W + lane] = v[r][co];
+          const float v = (co & 1) ? v2[r][co >> 1].y : v2[r][co >> 1].x;
+          if (l < DB_MAXL - 1) NEW[((size_t)(l * DS_CH + co) * DS_H + r0 + r) * DB_W + lane] = v;
+          bn_[(long long)(a.c0 + 4 * l + co) * HW + (r0 + r) * DB_W + lane] = v;
         }
     };
     for (int k = 0; k < nchunks; ++k) {

@@ -97,9 +97,11 @@ __device__ void stage_group(const KsNet& n, int grp, float* __restrict__ dst, in
 template <int CIN>
 __device__ __forceinline__ void dense_layer(float* __restrict__ D, const float* __restrict__ wj, const float* __restrict__ sc,
                                             const float* __restrict__ sh, int l, int h) {
-  float acc[4][3];
+  // packed fp32 FMAs (fma.rn.f32x2) over output-channel pairs: acc2[pair][position]; every lane of a pair is the same IEEE fma chain as
+  // the scalar form (bit-identical), at half the FMA issue slots
+  float2 acc2[2][3];
 #pragma unroll
-  for (int c = 0; c < 4; ++c) { acc[c][0] = 0.f; acc[c][1] = 0.f; acc[c][2] = 0.f; }
+  for (int c = 0; c < 2; ++c) { acc2[c][0] = make_float2(0.f, 0.f); acc2[c][1] = make_float2(0.f, 0.f); acc2[c][2] = make_float2(0.f, 0.f); }
   constexpr int HC = CIN / 2;
   const int c0 = h * HC;
 #pragma unroll 2
@@ -111,14 +113,21 @@ __device__ __forceinline__ void dense_layer(float* __restrict__ D, const float* 
     const float aL = __shfl_sync(0xffffffffu, a2, l + 15, 16), aR = __shfl_sync(0xffffffffu, a0, l + 1, 16);
     const float4 w0 = *reinterpret_cast<const float4*>(wj + ci * 12), w1 = *reinterpret_cast<const float4*>(wj + ci * 12 + 4),
                  w2 = *reinterpret_cast<const float4*>(wj + ci * 12 + 8);
-    const float k0[4] = {w0.x, w0.y, w0.z, w0.w}, k1[4] = {w1.x, w1.y, w1.z, w1.w}, k2[4] = {w2.x, w2.y, w2.z, w2.w};
+    const float2 k0[2] = {make_float2(w0.x, w0.y), make_float2(w0.z, w0.w)}, k1[2] = {make_float2(w1.x, w1.y), make_float2(w1.z, w1.w)},
+                 k2[2] = {make_float2(w2.x, w2.y), make_float2(w2.z, w2.w)};
+    const float2 vL = make_float2(aL, aL), v0 = make_float2(a0, a0), v1 = make_float2(a1, a1), v2 = make_float2(a2, a2), vR = make_float2(aR, aR);
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      acc[c][0] = fmaf(k0[c], aL, fmaf(k1[c], a0, fmaf(k2[c], a1, acc[c][0])));
-      acc[c][1] = fmaf(k0[c], a0, fmaf(k1[c], a1, fmaf(k2[c], a2, acc[c][1])));
-      acc[c][2] = fmaf(k0[c], a1, fmaf(k1[c], a2, fmaf(k2[c], aR, acc[c][2])));
+    for (int c = 0; c < 2; ++c) {
+      acc2[c][0] = __ffma2_rn(k0[c], vL, __ffma2_rn(k1[c], v0, __ffma2_rn(k2[c], v1, acc2[c][0])));
+      acc2[c][1] = __ffma2_rn(k0[c], v0, __ffma2_rn(k1[c], v1, __ffma2_rn(k2[c], v2, acc2[c][1])));
+      acc2[c][2] = __ffma2_rn(k0[c], v1, __ffma2_rn(k1[c], v2, __ffma2_rn(k2[c], vR, acc2[c][2])));
     }
   }
+  float acc[4][3];
+#pragma unroll
+  for (int c = 0; c < 2; ++c)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { acc[2 * c][j] = acc2[c][j].x; acc[2 * c + 1][j] = acc2[c][j].y; }
 #pragma unroll
   for (int c = 0; c < 4; ++c)
 #pragma unroll
@@ -173,25 +182,28 @@ __global__ void __launch_bounds__(512, 1) ks_rollout_kernel(KsNet net, float* __
 #pragma unroll
         for (int pass = 0; pass < 2; ++pass) {
           const int ct = h + 2 * pass;
-          float acc[8][3];
+          float2 acc2[4][3];                                // [output-channel pair][position]
 #pragma unroll
-          for (int c = 0; c < 8; ++c) { acc[c][0] = 0.f; acc[c][1] = 0.f; acc[c][2] = 0.f; }
+          for (int c = 0; c < 4; ++c) { acc2[c][0] = make_float2(0.f, 0.f); acc2[c][1] = make_float2(0.f, 0.f); acc2[c][2] = make_float2(0.f, 0.f); }
 #pragma unroll
           for (int ci = 0; ci < 2; ++ci)
 #pragma unroll
             for (int k = 0; k < 7; ++k) {
               const float4 wa = *reinterpret_cast<const float4*>(P + W0 + (ci * 7 + k) * 32 + ct * 8);
               const float4 wb = *reinterpret_cast<const float4*>(P + W0 + (ci * 7 + k) * 32 + ct * 8 + 4);
-              const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+              const float2 wv[4] = {make_float2(wa.x, wa.y), make_float2(wa.z, wa.w), make_float2(wb.x, wb.y), make_float2(wb.z, wb.w)};
 #pragma unroll
-              for (int c = 0; c < 8; ++c)
+              for (int j = 0; j < 3; ++j) {
+                const float2 vv = make_float2(v[ci][2 * j + k], v[ci][2 * j + k]);
 #pragma unroll
-                for (int j = 0; j < 3; ++j) acc[c][j] = fmaf(wv[c], v[ci][2 * j + k], acc[c][j]);
+                for (int c = 0; c < 4; ++c) acc2[c][j] = __ffma2_rn(wv[c], vv, acc2[c][j]);
+              }
             }
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            float* o = D + (ct * 8 + c) * LH + 3 * l;
-            o[0] = acc[c][0]; o[1] = acc[c][1]; o[2] = acc[c][2];
+          for (int c = 0; c < 4; ++c) {
+            float* o = D + (ct * 8 + 2 * c) * LH + 3 * l;
+            o[0] = acc2[c][0].x; o[1] = acc2[c][1].x; o[2] = acc2[c][2].x;
+            o[LH] = acc2[c][0].y; o[LH + 1] = acc2[c][1].y; o[LH + 2] = acc2[c][2].y;
           }
         }
         __syncwarp();
@@ -203,27 +215,30 @@ __global__ void __launch_bounds__(512, 1) ks_rollout_kernel(KsNet net, float* __
       dense_layer<44>(D, P + WD3, P + SC + 108, P + SH + 108, l, h);
       // ---- LastTransUp.conv1: BN, ReLU, 1x1 conv 48 -> 24; half-warp h computes channels [12h, 12h + 12); the result replaces D
       {
-        float acc[12][3];
+        float2 acc2[6][3];                                  // [output-channel pair][position]
 #pragma unroll
-        for (int c = 0; c < 12; ++c) { acc[c][0] = 0.f; acc[c][1] = 0.f; acc[c][2] = 0.f; }
+        for (int c = 0; c < 6; ++c) { acc2[c][0] = make_float2(0.f, 0.f); acc2[c][1] = make_float2(0.f, 0.f); acc2[c][2] = make_float2(0.f, 0.f); }
 #pragma unroll 2
         for (int ci = 0; ci < 48; ++ci) {
           const float s = P[SC + 152 + ci], tt = P[SH + 152 + ci];
           const float* row = D + ci * LH + 3 * l;
           const float a0 = act(row[0], s, tt), a1 = act(row[1], s, tt), a2 = act(row[2], s, tt);
+          const float2 v0 = make_float2(a0, a0), v1 = make_float2(a1, a1), v2 = make_float2(a2, a2);
           const float* wp = P + W1 + ci * 24 + 12 * h;
           const float4 wa = *reinterpret_cast<const float4*>(wp), wb = *reinterpret_cast<const float4*>(wp + 4), wc = *reinterpret_cast<const float4*>(wp + 8);
-          const float wv[12] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w, wc.x, wc.y, wc.z, wc.w};
+          const float2 wv[6] = {make_float2(wa.x, wa.y), make_float2(wa.z, wa.w), make_float2(wb.x, wb.y), make_float2(wb.z, wb.w),
+                                make_float2(wc.x, wc.y), make_float2(wc.z, wc.w)};
 #pragma unroll
-          for (int c = 0; c < 12; ++c) {
-            acc[c][0] = fmaf(wv[c], a0, acc[c][0]); acc[c][1] = fmaf(wv[c], a1, acc[c][1]); acc[c][2] = fmaf(wv[c], a2, acc[c][2]);
+          for (int c = 0; c < 6; ++c) {
+            acc2[c][0] = __ffma2_rn(wv[c], v0, acc2[c][0]); acc2[c][1] = __ffma2_rn(wv[c], v1, acc2[c][1]); acc2[c][2] = __ffma2_rn(wv[c], v2, acc2[c][2]);
           }
         }
         __syncwarp();                                      // every lane has read D
 #pragma unroll
-        for (int c = 0; c < 12; ++c) {
-          float* o = D + (12 * h + c) * LH + 3 * l;        // E [24][48] over the dead dense-block buffer
-          o[0] = acc[c][0]; o[1] = acc[c][1]; o[2] = acc[c][2];
+        for (int c = 0; c < 6; ++c) {
+          float* o = D + (12 * h + 2 * c) * LH + 3 * l;    // E [24][48] over the dead dense-block buffer
+          o[0] = acc2[c][0].x; o[1] = acc2[c][1].x; o[2] = acc2[c][2].x;
+          o[LH] = acc2[c][0].y; o[LH + 1] = acc2[c][1].y; o[LH + 2] = acc2[c][2].y;
         }
         __syncwarp();
       }
@@ -231,11 +246,11 @@ __global__ void __launch_bounds__(512, 1) ks_rollout_kernel(KsNet net, float* __
       //      out[2p] = w0 a[p-1] + (w1 + w2) a[p],  out[2p+1] = (w0 + w1) a[p] + w2 a[p+1]; half-warp h computes channels [6h, 6h + 6)
       {
         float* F = D + 1152;                               // F [12][96]
-        float acc[6][6];
+        float2 acc2[3][6];                                  // [output-channel pair][high-resolution position]
 #pragma unroll
-        for (int c = 0; c < 6; ++c)
+        for (int c = 0; c < 3; ++c)
 #pragma unroll
-          for (int q = 0; q < 6; ++q) acc[c][q] = 0.f;
+          for (int q = 0; q < 6; ++q) acc2[c][q] = make_float2(0.f, 0.f);
 #pragma unroll 2
         for (int ci = 0; ci < 24; ++ci) {
           const float s = P[SC + 200 + ci], tt = P[SH + 200 + ci];
@@ -245,26 +260,32 @@ __global__ void __launch_bounds__(512, 1) ks_rollout_kernel(KsNet net, float* __
           a[0] = __shfl_sync(0xffffffffu, a[3], l + 15, 16);
           a[4] = __shfl_sync(0xffffffffu, a[1], l + 1, 16);
           const float* wp = P + W2 + (ci * 2 + h) * 32;
-          float f[4][6];
+          float2 f[4][3];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const float4 wa = *reinterpret_cast<const float4*>(wp + q * 8);
             const float2 wb = *reinterpret_cast<const float2*>(wp + q * 8 + 4);
-            f[q][0] = wa.x; f[q][1] = wa.y; f[q][2] = wa.z; f[q][3] = wa.w; f[q][4] = wb.x; f[q][5] = wb.y;
+            f[q][0] = make_float2(wa.x, wa.y); f[q][1] = make_float2(wa.z, wa.w); f[q][2] = wb;
           }
+          float2 a2[5];
 #pragma unroll
-          for (int c = 0; c < 6; ++c)
+          for (int j = 0; j < 5; ++j) a2[j] = make_float2(a[j], a[j]);
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
 #pragma unroll
             for (int j = 0; j < 3; ++j) {
-              acc[c][2 * j] = fmaf(f[0][c], a[j], fmaf(f[1][c], a[j + 1], acc[c][2 * j]));
-              acc[c][2 * j + 1] = fmaf(f[2][c], a[j + 1], fmaf(f[3][c], a[j + 2], acc[c][2 * j + 1]));
+              acc2[c][2 * j] = __ffma2_rn(f[0][c], a2[j], __ffma2_rn(f[1][c], a2[j + 1], acc2[c][2 * j]));
+              acc2[c][2 * j + 1] = __ffma2_rn(f[2][c], a2[j + 1], __ffma2_rn(f[3][c], a2[j + 2], acc2[c][2 * j + 1]));
             }
         }
 #pragma unroll
-        for (int c = 0; c < 6; ++c) {
-          float* o = F + (6 * h + c) * L + 6 * l;
+        for (int c = 0; c < 3; ++c) {
+          float* o = F + (6 * h + 2 * c) * L + 6 * l;
 #pragma unroll
-          for (int q = 0; q < 6; q += 2) *reinterpret_cast<float2*>(o + q) = make_float2(acc[c][q], acc[c][q + 1]);
+          for (int q = 0; q < 6; q += 2) {
+            *reinterpret_cast<float2*>(o + q) = make_float2(acc2[c][q].x, acc2[c][q + 1].x);
+            *reinterpret_cast<float2*>(o + L + q) = make_float2(acc2[c][q].y, acc2[c][q + 1].y);
+          }
         }
         __syncwarp();
       }

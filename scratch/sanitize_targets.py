@@ -41,6 +41,16 @@ for N, n in ((3, 64), (2, 256), (2, 24)):
     for mode in (0, 1):
         L.call('arpde_cn_burgers2d_bwd', L.ptr(hist[:, 4:6]), hist.stride(0), L.ptr(hist[:, 2:4]), hist.stride(0), L.ptr(gg), L.ptr(ga), L.ptr(gb), N, n, n, 1.0 / n, 0.005, 0.003, mode, L.stream())
 torch.cuda.synchronize(); print('stencil bwd ok')
+# stencil forward (bulk-copy ring kernels incl. EDGE variant, ragged strips, many items per CTA), API form + fused loss
+for N, H, W in ((3, 64, 64), (2, 256, 256), (400, 16, 16), (3, 18, 64), (2, 10, 384), (1, 8, 1024), (2, 17, 23)):
+    hist = torch.randn(N, 6, H, W, device=dev); up = torch.randn(N, 2, H, W, device=dev)
+    out = torch.empty(N, 2, H, W, device=dev); sse = torch.zeros((), device=dev, dtype=torch.float64)
+    for mode in (0, 1):
+        L.call('arpde_cn_burgers2d_fwd', L.ptr(up), 2 * H * W, L.ptr(hist[:, -2:]), 6 * H * W, L.ptr(out), L.ptr(sse), N, H, W, 1.0 / W, 0.005, 0.004, mode, L.stream())
+        L.call('arpde_cn_burgers2d_fwd', L.ptr(up), 2 * H * W, L.ptr(hist[:, -2:]), 6 * H * W, 0, L.ptr(sse), N, H, W, 1.0 / W, 0.005, 0.004, mode, L.stream())
+        ga = torch.empty(N, 2, H, W, device=dev); gb = torch.empty_like(ga)
+        L.call('arpde_cn_burgers2d_bwd', L.ptr(up), 2 * H * W, L.ptr(hist[:, -2:]), 6 * H * W, L.ptr(out), L.ptr(ga), L.ptr(gb), N, H, W, 1.0 / W, 0.005, 0.003, mode, L.stream())
+torch.cuda.synchronize(); print('stencil fwd ok')
 # FD solver
 u = solver.fd_burgers1d(torch.randn(2, 128, device=dev, dtype=torch.float64), 1e-4, 20, save_every=5)
 u2 = solver.fd_burgers1d(torch.randn(1, 2048, device=dev, dtype=torch.float64) * 0.1, 1e-5, 5, grad_order=(2, 4))

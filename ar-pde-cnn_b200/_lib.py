@@ -43,6 +43,7 @@ _PROTOS = {
     'arpde_cn_burgers2d_bwd': [f32p, i64, f32p, i64, f32p, f32p, f32p, i32, i32, i32, f64, f64, f64, i32, vp],
     'arpde_cn_burgers2d_bwd_generic': [f32p, i64, f32p, i64, f32p, f32p, f32p, i32, i32, i32, f64, f64, f64, i32, vp],
     'arpde_cn_1d_bwd': [i32, f32p, i64, f32p, i64, f32p, f32p, f32p, i32, i32, f64, f64, f64, i32, i32, i32, i32, vp],
+    'arpde_stencil_bulk_plan': [i32, i32, i32, i32, i32, vp, vp, vp, vp],
     'arpde_filter1d': [f32p, f32p, i64, i32, vp, vp],
     'arpde_filter2d': [f32p, f32p, i64, i32, i32, vp, vp],
     'arpde_neg_log_joint_fwd': [f32p, f32p, i64, i32, f32p, vp, vp, i32, f64, f64, f64, f64, f64, f32p, f64p, vp],

@@ -833,6 +833,19 @@ static bool bulk_plan(int N, int H, int W, int RB, int NCW, int NF, BulkPlan* p)
   return p->items < (1ll << 31);
 }
 
+extern "C" int arpde_stencil_bulk_plan(int N, int H, int W, int backward, int mode, int* rows_per_item, int* stages, int64_t* smem_bytes,
+                                       int64_t* items) {
+  if (N < 1 || H < 1 || W < 1 || (mode != ARPDE_CN && mode != ARPDE_BE)) return 0;
+  BulkPlan bp;
+  const bool ok = backward ? bulk_plan(N, H, W, 2, 8, mode == ARPDE_CN ? 6 : 4, &bp) : bulk_plan(N, H, W, 4, 8, 4, &bp);
+  if (!ok) return 0;
+  if (rows_per_item) *rows_per_item = bp.TY;
+  if (stages) *stages = bp.NS;
+  if (smem_bytes) *smem_bytes = (int64_t)bp.smem;
+  if (items) *items = bp.items;
+  return 1;
+}
+
 static int make_b2coef(double dx, double nu, double dt, int mode, B2Coef* k) {
   ARPDE_CHECK_ARG(dx > 0 && (mode == ARPDE_CN || mode == ARPDE_BE), "burgers2d: bad dx=%g or mode=%d", dx, mode);
   k->k1 = (float)(0.125 / dx); k->k1h = (float)(0.0625 / dx); k->k2 = (float)(nu * 0.5 / (dx * dx));

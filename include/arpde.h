@@ -83,6 +83,11 @@ int arpde_cn_burgers2d_bwd(const float* uPred, int64_t up_bstride, const float* 
 int arpde_cn_burgers2d_bwd_generic(const float* uPred, int64_t up_bstride, const float* uPred0, int64_t u0_bstride,
                                    const float* grad_ustar, float* grad_uPred, float* grad_uPred0, int N, int H, int W,
                                    double dx, double nu, double dt, int mode, arpde_stream_t stream);
+/* Host-only test hook (no device access): the tiling the bulk-copy ring kernels behind arpde_cn_burgers2d_fwd / _bwd use for a batch of N
+ * fields of H x W.  Returns 1 and fills rows_per_item, stages, smem_bytes, items when the shape takes that path (W/4 a power of two <= 32
+ * or a multiple of 32, a double-buffered tile within shared memory), 0 when it falls back to the other kernels. */
+int arpde_stencil_bulk_plan(int N, int H, int W, int backward, int mode, int* rows_per_item, int* stages, int64_t* smem_bytes,
+                            int64_t* items);
 int arpde_cn_1d_bwd(int system, const float* uPred, int64_t up_bstride, const float* uPred0, int64_t u0_bstride,
                     const float* grad_ustar, float* grad_uPred, float* grad_uPred0, int N, int L, double dx,
                     double nu, double dt, int k1, int k2, int k4, int mode, arpde_stream_t stream);

@@ -7,8 +7,9 @@
 // layer instead:
 //   * operands in the fp16 two-term split of conv_z.cu (x = x_hi + 2^-11 x_lo', products exact, fp32 accumulation in TMEM);
 //   * the whole input octet (cin <= 7 channels + the constant below) of a position is ONE 16-byte K unit, so the second K unit of a K = 16 MMA can be the
-//     SAME buffer one position further (descriptor LBO = 16 bytes): one MMA covers two horizontal taps -- 15 tap pairs instead of 25 taps
-//     for 5x5, every MMA with full K;
+//     SAME buffer at another position -- the descriptor's LBO is free: 16 bytes = the next column, pitch x 16 bytes = the next row.  Taps
+//     are paired vertically, (ky, kx) with (ky + 1, kx), the last filter row horizontally: 13 MMAs per accumulator half instead of 25
+//     taps for 5x5 (pairing along the rows only needed 15: every third pair carried a zero tap);
 //   * the prepared weights of a SWAG sample (15 x 2 x 2 cout rows x 16 B = 92 KB) stay resident in shared memory, the input patch of
 //     half a sample (36 rows x 68 positions, hi + lo = 78 KB) is loaded AND split by 8 warps into registers while the current item's MMAs
 //     run, so that only the 16-byte stores are left after the hand-over;
@@ -53,7 +54,7 @@ struct ConvStemArgs {
   const uint4* wz; long long wz_gs16;
   uint4* z; long long z_bs16;
   // lane `cin` (< 8) of every input octet is the constant 1, its centre-tap weight the consumer's BatchNorm shift; the scale is folded into the weights
-  int N, n_per_group, cin, H, W, cout, k, pad, npairs, kwp;       // kwp = ceil(k / 2) horizontal tap pairs
+  int N, n_per_group, cin, H, W, cout, k, pad, npairs, nvert;     // tap pairs: nvert vertical ones (ky even, every kx), then the last row in horizontal pairs
   int pitch, RI, items_per_sample, nt, P;                          // rows per item, M tiles per item, patch positions (padded)
   int w16;                                                          // 16-byte units of the resident weight image
   long long* tl;                                                    // development build: clock64 timeline of CTA 0 (arpde_conv_tc_set_debug buffer)
@@ -79,6 +80,13 @@ __device__ __forceinline__ void split2(float e0, float e1, uint32_t* hw, uint32_
   const uint32_t h = pack_sat(e0, e1);
   const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&h));
   *hw = h; *lw = pack_sat((e0 - hf.x) * 2048.f, (e1 - hf.y) * 2048.f);
+}
+
+// tap pair p of a k x k filter: unit 0 = tap (ky, kx), unit 1 = the tap below it (vertical pairs, p < nvert) or to its right (the last
+// filter row; kx + 1 == k: no second tap).  Shared by the MMA issue loop (patch offset, LBO) and the weight preparation.
+__host__ __device__ __forceinline__ void stem_pair_taps(int p, int k, int nvert, int* ky, int* kx, int* vertical) {
+  if (p < nvert) { *ky = 2 * (p / k); *kx = p - (p / k) * k; *vertical = 1; }
+  else { *ky = k - 1; *kx = 2 * (p - nvert); *vertical = 0; }
 }
 
 __global__ void __launch_bounds__(CS_THREADS, 1) conv_stem_kernel(const __grid_constant__ ConvStemArgs a) {
@@ -250,11 +258,10 @@ __global__ void __launch_bounds__(CS_THREADS, 1) conv_stem_kernel(const __grid_c
     const bool leader = elect_one();
     const uint32_t idesc1 = umma_idesc_f16(128, 2 * a.cout), idesc2 = umma_idesc_f16(128, a.cout);
     const uint64_t hi64 = (uint64_t)((128u >> 4) | (1u << 14)) << 32;          // SBO = 128 B, descriptor version 1
-    const uint32_t a_hi = (smem_u32(patch_hi) >> 4) | (1u << 16);              // LBO = 16 B: the second K unit is the next position
-    const uint32_t a_lo = (smem_u32(patch_lo) >> 4) | (1u << 16);
+    const uint32_t a_hi = smem_u32(patch_hi) >> 4, a_lo = smem_u32(patch_lo) >> 4;   // + LBO per pair: where the second K unit sits
     const uint32_t b_base = (smem_u32(wbuf) >> 4) | ((uint32_t)(2 * a.cout) << 16);
     const uint32_t pair16 = 4u * (uint32_t)a.cout, cout = (uint32_t)a.cout;
-    const int nt = a.nt, kwp = a.kwp, k = a.k, pitch = a.pitch;
+    const int nt = a.nt, k = a.k, pitch = a.pitch;
     int g_loaded = -1, wgen = 0, gt = 0;
     int tlc = 0; (void)tlc;
     for (int it = it_begin; it < it_end; ++it) {
@@ -273,15 +280,18 @@ __global__ void __launch_bounds__(CS_THREADS, 1) conv_stem_kernel(const __grid_c
         if (leader) {
           const uint32_t d = tmem + (uint32_t)slot * (2u * cout);
           uint32_t acc = 0u, wb = b_base;
-          for (int ky = 0; ky < k; ++ky) {
-            uint32_t off = (uint32_t)(t * 128 + ky * pitch);
-            for (int j = 0; j < kwp; ++j) {
-              const uint64_t db = hi64 | wb;
-              umma_f16(d, hi64 | (uint64_t)(a_hi + off), db, idesc1, acc);          // hi * [hi ; lo']
-              umma_f16(d + cout, hi64 | (uint64_t)(a_lo + off), db, idesc2, 1u);     // lo' * hi -> correction half
-              acc = 1u; off += 2; wb += pair16;
-            }
+          auto issue = [&](uint32_t off, uint32_t lbo) {
+            const uint64_t db = hi64 | wb;
+            umma_f16(d, hi64 | (uint64_t)((a_hi + off) | lbo), db, idesc1, acc);          // hi * [hi ; lo']
+            umma_f16(d + cout, hi64 | (uint64_t)((a_lo + off) | lbo), db, idesc2, 1u);     // lo' * hi -> correction half
+            acc = 1u; wb += pair16;
+          };
+          // pair order of stem_pair_taps(): vertical pairs (second K unit one row down), then the last filter row in horizontal pairs
+          for (int ky = 0; ky + 1 < k; ky += 2) {
+            const uint32_t off = (uint32_t)(t * 128 + ky * pitch);
+            for (int kx = 0; kx < k; ++kx) issue(off + (uint32_t)kx, (uint32_t)pitch << 16);
           }
+          for (int kx = 0; kx < k; kx += 2) issue((uint32_t)(t * 128 + (k - 1) * pitch + kx), 1u << 16);
         }
         __syncwarp();
         if (leader) umma_commit(tile_full + slot);
@@ -320,11 +330,13 @@ __global__ void __launch_bounds__(CS_THREADS, 1) conv_stem_kernel(const __grid_c
   if (warp == CS_WARP_MMA) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
 }
 
-// w [groups][cout][cin][k][k] -> out [groups][pair = ky * kwp + j][unit 2][row 2 cout][8 halfs]: unit u holds tap (ky, 2j + u) (zeros past
-// the filter edge), rows [0, cout) the fp16 hi part of output channel `row`, rows [cout, 2 cout) fp16((w' - hi) * 2^11) of the folded weight w'
+// w [groups][cout][cin][k][k] -> out [groups][pair][unit 2][row 2 cout][8 halfs]: unit u of pair p holds the tap stem_pair_taps() names
+// (zeros where the pair has no second tap), rows [0, cout) the fp16 hi part of output channel `row`, rows [cout, 2 cout)
+// fp16((w' - hi) * 2^11) of the folded weight w'
 __global__ void conv_stem_wprep_kernel(const float* __restrict__ w, long long w_gs, const float* __restrict__ scale, const float* __restrict__ shift,
-                                       long long ss_gs, __half* __restrict__ out, long long out_gs, int cin, int cout, int k, int kwp, int groups) {
-  const long long per_group = (long long)k * kwp * 2 * (2 * cout) * 8;
+                                       long long ss_gs, __half* __restrict__ out, long long out_gs, int cin, int cout, int k, int npairs, int nvert,
+                                       int groups) {
+  const long long per_group = (long long)npairs * 2 * (2 * cout) * 8;
   const int pad = (k - 1) / 2;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < per_group * groups; i += (long long)gridDim.x * blockDim.x) {
     const int g = (int)(i / per_group);
@@ -332,22 +344,27 @@ __global__ void conv_stem_wprep_kernel(const float* __restrict__ w, long long w_
     const int ci = (int)(r & 7); r >>= 3;
     const int row = (int)(r % (2 * cout)); r /= 2 * cout;
     const int u = (int)(r & 1); r >>= 1;
-    const int j = (int)(r % kwp), ky = (int)(r / kwp);
-    const int kx = 2 * j + u, co = row < cout ? row : row - cout;
+    int ky, kx, vertical;
+    stem_pair_taps((int)r, k, nvert, &ky, &kx, &vertical);
+    if (u) { if (vertical) ++ky; else ++kx; }
+    const int co = row < cout ? row : row - cout;
     // the consumer's eval-mode BatchNorm folded into the producer: scale * conv(x, w) + shift = conv([x, 1], [scale * w, shift at the centre tap])
     float v = 0.f;
-    if (ci < cin && kx < k) v = __ldg(scale + (long long)g * ss_gs + co) * w[(long long)g * w_gs + (((long long)co * cin + ci) * k + ky) * k + kx];
+    if (ci < cin && kx < k && ky < k) v = __ldg(scale + (long long)g * ss_gs + co) * w[(long long)g * w_gs + (((long long)co * cin + ci) * k + ky) * k + kx];
     else if (ci == cin && ky == pad && kx == pad) v = __ldg(shift + (long long)g * ss_gs + co);
     const __half hi = __float2half_rn(v);
     out[(long long)g * out_gs + (i - (long long)g * per_group)] = row < cout ? hi : __float2half_rn((v - __half2float(hi)) * 2048.f);
   }
 }
 
+static int stem_nvert(int k) { return ((k - 1) / 2) * k; }
+static int stem_npairs(int k) { return stem_nvert(k) + (k + 1) / 2; }
+
 bool cs_plan(const ConvDesc& d, ConvStemArgs& a, size_t* smem_out) {
   if (d.kh != d.kw || !(d.kh & 1) || d.kh > 7 || d.stride != 1 || d.up || d.dilate || d.pad_override >= 0 || d.act != 0 || d.relu_in) return false;
   if (d.cin > 7 || d.cout % 16 || d.cout < 16 || d.cout > 128 || (d.H & 1) || (d.W & 1) || d.H < 4 || d.W < 4 || d.W < d.kh) return false;
   memset(&a, 0, sizeof(a));
-  a.cin = d.cin; a.H = d.H; a.W = d.W; a.cout = d.cout; a.k = d.kh; a.pad = (d.kh - 1) / 2; a.kwp = (d.kh + 1) / 2; a.npairs = d.kh * a.kwp;
+  a.cin = d.cin; a.H = d.H; a.W = d.W; a.cout = d.cout; a.k = d.kh; a.pad = (d.kh - 1) / 2; a.nvert = stem_nvert(d.kh); a.npairs = stem_npairs(d.kh);
   a.pitch = d.W + d.kh - 1;
   a.w16 = a.npairs * 2 * 2 * d.cout;
   const size_t budget = 226 * 1024;
@@ -388,16 +405,15 @@ bool arpde_conv_stem_wanted(const ConvDesc& d) {
 }
 
 // prepared fp16 weights per group in fp32 floats of scratch (<= arpde_conv_tc_wprep_floats of the same layer)
-long long arpde_conv_stem_wprep_floats(int cout, int k) { return (long long)k * ((k + 1) / 2) * 2 * (2 * cout) * 8 / 2; }
+long long arpde_conv_stem_wprep_floats(int cout, int k) { return (long long)stem_npairs(k) * 2 * (2 * cout) * 8 / 2; }
 
 int arpde_conv_stem_prep_launch(const ConvDesc& d, const float* w, long long w_gs, int groups, float* wprep, long long wprep_gs, const ZOut& zo,
                                 cudaStream_t stream) {
   ARPDE_CHECK_ARG(zo.scale && zo.shift && (groups == 1 || zo.ss_gs > 0), "conv_stem: the consumer's BatchNorm scale / shift are folded into the prepared weights");
-  const int kwp = (d.kh + 1) / 2;
-  const long long n = (long long)d.kh * kwp * 2 * (2 * d.cout) * 8 * groups;
+  const long long n = (long long)stem_npairs(d.kh) * 2 * (2 * d.cout) * 8 * groups;
   long long blocks = (n + 255) / 256; if (blocks > 4096) blocks = 4096;
   conv_stem_wprep_kernel<<<(unsigned)blocks, 256, 0, stream>>>(w, w_gs, zo.scale, zo.shift, groups > 1 ? zo.ss_gs : 0, reinterpret_cast<__half*>(wprep), 2 * wprep_gs,
-                                                               d.cin, d.cout, d.kh, kwp, groups);
+                                                               d.cin, d.cout, d.kh, stem_npairs(d.kh), stem_nvert(d.kh), groups);
   ARPDE_LAUNCH_CHECK();
   return ARPDE_OK;
 }

@@ -28,6 +28,7 @@
 #include "conv_common.cuh"
 #include "../../include/arpde.h"
 #include <cuda_fp16.h>
+#include <stdlib.h>
 #include <mutex>
 #include "tc_ptx.cuh"
 
@@ -58,6 +59,7 @@ struct ConvStemArgs {
   int pitch, RI, items_per_sample, nt, P;                          // rows per item, M tiles per item, patch positions (padded)
   int w16;                                                          // 16-byte units of the resident weight image
   long long* tl;                                                    // development build: clock64 timeline of CTA 0 (arpde_conv_tc_set_debug buffer)
+  int dbg;                                                          // development build only (ARPDE_STEM_DBG): 1 = the epilogue skips its stores
 };
 
 __device__ __forceinline__ uint32_t umma_idesc_f16(int M, int N) { return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24); }
@@ -196,10 +198,10 @@ __global__ void __launch_bounds__(CS_THREADS, 1) conv_stem_kernel(const __grid_c
         const uint32_t trow = tmem + ((uint32_t)lanebase << 16) + (uint32_t)(slot * tile_cols);
         const int q = t * 128 + lanebase + lane;
         const int oyl = q / a.pitch, ox = q - oyl * a.pitch;
-        const bool valid = oyl < a.RI && ox < a.W;
+        const bool valid = oyl < a.RI && ox < a.W && !(a.dbg & 1);
         const int oy = b * a.RI + oyl;
         const int yy = (oy >> 1) + 1, xx = (ox >> 1) + 1;
-        uint4* zp0 = a.z + (long long)n * a.z_bs16 + (long long)((oy & 1) * 2 + (ox & 1)) * plane16;
+        uint4* zp0 = a.z + (long long)((a.dbg & 2) ? (n & 15) : n) * a.z_bs16 + (long long)((oy & 1) * 2 + (ox & 1)) * plane16;   // dbg 2: all stores into 16 samples of Z (27 MB, L2-resident)
         const bool hx = xx == PWz - 1, hy = yy == PHz - 1;
         // The accumulator slot is handed back as soon as this warp's LAST block has landed in registers: with two slots in TMEM the time a
         // slot is held stalls the MMAs (scratch/stem_timeline.py).  (A two-buffer software pipeline of the TMEM loads was measured slower:
@@ -427,6 +429,7 @@ int arpde_conv_stem_launch(const ConvDesc& d, const float* x, long long x_bs, co
   a.x = x; a.x_bs = x_bs; a.wz = reinterpret_cast<const uint4*>(wprep); a.wz_gs16 = wprep_gs / 4;
   a.z = reinterpret_cast<uint4*>(zo.z); a.z_bs16 = arpde_conv_z_sample16(d.cout, d.H, d.W);
   a.N = d.N; a.n_per_group = d.n_per_group; a.tl = arpde_tc_debug_buffer();
+  a.dbg = arpde_dev_env("ARPDE_STEM_DBG") ? atoi(arpde_dev_env("ARPDE_STEM_DBG")) : 0;
   static std::mutex attr_mutex;
   static bool attr_done[64] = {false};
   {

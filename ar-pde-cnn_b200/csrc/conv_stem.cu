@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(CS_THREADS, 1) conv_stem_kernel(const __grid_c
     const int e = warp - CS_WARP_EPI0;
     const int lanebase = (e & 3) * 32, half = e >> 2;
     const int PWz = (a.W >> 1) + 1, PHz = (a.H >> 1) + 1;
-    const long long plane16 = (long long)PHz * PWz, hl = 4 * plane16;
+    const long long plane16 = (long long)PHz * PWz, hl_planes = 4 * plane16;
     const int nblk = a.cout >> 4;
     const float lo_scale = 1.f / 2048.f;
     int gt = 0;
@@ -201,16 +201,21 @@ __global__ void __launch_bounds__(CS_THREADS, 1) conv_stem_kernel(const __grid_c
         const bool valid = oyl < a.RI && ox < a.W && !(a.dbg & 1);
         const int oy = b * a.RI + oyl;
         const int yy = (oy >> 1) + 1, xx = (ox >> 1) + 1;
-        uint4* zp0 = a.z + (long long)((a.dbg & 2) ? (n & 15) : n) * a.z_bs16 + (long long)((oy & 1) * 2 + (ox & 1)) * plane16;   // dbg 2: all stores into 16 samples of Z (27 MB, L2-resident)
+        const bool rowmajor = (a.dbg & 4) != 0;                       // dbg 4 (timing experiment only): Z as [c8][PH][hi|lo][plane][PW] -- the 8 rows of a plane-row index adjacent
+        const int pl = (oy & 1) * 2 + (ox & 1);
+        const long long hl = rowmajor ? 4 * PWz : hl_planes;
+        uint4* zp0 = a.z + (long long)((a.dbg & 2) ? (n & 15) : n) * a.z_bs16 + (rowmajor ? (long long)pl * PWz : (long long)pl * plane16);   // dbg 2: all stores into 16 samples of Z (27 MB, L2-resident)
         const bool hx = xx == PWz - 1, hy = yy == PHz - 1;
         // The accumulator slot is handed back as soon as this warp's LAST block has landed in registers: with two slots in TMEM the time a
         // slot is held stalls the MMAs (scratch/stem_timeline.py).  (A two-buffer software pipeline of the TMEM loads was measured slower:
         // 64 accumulator registers + spills, drain time 2.3-3.0 k -> 3.0-4.8 k cycles per tile.)
         // store pointers advance by constants (one channel octet = 8 planes of hi / lo): the epilogue is issue-bound, and 64-bit address
         // arithmetic per store was a quarter of its instructions
-        const long long cstride = 8 * plane16;                        // 16-byte units between channel octets: [c8][hi|lo][plane 4][plane16]
-        const int off_main = yy * PWz + xx;
-        const long long d_hx = -(long long)xx, d_hy = -(long long)yy * PWz, d_c = -(long long)off_main;   // halo column / row / corner relative to the pixel
+        const long long cstride = (a.dbg & 8) ? 8 * PWz : 8 * plane16;   // 16-byte units between channel octets: [c8][hi|lo][plane 4][plane16]
+        const bool rowmajor2 = (a.dbg & 8) != 0;                      // dbg 8: Z as [PH][c8][hi|lo][plane][PW] (with dbg 4): all channels of a plane-row index adjacent
+        const int rowpitch = rowmajor ? (rowmajor2 ? (a.cout >> 3) * 8 * PWz : 8 * PWz) : PWz;
+        const int off_main = yy * rowpitch + xx;
+        const long long d_hx = -(long long)xx, d_hy = -(long long)yy * rowpitch, d_c = -(long long)off_main;   // halo column / row / corner relative to the pixel
         uint4* pm = zp0 + (long long)(2 * half) * cstride + off_main;
         const bool halo = hx || hy;
         bool released = false;

@@ -324,11 +324,38 @@ def train_step_probe(dev, B_total=128, weak=False, tback=2, nwarm=3, nrep=10, ra
     e1.record(); torch.cuda.synchronize()
     launches = int(L.lib.arpde_launch_count(1)) // nrep
     ms = e0.elapsed_time(e1) / nrep
+    graph_ms = None
+    if world == 1:
+        # the same step with the BPTT window (forward + integrator + loss + backward into the bucket) replayed from a CUDA graph
+        # (engine.GraphedStep); the optimizer step stays eager
+        from arpde_b200 import engine
+
+        def window(ic_):
+            inp = ic_.repeat(1, 3, 1, 1)
+            loss = 0
+            bucket.zero_()
+            for _ in range(tback):
+                u_pred = swag(inp[:, -6:])
+                ustar = integ.crankNicolson(u_pred, inp[:, -2:], 0.003)
+                loss = loss + swag.calc_neg_log_joint(u_pred, ustar, ntrain)
+                inp = torch.cat([inp, u_pred], 1)
+            with bucket.capture():
+                loss.backward()
+            return loss.detach()
+        try:
+            gstep = engine.GraphedStep(window, (ic.clone(),))
+
+            def step_g(i):
+                gstep()
+                opt.step()
+            graph_ms = time_cuda(step_g, nrep)
+        except Exception as e:                     # capture refused (e.g. an older driver): report the eager number only
+            print('train_step: CUDA-graph capture unavailable (%s)' % repr(e)[:200], file=sys.stderr)
     if world > 1:                                   # slowest rank
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    return {'ms': ms, 'value': world * tback * B / ms * 1e3, 'unit': 'sample-steps/s', 'batch_total': world * B, 'batch_per_gpu': B, 'n_gpus': world,
+    return {'ms': ms, 'graph_ms': graph_ms, 'value': world * tback * B / ms * 1e3, 'unit': 'sample-steps/s', 'batch_total': world * B, 'batch_per_gpu': B, 'n_gpus': world,
             'tback': tback, 'scaling': 'weak' if weak else 'strong', 'library_launches_per_step': launches,
             'parallelism': 'mini-batch sharded x%d: global-batch BatchNorm (per-layer all-reduce of the fp64 sums: %s), gradients accumulated in one flat '
                            'bucket, one all-reduce (NCCL) per optimizer step' % (world, 'one NVLink peer-memory kernel each, csrc/peer.cu' if (

@@ -65,3 +65,48 @@ def test_adam_rejects_cpu_parameters():
     p.grad = torch.ones(3)
     with pytest.raises(RuntimeError, match='no CPU path'):
         Adam([p]).step()
+
+
+def test_graphed_training_window_matches_eager():
+    """engine.GraphedStep: the BPTT window (forward with batch-statistics BatchNorm, Crank-Nicolson, negative log joint, backward into
+    the flat gradient bucket) captured in a CUDA graph replays to the same loss and gradients as the eager calls, also for new inputs."""
+    import types
+    import numpy as np
+    from arpde_b200 import engine, parallel as PL
+    from arpde_b200.nn.densed import DenseED2d
+    from arpde_b200.nn.bayesnn import BayesNN
+    from arpde_b200.nn.integrators import Burger2DIntegrate
+    torch.manual_seed(0); np.random.seed(0)
+    a = types.SimpleNamespace(dt=0.005, device=torch.device(DEV), nic=3)
+    model = DenseED2d(6, 2, [4], growth_rate=4, init_features=48).to(DEV)
+    bayes = BayesNN(a, model)
+    integ = Burger2DIntegrate(1.0 / 32, nu=0.005, grad_kernels=[3, 3], device=DEV)
+    bayes.train()
+    bucket = PL.FlatGradBucket([bayes.model.log_beta] + list(bayes.model.features.parameters()))
+
+    def window(ic):
+        inp = ic.repeat(1, 3, 1, 1)
+        loss = 0
+        bucket.zero_()
+        for _ in range(2):
+            u = bayes(inp[:, -6:])
+            ustar = integ.crankNicolson(u, inp[:, -2:], 0.003)
+            loss = loss + bayes.calc_neg_log_joint(u, ustar, 10)
+            inp = torch.cat([inp, u], 1)
+        with bucket.capture():
+            loss.backward()
+        return loss.detach()
+
+    ic0, ic1 = torch.randn(6, 2, 32, 32, device=DEV), torch.randn(6, 2, 32, 32, device=DEV)
+    # running statistics advance with every call: compare loss and gradients (batch statistics), which do not depend on them
+    ref = []
+    for ic in (ic0, ic1):
+        l = window(ic); ref.append((l.clone(), bucket.flat.clone()))
+    gstep = engine.GraphedStep(window, (ic0.clone(),))
+    for ic, (l_ref, g_ref) in zip((ic0, ic1), ref):
+        l = gstep(ic)
+        torch.cuda.synchronize()
+        assert rel_err(l, l_ref) < 1e-6, (l, l_ref)                  # same launches; fp64 atomics may reorder
+        assert rel_err(bucket.flat, g_ref) < 1e-6
+    with pytest.raises(ValueError):
+        gstep(torch.randn(5, 2, 32, 32, device=DEV))

@@ -155,3 +155,29 @@ def test_bench_reference_arm_prints_the_contract_line():
     from oracle import ref_shims
     if ref_shims.ref_root() is not None:
         assert d['cpu_baseline']['kind'] == 'reference'
+
+
+def test_committed_bench_records_carry_the_contract_keys():
+    """The bench records under profiles/ are what DESIGN.md quotes: the latest one-GPU record and the latest 8-GPU record must hold every
+    key of the measurement contract (metric line, end-to-end number, roofline of the dominant kernel and of the stencil, CPU baseline,
+    clocks, launch counter), with fractions that follow from their own achieved / peak numbers."""
+    import glob
+    import json
+    recs = sorted(glob.glob(os.path.join(ROOT, 'profiles', 'r02*_bench_1gpu.json')))
+    assert recs, 'no one-GPU bench record committed'
+    d = json.loads(open(recs[-1]).read().strip().splitlines()[-1])
+    for k in ('metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling', 'vs_baseline', 'dtype', 'data',
+              'config', 'clocks', 'e2e', 'gpu_launches', 'roofline', 'roofline_stencil', 'cpu_baseline'):
+        assert k in d, k
+    assert d['metric'] == 'ar_steps_x_samples_per_s' and d['n_gpus'] == 1 and d['config']['workload'].startswith('C4')
+    assert d['gpu_launches'] > 0 and d['e2e']['h2d_bytes_per_step'] > 0 and d['e2e']['d2h_bytes_per_step'] > 0
+    assert 0 < d['e2e']['value'] <= d['value'] * 1.001
+    for r in (d['roofline'], d['roofline_stencil']):
+        assert r['bound'] in ('hbm', 'tensor') and abs(r['frac'] - r['achieved'] / r['peak']) < 1e-9
+    assert d['roofline_stencil']['frac'] >= 0.6                    # the north star's stencil target, on the API form at the C4 batch
+    assert d['cpu_baseline']['kind'] in ('reference', 'port') and d['cpu_baseline']['cores'] >= 1
+    assert not set(d['clocks']['reasons']) & {'hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown'}
+    recs8 = sorted(glob.glob(os.path.join(ROOT, 'profiles', 'r02*_bench_8gpu.json')))
+    if recs8:
+        d8 = json.loads(open(recs8[-1]).read().strip().splitlines()[-1])
+        assert d8['n_gpus'] == 8 and d8['scaling'] == 'strong' and d8['config']['ics_per_gpu'] == 8

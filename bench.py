@@ -896,8 +896,8 @@ def main():
         'roofline': {'kernel': 'conv_stem_kernel on In_conv1 (6->96, 5x5 circular, %d samples, 30 weight groups; epilogue = eval BatchNorm + ReLU + fp16 two-term operand '
                                'format for In_conv3): tcgen05 implicit GEMM, kind::f16 two-term split, two horizontal taps per K = 16 MMA (+ its weight-split launch)' % NT,
                      'bound': 'tensor', 'achieved': k1_tflops, 'peak': bf16, 'unit': 'TFLOP/s', 'frac': k1_tflops / bf16,
-                     'traffic': 3.445e9 if world == 1 else None,
-                     'traffic_source': 'ncu --set full, profiles/r02c_step_launches_ncu.md: dram read 0.260 GB + write 3.186 GB per launch at 1920 samples '
+                     'traffic': 3.433e9 if world == 1 else None,
+                     'traffic_source': 'ncu --set full, profiles/r02g_step_launches_ncu.md: dram read 0.252 GB + write 3.181 GB per launch at 1920 samples '
                                        '(algorithmic: 0.189 GB input + 3.211 GB operand-format output)',
                      'peak_source': peaks['source'] + ' bf16 dense (burst)',
                      'note': 'achieved = algorithmic fp32 FLOPs (2*N*H*W*cout*cin*k^2) / CUDA-event time; the 1e-5 parity contract needs the two-term fp16 split '

@@ -10,7 +10,7 @@
 //     SAME buffer at another position -- the descriptor's LBO is free: 16 bytes = the next column, pitch x 16 bytes = the next row.  Taps
 //     are paired vertically, (ky, kx) with (ky + 1, kx), the last filter row horizontally: 13 MMAs per accumulator half instead of 25
 //     taps for 5x5 (pairing along the rows only needed 15: every third pair carried a zero tap);
-//   * the prepared weights of a SWAG sample (15 x 2 x 2 cout rows x 16 B = 92 KB) stay resident in shared memory, the input patch of
+//   * the prepared weights of a SWAG sample (13 pairs x 2 units x 2 cout rows x 16 B = 80 KB) stay resident in shared memory, the input patch of
 //     half a sample (36 rows x 68 positions, hi + lo = 78 KB) is loaded AND split by 8 warps into registers while the current item's MMAs
 //     run, so that only the 16-byte stores are left after the hand-over;
 //   * the consumer's eval-mode BatchNorm is folded into the producer's GEMM: scale * conv(x, w) + shift = conv([x, 1], [scale * w, shift at
@@ -20,10 +20,12 @@
 //     F2FP), 16-byte stores into the four parity planes of Z (lanes = consecutive x alternate between two planes: 2 x 256 contiguous
 //     bytes per store instruction), plus the circular halo copies the consumer expects; a slot is handed back as soon as a warp's last
 //     block is in registers.
-// Roofline: tensor pipe.  Per 128 positions 15 x (N' = 2 cout = 192: 96 cycles + N = 96: 56 cycles) = 2280 cycles against 25 x 152 = 3800
-// for the TF32 form -- measured 2300 (scratch/stem_timeline.py, development build).  What the timeline showed: with the BatchNorm in the
-// epilogue (8 vector loads of scale / shift + 250 instructions per 16-channel block) the epilogue, not the tensor pipe, set the pace: 3500
-// cycles per tile, 6 k cycles of idle tensor pipe at every item boundary while the patch was split.  Now 2700 per tile, 4 k per boundary.
+// Roofline: nominally the tensor pipe -- per 128 positions 13 x (N' = 2 cout = 192: 96 cycles + N = 96: 56 cycles) = 1980 cycles against
+// 25 x 152 = 3800 for the TF32 form (measured: 2005-2060, scratch/stem_timeline.py, development build) -- but the launch is bound by its
+// epilogue and the Z stores: 0.59 ms of MMAs, 0.17 ms of ReLU + split that the two-slot accumulator ring cannot hide, 0.20 ms of DRAM write
+// pattern (ablations ARPDE_STEM_DBG = 1 / 2 / 4).  History: with the BatchNorm in the epilogue (8 vector loads of
+// scale / shift + 250 instructions per 16-channel block) the epilogue set the pace at 3500 cycles per tile and 6 k cycles of idle tensor
+// pipe at every item boundary while the patch was split; folding it into the GEMM gave 2700 per tile, 4 k per boundary.
 #include "common.cuh"
 #include "conv_common.cuh"
 #include "../../include/arpde.h"
